@@ -1,0 +1,190 @@
+"""Device-side operator API: torch CUDA tensors in, torch CUDA tensors out, all compute in libdc_b200.so.
+
+Function names follow the reference's (histogram, huffman -> huff_build, represent_items_with_codes ->
+huff_encode, nybble pack/unpack); every call is stream-ordered on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DC_NSLOTS, TABLE_BYTES, HuffTableStruct, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: data_compression_b200 has no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def launch_count() -> int:
+    return int(lib().dc_launch_count())
+
+
+class HuffTable:
+    """A device-resident ``dc_huff_table`` (lengths, canonical values, encode entries, decode LUT)."""
+
+    def __init__(self, device=None):
+        self.buf = torch.empty(TABLE_BYTES, dtype=torch.uint8, device=device or torch.cuda.current_device())
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def download(self) -> HuffTableStruct:
+        """Blocking copy to the host."""
+        h = HuffTableStruct()
+        check(lib().dc_huff_table_download(self.ptr, C.addressof(h), _stream()), "dc_huff_table_download")
+        return h
+
+    def lengths(self) -> np.ndarray:
+        return np.array(self.download().lengths[:DC_NSLOTS], dtype=np.int32)
+
+
+def histogram(data: torch.Tensor, out: torch.Tensor | None = None, variant: int | None = None) -> torch.Tensor:
+    """259 x int64 byte counts of `data` (uint8, CUDA).  Replaces histogram() n_ary_huffman.c:461."""
+    _need_cuda(data, "data")
+    if out is None:
+        out = torch.empty(DC_NSLOTS, dtype=torch.int64, device=data.device)
+    if variant is None:
+        st = lib().dc_histogram_u8(data.data_ptr(), data.numel(), out.data_ptr(), _stream())
+    else:
+        st = lib().dc_histogram_u8_variant(data.data_ptr(), data.numel(), out.data_ptr(), variant, _stream())
+    check(st, "dc_histogram_u8")
+    return out
+
+
+def huff_build(hist: torch.Tensor, n_ary: int, table: HuffTable | None = None) -> HuffTable:
+    """hist (259 x int64, CUDA) -> code table.  Replaces huffman() :1161 + convert_lengths_to_encode_table() :1382."""
+    _need_cuda(hist, "hist")
+    if hist.numel() != DC_NSLOTS or hist.dtype != torch.int64:
+        raise ValueError("hist must be 259 x int64")
+    table = table or HuffTable(hist.device)
+    check(lib().dc_huff_build(hist.data_ptr(), n_ary, table.ptr, _stream()), "dc_huff_build")
+    return table
+
+
+def huff_table_from_lengths(lengths: torch.Tensor, n_ary: int, table: HuffTable | None = None) -> HuffTable:
+    _need_cuda(lengths, "lengths")
+    if lengths.numel() != DC_NSLOTS or lengths.dtype != torch.int32:
+        raise ValueError("lengths must be 259 x int32")
+    table = table or HuffTable(lengths.device)
+    check(lib().dc_huff_table_from_lengths(lengths.data_ptr(), n_ary, table.ptr, _stream()), "dc_huff_table_from_lengths")
+    return table
+
+
+def huff_bits_for_hist(hist: torch.Tensor, table: HuffTable, out: torch.Tensor | None = None) -> torch.Tensor:
+    """1 x int64: bits a shard with LOCAL histogram `hist` emits under `table`."""
+    _need_cuda(hist, "hist")
+    if out is None:
+        out = torch.empty(1, dtype=torch.int64, device=hist.device)
+    check(lib().dc_huff_bits_for_hist(hist.data_ptr(), table.ptr, out.data_ptr(), _stream()), "dc_huff_bits_for_hist")
+    return out
+
+
+class EncodeResult:
+    __slots__ = ("payload", "total_bits", "status")
+
+    def __init__(self, payload, total_bits, status):
+        self.payload, self.total_bits, self.status = payload, total_bits, status
+
+    def bits(self) -> int:
+        """Blocking: number of code bits emitted (raises on a device-side error)."""
+        st = int(self.status.item())
+        check(st, "dc_huff_encode")
+        return int(self.total_bits.item())
+
+
+def huff_encode(data: torch.Tensor, table: HuffTable, out: torch.Tensor | None = None, bit_phase: int = 0,
+                workspace: torch.Tensor | None = None) -> EncodeResult:
+    """Encode `data` (uint8, CUDA) with `table`.  Replaces represent_items_with_codes() :1621.
+
+    Returns the payload buffer (capacity-sized; the first ceil((bit_phase+bits)/8) bytes are valid) together
+    with 1-element device tensors for the bit count and the status; nothing blocks."""
+    _need_cuda(data, "data")
+    n = data.numel()
+    if out is None:
+        out = torch.empty(n + n // 4 + 64, dtype=torch.uint8, device=data.device)
+    need = lib().dc_huff_encode_workspace_bytes(n)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=data.device)
+    total_bits = torch.empty(1, dtype=torch.int64, device=data.device)
+    status = torch.empty(1, dtype=torch.int32, device=data.device)
+    check(lib().dc_huff_encode(data.data_ptr(), n, table.ptr, out.data_ptr(), out.numel(), bit_phase,
+                               total_bits.data_ptr(), status.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                               _stream()), "dc_huff_encode")
+    return EncodeResult(out, total_bits, status)
+
+
+def huff_decode(bits: torch.Tensor, nbits: int, table: HuffTable, n_out: int, bit_start: int = 0,
+                out: torch.Tensor | None = None, workspace: torch.Tensor | None = None,
+                status: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Self-synchronising parallel decode of `nbits` code bits -> n_out symbols.  Returns (out, status)."""
+    _need_cuda(bits, "bits")
+    if out is None:
+        out = torch.empty(max(n_out, 1), dtype=torch.uint8, device=bits.device)
+    need = lib().dc_huff_decode_workspace_bytes(bit_start, nbits)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=bits.device)
+    if status is None:
+        status = torch.empty(1, dtype=torch.int32, device=bits.device)
+    check(lib().dc_huff_decode(bits.data_ptr(), bit_start, nbits, table.ptr, out.data_ptr(), n_out, status.data_ptr(),
+                               workspace.data_ptr(), workspace.numel(), _stream()), "dc_huff_decode")
+    return out[:n_out], status
+
+
+def huff_compress(data: torch.Tensor, n_ary: int):
+    """histogram -> table -> encode on one GPU.  Returns (payload tensor, total_bits int, HuffTable)."""
+    hist = histogram(data)
+    table = huff_build(hist, n_ary)
+    res = huff_encode(data, table)
+    nbits = res.bits()
+    return res.payload[: (nbits + 7) // 8], nbits, table
+
+
+def huff_decompress(payload: torch.Tensor, nbits: int, table: HuffTable, n_out: int) -> torch.Tensor:
+    out, status = huff_decode(payload, nbits, table, n_out)
+    check(int(status.item()), "dc_huff_decode")
+    return out
+
+
+def nybble_pack(sym: torch.Tensor, out: torch.Tensor | None = None, status: torch.Tensor | None = None):
+    """One 4-bit symbol per byte -> two per byte, high nibble first (write_nybble nybble_compression.c:1091)."""
+    _need_cuda(sym, "sym")
+    n = sym.numel()
+    if out is None:
+        out = torch.empty((n + 1) // 2, dtype=torch.uint8, device=sym.device)
+    if status is None:
+        status = torch.empty(1, dtype=torch.int32, device=sym.device)
+    check(lib().dc_nybble_pack(sym.data_ptr(), n, out.data_ptr(), status.data_ptr(), _stream()), "dc_nybble_pack")
+    return out, status
+
+
+def nybble_unpack(packed: torch.Tensor, n_sym: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Inverse of nybble_pack (decoder split nybble_compression.c:767-769)."""
+    _need_cuda(packed, "packed")
+    if packed.numel() < (n_sym + 1) // 2:
+        raise ValueError("packed buffer too small")
+    if out is None:
+        out = torch.empty(n_sym, dtype=torch.uint8, device=packed.device)
+    check(lib().dc_nybble_unpack(packed.data_ptr(), n_sym, out.data_ptr(), _stream()), "dc_nybble_unpack")
+    return out
+
+
+def synth_fill(out: torch.Tensor, seed: int, thresholds: torch.Tensor, value_base: int) -> torch.Tensor:
+    """Fill `out` (uint8, CUDA) with the counter-based synthetic stream (see synth.py)."""
+    _need_cuda(out, "out")
+    _need_cuda(thresholds, "thresholds")
+    if thresholds.dtype != torch.int64 and thresholds.dtype != torch.int32:
+        raise ValueError("thresholds: int32 view of the u32 table expected")
+    check(lib().dc_synth_fill(out.data_ptr(), out.numel(), seed, thresholds.data_ptr(), thresholds.numel(), value_base,
+                              _stream()), "dc_synth_fill")
+    return out

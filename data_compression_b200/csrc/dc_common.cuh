@@ -1,0 +1,101 @@
+// dc_common.cuh -- shared device/host helpers for libdc_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dc_b200.h"
+
+namespace dc {
+
+// every kernel launch in the library goes through LaunchScope: it feeds the launch counter (bench
+// "gpu_launches") and, when dc_profile_enable(1) was called, brackets the launch with CUDA events on the
+// launching stream so per-kernel durations can be read back (dc_profile_kernel).
+extern unsigned long long g_launches;
+void prof_begin(int kernel_id, cudaStream_t st);
+void prof_end(int kernel_id, cudaStream_t st);
+struct LaunchScope {
+    int id;
+    cudaStream_t st;
+    LaunchScope(int kernel_id, cudaStream_t stream) : id(kernel_id), st(stream) {
+        g_launches++;
+        prof_begin(id, st);
+    }
+    ~LaunchScope() { prof_end(id, st); }
+};
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? DC_OK : DC_ERR_CUDA; }
+
+#define DC_CUDA_TRY(expr)                          \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) return DC_ERR_CUDA; \
+    } while (0)
+
+// SM count of the current device (cached); the grids below are sized in multiples of it
+int sm_count();
+
+// K2 internals shared with the host-pointer entry points (generic alphabets, raw arrays)
+struct TableRaw {
+    int32_t *lengths;   // [nsym] code lengths in digits
+    uint32_t *values;   // [nsym] canonical code values
+    int32_t *assigned;  // [nsym] 1 if convert_lengths_to_encode_table() assigns the slot
+    int32_t *status;    // [1]
+};
+int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
+                 TableRaw raw, cudaStream_t st);
+
+// ---------------------------------------------------------------- device helpers
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// streaming 128-bit global accesses: data is touched once, keep it out of L1
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 ldg_stream8(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream8(uint2 *p, const uint2 &v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// acquire/release accesses for inter-CTA descriptors (decoupled look-back)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cg_u128(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// set a sticky error code once (first error wins)
+__device__ __forceinline__ void set_status(int32_t *d_status, int code) {
+    if (d_status) atomicCAS(d_status, DC_OK, code);
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+}  // namespace dc

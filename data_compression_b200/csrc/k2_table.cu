@@ -1,0 +1,280 @@
+// k2_table.cu -- K2: n-ary code lengths and canonical code table in ONE single-CTA kernel.
+//
+// Replaces huffman() (n_ary_huffman.c:1161-1208 = setup_nodes :773, generate_huffman_tree :868,
+// summarize_tree_with_lengths :1033) and convert_lengths_to_encode_table() (:1382-1612), as the reference
+// behaves when compiled with -DNDEBUG:
+//   * nz  = symbols with non-zero count                                   (:880-886)
+//   * d   = (n-1) - ((nz-1) % (n-1)) dummy leaves of count 1, indexed after the real symbols (:900-929)
+//   * the reference's repeated stable bubble sort (:672-731) orders nodes by (count, node index) and a
+//     freshly merged node is appended on the right, so it follows every node of equal count (:962-1002).
+//     That is exactly: rank-sort the leaves once by (count, index), then merge from two queues -- sorted
+//     leaves and a FIFO of internal nodes -- where a leaf wins a tie.
+//   * length = number of parent hops to the root                          (:1069-1076)
+//   * canonical values: for len = min..max, symbols ascending, value = code++, then code *= n (:1540-1568);
+//     min/max are taken over i < max_symbol_value (the last slot is skipped, :1336/:1360).
+//
+// O(alphabet^2) work, ~10 us: off the time-critical path but it fixes every output bit, so it is
+// written for exactness, not throughput.  Counts are 64-bit.
+#include "dc_common.cuh"
+
+namespace dc {
+
+constexpr int kTabThreads = 1024;
+constexpr int kTabCap = 1040;  // >= DC_MAX_LEAVES + max dummy leaves (n_ary <= 512)
+
+__device__ __forceinline__ int bits_per_digit_of(int n) { return n == 2 ? 1 : n == 4 ? 2 : n == 16 ? 4 : 0; }
+
+__global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long long *__restrict__ d_hist,
+                                                            const int32_t *__restrict__ d_lengths_in, int nsym,
+                                                            int n_ary, dc_huff_table *__restrict__ tab, TableRaw raw) {
+    __shared__ unsigned long long s_cnt[kTabCap];     // compacted leaf counts (index order)
+    __shared__ unsigned long long s_scnt[kTabCap];    // leaf counts sorted by (count, index)
+    __shared__ unsigned long long s_icount[kTabCap];  // internal node counts, creation order
+    __shared__ int s_idx[kTabCap];                    // compacted leaf -> symbol (>= nsym: dummy)
+    __shared__ int s_ssym[kTabCap];                   // sorted leaf -> symbol
+    __shared__ int s_lparent[kTabCap];                // sorted leaf -> internal node
+    __shared__ int s_iparent[kTabCap];                // internal node -> internal node
+    __shared__ int s_len[kTabCap];                    // symbol -> length in digits
+    __shared__ unsigned int s_lencount[64], s_first[64], s_off[64];
+    __shared__ int s_warp[32];
+    __shared__ int s_nint, s_minlen, s_maxlen, s_status;
+    __shared__ unsigned long long s_totsym, s_totbits;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) { s_lencount[tid] = 0; s_first[tid] = 0; s_off[tid] = 0; }
+    if (tid == 0) { s_nint = 0; s_minlen = 300; s_maxlen = 0; s_status = DC_OK; s_totsym = 0; s_totbits = 0; }
+    for (int i = tid; i < kTabCap; i += kTabThreads) s_len[i] = 0;
+
+    unsigned long long my_count = 0;
+    int nz = 0, dummies = 0;
+    if (d_hist) {
+        // ---- 1. compact the non-zero leaves in index order, append the dummy leaves
+        my_count = tid < nsym ? d_hist[tid] : 0ull;
+        const bool used = my_count != 0;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, used);
+        if (lane == 0) s_warp[warp] = __popc(ball);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < 32; w++) {
+            const int c = s_warp[w];
+            if (w < warp) before += c;
+            nz += c;
+        }
+        const int pos = before + __popc(ball & ((1u << lane) - 1u));
+        const int k = n_ary - 1;
+        dummies = k - ((nz - 1) % k);  // as written, :900-903 (C remainder semantics)
+        const int nleaf = nz + dummies;
+        if (used) { s_cnt[pos] = my_count; s_idx[pos] = tid; }
+        for (int j = tid; j < dummies; j += kTabThreads) { s_cnt[nz + j] = 1ull; s_idx[nz + j] = nsym + j; }
+        __syncthreads();
+
+        // ---- 2. rank sort by (count, index): position order == index order, dummies last
+        for (int p = tid; p < nleaf; p += kTabThreads) {
+            const unsigned long long mine = s_cnt[p];
+            int rank = 0;
+            for (int q = 0; q < nleaf; q++) {
+                const unsigned long long cq = s_cnt[q];
+                rank += (cq < mine) || (cq == mine && q < p);
+            }
+            s_scnt[rank] = mine;
+            s_ssym[rank] = s_idx[p];
+        }
+        __syncthreads();
+
+        // ---- 3. two-queue n-way merge (serial: every step depends on the previous sum)
+        if (tid == 0) {
+            int lh = 0, ih = 0, it = 0, remaining = nleaf;
+            unsigned long long lc = nleaf > 0 ? s_scnt[0] : 0ull, ic = 0ull;
+            while (remaining > 1) {
+                unsigned long long sum = 0;
+                for (int c = 0; c < n_ary; c++) {
+                    const bool leaf_ok = lh < nleaf, int_ok = ih < it;
+                    if (leaf_ok && (!int_ok || lc <= ic)) {  // leaf wins ties
+                        sum += lc;
+                        s_lparent[lh] = it;
+                        lh++;
+                        if (lh < nleaf) lc = s_scnt[lh];
+                    } else {
+                        sum += ic;
+                        s_iparent[ih] = it;
+                        ih++;
+                        if (ih < it) ic = s_icount[ih];
+                    }
+                }
+                s_icount[it] = sum;
+                if (ih == it) ic = sum;  // the new node is now the head of the internal FIFO
+                it++;
+                remaining -= k;
+            }
+            s_nint = it;
+        }
+        __syncthreads();
+
+        // ---- 4. depth of every real leaf = hops to the root (the last internal node)
+        const int root = s_nint - 1;
+        if (root >= 0) {
+            for (int r = tid; r < nleaf; r += kTabThreads) {
+                int node = s_lparent[r], depth = 1;
+                while (node != root) { node = s_iparent[node]; depth++; }
+                const int sym = s_ssym[r];
+                if (sym < nsym) s_len[sym] = depth;
+            }
+        }
+        __syncthreads();
+    } else {
+        if (tid < nsym) s_len[tid] = d_lengths_in[tid];
+        __syncthreads();
+    }
+
+    // ---- 5. canonical code values
+    const int my_len = tid < nsym ? s_len[tid] : 0;
+    const int max_symbol_value = nsym - 1;
+    if (tid < max_symbol_value) {  // the reference's scans skip the last slot (:1336, :1360)
+        if (my_len > 0) { atomicMax(&s_maxlen, my_len); atomicMin(&s_minlen, my_len); }
+    }
+    if (tid < nsym && my_len > 0 && my_len < 64) atomicAdd(&s_lencount[my_len], 1u);
+    if (tid < nsym && (my_len < 0 || my_len >= 64)) s_status = DC_ERR_CODE_TOO_LONG;
+    __syncthreads();
+    const int min_len = s_minlen, max_len = s_maxlen;
+    if (tid == 0) {
+        if (max_len >= 16) s_status = DC_ERR_CODE_TOO_LONG;  // assert :1414
+        unsigned long long code = 0;
+        unsigned int off = 0;
+        for (int cl = min_len; cl <= max_len && cl < 64; cl++) {
+            s_first[cl] = (unsigned int)code;
+            s_off[cl] = off;
+            const unsigned int c = s_lencount[cl];
+            if (c && code + c - 1 > 0x7FFFFFFFull) s_status = DC_ERR_CODE_TOO_LONG;  // int current_code :1540
+            code += c;
+            off += c;
+            code *= (unsigned long long)n_ary;
+            if (code > (1ull << 40)) { s_status = DC_ERR_CODE_TOO_LONG; code &= (1ull << 40) - 1; }
+        }
+    }
+    __syncthreads();
+    unsigned int my_value = 0;
+    int my_rank = 0, assigned = 0;
+    if (tid < nsym && my_len > 0 && my_len >= min_len && my_len <= max_len && my_len < 64) {
+        for (int j = 0; j < tid; j++) my_rank += (s_len[j] == my_len);
+        my_value = s_first[my_len] + (unsigned int)my_rank;
+        assigned = 1;
+    }
+    const int status = s_status;
+
+    if (raw.lengths && tid < nsym) raw.lengths[tid] = my_len;
+    if (raw.values && tid < nsym) raw.values[tid] = my_value;
+    if (raw.assigned && tid < nsym) raw.assigned[tid] = assigned;
+    if (raw.status && tid == 0) *raw.status = status;
+
+    // ---- 6. device table for the encode / decode kernels (byte alphabet in 259 slots)
+    if (!tab) return;
+    const int bpd = bits_per_digit_of(n_ary);
+    const int nbits = my_len * bpd;
+    if (tid <= DC_NSLOTS) {
+        tab->lengths[tid] = tid < nsym ? my_len : 0;
+        tab->values[tid] = tid < nsym ? my_value : 0u;
+        tab->sorted[tid] = 0;
+    }
+    if (tid < 256) {
+        tab->enc[tid] = (assigned && nbits <= 26) ? ((my_value << 6) | (unsigned int)nbits) : 0u;
+        tab->enc64[tid] = assigned ? ((unsigned long long)my_value | ((unsigned long long)nbits << 32)) : 0ull;
+    }
+    if (tid < 32) {
+        tab->first_code[tid] = s_first[tid];
+        tab->len_count[tid] = s_lencount[tid];
+        tab->len_offset[tid] = s_off[tid];
+    }
+    if (d_hist && my_count) {
+        atomicAdd(&s_totsym, my_count);
+        atomicAdd(&s_totbits, my_count * (unsigned long long)nbits);
+    }
+    __syncthreads();
+    if (assigned && tid <= DC_NSLOTS) tab->sorted[s_off[my_len] + my_rank] = (uint16_t)tid;
+    // reuse s_ssym as the canonical order for the LUT fill
+    if (assigned) s_ssym[s_off[my_len] + my_rank] = tid;
+    __syncthreads();
+    for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
+        unsigned int entry = 0;
+        if (bpd) {
+            for (int l = min_len; l <= max_len && l < 32; l++) {
+                const int lb = l * bpd;
+                if (lb > DC_LUT_BITS) break;
+                const unsigned int v = (unsigned int)e >> (DC_LUT_BITS - lb);
+                if (s_lencount[l] && v >= s_first[l] && v - s_first[l] < s_lencount[l]) {
+                    entry = ((unsigned int)lb << 8) | (unsigned int)(s_ssym[s_off[l] + (v - s_first[l])] & 0xFF);
+                    break;
+                }
+            }
+        }
+        tab->lut[e] = (uint16_t)entry;
+    }
+    if (tid == 0) {
+        tab->n_ary = n_ary;
+        tab->bits_per_digit = bpd;
+        tab->max_symbol_value = max_symbol_value;
+        tab->nonzero_symbols = nz;
+        tab->dummy_nodes = dummies;
+        tab->min_len = min_len;
+        tab->max_len = max_len;
+        tab->max_bits = max_len * bpd;
+        tab->status = (status == DC_OK && max_len * bpd > 32) ? DC_ERR_CODE_TOO_LONG : status;
+        tab->reserved0 = 0;
+        tab->total_symbols = s_totsym;
+        tab->total_bits = s_totbits;
+    }
+}
+
+__global__ void bits_for_hist_kernel(const unsigned long long *__restrict__ d_hist, const dc_huff_table *__restrict__ tab,
+                                     unsigned long long *__restrict__ d_bits) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int b = threadIdx.x;
+    if (b < 256) {
+        const unsigned long long c = d_hist[b];
+        if (c) atomicAdd(&s_sum, c * (unsigned long long)(tab->lengths[b] * tab->bits_per_digit));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *d_bits = s_sum;
+}
+
+int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
+                 TableRaw raw, cudaStream_t st) {
+    if (n_ary < 2 || n_ary > 512 || nsym < 1 || nsym > DC_MAX_LEAVES) return DC_ERR_ARG;
+    if (tab && nsym != DC_NSLOTS) return DC_ERR_ARG;
+    LaunchScope ls(DC_K_TABLE, st);
+    table_kernel<<<1, kTabThreads, 0, st>>>(d_hist, d_lengths, nsym, n_ary, tab, raw);
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" int dc_huff_build(const uint64_t *d_hist, int n_ary, dc_huff_table *d_table, void *stream) {
+    if (!d_hist || !d_table) return DC_ERR_ARG;
+    TableRaw raw = {nullptr, nullptr, nullptr, nullptr};
+    return launch_table((const unsigned long long *)d_hist, nullptr, DC_NSLOTS, n_ary, d_table, raw, (cudaStream_t)stream);
+}
+
+extern "C" int dc_huff_table_from_lengths(const int32_t *d_lengths, int n_ary, dc_huff_table *d_table, void *stream) {
+    if (!d_lengths || !d_table) return DC_ERR_ARG;
+    TableRaw raw = {nullptr, nullptr, nullptr, nullptr};
+    return launch_table(nullptr, d_lengths, DC_NSLOTS, n_ary, d_table, raw, (cudaStream_t)stream);
+}
+
+extern "C" int dc_huff_table_download(const dc_huff_table *d_table, dc_huff_table *h_table, void *stream) {
+    if (!d_table || !h_table) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    DC_CUDA_TRY(cudaMemcpyAsync(h_table, d_table, sizeof(dc_huff_table), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    return DC_OK;
+}
+
+extern "C" int dc_huff_bits_for_hist(const uint64_t *d_hist, const dc_huff_table *d_table, uint64_t *d_bits, void *stream) {
+    if (!d_hist || !d_table || !d_bits) return DC_ERR_ARG;
+    LaunchScope ls(DC_K_BITS_FOR_HIST, (cudaStream_t)stream);
+    bits_for_hist_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)d_hist, d_table,
+                                                              (unsigned long long *)d_bits);
+    return cuda_status(cudaGetLastError());
+}

@@ -1,0 +1,233 @@
+/*
+ * dc_b200.h -- C-ABI of the B200-native n-ary Huffman / nybble hot path (libdc_b200.so).
+ *
+ * Drop-in boundary for the data-parallel path of carycode/data_compression
+ * (n_ary_huffman.c, nybble_compression.c).  The reference has no plugin/FFI layer
+ * (SURVEY 8b): its boundary is its non-static C functions.  Each entry point below
+ * cites the reference interface it replaces (file:line into the reference tree).
+ *
+ * Two families:
+ *   dc_*          size-explicit, DEVICE pointers, stream-ordered, never block
+ *                 (except where stated), never allocate, never print, never abort.
+ *   dc_host_*     HOST pointers: copy in, run the device path, copy out, synchronise.
+ *                 These are what a C caller of the reference functions links against;
+ *                 refapi.h maps the reference's verbatim names onto them.
+ *
+ * There is no CPU fallback: every function that computes launches sm_100a kernels and
+ * returns DC_ERR_CUDA when no device is usable.
+ *
+ * Plain C types only (no CUDA, no torch types).  A stream is passed as `void *`
+ * (a cudaStream_t; NULL = the legacy default stream).
+ */
+#ifndef DC_B200_H
+#define DC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- constants */
+
+#define DC_MAX_SYMBOL_VALUE 258 /* n_ary_huffman.c:2524 */
+#define DC_NSLOTS 259           /* max_symbol_value + 1 histogram / length slots */
+#define DC_MAX_LEAVES 512       /* dc_host_huffman accepts max_leaf_value < DC_MAX_LEAVES */
+#define DC_LUT_BITS 12          /* decode look-up table index width */
+
+enum dc_status {
+    DC_OK = 0,
+    DC_ERR_ARG = -1,           /* bad argument (null pointer, misalignment, radix, phase) */
+    DC_ERR_CUDA = -2,          /* CUDA runtime error or no device (no CPU fallback exists) */
+    DC_ERR_CODE_TOO_LONG = -3, /* reference limits: length < 16 digits (:1414), value fits int (:1540) */
+    DC_ERR_CAPACITY = -4,      /* output buffer too small */
+    DC_ERR_CORRUPT = -5,       /* bitstream hits an unused code slot / ends inside a code */
+    DC_ERR_SYMBOL = -6,        /* input symbol has no code (length 0), or nibble symbol >= 16 (:1093) */
+    DC_ERR_RADIX = -7          /* payload packing is defined for n in {2,4,16} only */
+};
+
+/*
+ * Device-resident code table.  Written by dc_huff_build / dc_huff_table_from_lengths, read by the
+ * encode/decode kernels.  The layout is part of the ABI so a host may cudaMemcpy it back and read
+ * lengths/values (dc_huff_table_download does exactly that).
+ *   lengths[]  == canonical_lengths of huffman()                       n_ary_huffman.c:1161-1208
+ *   values[]   == encode_value_table of convert_lengths_to_encode_table n_ary_huffman.c:1382-1612
+ * Lengths are in DIGITS of radix n_ary (the reference's unit); a digit is bits_per_digit bits.
+ */
+typedef struct dc_huff_table {
+    int32_t n_ary;            /* compressed_symbols */
+    int32_t bits_per_digit;   /* 1, 2, 4 for n = 2, 4, 16; 0 = table only (no payload packing) */
+    int32_t max_symbol_value; /* 258 */
+    int32_t nonzero_symbols;  /* :880-886 */
+    int32_t dummy_nodes;      /* :900-903, as written */
+    int32_t min_len;          /* digits, over non-zero lengths (:1354-1379) */
+    int32_t max_len;          /* digits (:1330-1352) */
+    int32_t max_bits;         /* max_len * bits_per_digit */
+    int32_t status;           /* DC_OK or DC_ERR_CODE_TOO_LONG / DC_ERR_RADIX */
+    int32_t reserved0;
+    uint64_t total_symbols;   /* sum of the histogram the table was built from (0 if from lengths) */
+    uint64_t total_bits;      /* sum hist[s] * lengths[s] * bits_per_digit (0 if from lengths) */
+    int32_t lengths[DC_NSLOTS + 1];
+    uint32_t values[DC_NSLOTS + 1];
+    uint32_t enc[256];        /* per byte: (value << 6) | nbits, valid when max_bits <= 26 */
+    uint64_t enc64[256];      /* per byte: value | (uint64)nbits << 32 */
+    /* canonical decode: per digit-length first code value, number of codes, offset into sorted[] */
+    uint32_t first_code[32];
+    uint32_t len_count[32];
+    uint32_t len_offset[32];
+    uint16_t sorted[DC_NSLOTS + 1]; /* symbols in (length, value) order */
+    uint16_t lut[1 << DC_LUT_BITS]; /* index = next 12 bits: nbits << 8 | symbol; 0 = escape (longer/unused) */
+} dc_huff_table;
+
+/* ------------------------------------------------------------------------- library */
+
+const char *dc_version(void);
+const char *dc_status_string(int status);
+/* number of CUDA devices visible, or a negative dc_status */
+int dc_device_count(void);
+/* total kernels this library has launched in this process (bench "gpu_launches") */
+uint64_t dc_launch_count(void);
+
+/* ------------------------------------------------------------------------- tracing */
+
+/* kernel groups of this library (the reference's "# ..." printf narration and `make time_test` are
+ * replaced by CUDA events around every launch) */
+enum dc_kernel_id {
+    DC_K_HISTOGRAM = 0,
+    DC_K_TABLE,
+    DC_K_BITS_FOR_HIST,
+    DC_K_ENCODE,
+    DC_K_DECODE_SYNC,
+    DC_K_DECODE_HANDOFF,
+    DC_K_DECODE_SCAN,
+    DC_K_DECODE_WRITE,
+    DC_K_NYBBLE_PACK,
+    DC_K_NYBBLE_UNPACK,
+    DC_K_NYBBLE_TAIL,
+    DC_K_SYNTH,
+    DC_K_COUNT
+};
+/* on != 0: bracket every kernel launch with CUDA events on its launching stream */
+int dc_profile_enable(int on);
+/* drop accumulated timings */
+int dc_profile_reset(void);
+/* blocking: total device milliseconds and launch count of one kernel group since the last reset */
+int dc_profile_kernel(int kernel_id, double *total_ms, uint64_t *launches);
+const char *dc_profile_kernel_name(int kernel_id);
+
+/* ------------------------------------------------------------------------- K1 histogram */
+
+/*
+ * Replaces histogram() n_ary_huffman.c:461-493 (length-explicit, 0x00 allowed).
+ * d_hist[0..258] is overwritten (the reference zeroes it first, :474-476); slots 256..258 stay 0.
+ */
+int dc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *stream);
+
+/* ------------------------------------------------------------------------- K2 table */
+
+/*
+ * Replaces huffman() :1161-1208 + convert_lengths_to_encode_table() :1382-1612.
+ * d_hist: 259 x u64 (e.g. the all-reduced histogram).  Single-CTA kernel; reproduces the as-written
+ * dummy rule d = (n-1) - ((nz-1) % (n-1)) and the stable-sort tie-break exactly.
+ * n_ary >= 2; payload packing needs n_ary in {2,4,16}, other radices produce lengths/values only.
+ */
+int dc_huff_build(const uint64_t *d_hist, int n_ary, dc_huff_table *d_table, void *stream);
+
+/* Decode side: rebuild values/LUT from 259 lengths (digits), as read from a table header (:1727-1744). */
+int dc_huff_table_from_lengths(const int32_t *d_lengths, int n_ary, dc_huff_table *d_table, void *stream);
+
+/* Blocking copy of the table to host memory. */
+int dc_huff_table_download(const dc_huff_table *d_table, dc_huff_table *h_table, void *stream);
+
+/* bits a shard will emit for its LOCAL histogram under a (global) table: sum hist[s]*len[s]*bpd.
+ * Lets every GPU know its bit total before encoding.  d_bits: 1 x u64. */
+int dc_huff_bits_for_hist(const uint64_t *d_hist, const dc_huff_table *d_table, uint64_t *d_bits, void *stream);
+
+/* ------------------------------------------------------------------------- K3 encode */
+
+size_t dc_huff_encode_workspace_bytes(size_t n);
+
+/*
+ * Replaces represent_items_with_codes() :1621-1678 (a stub in the reference; the payload layout is the
+ * one DESIGN.md defines: codes MSB-first, concatenated in input order, final byte zero-padded).
+ *   d_out        16-byte aligned; byte 0 is the byte the first code bit lands in
+ *   bit_phase    0..7: number of leading bits of d_out[0] owned by the previous shard (written as 0)
+ *   d_total_bits 1 x u64: code bits emitted (excluding bit_phase)
+ *   d_status     1 x i32: DC_OK / DC_ERR_SYMBOL / DC_ERR_CAPACITY / table status; may be NULL
+ * Bytes [0, ceil((bit_phase+total_bits)/8)) of d_out are written, nothing else.
+ */
+int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out,
+                   size_t out_capacity, unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status,
+                   void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- K4 decode */
+
+size_t dc_huff_decode_workspace_bytes(uint64_t bit_start, uint64_t nbits);
+
+/*
+ * Replaces the absent Huffman block decoder (decompress() case 'X'/'Z', :2081-2089).
+ * Self-synchronising parallel decode of `nbits` code bits that start `bit_start` (< 128) bits into
+ * d_bits (16-byte aligned; at least ceil((bit_start+nbits)/8) readable bytes).  Exactly n_out symbols
+ * are expected.  May block on the stream internally while neighbouring tiles resynchronise.
+ *   d_status     1 x i32: DC_OK / DC_ERR_CORRUPT / DC_ERR_CAPACITY; may be NULL
+ */
+int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, const dc_huff_table *d_table,
+                   uint8_t *d_out, size_t n_out, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* ------------------------------------------------------------------------- K5 nybble */
+
+/*
+ * Stream form of write_nybble() nybble_compression.c:1091-1114: symbol 2i -> high nibble of byte i,
+ * symbol 2i+1 -> low nibble; an odd tail leaves the low nibble 0.  Symbols must be < 16 (:1093);
+ * a larger value sets *d_status = DC_ERR_SYMBOL (its low nibble is packed).  d_status may be NULL.
+ */
+int dc_nybble_pack(const uint8_t *d_sym, size_t n_sym, uint8_t *d_packed, int32_t *d_status, void *stream);
+/* Inverse: the decoder's split nybble_compression.c:767-769 (high nibble first). */
+int dc_nybble_unpack(const uint8_t *d_packed, size_t n_sym, uint8_t *d_sym, void *stream);
+
+/* ------------------------------------------------------------------------- synthetic inputs (bench/tests) */
+
+/*
+ * Counter-based generator shared by bench.py and the tests: byte i = value_base + rank, where
+ * rank = #{k : thresholds[k] <= (splitmix64(seed + i) >> 32)} over `nthresh` ascending u32 thresholds
+ * (d_thresholds on device).  The same arithmetic in numpy reproduces the stream on the host.
+ */
+int dc_synth_fill(uint8_t *d_out, size_t n, uint64_t seed, const uint32_t *d_thresholds, int nthresh,
+                  int value_base, void *stream);
+
+/* ------------------------------------------------------------------------- host-pointer entry points */
+
+/* histogram(text, max_symbol_value, h) :461 -- NUL-terminated text, int counts, h[0..max_symbol_value] */
+int dc_host_histogram(const char *text, int max_symbol_value, int h[]);
+/* length-explicit host form */
+int dc_host_histogram_u8(const uint8_t *in, size_t n, uint64_t h[DC_NSLOTS]);
+/* huffman(max_leaf_value, freqs, compressed_symbols, lengths) :1161 */
+int dc_host_huffman(int max_leaf_value, const int symbol_frequencies[], int compressed_symbols, int lengths[]);
+/* 64-bit-count form */
+int dc_host_huffman_u64(int max_leaf_value, const uint64_t symbol_frequencies[], int compressed_symbols,
+                        int lengths[]);
+/* convert_lengths_to_encode_table(...) :1382 */
+int dc_host_convert_lengths_to_encode_table(int max_symbol_value, const int canonical_lengths[],
+                                            int compressed_symbols, int encode_length_table[],
+                                            unsigned int encode_value_table[]);
+/* represent_items_with_codes(...) :1621 -- writes the payload at compressed_text[start...]; returns the
+ * number of bytes written (>= 0) or a negative dc_status.  *total_bits (may be NULL) gets the bit count. */
+int dc_host_represent_items_with_codes(int max_symbol_value, const int canonical_lengths[], int compressed_symbols,
+                                       int bufsize, int original_length, const char original_text[], int start,
+                                       char compressed_text[], uint64_t *total_bits);
+/* whole encode path on host buffers: histogram -> table -> payload.  lengths_out[259] and total_bits
+ * are the side information a decoder needs.  Returns bytes written or a negative dc_status. */
+long long dc_host_huff_compress(const uint8_t *in, size_t n, int compressed_symbols, uint8_t *out,
+                                size_t out_capacity, int lengths_out[DC_NSLOTS], uint64_t *total_bits);
+/* inverse on host buffers */
+int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bits, const int lengths[DC_NSLOTS],
+                            int compressed_symbols, uint8_t *out, size_t n_out);
+int dc_host_nybble_pack(const uint8_t *sym, size_t n_sym, uint8_t *packed);
+int dc_host_nybble_unpack(const uint8_t *packed, size_t n_sym, uint8_t *sym);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DC_B200_H */

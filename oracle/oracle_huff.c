@@ -221,8 +221,10 @@ static int pack_at(const uint8_t *in, size_t n, const int elen[], const unsigned
     size_t o = (size_t)(bitpos >> 3);
     int nacc = (int)(bitpos & 7);
     uint64_t acc = 0;
+    size_t i = 0;
+    /* lead-in: until the byte shared with the previous block has been emitted (atomic OR) */
     int first = nacc != 0;
-    for (size_t i = 0; i < n; i++) {
+    for (; i < n && first; i++) {
         const unsigned s = in[i];
         const int l = code_bits(elen, bpd, s);
         if (l <= 0) return ORC_ERR_SYMBOL;
@@ -237,11 +239,34 @@ static int pack_at(const uint8_t *in, size_t n, const int elen[], const unsigned
             o++;
             nacc -= 8;
         }
-        acc &= 0xFF;
     }
-    if (nacc > 0 && !(first && n == 0)) {
+    /* main: bytes from here on are owned by this block alone; flush 32 bits at a time */
+    for (; i < n; i++) {
+        const unsigned s = in[i];
+        const int l = code_bits(elen, bpd, s);
+        if (l <= 0) return ORC_ERR_SYMBOL;
+        if (l > 32) return ORC_ERR_CODE_TOO_LONG;
+        acc = (acc << l) | (uint64_t)eval[s];
+        nacc += l;
+        if (nacc >= 32) {
+            if (o + 4 > cap) return ORC_ERR_CAPACITY;
+            const uint32_t w = __builtin_bswap32((uint32_t)(acc >> (nacc - 32)));
+            memcpy(out + o, &w, 4);
+            o += 4;
+            nacc -= 32;
+        }
+    }
+    while (nacc >= 8) {
         if (o >= cap) return ORC_ERR_CAPACITY;
-        __atomic_fetch_or(&out[o], (uint8_t)(acc << (8 - nacc)), __ATOMIC_RELAXED);
+        const uint8_t b = (uint8_t)(acc >> (nacc - 8));
+        if (first) { __atomic_fetch_or(&out[o], b, __ATOMIC_RELAXED); first = 0; }
+        else out[o] = b;
+        o++;
+        nacc -= 8;
+    }
+    if (nacc > 0 && n != 0) {
+        if (o >= cap) return ORC_ERR_CAPACITY;
+        __atomic_fetch_or(&out[o], (uint8_t)((acc << (8 - nacc)) & 0xFF), __ATOMIC_RELAXED);
     }
     return ORC_OK;
 }
@@ -346,9 +371,14 @@ static void dec_free(orc_dec *d) { free(d->lut); d->lut = NULL; }
 static inline uint32_t peek_bits(const uint8_t *p, uint64_t pos, int k, uint64_t limit_bits) {
     uint64_t w = 0;
     const uint64_t byte0 = pos >> 3, nbytes = (limit_bits + 7) >> 3;
-    for (int j = 0; j < 8; j++) {
-        const uint64_t b = byte0 + (uint64_t)j;
-        w = (w << 8) | (b < nbytes ? p[b] : 0);
+    if (byte0 + 8 <= nbytes) {
+        memcpy(&w, p + byte0, 8);
+        w = __builtin_bswap64(w);
+    } else {
+        for (int j = 0; j < 8; j++) {
+            const uint64_t b = byte0 + (uint64_t)j;
+            w = (w << 8) | (b < nbytes ? p[b] : 0);
+        }
     }
     w <<= (pos & 7);
     return (uint32_t)(w >> (64 - k));

@@ -1,0 +1,283 @@
+"""GPU: bit-exact parity of every kernel with the CPU oracle / the reference-generated golden vectors,
+called through the C-ABI (ctypes) exactly as a host program would."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import dense
+
+pytestmark = pytest.mark.gpu
+
+RADICES = (2, 3, 4, 5, 10, 16)
+PACKABLE = (2, 4, 16)
+
+
+def _dev(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _zipf(dc, n, seed=3):
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_bytes_spec()
+    data = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(data, synth.SEED_BASE + seed, synth.device_thresholds(thr, "cuda"), base)
+    return data
+
+
+def test_synth_matches_host_twin(dc):
+    from data_compression_b200 import synth
+    for spec in (synth.zipf_bytes_spec, synth.zipf_7bit_spec, synth.zipf_nybble_spec):
+        thr, base = spec()
+        for n in (1, 17, 4096, 100003):
+            d = torch.empty(n, dtype=torch.uint8, device="cuda")
+            dc.synth_fill(d, 12345, synth.device_thresholds(thr, "cuda"), base)
+            assert np.array_equal(d.cpu().numpy(), synth.host_stream(n, 12345, thr, base))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_histogram_variants_match_oracle(dc, oracle, variant):
+    rng = np.random.default_rng(variant)
+    zipf = _zipf(dc, (1 << 22) + 5).cpu().numpy()
+    cases = [zipf, rng.integers(0, 256, size=1 << 20, dtype=np.uint8), np.full(300001, 7, dtype=np.uint8),
+             np.zeros(0, dtype=np.uint8)]
+    cases += [rng.integers(0, 256, size=k, dtype=np.uint8) for k in (1, 15, 16, 17, 255, 7681, 65537)]
+    for a in cases:
+        got = dc.histogram(_dev(a) if a.size else torch.empty(0, dtype=torch.uint8, device="cuda"), variant=variant)
+        assert np.array_equal(got.cpu().numpy().astype(np.uint64), oracle.histogram_u8(a)), (variant, a.size)
+    # unaligned base pointer
+    buf = _dev(zipf)
+    got = dc.histogram(buf[3:100000], variant=variant)
+    assert np.array_equal(got.cpu().numpy().astype(np.uint64), oracle.histogram_u8(zipf[3:100000]))
+
+
+def test_histogram_zeroes_all_slots(dc):
+    out = torch.full((259,), 0xBEEF, dtype=torch.int64, device="cuda")  # the reference's canary (:2663)
+    dc.histogram(_dev(np.array([65, 66, 66], dtype=np.uint8)), out=out)
+    h = out.cpu().numpy()
+    assert h[65] == 1 and h[66] == 2 and h.sum() == 3 and h[258] == 0
+
+
+def test_tables_match_reference_golden(dc, oracle, table_cases):
+    """lengths and canonical values equal the UNMODIFIED reference's, for every golden histogram and radix."""
+    for case in table_cases:
+        hist = _dev(dense(case["hist"]))
+        for n in RADICES:
+            rec = case["radix"][str(n)]
+            t = dc.huff_build(hist, n).download()
+            want_len = dense(rec["lengths"], dtype=np.int32)
+            assert np.array_equal(np.array(t.lengths[:259], dtype=np.int32), want_len), (case["name"], n)
+            nz = int((dense(case["hist"]) != 0).sum())
+            assert t.nonzero_symbols == nz
+            assert t.dummy_nodes == (n - 1) - int(np.fmod(nz - 1, n - 1))  # as written (:900-903)
+            if "values" in rec:
+                assert t.status == 0
+                assert np.array_equal(np.array(t.values[:259], dtype=np.uint32), dense(rec["values"], dtype=np.uint32)), \
+                    (case["name"], n)
+                bpd = oracle.bits_per_digit(n)
+                assert t.bits_per_digit == bpd and t.max_bits == int(want_len.max()) * bpd
+                assert t.total_bits == int((dense(case["hist"]) * want_len * bpd).sum())
+            else:
+                assert t.status == dc.DC_ERR_CODE_TOO_LONG
+
+
+def test_tables_random_differential(dc, oracle):
+    rng = np.random.default_rng(99)
+    for t in range(40):
+        h = np.zeros(259, dtype=np.int64)
+        k = int(rng.integers(1, 257))
+        idx = rng.choice(np.arange(0, 256), size=k, replace=False)
+        h[idx] = rng.integers(1, 6, size=k) if t % 2 else rng.integers(1, 1 << 40, size=k)
+        for n in RADICES:
+            tab = dc.huff_build(_dev(h), n).download()
+            ln = oracle.huffman(h.astype(np.uint64), n)
+            assert np.array_equal(np.array(tab.lengths[:259], dtype=np.int32), ln), (t, n)
+            el, ev, st = oracle.convert_lengths_to_encode_table(ln, n)
+            if st == 0:
+                assert tab.status == 0
+                assert np.array_equal(np.array(tab.values[:259], dtype=np.uint32), ev), (t, n)
+            else:
+                assert tab.status == dc.DC_ERR_CODE_TOO_LONG
+
+
+def test_table_from_lengths_and_lut(dc, oracle, table_cases):
+    case = next(c for c in table_cases if c["name"] == "zipf_2p30")
+    for n in PACKABLE:
+        ln = dense(case["radix"][str(n)]["lengths"], dtype=np.int32)
+        t = dc.huff_table_from_lengths(_dev(ln), n).download()
+        el, ev, st = oracle.convert_lengths_to_encode_table(ln, n)
+        assert np.array_equal(np.array(t.values[:259], dtype=np.uint32), ev)
+        bpd = oracle.bits_per_digit(n)
+        lut = np.array(t.lut, dtype=np.uint16)
+        for s in np.nonzero(ln)[0]:
+            nb = int(ln[s]) * bpd
+            if nb <= 12:
+                lo = int(ev[s]) << (12 - nb)
+                assert (lut[lo: lo + (1 << (12 - nb))] == ((nb << 8) | int(s))).all()
+
+
+@pytest.mark.parametrize("n_ary", PACKABLE)
+def test_encode_matches_oracle_and_roundtrips(dc, oracle, n_ary):
+    big = _zipf(dc, (1 << 20) + 3)
+    host = big.cpu().numpy()
+    hist = dc.histogram(big)
+    table = dc.huff_build(hist, n_ary)
+    ln, el, ev, st = oracle.build_tables(hist.cpu().numpy().astype(np.uint64), n_ary)
+    bpd = oracle.bits_per_digit(n_ary)
+    for size in (1, 2, 15, 16, 17, 255, 4095, 4096, 4097, 8192, 12289, host.size):
+        for phase in ((0, 5) if size < host.size else (0, 3)):
+            res = dc.huff_encode(big[:size], table, bit_phase=phase)
+            nbits = res.bits()
+            want, wbits = oracle.pack(host[:size], el, ev, bpd, phase)
+            assert nbits == wbits, (size, phase)
+            got = res.payload[: (nbits + phase + 7) // 8].cpu().numpy()
+            assert np.array_equal(got, want), (n_ary, size, phase)
+            out, status = dc.huff_decode(res.payload, nbits, table, size, bit_start=phase)
+            assert int(status.item()) == 0, (n_ary, size, phase)
+            assert torch.equal(out, big[:size]), (n_ary, size, phase)
+
+
+def test_encode_only_writes_its_bytes(dc, oracle):
+    data = _zipf(dc, 50000)
+    table = dc.huff_build(dc.histogram(data), 2)
+    out = torch.full((60000,), 0xAB, dtype=torch.uint8, device="cuda")
+    res = dc.huff_encode(data, table, out=out)
+    nb = (res.bits() + 7) // 8
+    assert (out[nb:] == 0xAB).all()
+    # capacity one byte short -> DC_ERR_CAPACITY, nothing beyond the buffer touched
+    small = torch.full((nb + 15,), 0xCD, dtype=torch.uint8, device="cuda")
+    res = dc.huff_encode(data, table, out=small[: nb - 1])
+    assert int(res.status.item()) == dc.DC_ERR_CAPACITY
+    assert (small[nb - 1:] == 0xCD).all()
+
+
+def test_encode_symbol_without_code(dc):
+    data = _dev(np.array([65] * 100 + [66], dtype=np.uint8))
+    table = dc.huff_build(dc.histogram(data[:100]), 2)  # 66 has no code
+    res = dc.huff_encode(data, table)
+    assert int(res.status.item()) == dc.DC_ERR_SYMBOL
+
+
+def test_wide_codes_up_to_30_bits(dc, oracle):
+    """n=4 with 15-digit (30-bit) codes: the enc64 path of the encoder and the canonical slow path of the decoder."""
+    ln = np.zeros(259, dtype=np.int32)
+    # a complete 4-ary code: 3 symbols at each depth 1..14, 4 at depth 15 (Kraft sum == 1)
+    sym = 1
+    for depth in range(1, 15):
+        for _ in range(3):
+            ln[sym] = depth; sym += 1
+    for _ in range(4):
+        ln[sym] = 15; sym += 1
+    el, ev, st = oracle.convert_lengths_to_encode_table(ln, 4)
+    assert st == 0
+    table = dc.huff_table_from_lengths(_dev(ln), 4)
+    t = table.download()
+    assert t.status == 0 and t.max_bits == 30
+    assert np.array_equal(np.array(t.values[:259], dtype=np.uint32), ev)
+    rng = np.random.default_rng(4)
+    data = rng.integers(1, sym, size=70001).astype(np.uint8)
+    res = dc.huff_encode(_dev(data), table, out=torch.empty(data.size * 4 + 64, dtype=torch.uint8, device="cuda"))
+    nbits = res.bits()
+    want, wbits = oracle.pack(data, el, ev, 2)
+    assert nbits == wbits
+    assert np.array_equal(res.payload[: (nbits + 7) // 8].cpu().numpy(), want)
+    out, status = dc.huff_decode(res.payload, nbits, table, data.size)
+    assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
+
+
+def test_degenerate_alphabets(dc, oracle):
+    # one distinct symbol: 1-bit codes (binary), 128 symbols per 128-bit subsequence
+    for n_ary in PACKABLE:
+        data = np.full(100000, 200, dtype=np.uint8)
+        d = _dev(data)
+        table = dc.huff_build(dc.histogram(d), n_ary)
+        res = dc.huff_encode(d, table)
+        nbits = res.bits()
+        ln, el, ev, st = oracle.build_tables(oracle.histogram_u8(data), n_ary)
+        want, wbits = oracle.pack(data, el, ev, oracle.bits_per_digit(n_ary))
+        assert nbits == wbits and np.array_equal(res.payload[: (nbits + 7) // 8].cpu().numpy(), want)
+        assert torch.equal(dc.huff_decompress(res.payload, nbits, table, data.size), d)
+    # all 256 byte values, equal counts (incl. 0x00): lengths 8..9 in binary
+    data = np.tile(np.arange(256, dtype=np.uint8), 300)
+    np.random.default_rng(1).shuffle(data)
+    d = _dev(data)
+    table = dc.huff_build(dc.histogram(d), 2)
+    res = dc.huff_encode(d, table)
+    assert torch.equal(dc.huff_decompress(res.payload, res.bits(), table, data.size), d)
+
+
+def test_decode_matches_oracle_on_oracle_stream(dc, oracle):
+    """'reference-produced bitstream' (config 5): the oracle packs, the GPU decodes."""
+    data = _zipf(dc, 300007, seed=5).cpu().numpy()
+    hist = oracle.histogram_u8(data)
+    for n_ary in PACKABLE:
+        ln, el, ev, st = oracle.build_tables(hist, n_ary)
+        for phase in (0, 6):
+            payload, bits = oracle.pack(data, el, ev, oracle.bits_per_digit(n_ary), phase)
+            buf = torch.zeros(payload.size + 64, dtype=torch.uint8, device="cuda")
+            buf[: payload.size] = _dev(payload)
+            table = dc.huff_table_from_lengths(_dev(ln), n_ary)
+            out, status = dc.huff_decode(buf, bits, table, data.size, bit_start=phase)
+            assert int(status.item()) == 0
+            assert np.array_equal(out.cpu().numpy(), data), (n_ary, phase)
+            assert np.array_equal(oracle.unpack(payload, phase, bits, ln, n_ary, data.size), data)
+
+
+def test_decode_reports_corruption(dc, oracle):
+    data = _zipf(dc, 100000, seed=6)
+    table = dc.huff_build(dc.histogram(data), 2)
+    res = dc.huff_encode(data, table)
+    nbits = res.bits()
+    # wrong symbol count
+    out, status = dc.huff_decode(res.payload, nbits, table, data.numel() - 1)
+    assert int(status.item()) in (dc.DC_ERR_CAPACITY, dc.DC_ERR_CORRUPT)
+    # truncated stream: ends inside a code or yields fewer symbols
+    out, status = dc.huff_decode(res.payload, nbits - 3, table, data.numel())
+    assert int(status.item()) == dc.DC_ERR_CORRUPT
+    # a stream made of the unused (dummy) slot: binary always has one
+    h = np.zeros(259, dtype=np.int64); h[[97, 98, 99, 100]] = [1, 1, 2, 2]
+    t2 = dc.huff_build(_dev(h), 2)
+    bad = torch.full((64,), 0xFF, dtype=torch.uint8, device="cuda")
+    out, status = dc.huff_decode(bad, 64, t2, 32)
+    assert int(status.item()) == dc.DC_ERR_CORRUPT
+
+
+def test_radix_without_packing_is_table_only(dc):
+    data = _zipf(dc, 4096)
+    table = dc.huff_build(dc.histogram(data), 3)
+    assert table.download().bits_per_digit == 0
+    res = dc.huff_encode(data, table)
+    assert int(res.status.item()) == dc.DC_ERR_RADIX
+
+
+def test_nybble_pack_unpack(dc, oracle):
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_nybble_spec()
+    for n in (0, 1, 2, 31, 32, 33, 63, 64, 65, 4097, (1 << 20) + 1, (1 << 22)):
+        sym = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dc.synth_fill(sym, synth.SEED_BASE + 2, synth.device_thresholds(thr, "cuda"), base)
+        packed, status = dc.nybble_pack(sym)
+        assert int(status.item()) == 0
+        assert np.array_equal(packed.cpu().numpy(), oracle.nybble_pack(sym.cpu().numpy())), n
+        assert torch.equal(dc.nybble_unpack(packed, n), sym), n
+    # unaligned views take the byte-granular kernels
+    sym = torch.empty(10001, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(sym, 9, synth.device_thresholds(thr, "cuda"), base)
+    v = sym[1:]
+    packed, status = dc.nybble_pack(v)
+    assert np.array_equal(packed.cpu().numpy(), oracle.nybble_pack(v.cpu().numpy()))
+    assert torch.equal(dc.nybble_unpack(packed, v.numel()), v)
+    # a symbol >= 16 is reported (assert at nybble_compression.c:1093), its low nibble is packed
+    bad = _dev(np.array([1, 2, 0x13, 4] * 16, dtype=np.uint8))
+    packed, status = dc.nybble_pack(bad)
+    assert int(status.item()) == dc.DC_ERR_SYMBOL
+    assert packed.cpu().numpy()[1] == 0x34
+
+
+def test_shard_bit_totals(dc, oracle):
+    """dot(local histogram, global lengths) == bits the shard really emits."""
+    data = _zipf(dc, 200000)
+    table = dc.huff_build(dc.histogram(data), 16)
+    for lo, hi in ((0, 70000), (70000, 200000)):
+        want = dc.huff_encode(data[lo:hi].clone(), table).bits()
+        got = int(dc.huff_bits_for_hist(dc.histogram(data[lo:hi].clone()), table).item())
+        assert got == want

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Per-kernel timings (CUDA events, inputs resident in HBM, > L2) for every kernel and histogram layout.
+Development tool: prints one JSON object per line; bench.py is the contract benchmark."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import data_compression_b200 as dc  # noqa: E402
+from data_compression_b200 import synth  # noqa: E402
+
+PEAK = 6537.3
+if os.path.exists("MEASURED_PEAKS.json"):
+    PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def report(name, alg_bytes, n, best, med, **kw):
+    print(json.dumps({"kernel": name, "ms_best": round(best, 4), "ms_median": round(med, 4),
+                      "uncompressed_GBps": round(n / best / 1e6, 1), "algorithmic_GBps": round(alg_bytes / best / 1e6, 1),
+                      "frac_of_hbm_peak": round(alg_bytes / best / 1e6 / PEAK, 4), **kw}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size-mib", type=int, default=1024)
+    ap.add_argument("--radices", default="2,4,16")
+    ap.add_argument("--hist-variants", default="0,1,2,3,4,5")
+    args = ap.parse_args()
+    n = args.size_mib << 20
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    thr, base = synth.zipf_bytes_spec()
+    data = torch.empty(n, dtype=torch.uint8, device=dev)
+    dc.synth_fill(data, synth.SEED_BASE + 2, synth.device_thresholds(thr, dev), base)
+    hist = torch.empty(259, dtype=torch.int64, device=dev)
+
+    for v in [int(x) for x in args.hist_variants.split(",") if x != ""]:
+        best, med = timeit(lambda: dc.histogram(data, out=hist, variant=v))
+        report(f"histogram[variant {v}]", n, n, best, med)
+    uni = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev)
+    for v in [int(x) for x in args.hist_variants.split(",") if x != ""]:
+        best, med = timeit(lambda: dc.histogram(uni, out=hist, variant=v))
+        report(f"histogram[variant {v}, uniform bytes]", n, n, best, med)
+    del uni
+    dc.histogram(data, out=hist)
+
+    L = dc.lib()
+    payload = torch.empty(n + n // 4 + 64, dtype=torch.uint8, device=dev)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.dc_huff_encode_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    for n_ary in [int(x) for x in args.radices.split(",") if x != ""]:
+        table = dc.HuffTable(dev)
+        best, med = timeit(lambda: dc.huff_build(hist, n_ary, table))
+        report(f"table[n={n_ary}]", 259 * 8, 0, best, med)
+        res = dc.huff_encode(data, table, out=payload, workspace=ws)
+        nbits = res.bits()
+        c = (nbits + 7) // 8
+        best, med = timeit(lambda: dc.huff_encode(data, table, out=payload, workspace=ws))
+        report(f"encode[n={n_ary}]", n + c, n, best, med, compressed_ratio=round(c / n, 4))
+        dws = torch.empty(L.dc_huff_decode_workspace_bytes(0, nbits), dtype=torch.uint8, device=dev)
+        st = torch.empty(1, dtype=torch.int32, device=dev)
+        L.dc_profile_reset(); L.dc_profile_enable(1)
+        best, med = timeit(lambda: dc.huff_decode(payload, nbits, table, n, out=out, workspace=dws, status=st), reps=3, warm=1)
+        L.dc_profile_enable(0)
+        assert int(st.item()) == 0 and torch.equal(out, data)
+        parts = {}
+        import ctypes as C
+        for kid in range(12):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                parts[L.dc_profile_kernel_name(kid).decode()] = [round(ms.value / cnt.value, 4), cnt.value]
+        report(f"decode[n={n_ary}]", n + c, n, best, med, kernels_ms_avg_and_launches=parts)
+        del dws
+
+    thr4, base4 = synth.zipf_nybble_spec()
+    sym = data
+    dc.synth_fill(sym, synth.SEED_BASE + 1, synth.device_thresholds(thr4, dev), base4)
+    packed = payload[: n // 2]
+    stt = torch.empty(1, dtype=torch.int32, device=dev)
+    best, med = timeit(lambda: dc.nybble_pack(sym, out=packed, status=stt))
+    report("nybble_pack", n + n // 2, n, best, med)
+    best, med = timeit(lambda: dc.nybble_unpack(packed, n, out=out))
+    report("nybble_unpack", n + n // 2, n, best, med)
+    assert torch.equal(out, sym)
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    best, med = timeit(lambda: a.copy_(sym))
+    report("torch copy_ (reference point)", 2 * n, n, best, med)
+
+
+if __name__ == "__main__":
+    main()
