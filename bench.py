@@ -286,7 +286,7 @@ def run_ours(args) -> None:
 
     # ---- per-kernel durations (CUDA events around every launch, on the launching stream)
     kern = {}
-    for kid in range(12):
+    for kid in range(32):
         ms, cnt = C.c_double(0), C.c_uint64(0)
         L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
         if cnt.value:

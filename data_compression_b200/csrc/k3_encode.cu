@@ -1,4 +1,4 @@
-// k3_encode.cu -- K3: Huffman payload encode in a single pass over the input.
+// k3_encode.cu -- K3: Huffman payload encode.
 //
 // Replaces represent_items_with_codes() (n_ary_huffman.c:1621-1678).  In the reference that function is a
 // stub (assert(0) at :1661, returns 32767); its stated intent is "for each input byte append
@@ -6,33 +6,42 @@
 // (DESIGN.md): a code of `len` digits is the len*log2(n)-bit big-endian numeral of encode_value; codes are
 // concatenated in input order, MSB-first within each byte; the final byte is zero-padded.
 //
-// One CTA per tile of 4096 symbols (256 threads x 16 symbols = one 16-byte load per thread):
-//   A. per-symbol code lookup from a shared-memory copy of the table; per-thread bit total
-//   B. CTA-wide exclusive scan of bit totals; the tile total is published at once (decoupled look-back)
-//   C. every thread streams its codes through a 64-bit accumulator into a shared-memory staging buffer at
-//      its tile-relative bit offset (whole words: plain stores; the two edge words: shared atomicOr)
-//   D. the tile publishes its last 128 bits; warp 0 resolves the tile's global bit offset by look-back
-//   E. coalesced copy-out: every thread funnel-shifts staging words to the global alignment and stores
-//      16 bytes.  A 16-byte output word that straddles two tiles is written by the LATER tile, which
-//      pulls the missing leading bits from its predecessor's published tail -- no global atomics, no
-//      pre-zeroed output, every output byte written exactly once.
-// HBM traffic = N (read) + C (write) + 24 bytes of descriptor per tile.
+// The input is cut into RUNS of 32 KB (8 tiles of 4096 symbols).  Three launches, no spin-waits:
+//   E1 count   : bits per run = sum of code lengths (one streaming read of the input)
+//   E2 scan    : exclusive scan of the run totals -> global bit offset of every run, total bit count
+//   E3 encode  : one CTA per run walks its 8 tiles.  Per tile (256 threads x 16 symbols):
+//        A. 16 code look-ups from a shared-memory copy of the table, combined pairwise in registers
+//        B. CTA-wide exclusive scan of the per-thread bit totals
+//        C. every thread streams its 8 code pairs through a 64-bit accumulator into a shared-memory
+//           staging buffer at its tile-relative bit offset (shared-memory OR)
+//        D. coalesced copy-out: staging words are funnel-shifted to the global bit alignment and stored
+//           as 16-byte words.  The partial 16-byte word at the end of a tile is carried into the next
+//           tile through shared memory; the one shared between two RUNS is merged by whichever CTA
+//           arrives second (both sides deposit their half in the workspace and bump a counter), so
+//           every output byte is written exactly once, in any CTA order, with no pre-zeroed output.
+// HBM traffic = 2N (count + encode reads) + C (write).
 #include "dc_common.cuh"
 
 namespace dc {
 
 constexpr int kEncThreads = 256;
 constexpr int kEncPerThread = 16;
-constexpr int kEncTile = kEncThreads * kEncPerThread;        // 4096 symbols
-constexpr int kEncStageWords = 4 + kEncTile + 8;             // pred. tail + 32 bits/symbol worst case + pad
+constexpr int kEncTile = kEncThreads * kEncPerThread;  // 4096 symbols
+constexpr int kRunTiles = 8;
+constexpr int kRunBytes = kEncTile * kRunTiles;        // 32 KB
+constexpr int kNarrowBits = 16;                        // code pairs fit 32 bits
 
-constexpr unsigned long long kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescTail = 1ull << 61;
-constexpr unsigned long long kDescValue = (1ull << 61) - 1;
+template <bool WIDE>
+struct EncCfg {
+    static constexpr int kMaxBits = WIDE ? 32 : kNarrowBits;
+    static constexpr int kStageWords = 4 + kEncTile * kMaxBits / 32 + 12;  // carried tail + worst case + pad
+};
 
 struct EncWorkspace {
-    unsigned int *ticket;        // dynamic tile id (tiles must start in id order for the look-back)
-    unsigned long long *desc;    // [ntiles] status | tail-ready | bits
-    uint4 *tails;                // [ntiles] last 128 bits of each tile, big-endian word domain
+    uint32_t *run_bits;            // [nruns]   E1
+    unsigned long long *run_off;   // [nruns+1] E2 (exclusive; last = total)
+    uint32_t *bstate;              // [nruns+1] arrivals at the boundary word between run b-1 and run b
+    uint4 *bleft, *bright;         // [nruns+1] the two halves of that word (big-endian word domain)
 };
 
 // bits [bit, bit+32) of a big-endian word array
@@ -41,203 +50,305 @@ __device__ __forceinline__ uint32_t stage_word(const uint32_t *stage, uint32_t b
     return __funnelshift_l(stage[a + 1], stage[a], s);
 }
 
-template <bool WIDE>
-__device__ __forceinline__ void encode_tile(const uint8_t *__restrict__ in, size_t n, const dc_huff_table *__restrict__ tab,
-                                            uint8_t *__restrict__ out, size_t out_cap, unsigned phase,
-                                            unsigned long long *__restrict__ d_total_bits, int32_t *__restrict__ d_status,
-                                            const EncWorkspace &ws, unsigned int ntiles, uint32_t *smem) {
-    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type entry_t;
-    uint32_t *stage = smem;                                        // [kEncStageWords]
-    entry_t *s_enc = (entry_t *)(smem + kEncStageWords);           // [256]
-    __shared__ uint32_t s_warp_bits[kEncThreads / 32];
-    __shared__ unsigned int s_tile;
-    __shared__ unsigned long long s_excl;
+__device__ __forceinline__ bool table_usable(const dc_huff_table *tab, int32_t *d_status) {
+    const int tstatus = tab->status, bpd = tab->bits_per_digit;
+    if (tstatus == DC_OK && bpd != 0) return true;
+    if (blockIdx.x == 0 && threadIdx.x == 0) set_status(d_status, tstatus != DC_OK ? tstatus : DC_ERR_RADIX);
+    return false;
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ws.ticket, 1u);
-    s_enc[tid] = WIDE ? (entry_t)tab->enc64[tid] : (entry_t)tab->enc[tid];
-    for (int i = tid; i < kEncStageWords / 4; i += kEncThreads) ((uint4 *)stage)[i] = make_uint4(0, 0, 0, 0);
+// ------------------------------------------------------------------------------------------ E1 count
+__global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                   const dc_huff_table *__restrict__ tab,
+                                                                   uint32_t *__restrict__ run_bits, unsigned int nruns,
+                                                                   int32_t *__restrict__ d_status) {
+    __shared__ uint32_t s_len[256];
+    __shared__ uint32_t s_sum;
+    if (!table_usable(tab, d_status)) return;
+    const int tid = threadIdx.x;
+    s_len[tid] = (uint32_t)(tab->enc64[tid] >> 32);
+    if (tid == 0) s_sum = 0;
     __syncthreads();
-    const unsigned int tile = s_tile;
-    const size_t base = (size_t)tile * kEncTile + (size_t)tid * kEncPerThread;
-
-    // ---- A. load 16 symbols, look their codes up
-    int valid = 0;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (base + kEncPerThread <= n) {
-        const uint4 v = ldg_stream((const uint4 *)(in + base));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        valid = kEncPerThread;
-    } else if (base < n) {
-        valid = (int)(n - base);
-        for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
-    }
-    entry_t e[kEncPerThread];
-    uint32_t my_bits = 0;
     bool missing = false;
+    for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        const size_t base = (size_t)run * kRunBytes;
+        uint32_t sum = 0;
+        if (base + kRunBytes <= n) {
+            uint4 v[kRunTiles];
 #pragma unroll
-    for (int k = 0; k < kEncPerThread; k++) {
-        const uint32_t b = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-        entry_t x = s_enc[b];
-        if (k >= valid) x = 0;
-        const uint32_t len = WIDE ? (uint32_t)(x >> 32) : ((uint32_t)x & 63u);
-        missing |= (k < valid) && (len == 0);
-        my_bits += len;
-        e[k] = x;
+            for (int j = 0; j < kRunTiles; j++) v[j] = ldg_stream((const uint4 *)(in + base) + j * kEncThreads + tid);
+#pragma unroll
+            for (int j = 0; j < kRunTiles; j++) {
+                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t l = s_len[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+                    missing |= l == 0;
+                    sum += l;
+                }
+            }
+        } else {
+            for (size_t i = base + tid; i < n; i += kEncThreads) {
+                const uint32_t l = s_len[in[i]];
+                missing |= l == 0;
+                sum += l;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if ((tid & 31) == 0) atomicAdd(&s_sum, sum);
+        __syncthreads();
+        if (tid == 0) { run_bits[run] = s_sum; s_sum = 0; }
+        __syncthreads();
     }
     if (missing) set_status(d_status, DC_ERR_SYMBOL);
-
-    // ---- B. exclusive scan of bit totals over the CTA
-    uint32_t incl = my_bits;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp_bits[warp] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, tile_bits = 0;
-#pragma unroll
-    for (int i = 0; i < kEncThreads / 32; i++) {
-        const uint32_t t = s_warp_bits[i];
-        if (i < warp) warp_off += t;
-        tile_bits += t;
-    }
-    const unsigned long long first_status = tile == 0 ? kDescPrefix : kDescAgg;
-    if (tid == 0) st_release_u64(&ws.desc[tile], first_status | tile_bits);
-
-    // ---- C. stream this thread's codes into the staging buffer (own bits start at staging bit 128)
-    if (my_bits) {
-        const uint32_t pos = 128u + warp_off + incl - my_bits;
-        uint32_t wi = pos >> 5;
-        uint32_t nb = pos & 31;
-        bool shared_word = nb != 0;
-        unsigned long long acc = 0;
-#pragma unroll
-        for (int k = 0; k < kEncPerThread; k++) {
-            const uint32_t len = WIDE ? (uint32_t)(e[k] >> 32) : ((uint32_t)e[k] & 63u);
-            const uint32_t val = WIDE ? (uint32_t)e[k] : ((uint32_t)e[k] >> 6);
-            acc = (acc << len) | val;
-            nb += len;
-            if (nb >= 32) {
-                const uint32_t word = (uint32_t)(acc >> (nb - 32));
-                if (shared_word) { atomicOr(&stage[wi], word); shared_word = false; }
-                else stage[wi] = word;
-                wi++;
-                nb -= 32;
-            }
-        }
-        if (nb) atomicOr(&stage[wi], (uint32_t)(acc << (32 - nb)));
-    }
-    __syncthreads();
-
-    // ---- D. publish the tail, resolve the global bit offset, fetch the predecessor's tail
-    if (warp == 0) {
-        if (lane == 0) {
-            uint4 t;
-            t.x = stage_word(stage, tile_bits);
-            t.y = stage_word(stage, tile_bits + 32);
-            t.z = stage_word(stage, tile_bits + 64);
-            t.w = stage_word(stage, tile_bits + 96);
-            ws.tails[tile] = t;
-            __threadfence();
-            st_release_u64(&ws.desc[tile], first_status | kDescTail | tile_bits);
-        }
-        unsigned long long excl = 0;
-        if (tile != 0) {
-            long long idx = (long long)tile - 1 - lane;
-            while (true) {
-                unsigned long long d;
-                do {
-                    d = idx >= 0 ? ld_acquire_u64(&ws.desc[idx]) : kDescPrefix;
-                } while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0));
-                const unsigned prefix_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-                unsigned long long v = d & kDescValue;
-                if (prefix_mask) {
-                    const int first = __ffs(prefix_mask) - 1;  // nearest predecessor that knows its prefix
-                    if (lane > first) v = 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                excl += v;
-                if (prefix_mask) break;
-                idx -= 32;
-            }
-            if (lane == 0) {
-                st_release_u64(&ws.desc[tile], kDescPrefix | kDescTail | (excl + tile_bits));
-                while ((ld_acquire_u64(&ws.desc[tile - 1]) & kDescTail) == 0) {}
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const uint4 t = ld_cg_u128(&ws.tails[tile - 1]);
-                stage[0] = t.x; stage[1] = t.y; stage[2] = t.z; stage[3] = t.w;
-            }
-        }
-        if (lane == 0) s_excl = excl;
-    }
-    __syncthreads();
-
-    // ---- E. copy-out at the global alignment
-    const unsigned long long g = (unsigned long long)phase + s_excl;   // global bit position of the tile's first bit
-    const unsigned long long gend = g + tile_bits;
-    const unsigned long long v0 = g >> 7, v1 = gend >> 7;              // 16-byte words [v0, v1) end inside this tile
-    const uint32_t r = (uint32_t)(g & 127);
-    const bool last = tile == ntiles - 1;
-    const size_t need = (size_t)((last ? gend + 7 : v1 * 128) >> 3);
-    if (need > out_cap) {
-        if (tid == 0) set_status(d_status, DC_ERR_CAPACITY);
-    } else {
-        for (unsigned long long v = v0 + tid; v < v1; v += kEncThreads) {
-            const uint32_t sbit = (uint32_t)(v - v0) * 128u + (128u - r);
-            uint4 o;
-            o.x = bswap32(stage_word(stage, sbit));
-            o.y = bswap32(stage_word(stage, sbit + 32));
-            o.z = bswap32(stage_word(stage, sbit + 64));
-            o.w = bswap32(stage_word(stage, sbit + 96));
-            stg_stream((uint4 *)out + v, o);
-        }
-        if (last) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
-            const uint32_t rem_bytes = (uint32_t)(((gend & 127) + 7) >> 3);
-            const uint32_t sbit = (uint32_t)(v1 - v0) * 128u + (128u - r);
-            if (tid < (int)rem_bytes) out[v1 * 16 + tid] = (uint8_t)(stage_word(stage, sbit + 8u * tid) >> 24);
-        }
-    }
-    if (last && tid == 0 && d_total_bits) *d_total_bits = s_excl + tile_bits;
 }
 
-__global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint8_t *__restrict__ in, size_t n,
-                                                             const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
-                                                             size_t out_cap, unsigned phase,
-                                                             unsigned long long *__restrict__ d_total_bits,
-                                                             int32_t *__restrict__ d_status, EncWorkspace ws,
-                                                             unsigned int ntiles) {
-    extern __shared__ __align__(16) uint32_t enc_smem[];
-    const int tstatus = tab->status, bpd = tab->bits_per_digit, max_bits = tab->max_bits;
-    if (tstatus != DC_OK || bpd == 0) {  // uniform across the grid: nobody takes a ticket
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            set_status(d_status, tstatus != DC_OK ? tstatus : DC_ERR_RADIX);
-            if (d_total_bits) *d_total_bits = 0;
+// ------------------------------------------------------------------------------------------ E2 scan
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+
+__global__ void __launch_bounds__(kScanThreads) encode_scan_kernel(const dc_huff_table *__restrict__ tab, EncWorkspace ws,
+                                                                   unsigned int nruns,
+                                                                   unsigned long long *__restrict__ d_total_bits) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ok = tab->status == DC_OK && tab->bits_per_digit != 0;
+    if (tid == 0) s_carry = 0;
+    for (unsigned int i = tid; i <= nruns; i += kScanThreads) ws.bstate[i] = 0;
+    __syncthreads();
+    for (unsigned int base = 0; base < nruns; base += kScanThreads * kScanItems) {
+        const unsigned int first = base + tid * kScanItems;
+        uint32_t item[kScanItems];
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            item[k] = (ok && first + k < nruns) ? ws.run_bits[first + k] : 0u;
+            mine += item[k];
         }
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry;
+        for (int w = 0; w < warp; w++) off += s_warp[w];
+        off += incl - mine;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (first + k < nruns) ws.run_off[first + k] = off;
+            off += item[k];
+        }
+        __syncthreads();
+        if (tid == kScanThreads - 1) s_carry = off;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ws.run_off[nruns] = s_carry;
+        if (d_total_bits) *d_total_bits = s_carry;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ E3 encode
+
+// deposit one half of the 16-byte word shared by two runs; the second arrival merges and stores it
+__device__ __forceinline__ void boundary_merge(const EncWorkspace &ws, unsigned int b, bool left_side, uint4 mine,
+                                               uint8_t *__restrict__ out, unsigned long long vec, size_t stream_bytes) {
+    uint4 *my_slot = left_side ? ws.bleft + b : ws.bright + b;
+    const uint4 *other_slot = left_side ? ws.bright + b : ws.bleft + b;
+    *my_slot = mine;
+    __threadfence();
+    if (atomicAdd(&ws.bstate[b], 1u) == 1u) {
+        __threadfence();
+        const uint4 o = ld_cg_u128(other_slot);
+        uint4 r;
+        r.x = bswap32(mine.x | o.x);
+        r.y = bswap32(mine.y | o.y);
+        r.z = bswap32(mine.z | o.z);
+        r.w = bswap32(mine.w | o.w);
+        if ((vec + 1) * 16 <= stream_bytes) {
+            stg_stream((uint4 *)out + vec, r);
+        } else {  // the shared word is also the last, partial word of the stream
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            for (size_t i = vec * 16; i < stream_bytes; i++) out[i] = (uint8_t)(rw[(i & 15) >> 2] >> (8 * (i & 3)));
+        }
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kEncThreads) encode_run_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                 const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
+                                                                 size_t out_cap, unsigned phase, EncWorkspace ws,
+                                                                 unsigned int nruns, int32_t *__restrict__ d_status) {
+    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type entry_t;
+    constexpr int kStageWords = EncCfg<WIDE>::kStageWords;
+    constexpr int kItems = WIDE ? kEncPerThread : kEncPerThread / 2;  // codes (WIDE) or code pairs per thread
+    __shared__ __align__(16) uint32_t stage[kStageWords];
+    __shared__ entry_t s_enc[256];
+    __shared__ uint32_t s_warp_bits[kEncThreads / 32];
+
+    if (tab->status != DC_OK || tab->bits_per_digit == 0) return;  // reported by the count kernel
+    if ((tab->max_bits > kNarrowBits) != WIDE) return;            // the other instantiation handles this table
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // bytes [0, stream_bytes) of `out` are written, nothing else; refuse the whole stream if they do not fit
+    const size_t stream_bytes = (size_t)(((unsigned long long)phase + ws.run_off[nruns] + 7) >> 3);
+    if (stream_bytes > out_cap) {
+        if (blockIdx.x == 0 && tid == 0) set_status(d_status, DC_ERR_CAPACITY);
         return;
     }
-    if (max_bits <= 26) encode_tile<false>(in, n, tab, out, out_cap, phase, d_total_bits, d_status, ws, ntiles, enc_smem);
-    else encode_tile<true>(in, n, tab, out, out_cap, phase, d_total_bits, d_status, ws, ntiles, enc_smem);
+    s_enc[tid] = WIDE ? (entry_t)tab->enc64[tid] : (entry_t)tab->enc[tid];
+
+    for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        const size_t run_base = (size_t)run * kRunBytes;
+        const int ntiles = (int)min((size_t)kRunTiles, (n - run_base + kEncTile - 1) / kEncTile);
+        unsigned long long g = (unsigned long long)phase + ws.run_off[run];  // global bit position of the next tile
+        const bool last_run = run == nruns - 1;
+        uint32_t carried = 0;  // threads 0..3: the last 128 bits of the previous tile of this run
+
+        uint4 next = make_uint4(0, 0, 0, 0);
+        if (run_base + (size_t)tid * kEncPerThread + kEncPerThread <= n)
+            next = ldg_stream((const uint4 *)(in + run_base) + tid);
+
+        for (int t = 0; t < ntiles; t++) {
+            const size_t base = run_base + (size_t)t * kEncTile + (size_t)tid * kEncPerThread;
+            __syncthreads();  // the previous tile's copy-out has read the staging buffer
+            for (int i = tid; i < kStageWords / 4; i += kEncThreads) ((uint4 *)stage)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            if (tid < 4) stage[tid] = carried;
+
+            // ---- A. 16 symbols -> codes (pairs)
+            uint32_t w[4] = {next.x, next.y, next.z, next.w};
+            int valid = kEncPerThread;
+            if (base + kEncPerThread > n) {
+                valid = base < n ? (int)(n - base) : 0;
+                w[0] = w[1] = w[2] = w[3] = 0;
+                for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
+            }
+            if (t + 1 < ntiles && base + kEncTile + kEncPerThread <= n) next = ldg_stream((const uint4 *)(in + base + kEncTile));
+            uint32_t item_val[kItems], item_len[kItems];
+            uint32_t my_bits = 0;
+            if (WIDE) {
+#pragma unroll
+                for (int k = 0; k < kEncPerThread; k++) {
+                    unsigned long long e = s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+                    if (k >= valid) e = 0;
+                    item_val[k % kItems] = (uint32_t)e;
+                    item_len[k % kItems] = (uint32_t)(e >> 32);
+                    my_bits += (uint32_t)(e >> 32);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kEncPerThread; k += 2) {
+                    uint32_t e0 = (uint32_t)s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+                    uint32_t e1 = (uint32_t)s_enc[(w[k >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu];
+                    if (k >= valid) e0 = 0;
+                    if (k + 1 >= valid) e1 = 0;
+                    const uint32_t l1 = e1 & 63u;
+                    item_val[(k / 2) % kItems] = ((e0 >> 6) << l1) | (e1 >> 6);
+                    item_len[(k / 2) % kItems] = (e0 & 63u) + l1;
+                    my_bits += (e0 & 63u) + l1;
+                }
+            }
+
+            // ---- B. exclusive scan of bit totals over the CTA
+            uint32_t incl = my_bits;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += x;
+            }
+            if (lane == 31) s_warp_bits[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off = 0, tile_bits = 0;
+#pragma unroll
+            for (int i = 0; i < kEncThreads / 32; i++) {
+                const uint32_t x = s_warp_bits[i];
+                if (i < warp) warp_off += x;
+                tile_bits += x;
+            }
+
+            // ---- C. stream the codes into the staging buffer (own bits start at staging bit 128)
+            if (my_bits) {
+                const uint32_t pos = 128u + warp_off + incl - my_bits;
+                uint32_t wi = pos >> 5, nb = pos & 31;
+                unsigned long long acc = 0;
+#pragma unroll
+                for (int k = 0; k < kItems; k++) {
+                    acc = (acc << item_len[k]) | item_val[k];
+                    nb += item_len[k];
+                    if (nb >= 32) {
+                        atomicOr(&stage[wi], (uint32_t)(acc >> (nb - 32)));
+                        wi++;
+                        nb -= 32;
+                    }
+                }
+                if (nb) atomicOr(&stage[wi], (uint32_t)(acc << (32 - nb)));
+            }
+            __syncthreads();
+
+            // ---- D. copy-out at the global alignment
+            const unsigned long long gend = g + tile_bits;
+            const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this tile
+            const uint32_t r = (uint32_t)(g & 127);
+            const bool last_tile = t == ntiles - 1;
+            const bool stream_end = last_run && last_tile;
+            const bool shared_first = t == 0 && run != 0 && r != 0;  // first word also holds the previous run's bits
+            for (unsigned long long v = v0 + (shared_first ? 1 : 0) + tid; v < v1; v += kEncThreads) {
+                const uint32_t sbit = (uint32_t)(v - v0) * 128u + (128u - r);
+                uint4 o;
+                o.x = bswap32(stage_word(stage, sbit));
+                o.y = bswap32(stage_word(stage, sbit + 32));
+                o.z = bswap32(stage_word(stage, sbit + 64));
+                o.w = bswap32(stage_word(stage, sbit + 96));
+                stg_stream((uint4 *)out + v, o);
+            }
+            if (shared_first && tid == 32) {  // (v1 == v0 only for a tiny final run: the word is shared AND last)
+                const uint32_t sbit = 128u - r;
+                const uint4 m = make_uint4(stage_word(stage, sbit), stage_word(stage, sbit + 32),
+                                           stage_word(stage, sbit + 64), stage_word(stage, sbit + 96));
+                boundary_merge(ws, run, false, m, out, v0, stream_bytes);
+            }
+            if (last_tile && (gend & 127) != 0 && !(shared_first && v1 == v0)) {
+                const uint32_t sbit = (uint32_t)(v1 - v0) * 128u + (128u - r);
+                if (stream_end) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
+                    const uint32_t rem_bytes = (uint32_t)(((gend & 127) + 7) >> 3);
+                    if (tid < (int)rem_bytes) out[v1 * 16 + tid] = (uint8_t)(stage_word(stage, sbit + 8u * tid) >> 24);
+                } else if (tid == 64) {  // the word shared with the next run
+                    const uint4 m = make_uint4(stage_word(stage, sbit), stage_word(stage, sbit + 32),
+                                               stage_word(stage, sbit + 64), stage_word(stage, sbit + 96));
+                    boundary_merge(ws, run + 1, true, m, out, v1, stream_bytes);
+                }
+            }
+            if (tid < 4) carried = stage_word(stage, tile_bits + 32u * tid);  // last 128 bits of this tile
+            g = gend;
+        }
+    }
 }
 
-static size_t enc_ws_layout(size_t n, size_t *desc_off, size_t *tails_off) {
-    const size_t ntiles = (n + kEncTile - 1) / kEncTile;
-    const size_t d = 16;
-    const size_t t = d + ((ntiles * 8 + 15) & ~(size_t)15);
-    if (desc_off) *desc_off = d;
-    if (tails_off) *tails_off = t;
-    return t + ntiles * 16;
+static size_t enc_ws_layout(size_t n, size_t off[5]) {
+    const size_t nruns = (n + kRunBytes - 1) / kRunBytes;
+    size_t p = 64;
+    auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
+    size_t o[5];
+    o[0] = take(nruns * 4);         // run_bits
+    o[1] = take((nruns + 1) * 8);   // run_off
+    o[2] = take((nruns + 1) * 4);   // bstate
+    o[3] = take((nruns + 1) * 16);  // bleft
+    o[4] = take((nruns + 1) * 16);  // bright
+    if (off) for (int i = 0; i < 5; i++) off[i] = o[i];
+    return p;
 }
 
 }  // namespace dc
 
 using namespace dc;
 
-extern "C" size_t dc_huff_encode_workspace_bytes(size_t n) { return enc_ws_layout(n, nullptr, nullptr); }
+extern "C" size_t dc_huff_encode_workspace_bytes(size_t n) { return enc_ws_layout(n, nullptr); }
 
 extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out,
                               size_t out_capacity, unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status,
@@ -248,21 +359,39 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     if (d_total_bits) DC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), st));
     if (n == 0) return DC_OK;
-    size_t desc_off, tails_off;
-    const size_t need = enc_ws_layout(n, &desc_off, &tails_off);
+    size_t off[5];
+    const size_t need = enc_ws_layout(n, off);
     if (workspace_bytes < need) return DC_ERR_CAPACITY;
-    const size_t ntiles = (n + kEncTile - 1) / kEncTile;
-    if (ntiles > 0xFFFFFFF0ull) return DC_ERR_ARG;
-    // ticket + descriptors must start at zero; the tails are written before they are read
-    DC_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, tails_off, st));
+    const size_t nruns64 = (n + kRunBytes - 1) / kRunBytes;
+    if (nruns64 > 0x7FFFFFF0ull) return DC_ERR_ARG;
+    const unsigned int nruns = (unsigned int)nruns64;
+    char *w = (char *)d_workspace;
     EncWorkspace ws;
-    ws.ticket = (unsigned int *)d_workspace;
-    ws.desc = (unsigned long long *)((char *)d_workspace + desc_off);
-    ws.tails = (uint4 *)((char *)d_workspace + tails_off);
-    const size_t smem = (size_t)kEncStageWords * 4 + 256 * 8;
-    LaunchScope ls(DC_K_ENCODE, st);
-    encode_kernel<<<(unsigned int)ntiles, kEncThreads, smem, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
-                                                                  (unsigned long long *)d_total_bits, d_status, ws,
-                                                                  (unsigned int)ntiles);
+    ws.run_bits = (uint32_t *)(w + off[0]);
+    ws.run_off = (unsigned long long *)(w + off[1]);
+    ws.bstate = (uint32_t *)(w + off[2]);
+    ws.bleft = (uint4 *)(w + off[3]);
+    ws.bright = (uint4 *)(w + off[4]);
+    const unsigned int sms = (unsigned int)sm_count();
+    {
+        LaunchScope ls(DC_K_ENCODE_COUNT, st);
+        encode_count_kernel<<<min(nruns, sms * 8u), kEncThreads, 0, st>>>(d_in, n, d_table, ws.run_bits, nruns, d_status);
+    }
+    {
+        LaunchScope ls(DC_K_ENCODE_SCAN, st);
+        encode_scan_kernel<<<1, kScanThreads, 0, st>>>(d_table, ws, nruns, (unsigned long long *)d_total_bits);
+    }
+    {
+        LaunchScope ls(DC_K_ENCODE, st);
+        encode_run_kernel<false><<<min(nruns, sms * 32u), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
+                                                                              ws, nruns, d_status);
+    }
+    {
+        // tables with codes longer than 16 bits take the 64-bit-entry instantiation; for all others this
+        // launch is a few hundred CTAs that return at once
+        LaunchScope ls(DC_K_ENCODE_WIDE, st);
+        encode_run_kernel<true><<<min(nruns, sms * 4u), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
+                                                                             ws, nruns, d_status);
+    }
     return cuda_status(cudaGetLastError());
 }

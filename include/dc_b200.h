@@ -97,7 +97,10 @@ enum dc_kernel_id {
     DC_K_HISTOGRAM = 0,
     DC_K_TABLE,
     DC_K_BITS_FOR_HIST,
+    DC_K_ENCODE_COUNT,
+    DC_K_ENCODE_SCAN,
     DC_K_ENCODE,
+    DC_K_ENCODE_WIDE,
     DC_K_DECODE_SYNC,
     DC_K_DECODE_HANDOFF,
     DC_K_DECODE_SCAN,
