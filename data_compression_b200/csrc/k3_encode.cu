@@ -6,48 +6,87 @@
 // (DESIGN.md): a code of `len` digits is the len*log2(n)-bit big-endian numeral of encode_value; codes are
 // concatenated in input order, MSB-first within each byte; the final byte is zero-padded.
 //
-// The input is cut into RUNS of 32 KB (8 tiles of 4096 symbols).  Three launches, no spin-waits:
-//   E1 count   : bits per run = sum of code lengths (one streaming read of the input)
+// The input is cut into CHUNKS of 4 KB (one warp each); 8 chunks form a 32 KB RUN (one CTA).
+// Three launches, no spin-waits, no CTA-wide barriers in the hot kernel:
+//   E1 count   : bits per chunk = sum of code lengths (one streaming read of the input); per run the
+//                exclusive offsets of its 8 chunks and the run total
 //   E2 scan    : exclusive scan of the run totals -> global bit offset of every run, total bit count
-//   E3 encode  : one CTA per run walks its 8 tiles.  Per tile (256 threads x 16 symbols):
+//   E3 encode  : every WARP walks its chunk in 8 sub-tiles of 512 symbols (32 lanes x 16 symbols):
 //        A. 16 code look-ups from a shared-memory copy of the table, combined pairwise in registers
-//        B. CTA-wide exclusive scan of the per-thread bit totals
-//        C. every thread streams its 8 code pairs through a 64-bit accumulator into a shared-memory
-//           staging buffer at its tile-relative bit offset (shared-memory OR)
+//        B. warp-wide exclusive scan of the per-lane bit totals (shuffles)
+//        C. every lane streams its 8 code pairs through a 64-bit accumulator into the warp's staging
+//           buffer at its bit offset.  When every lane holds >= 32 bits each staging word is shared by at
+//           most two neighbouring lanes, so words are written with plain stores and the one shared partial
+//           word travels by shuffle; otherwise (very compressible or ragged data) shared-memory OR is used
 //        D. coalesced copy-out: staging words are funnel-shifted to the global bit alignment and stored
-//           as 16-byte words.  The partial 16-byte word at the end of a tile is carried into the next
-//           tile through shared memory; the one shared between two RUNS is merged by whichever CTA
-//           arrives second (both sides deposit their half in the workspace and bump a counter), so
-//           every output byte is written exactly once, in any CTA order, with no pre-zeroed output.
+//           as 16-byte words.  The partial 16-byte word at the end of a sub-tile is carried into the next
+//           one in registers; the one shared between two CHUNKS is merged by whichever warp arrives
+//           second (both sides deposit their half in the workspace and bump a counter), so every output
+//           byte is written exactly once, in any scheduling order, with no pre-zeroed output.
 // HBM traffic = 2N (count + encode reads) + C (write).
 #include "dc_common.cuh"
 
 namespace dc {
 
 constexpr int kEncThreads = 256;
+constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kEncPerThread = 16;
-constexpr int kEncTile = kEncThreads * kEncPerThread;  // 4096 symbols
-constexpr int kRunTiles = 8;
-constexpr int kRunBytes = kEncTile * kRunTiles;        // 32 KB
-constexpr int kNarrowBits = 16;                        // code pairs fit 32 bits
+constexpr int kSubTile = 32 * kEncPerThread;           // 512 symbols per warp step
+constexpr int kChunkSubs = 8;
+constexpr int kChunkBytes = kSubTile * kChunkSubs;      // 4 KB per warp
+constexpr int kRunBytes = kChunkBytes * kEncWarps;      // 32 KB per CTA
+constexpr int kNarrowBits = 16;                         // code pairs fit 32 bits
 
 template <bool WIDE>
 struct EncCfg {
     static constexpr int kMaxBits = WIDE ? 32 : kNarrowBits;
-    static constexpr int kStageWords = 4 + kEncTile * kMaxBits / 32 + 12;  // carried tail + worst case + pad
+    static constexpr int kStageWords = 4 + kSubTile * kMaxBits / 32 + 12;  // carried tail + worst case + pad (per warp)
 };
 
 struct EncWorkspace {
-    uint32_t *run_bits;            // [nruns]   E1
-    unsigned long long *run_off;   // [nruns+1] E2 (exclusive; last = total)
-    uint32_t *bstate;              // [nruns+1] arrivals at the boundary word between run b-1 and run b
-    uint4 *bleft, *bright;         // [nruns+1] the two halves of that word (big-endian word domain)
+    uint32_t *run_bits;            // [nruns]      E1
+    uint32_t *chunk_rel;           // [nruns * 8]  E1: bit offset of each chunk inside its run
+    unsigned long long *run_off;   // [nruns+1]    E2 (exclusive; last = total)
+    uint32_t *bstate;              // [nchunks+1]  arrivals at the boundary word between chunk b-1 and chunk b
+    uint4 *bleft, *bright;         // [nchunks+1]  the two halves of that word (big-endian word domain)
 };
 
 // bits [bit, bit+32) of a big-endian word array
 __device__ __forceinline__ uint32_t stage_word(const uint32_t *stage, uint32_t bit) {
     const uint32_t a = bit >> 5, s = bit & 31;
     return __funnelshift_l(stage[a + 1], stage[a], s);
+}
+
+// stage[wi] |= word when pred (predicated RED.OR on shared memory: no branch, no BSSY/BSYNC)
+__device__ __forceinline__ void stage_or_if(uint32_t *addr, uint32_t word, bool pred) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(addr);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(a), "r"(word),
+                 "r"((uint32_t)pred)
+                 : "memory");
+}
+
+// append `len` (<= 32) bits of `val` to the 64-bit accumulator (hi:lo), then emit one 32-bit word if at least 32
+// bits are pending.  nb = pending bits (< 32 on entry and on exit); wi = next staging word.
+__device__ __forceinline__ void emit_bits(uint32_t *stage, uint32_t &hi, uint32_t &lo, uint32_t &nb, uint32_t &wi, uint32_t val,
+                                          uint32_t len) {
+    hi = __funnelshift_lc(lo, hi, len);
+    lo = __funnelshift_lc(0u, lo, len) | val;
+    nb += len;
+    // pending bits are the low nb bits of hi:lo; the oldest 32 of them are (hi:lo) >> (nb - 32)
+    stage_or_if(stage + wi, __funnelshift_r(lo, hi, nb), nb >= 32u);
+    wi += nb >> 5;
+    nb &= 31u;
+}
+
+// same as emit_bits, for the case where every word completed by this thread is owned by it alone (plain store)
+__device__ __forceinline__ void emit_bits_owned(uint32_t *stage, uint32_t &hi, uint32_t &lo, uint32_t &nb, uint32_t &wi,
+                                                uint32_t val, uint32_t len) {
+    hi = __funnelshift_lc(lo, hi, len);
+    lo = __funnelshift_lc(0u, lo, len) | val;
+    nb += len;
+    if (nb >= 32u) stage[wi] = __funnelshift_r(lo, hi, nb);
+    wi += nb >> 5;
+    nb &= 31u;
 }
 
 __device__ __forceinline__ bool table_usable(const dc_huff_table *tab, int32_t *d_status) {
@@ -59,26 +98,24 @@ __device__ __forceinline__ bool table_usable(const dc_huff_table *tab, int32_t *
 
 // ------------------------------------------------------------------------------------------ E1 count
 __global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t *__restrict__ in, size_t n,
-                                                                   const dc_huff_table *__restrict__ tab,
-                                                                   uint32_t *__restrict__ run_bits, unsigned int nruns,
-                                                                   int32_t *__restrict__ d_status) {
+                                                                   const dc_huff_table *__restrict__ tab, EncWorkspace ws,
+                                                                   unsigned int nruns, int32_t *__restrict__ d_status) {
     __shared__ uint32_t s_len[256];
-    __shared__ uint32_t s_sum;
+    __shared__ uint32_t s_chunk[kEncWarps];
     if (!table_usable(tab, d_status)) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_len[tid] = (uint32_t)(tab->enc64[tid] >> 32);
-    if (tid == 0) s_sum = 0;
     __syncthreads();
     bool missing = false;
     for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
-        const size_t base = (size_t)run * kRunBytes;
+        const size_t base = (size_t)run * kRunBytes + (size_t)warp * kChunkBytes;  // this warp's chunk
         uint32_t sum = 0;
-        if (base + kRunBytes <= n) {
-            uint4 v[kRunTiles];
+        if (base + kChunkBytes <= n) {
+            uint4 v[kChunkSubs];
 #pragma unroll
-            for (int j = 0; j < kRunTiles; j++) v[j] = ldg_stream((const uint4 *)(in + base) + j * kEncThreads + tid);
+            for (int j = 0; j < kChunkSubs; j++) v[j] = ldg_stream((const uint4 *)(in + base) + j * 32 + lane);
 #pragma unroll
-            for (int j = 0; j < kRunTiles; j++) {
+            for (int j = 0; j < kChunkSubs; j++) {
                 const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
@@ -88,7 +125,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t
                 }
             }
         } else {
-            for (size_t i = base + tid; i < n; i += kEncThreads) {
+            for (size_t i = base + lane; i < n && i < base + kChunkBytes; i += 32) {
                 const uint32_t l = s_len[in[i]];
                 missing |= l == 0;
                 sum += l;
@@ -96,9 +133,19 @@ __global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-        if ((tid & 31) == 0) atomicAdd(&s_sum, sum);
+        if (lane == 0) s_chunk[warp] = sum;
         __syncthreads();
-        if (tid == 0) { run_bits[run] = s_sum; s_sum = 0; }
+        if (tid < kEncWarps) {
+            uint32_t rel = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < kEncWarps; w++) {
+                const uint32_t x = s_chunk[w];
+                if (w < tid) rel += x;
+                tot += x;
+            }
+            ws.chunk_rel[(size_t)run * kEncWarps + tid] = rel;
+            if (tid == 0) ws.run_bits[run] = tot;
+        }
         __syncthreads();
     }
     if (missing) set_status(d_status, DC_ERR_SYMBOL);
@@ -116,7 +163,6 @@ __global__ void __launch_bounds__(kScanThreads) encode_scan_kernel(const dc_huff
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ok = tab->status == DC_OK && tab->bits_per_digit != 0;
     if (tid == 0) s_carry = 0;
-    for (unsigned int i = tid; i <= nruns; i += kScanThreads) ws.bstate[i] = 0;
     __syncthreads();
     for (unsigned int base = 0; base < nruns; base += kScanThreads * kScanItems) {
         const unsigned int first = base + tid * kScanItems;
@@ -179,17 +225,46 @@ __device__ __forceinline__ void boundary_merge(const EncWorkspace &ws, unsigned 
     }
 }
 
+// ---- A. 16 symbols -> 8 code pairs (narrow) or 16 codes (wide), kept in registers; returns the thread's bit total
+template <bool WIDE, bool FULL, typename entry_t, int kItems>
+__device__ __forceinline__ uint32_t lookup_items(const entry_t *s_enc, const uint32_t (&w)[4], int valid,
+                                                 uint32_t (&item_val)[kItems], uint32_t (&item_len)[kItems]) {
+    uint32_t bits = 0;
+    if (WIDE) {
+#pragma unroll
+        for (int k = 0; k < kEncPerThread; k++) {
+            unsigned long long e = s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+            if (!FULL && k >= valid) e = 0;
+            item_val[k % kItems] = (uint32_t)e;
+            item_len[k % kItems] = (uint32_t)(e >> 32);
+            bits += (uint32_t)(e >> 32);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kEncPerThread; k += 2) {
+            uint32_t e0 = (uint32_t)s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+            uint32_t e1 = (uint32_t)s_enc[(w[k >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu];
+            if (!FULL && k >= valid) e0 = 0;
+            if (!FULL && k + 1 >= valid) e1 = 0;
+            const uint32_t l1 = e1 & 63u;
+            item_val[(k / 2) % kItems] = ((e0 >> 6) << l1) | (e1 >> 6);
+            item_len[(k / 2) % kItems] = (e0 & 63u) + l1;
+            bits += (e0 & 63u) + l1;
+        }
+    }
+    return bits;
+}
+
 template <bool WIDE>
-__global__ void __launch_bounds__(kEncThreads) encode_run_kernel(const uint8_t *__restrict__ in, size_t n,
+__global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(const uint8_t *__restrict__ in, size_t n,
                                                                  const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
                                                                  size_t out_cap, unsigned phase, EncWorkspace ws,
                                                                  unsigned int nruns, int32_t *__restrict__ d_status) {
     typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type entry_t;
     constexpr int kStageWords = EncCfg<WIDE>::kStageWords;
-    constexpr int kItems = WIDE ? kEncPerThread : kEncPerThread / 2;  // codes (WIDE) or code pairs per thread
-    __shared__ __align__(16) uint32_t stage[kStageWords];
+    constexpr int kItems = WIDE ? kEncPerThread : kEncPerThread / 2;  // codes (WIDE) or code pairs per lane
+    __shared__ __align__(16) uint32_t s_stage[kEncWarps][kStageWords];
     __shared__ entry_t s_enc[256];
-    __shared__ uint32_t s_warp_bits[kEncThreads / 32];
 
     if (tab->status != DC_OK || tab->bits_per_digit == 0) return;  // reported by the count kernel
     if ((tab->max_bits > kNarrowBits) != WIDE) return;            // the other instantiation handles this table
@@ -202,145 +277,135 @@ __global__ void __launch_bounds__(kEncThreads) encode_run_kernel(const uint8_t *
         return;
     }
     s_enc[tid] = WIDE ? (entry_t)tab->enc64[tid] : (entry_t)tab->enc[tid];
+    __syncthreads();
+    uint32_t *stage = s_stage[warp];
+    const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
 
     for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
-        const size_t run_base = (size_t)run * kRunBytes;
-        const int ntiles = (int)min((size_t)kRunTiles, (n - run_base + kEncTile - 1) / kEncTile);
-        unsigned long long g = (unsigned long long)phase + ws.run_off[run];  // global bit position of the next tile
-        const bool last_run = run == nruns - 1;
-        uint32_t carried = 0;  // threads 0..3: the last 128 bits of the previous tile of this run
+        const size_t chunk = (size_t)run * kEncWarps + warp;
+        if (chunk >= nchunks) continue;
+        const size_t chunk_base = chunk * kChunkBytes;
+        const size_t chunk_len = min((size_t)kChunkBytes, n - chunk_base);
+        const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
+        const int nfull = (int)(chunk_len / kSubTile);  // sub-tiles in which every lane has 16 symbols
+        unsigned long long g = (unsigned long long)phase + ws.run_off[run] + ws.chunk_rel[chunk];  // next bit to write
+        const bool last_chunk = chunk == nchunks - 1;
+        uint32_t carried = 0;  // lanes 0..3: the last 128 bits of the previous sub-tile of this chunk
+        const uint8_t *src = in + chunk_base + (size_t)lane * kEncPerThread;  // this lane's 16 symbols of sub-tile 0
 
         uint4 next = make_uint4(0, 0, 0, 0);
-        if (run_base + (size_t)tid * kEncPerThread + kEncPerThread <= n)
-            next = ldg_stream((const uint4 *)(in + run_base) + tid);
+        if (nfull > 0) next = ldg_stream((const uint4 *)src);
 
-        for (int t = 0; t < ntiles; t++) {
-            const size_t base = run_base + (size_t)t * kEncTile + (size_t)tid * kEncPerThread;
-            __syncthreads();  // the previous tile's copy-out has read the staging buffer
-            for (int i = tid; i < kStageWords / 4; i += kEncThreads) ((uint4 *)stage)[i] = make_uint4(0, 0, 0, 0);
-            __syncthreads();
-            if (tid < 4) stage[tid] = carried;
-
-            // ---- A. 16 symbols -> codes (pairs)
-            uint32_t w[4] = {next.x, next.y, next.z, next.w};
-            int valid = kEncPerThread;
-            if (base + kEncPerThread > n) {
-                valid = base < n ? (int)(n - base) : 0;
-                w[0] = w[1] = w[2] = w[3] = 0;
-                for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
-            }
-            if (t + 1 < ntiles && base + kEncTile + kEncPerThread <= n) next = ldg_stream((const uint4 *)(in + base + kEncTile));
+#pragma unroll 1
+        for (int t = 0; t < nsub; t++, src += kSubTile) {
             uint32_t item_val[kItems], item_len[kItems];
-            uint32_t my_bits = 0;
-            if (WIDE) {
-#pragma unroll
-                for (int k = 0; k < kEncPerThread; k++) {
-                    unsigned long long e = s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-                    if (k >= valid) e = 0;
-                    item_val[k % kItems] = (uint32_t)e;
-                    item_len[k % kItems] = (uint32_t)(e >> 32);
-                    my_bits += (uint32_t)(e >> 32);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kEncPerThread; k += 2) {
-                    uint32_t e0 = (uint32_t)s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-                    uint32_t e1 = (uint32_t)s_enc[(w[k >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu];
-                    if (k >= valid) e0 = 0;
-                    if (k + 1 >= valid) e1 = 0;
-                    const uint32_t l1 = e1 & 63u;
-                    item_val[(k / 2) % kItems] = ((e0 >> 6) << l1) | (e1 >> 6);
-                    item_len[(k / 2) % kItems] = (e0 & 63u) + l1;
-                    my_bits += (e0 & 63u) + l1;
-                }
+            uint32_t my_bits;
+            if (t < nfull) {
+                const uint32_t w[4] = {next.x, next.y, next.z, next.w};
+                if (t + 1 < nfull) next = ldg_stream((const uint4 *)(src + kSubTile));
+                my_bits = lookup_items<WIDE, true, entry_t, kItems>(s_enc, w, kEncPerThread, item_val, item_len);
+            } else {  // the ragged last sub-tile of the stream
+                const size_t base = chunk_base + (size_t)t * kSubTile + (size_t)lane * kEncPerThread;
+                const int valid = base < n ? (int)min((size_t)kEncPerThread, n - base) : 0;
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)src[k] << (8 * (k & 3));
+                my_bits = lookup_items<WIDE, false, entry_t, kItems>(s_enc, w, valid, item_val, item_len);
             }
 
-            // ---- B. exclusive scan of bit totals over the CTA
+            // ---- B. exclusive scan of bit totals over the warp
             uint32_t incl = my_bits;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= d) incl += x;
             }
-            if (lane == 31) s_warp_bits[warp] = incl;
-            __syncthreads();
-            uint32_t warp_off = 0, tile_bits = 0;
-#pragma unroll
-            for (int i = 0; i < kEncThreads / 32; i++) {
-                const uint32_t x = s_warp_bits[i];
-                if (i < warp) warp_off += x;
-                tile_bits += x;
-            }
+            const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            // every lane holds >= 32 bits: each staging word is then shared by at most two NEIGHBOURING lanes
+            const bool fast = __all_sync(0xFFFFFFFFu, my_bits >= 32u);
 
             // ---- C. stream the codes into the staging buffer (own bits start at staging bit 128)
-            if (my_bits) {
-                const uint32_t pos = 128u + warp_off + incl - my_bits;
-                uint32_t wi = pos >> 5, nb = pos & 31;
-                unsigned long long acc = 0;
+            __syncwarp();  // the previous sub-tile's copy-out has read the staging buffer
+            if (lane < 4) stage[lane] = carried;
+            const uint32_t pos = 128u + incl - my_bits;
+            uint32_t wi = pos >> 5, nb = pos & 31, hi = 0, lo = 0;
+            if (fast) {
+                // plain stores: a lane writes every word it completes; the leading `nb` bits of its first word
+                // belong to its left neighbour, whose trailing partial word arrives by shuffle afterwards
+                const uint32_t first_wi = wi, lead = nb;
 #pragma unroll
-                for (int k = 0; k < kItems; k++) {
-                    acc = (acc << item_len[k]) | item_val[k];
-                    nb += item_len[k];
-                    if (nb >= 32) {
-                        atomicOr(&stage[wi], (uint32_t)(acc >> (nb - 32)));
-                        wi++;
-                        nb -= 32;
-                    }
+                for (int k = 0; k < kItems; k++) emit_bits_owned(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
+                const uint32_t my_tail = nb ? lo << (32u - nb) : 0u;  // trailing partial word, left-aligned
+                const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, my_tail, 1);
+                if (lane != 0 && lead != 0) stage[first_wi] |= left_tail;
+                if (lane == 31) {  // zero padding behind the last bit: the copy-out reads up to 160 bits past it
+                    stage[wi] = my_tail;
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) stage[wi + k] = 0;
                 }
-                if (nb) atomicOr(&stage[wi], (uint32_t)(acc << (32 - nb)));
+            } else {
+                for (int i = 4 + lane; i < kStageWords; i += 32) stage[i] = 0;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < kItems; k++) emit_bits(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
+                stage_or_if(stage + wi, lo << ((32u - nb) & 31u), nb != 0u);
             }
-            __syncthreads();
+            __syncwarp();
 
             // ---- D. copy-out at the global alignment
             const unsigned long long gend = g + tile_bits;
-            const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this tile
+            const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this sub-tile
             const uint32_t r = (uint32_t)(g & 127);
-            const bool last_tile = t == ntiles - 1;
-            const bool stream_end = last_run && last_tile;
-            const bool shared_first = t == 0 && run != 0 && r != 0;  // first word also holds the previous run's bits
-            for (unsigned long long v = v0 + (shared_first ? 1 : 0) + tid; v < v1; v += kEncThreads) {
-                const uint32_t sbit = (uint32_t)(v - v0) * 128u + (128u - r);
-                uint4 o;
-                o.x = bswap32(stage_word(stage, sbit));
-                o.y = bswap32(stage_word(stage, sbit + 32));
-                o.z = bswap32(stage_word(stage, sbit + 64));
-                o.w = bswap32(stage_word(stage, sbit + 96));
-                stg_stream((uint4 *)out + v, o);
+            const bool last_sub = t == nsub - 1;
+            const bool stream_end = last_chunk && last_sub;
+            const bool shared_first = t == 0 && chunk != 0 && r != 0;  // first word also holds the previous chunk's bits
+            {
+                const uint32_t nvec = (uint32_t)(v1 - v0);
+                uint4 *dst = (uint4 *)out + v0;
+                for (uint32_t j = (shared_first ? 1u : 0u) + lane; j < nvec; j += 32) {
+                    const uint32_t sbit = j * 128u + (128u - r);
+                    uint4 o;
+                    o.x = bswap32(stage_word(stage, sbit));
+                    o.y = bswap32(stage_word(stage, sbit + 32));
+                    o.z = bswap32(stage_word(stage, sbit + 64));
+                    o.w = bswap32(stage_word(stage, sbit + 96));
+                    stg_stream(dst + j, o);
+                }
             }
-            if (shared_first && tid == 32) {  // (v1 == v0 only for a tiny final run: the word is shared AND last)
+            if (shared_first && lane == 8) {  // (v1 == v0 only for a tiny final chunk: the word is shared AND last)
                 const uint32_t sbit = 128u - r;
                 const uint4 m = make_uint4(stage_word(stage, sbit), stage_word(stage, sbit + 32),
                                            stage_word(stage, sbit + 64), stage_word(stage, sbit + 96));
-                boundary_merge(ws, run, false, m, out, v0, stream_bytes);
+                boundary_merge(ws, chunk, false, m, out, v0, stream_bytes);
             }
-            if (last_tile && (gend & 127) != 0 && !(shared_first && v1 == v0)) {
+            if (last_sub && (gend & 127) != 0 && !(shared_first && v1 == v0)) {
                 const uint32_t sbit = (uint32_t)(v1 - v0) * 128u + (128u - r);
                 if (stream_end) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
                     const uint32_t rem_bytes = (uint32_t)(((gend & 127) + 7) >> 3);
-                    if (tid < (int)rem_bytes) out[v1 * 16 + tid] = (uint8_t)(stage_word(stage, sbit + 8u * tid) >> 24);
-                } else if (tid == 64) {  // the word shared with the next run
+                    if (lane < (int)rem_bytes) out[v1 * 16 + lane] = (uint8_t)(stage_word(stage, sbit + 8u * lane) >> 24);
+                } else if (lane == 16) {  // the word shared with the next chunk
                     const uint4 m = make_uint4(stage_word(stage, sbit), stage_word(stage, sbit + 32),
                                                stage_word(stage, sbit + 64), stage_word(stage, sbit + 96));
-                    boundary_merge(ws, run + 1, true, m, out, v1, stream_bytes);
+                    boundary_merge(ws, chunk + 1, true, m, out, v1, stream_bytes);
                 }
             }
-            if (tid < 4) carried = stage_word(stage, tile_bits + 32u * tid);  // last 128 bits of this tile
+            if (lane < 4) carried = stage_word(stage, tile_bits + 32u * lane);  // last 128 bits of this sub-tile
             g = gend;
         }
     }
 }
 
-static size_t enc_ws_layout(size_t n, size_t off[5]) {
-    const size_t nruns = (n + kRunBytes - 1) / kRunBytes;
+static size_t enc_ws_layout(size_t n, size_t off[6]) {
+    const size_t nruns = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o[5];
-    o[0] = take(nruns * 4);         // run_bits
-    o[1] = take((nruns + 1) * 8);   // run_off
-    o[2] = take((nruns + 1) * 4);   // bstate
-    o[3] = take((nruns + 1) * 16);  // bleft
-    o[4] = take((nruns + 1) * 16);  // bright
-    if (off) for (int i = 0; i < 5; i++) off[i] = o[i];
+    size_t o[6];
+    o[0] = take(nruns * 4);              // run_bits
+    o[1] = take(nruns * kEncWarps * 4);  // chunk_rel
+    o[2] = take((nruns + 1) * 8);        // run_off
+    o[3] = take((nchunks + 1) * 4);      // bstate
+    o[4] = take((nchunks + 1) * 16);     // bleft
+    o[5] = take((nchunks + 1) * 16);     // bright
+    if (off) for (int i = 0; i < 6; i++) off[i] = o[i];
     return p;
 }
 
@@ -359,23 +424,25 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     if (d_total_bits) DC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), st));
     if (n == 0) return DC_OK;
-    size_t off[5];
+    size_t off[6];
     const size_t need = enc_ws_layout(n, off);
     if (workspace_bytes < need) return DC_ERR_CAPACITY;
-    const size_t nruns64 = (n + kRunBytes - 1) / kRunBytes;
-    if (nruns64 > 0x7FFFFFF0ull) return DC_ERR_ARG;
+    const size_t nruns64 = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
+    if (nruns64 > 0x0FFFFFF0ull) return DC_ERR_ARG;
     const unsigned int nruns = (unsigned int)nruns64;
     char *w = (char *)d_workspace;
     EncWorkspace ws;
     ws.run_bits = (uint32_t *)(w + off[0]);
-    ws.run_off = (unsigned long long *)(w + off[1]);
-    ws.bstate = (uint32_t *)(w + off[2]);
-    ws.bleft = (uint4 *)(w + off[3]);
-    ws.bright = (uint4 *)(w + off[4]);
+    ws.chunk_rel = (uint32_t *)(w + off[1]);
+    ws.run_off = (unsigned long long *)(w + off[2]);
+    ws.bstate = (uint32_t *)(w + off[3]);
+    ws.bleft = (uint4 *)(w + off[4]);
+    ws.bright = (uint4 *)(w + off[5]);
+    DC_CUDA_TRY(cudaMemsetAsync(ws.bstate, 0, (nchunks + 1) * 4, st));
     const unsigned int sms = (unsigned int)sm_count();
     {
         LaunchScope ls(DC_K_ENCODE_COUNT, st);
-        encode_count_kernel<<<min(nruns, sms * 8u), kEncThreads, 0, st>>>(d_in, n, d_table, ws.run_bits, nruns, d_status);
+        encode_count_kernel<<<min(nruns, sms * 8u), kEncThreads, 0, st>>>(d_in, n, d_table, ws, nruns, d_status);
     }
     {
         LaunchScope ls(DC_K_ENCODE_SCAN, st);
