@@ -38,6 +38,7 @@ class HuffTableStruct(C.Structure):
         ("enc", C.c_uint32 * 256), ("enc64", C.c_uint64 * 256),
         ("first_code", C.c_uint32 * 32), ("len_count", C.c_uint32 * 32), ("len_offset", C.c_uint32 * 32),
         ("sorted", C.c_uint16 * (DC_NSLOTS + 1)), ("lut", C.c_uint16 * (1 << DC_LUT_BITS)),
+        ("lut_count", C.c_uint32 * (1 << DC_LUT_BITS)), ("lut_pair", C.c_uint32 * (1 << DC_LUT_BITS)),
     ]
 
 
@@ -81,6 +82,7 @@ SYMBOLS = [
 # bench/test hooks that are exported but not part of the public header
 EXTRA_SYMBOLS = [
     ("dc_histogram_u8_variant", _i, [_vp, _sz, _vp, _i, _vp]),
+    ("dc_debug_decode_mode", _i, [_i]),
 ]
 
 _lib = None

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     __shared__ int s_len[kTabCap];                    // symbol -> length in digits
     __shared__ unsigned int s_lencount[64], s_first[64], s_off[64];
     __shared__ int s_warp[32];
+    uint16_t *s_lut = (uint16_t *)s_cnt;  // the single-symbol LUT, reusing the leaf-count array (8 KB) once the tree is done
     __shared__ int s_nint, s_minlen, s_maxlen, s_status;
     __shared__ unsigned long long s_totsym, s_totbits;
 
@@ -207,6 +208,24 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             }
         }
         tab->lut[e] = (uint16_t)entry;
+        s_lut[e] = (uint16_t)entry;
+    }
+    __syncthreads();
+    // multi-symbol tables: greedily take every code that lies completely inside the 12 index bits
+    for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
+        unsigned int used = 0, count = 0, first = 0, sym0 = 0, sym1 = 0, used2 = 0;
+        while (used < DC_LUT_BITS) {
+            const unsigned int one = s_lut[((unsigned int)e << used) & ((1u << DC_LUT_BITS) - 1u)];
+            const unsigned int nb = one >> 8;
+            if (nb == 0 || used + nb > DC_LUT_BITS) break;
+            if (count == 0) { first = nb; sym0 = one & 0xFFu; }
+            if (count == 1) sym1 = one & 0xFFu;
+            used += nb;
+            count++;
+            if (count <= 2) used2 = used;
+        }
+        tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : 0u;
+        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | ((count < 2 ? count : 2u) << 22) | (first << 24)) : 0u;
     }
     if (tid == 0) {
         tab->n_ary = n_ary;

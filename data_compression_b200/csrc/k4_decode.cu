@@ -5,19 +5,25 @@
 // layout of k3_encode.cu from the bitstream alone -- no side information besides the code lengths, the
 // bit count and the symbol count.
 //
-// The stream is cut into 128-bit subsequences; a tile is 256 subsequences (4 KB of bitstream):
-//   D1 speculate+synchronise: every thread decodes its subsequence from bit 0 as if a code started there,
-//      then repeatedly restarts from the exit point of its left neighbour until no start changes.  Codes
-//      self-synchronise after a few symbols, so this converges in ~2 rounds.  Per subsequence the start
-//      offset and symbol count are recorded; per tile the exit offset and symbol count.
-//   D2 tile hand-off: a tile assumed its first code starts at bit 0; one thread per tile re-decodes from
-//      the predecessor tile's exit until its path merges with the recorded one.  Re-run until quiescent
-//      (normally one pass + one confirming pass).
-//   D3 exclusive scan of tile symbol counts -> output offsets; total checked against n_out.
-//   D4 decode+write: every thread decodes its subsequence from its now-exact start into a shared-memory
-//      staging tile, which is copied out with aligned 16-byte stores.
+// The stream is cut into 128-bit subsequences (one per lane), 32 of them form a warp tile (512 B) and 32
+// tiles a segment (16 KB, one warp).  FAST PATH (three launches, no spin-waits):
+//   F1 synchronise+count: a warp walks its segment tile by tile.  Every lane decodes its subsequence from
+//      a guessed start as if a code began there, then restarts from the exit point of its left
+//      neighbour (shuffle) until no start changes; codes self-synchronise after a few symbols, so this is
+//      ~2 rounds.  Multi-symbol look-ups (every code that lies inside the next 12 bits) keep a round at
+//      ~0.5 table reads per symbol.  Per subsequence the exact start offset and symbol count are stored
+//      (2 bytes per 16 bytes of bitstream); per segment the symbol count.  The first code of a segment is
+//      found by synchronising over the LAST tile of the previous segment (1/32 extra work); that is an
+//      assumption, so F2 checks it: assumed start of segment s == exit of segment s-1, for every s.
+//   F2 verify + exclusive scan of the segment counts -> output offsets; total checked against n_out.
+//   F3 decode+write: a warp re-walks its segment with exact starts, decodes two symbols per look-up into a
+//      shared-memory staging tile and copies it out with aligned 16-byte stores.
+// ROBUST PATH (the v1 kernels D1..D4 below): used when F2's check fails (a stream whose codes do not
+// self-synchronise within 4096 bits); hands the tile starts over iteratively, always terminates.
 // Unused code slots (the reference's dummy leaves) are legal on speculative paths -- they
 // advance by one digit and produce no symbol -- and are reported as DC_ERR_CORRUPT on the true path.
+#include <stdlib.h>
+
 #include "dc_common.cuh"
 
 namespace dc {
@@ -325,21 +331,346 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(const uint8_t
     }
 }
 
-static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbits, size_t off[8], unsigned long long *nsub_out,
+// ================================================================================================ fast path
+
+constexpr int kF_Threads = 256;
+constexpr int kF_Warps = kF_Threads / 32;
+constexpr int kF_TileWords = 32 * kSubBits / 32;   // 128 words = 512 B per warp tile
+constexpr int kF_Halo = 8;
+constexpr int kF_SegTiles = 32;                    // 16 KB of bitstream per warp
+constexpr int kF_StageBytes = 32 * kMaxSymPerSub + 32;
+
+struct FastTables {  // shared-memory copy: one multi-symbol LUT + the canonical arrays for the escape path
+    uint32_t lut[1 << DC_LUT_BITS];
+    uint32_t first_code[32], len_count[32], len_offset[32];
+    uint16_t sorted[DC_NSLOTS + 1];
+    int bpd, min_len, max_len;
+};
+
+__device__ __forceinline__ void load_fast_tables(FastTables *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut) {
+    for (int i = threadIdx.x; i < (1 << DC_LUT_BITS); i += blockDim.x) t->lut[i] = lut[i];
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        t->first_code[i] = tab->first_code[i];
+        t->len_count[i] = tab->len_count[i];
+        t->len_offset[i] = tab->len_offset[i];
+    }
+    for (int i = threadIdx.x; i <= DC_NSLOTS; i += blockDim.x) t->sorted[i] = tab->sorted[i];
+    if (threadIdx.x == 0) {
+        t->bpd = tab->bits_per_digit;
+        t->min_len = tab->min_len;
+        t->max_len = tab->max_len;
+    }
+}
+
+// escape path: canonical search over all lengths; returns the code's bits (0 = unused slot)
+__device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *sym) {
+    for (int l = t->min_len; l <= t->max_len; l++) {
+        const int lb = l * t->bpd;
+        const uint32_t v = lb >= 32 ? w : (w >> (32 - lb));
+        const uint32_t f = t->first_code[l], c = t->len_count[l];
+        if (c && v >= f && v - f < c) {
+            *sym = (int)t->sorted[t->len_offset[l] + (v - f)];
+            return lb;
+        }
+    }
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t peek32(const uint32_t *words, uint32_t p) {
+    return __funnelshift_l(words[(p >> 5) + 1], words[p >> 5], p & 31);
+}
+
+// count-only decode of bits [p, lim) of the warp tile (positions relative to the tile); lut = lut_count
+__device__ __forceinline__ void sync_decode(const FastTables *t, const uint32_t *words, uint32_t p, uint32_t lim,
+                                            uint32_t *p_end, uint32_t *count) {
+    uint32_t c = 0;
+    while ((int)p <= (int)lim - DC_LUT_BITS) {  // every code inside the 12-bit window starts before lim
+        const uint32_t w = peek32(words, p);
+        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
+        if (e) {
+            p += e & 0xFFu;
+            c += (e >> 16) & 0xFFu;
+        } else {
+            int sym;
+            const int nb = decode_escape(t, w, &sym);
+            p += nb ? nb : t->bpd;
+            c += nb ? 1u : 0u;
+        }
+    }
+    while (p < lim) {  // the last few bits: one code at a time
+        const uint32_t w = peek32(words, p);
+        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
+        if (e) {
+            p += e >> 24;
+            c += 1u;
+        } else {
+            int sym;
+            const int nb = decode_escape(t, w, &sym);
+            p += nb ? nb : t->bpd;
+            c += nb ? 1u : 0u;
+        }
+    }
+    *p_end = p;
+    *count = c;
+}
+
+// decode bits [p, lim) into dst; lut = lut_pair (two symbols per look-up)
+__device__ __forceinline__ void write_decode(const FastTables *t, const uint32_t *words, uint32_t p, uint32_t lim, uint8_t *dst,
+                                             uint32_t *p_end, uint32_t *count, bool *corrupt) {
+    uint32_t c = 0;
+    while ((int)p <= (int)lim - DC_LUT_BITS) {
+        const uint32_t w = peek32(words, p);
+        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
+        if (e) {
+            dst[c] = (uint8_t)e;
+            if (e & (2u << 22)) dst[c + 1] = (uint8_t)(e >> 8);
+            p += (e >> 16) & 0x3Fu;
+            c += (e >> 22) & 3u;
+        } else {
+            int sym = 0;
+            const int nb = decode_escape(t, w, &sym);
+            if (nb) dst[c++] = (uint8_t)sym; else *corrupt = true;
+            p += nb ? nb : t->bpd;
+        }
+    }
+    while (p < lim) {
+        const uint32_t w = peek32(words, p);
+        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
+        if (e) {
+            dst[c++] = (uint8_t)e;
+            p += e >> 24;
+        } else {
+            int sym = 0;
+            const int nb = decode_escape(t, w, &sym);
+            if (nb) dst[c++] = (uint8_t)sym; else *corrupt = true;
+            p += nb ? nb : t->bpd;
+        }
+    }
+    *p_end = p;
+    *count = c;
+}
+
+struct FastWorkspace {
+    uint16_t *sub_info;                              // [nsub] start offset | symbol count << 8
+    uint32_t *seg_cnt, *seg_assumed, *seg_exit;      // [nseg]
+    unsigned long long *seg_off;                     // [nseg]
+    int32_t *mismatch;                               // F2: some segment started on a wrong guess
+};
+
+// warp-cooperative load of warp tile `tile` (+halo) as big-endian words
+__device__ __forceinline__ void load_warp_tile(uint32_t *words, const uint8_t *__restrict__ d_bits, unsigned long long tile,
+                                               unsigned long long nvec, int lane) {
+    const uint4 *v = (const uint4 *)d_bits;
+    const unsigned long long gv = tile * 32 + lane;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (gv < nvec) x = ldg_stream(v + gv);
+    uint4 y = make_uint4(bswap32(x.x), bswap32(x.y), bswap32(x.z), bswap32(x.w));
+    ((uint4 *)words)[lane] = y;
+    if (lane < kF_Halo / 4) {
+        const unsigned long long hv = tile * 32 + 32 + lane;
+        uint4 h = make_uint4(0, 0, 0, 0);
+        if (hv < nvec) h = ldg_stream(v + hv);
+        ((uint4 *)words)[32 + lane] = make_uint4(bswap32(h.x), bswap32(h.y), bswap32(h.z), bswap32(h.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ F1
+__global__ void __launch_bounds__(kF_Threads) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
+                                                                      unsigned long long end, const dc_huff_table *__restrict__ tab,
+                                                                      FastWorkspace ws, unsigned long long nsub,
+                                                                      unsigned long long ntiles, unsigned long long nseg) {
+    __shared__ FastTables s_t;
+    __shared__ __align__(16) uint32_t s_words[kF_Warps][kF_TileWords + kF_Halo];
+    load_fast_tables(&s_t, tab, tab->lut_count);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *words = s_words[warp];
+    const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
+    const uint32_t guess = (uint32_t)(bit_start & 7);  // fixed-length-like codes keep the stream's phase
+    for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
+         seg += (unsigned long long)gridDim.x * kF_Warps) {
+        const unsigned long long tile0 = seg * kF_SegTiles;
+        uint32_t carry = seg == 0 ? (uint32_t)bit_start : guess, assumed = carry, total = 0;
+        for (int tt = seg == 0 ? 0 : -1; tt < kF_SegTiles; tt++) {  // tt == -1: the warm-up tile of the previous segment
+            const unsigned long long tile = tile0 + tt;
+            if (tile >= ntiles) break;
+            __syncwarp();
+            load_warp_tile(words, d_bits, tile, nvec, lane);
+            __syncwarp();
+            const unsigned long long tile_bit0 = tile * (unsigned long long)(32 * kSubBits);
+            const uint32_t sub_lo = lane * kSubBits;
+            const bool active = tile_bit0 + sub_lo < end;
+            const unsigned long long rest = end - tile_bit0;  // > 0 for every launched tile
+            const uint32_t lim = rest < sub_lo + kSubBits ? (uint32_t)rest : sub_lo + kSubBits;
+            uint32_t start = lane == 0 ? carry : guess, p_end = sub_lo + kSubBits, cnt = 0;
+            if (active) sync_decode(&s_t, words, sub_lo + start, lim, &p_end, &cnt);
+            uint32_t my_exit = p_end >= sub_lo + kSubBits ? p_end - (sub_lo + kSubBits) : 0u;
+            while (true) {
+                uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, my_exit, 1);
+                if (lane == 0) ns = start;
+                const bool redo = active && ns != start;
+                if (!__any_sync(0xFFFFFFFFu, redo)) break;
+                if (redo) {
+                    start = ns;
+                    sync_decode(&s_t, words, sub_lo + start, lim, &p_end, &cnt);
+                    my_exit = p_end >= sub_lo + kSubBits ? p_end - (sub_lo + kSubBits) : 0u;
+                }
+            }
+            carry = __shfl_sync(0xFFFFFFFFu, my_exit, 31);
+            if (tt < 0) {
+                assumed = carry;
+            } else {
+                const unsigned long long sidx = tile * 32 + lane;
+                if (sidx < nsub) ws.sub_info[sidx] = (uint16_t)(start | (cnt << 8));
+                total += cnt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        if (lane == 0) {
+            ws.seg_cnt[seg] = total;
+            ws.seg_assumed[seg] = assumed;
+            ws.seg_exit[seg] = carry;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ F2
+__global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
+                                                                int32_t *__restrict__ d_status) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_bad = 0; }
+    __syncthreads();
+    constexpr int kItems = 4;
+    for (unsigned long long base = 0; base < nseg; base += 1024 * kItems) {
+        const unsigned long long first = base + (unsigned long long)tid * kItems;
+        uint32_t item[kItems];
+        unsigned long long mine = 0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < kItems; k++) {
+            const unsigned long long i = first + k;
+            item[k] = i < nseg ? ws.seg_cnt[i] : 0u;
+            mine += item[k];
+            if (i < nseg && i > 0) bad |= ws.seg_assumed[i] != ws.seg_exit[i - 1];
+        }
+        if (bad) s_bad = 1;
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += x;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry;
+        for (int w = 0; w < warp; w++) off += s_warp[w];
+        off += incl - mine;
+#pragma unroll
+        for (int k = 0; k < kItems; k++) {
+            if (first + k < nseg) ws.seg_off[first + k] = off;
+            off += item[k];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = off;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *ws.mismatch = s_bad;
+        if (!s_bad && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ F3
+__global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
+                                                                       const dc_huff_table *__restrict__ tab, FastWorkspace ws,
+                                                                       unsigned long long nsub, unsigned long long ntiles,
+                                                                       unsigned long long nseg, uint8_t *__restrict__ out,
+                                                                       unsigned long long n_out, int32_t *__restrict__ d_status) {
+    extern __shared__ __align__(16) uint8_t fast_smem[];
+    FastTables *s_t = (FastTables *)fast_smem;
+    uint32_t *s_words = (uint32_t *)(fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15));
+    uint8_t *s_stage = (uint8_t *)(s_words + kF_Warps * (kF_TileWords + kF_Halo));
+    if (*ws.mismatch) return;  // the robust path redoes the stream
+    load_fast_tables(s_t, tab, tab->lut_pair);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *words = s_words + warp * (kF_TileWords + kF_Halo);
+    uint8_t *stage = s_stage + warp * kF_StageBytes;
+    const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
+    bool corrupt = false;
+    for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
+         seg += (unsigned long long)gridDim.x * kF_Warps) {
+        unsigned long long ob = ws.seg_off[seg];
+        for (int tt = 0; tt < kF_SegTiles; tt++) {
+            const unsigned long long tile = seg * kF_SegTiles + tt;
+            if (tile >= ntiles) break;
+            __syncwarp();
+            load_warp_tile(words, d_bits, tile, nvec, lane);
+            const unsigned long long sidx = tile * 32 + lane;
+            const uint32_t info = sidx < nsub ? ws.sub_info[sidx] : 0u;
+            const uint32_t start = info & 0xFFu, my_cnt = info >> 8;
+            uint32_t incl = my_cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += x;
+            }
+            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t a = (uint32_t)(((uintptr_t)out + ob) & 15);
+            __syncwarp();
+            const unsigned long long tile_bit0 = tile * (unsigned long long)(32 * kSubBits);
+            const uint32_t sub_lo = lane * kSubBits;
+            if (tile_bit0 + sub_lo < end && sidx < nsub) {
+                const unsigned long long rest = end - tile_bit0;
+                const uint32_t lim = rest < sub_lo + kSubBits ? (uint32_t)rest : sub_lo + kSubBits;
+                uint32_t p_end, c;
+                write_decode(s_t, words, sub_lo + start, lim, stage + a + (incl - my_cnt), &p_end, &c, &corrupt);
+                if (c != my_cnt || tile_bit0 + p_end > end) corrupt = true;
+            }
+            __syncwarp();
+            // copy-out: staging byte i <-> out[ob - a + i]; 16-byte words are aligned on both sides
+            const uint32_t span = a + tile_total;
+            for (uint32_t j = lane; j * 16 < span; j += 32) {
+                const uint32_t lo = j * 16, hi = lo + 16;
+                const unsigned long long g = ob - a + lo;
+                if (lo >= a && hi <= span && g + 16 <= n_out) {
+                    stg_stream((uint4 *)(out + g), *(const uint4 *)(stage + lo));
+                } else {
+                    for (uint32_t k = lo < a ? a : lo; k < hi && k < span; k++)
+                        if (ob - a + k < n_out) out[ob - a + k] = stage[k];
+                }
+            }
+            ob += tile_total;
+        }
+    }
+    if (corrupt) set_status(d_status, DC_ERR_CORRUPT);
+}
+
+static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbits, size_t off[12], unsigned long long *nsub_out,
                             unsigned long long *ntiles_out) {
     const unsigned long long end = bit_start + nbits;
     const unsigned long long nsub = (end + kSubBits - 1) / kSubBits;
-    const unsigned long long ntiles = (nsub + kTileSubs - 1) / kTileSubs;
+    const unsigned long long ntiles = (nsub + kTileSubs - 1) / kTileSubs;        // robust path: 256 subsequences
+    const unsigned long long nwt = (nsub + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;  // fast path
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o[8];
+    size_t o[12];
     o[0] = take(nsub);            // sub_start
     o[1] = take(nsub);            // sub_cnt
     o[2] = take(ntiles * 4);      // tile_start
     o[3] = take(ntiles * 4);      // tile_exit
     o[4] = take(ntiles * 4);      // tile_cnt
     o[5] = take(ntiles * 8);      // tile_off
-    if (off) for (int i = 0; i < 6; i++) off[i] = o[i];
+    o[6] = take(nsub * 2);        // fast: sub_info
+    o[7] = take(nseg * 4);        // fast: seg_cnt
+    o[8] = take(nseg * 4);        // fast: seg_assumed
+    o[9] = take(nseg * 4);        // fast: seg_exit
+    o[10] = take(nseg * 8);       // fast: seg_off
+    if (off) for (int i = 0; i < 11; i++) off[i] = o[i];
     if (nsub_out) *nsub_out = nsub;
     if (ntiles_out) *ntiles_out = ntiles;
     return p;
@@ -353,39 +684,11 @@ extern "C" size_t dc_huff_decode_workspace_bytes(uint64_t bit_start, uint64_t nb
     return dec_ws_layout(bit_start, nbits, nullptr, nullptr, nullptr);
 }
 
-extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, const dc_huff_table *d_table,
-                              uint8_t *d_out, size_t n_out, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
-                              void *stream) {
-    if (!d_table || bit_start >= (uint64_t)kSubBits) return DC_ERR_ARG;
-    if (nbits && (!d_bits || !d_workspace || (n_out && !d_out))) return DC_ERR_ARG;
-    if ((((uintptr_t)d_bits | (uintptr_t)d_workspace) & 15) != 0) return DC_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
-    if (nbits == 0) return n_out == 0 ? DC_OK : DC_ERR_CORRUPT;
-    size_t off[8];
-    unsigned long long nsub, ntiles;
-    const size_t need = dec_ws_layout(bit_start, nbits, off, &nsub, &ntiles);
-    if (workspace_bytes < need) return DC_ERR_CAPACITY;
-    char *w = (char *)d_workspace;
-    DecWorkspace ws;
-    ws.changed = (int32_t *)w;
-    ws.total = (unsigned long long *)(w + 8);
-    ws.sub_start = (uint8_t *)(w + off[0]);
-    ws.sub_cnt = (uint8_t *)(w + off[1]);
-    ws.tile_start = (uint32_t *)(w + off[2]);
-    ws.tile_exit = (uint32_t *)(w + off[3]);
-    ws.tile_cnt = (uint32_t *)(w + off[4]);
-    ws.tile_off = (unsigned long long *)(w + off[5]);
-    const unsigned long long end = bit_start + nbits;
+// the v1 kernels: exact for any stream, iterates the tile hand-off until quiescent
+static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, const dc_huff_table *d_table,
+                         uint8_t *d_out, size_t n_out, int32_t *d_status, DecWorkspace ws, unsigned long long nsub,
+                         unsigned long long ntiles, cudaStream_t st) {
     const int sms = sm_count();
-
-    // the table must be usable before any bit is interpreted
-    int32_t tmeta[10];
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaStreamSynchronize(st));
-    if (tmeta[8] != DC_OK) return tmeta[8];
-    if (tmeta[1] == 0) return DC_ERR_RADIX;
-
     const int grid1 = (int)(ntiles < (unsigned long long)sms * 8 ? ntiles : (unsigned long long)sms * 8);
     {
         LaunchScope ls(DC_K_DECODE_SYNC, st);
@@ -420,4 +723,98 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     LaunchScope ls(DC_K_DECODE_WRITE, st);
     decode_write_kernel<<<grid4, kDecThreads, smem4, st>>>(d_bits, end, d_table, ws, nsub, ntiles, d_out, n_out, d_status);
     return cuda_status(cudaGetLastError());
+}
+
+// test hook: 1 = always take the robust path, 2 = pretend the fast path's guess failed after running it
+static int g_decode_force = -1;
+static int decode_force_mode() {
+    if (g_decode_force < 0) {
+        const char *e = getenv("DC_DECODE_FORCE");
+        g_decode_force = e ? atoi(e) : 0;
+    }
+    return g_decode_force;
+}
+// test hook (not in the public header): 0 = normal, 1 = robust path only, 2 = fast path, then the robust path anyway
+extern "C" int dc_debug_decode_mode(int mode) {
+    const int old = decode_force_mode();
+    g_decode_force = mode;
+    return old;
+}
+
+extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, const dc_huff_table *d_table,
+                              uint8_t *d_out, size_t n_out, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                              void *stream) {
+    if (!d_table || bit_start >= (uint64_t)kSubBits) return DC_ERR_ARG;
+    if (nbits && (!d_bits || !d_workspace || (n_out && !d_out))) return DC_ERR_ARG;
+    if ((((uintptr_t)d_bits | (uintptr_t)d_workspace) & 15) != 0) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    if (nbits == 0) return n_out == 0 ? DC_OK : DC_ERR_CORRUPT;
+    size_t off[12];
+    unsigned long long nsub, ntiles;
+    const size_t need = dec_ws_layout(bit_start, nbits, off, &nsub, &ntiles);
+    if (workspace_bytes < need) return DC_ERR_CAPACITY;
+    char *w = (char *)d_workspace;
+    DecWorkspace ws;
+    ws.changed = (int32_t *)w;
+    ws.total = (unsigned long long *)(w + 8);
+    ws.sub_start = (uint8_t *)(w + off[0]);
+    ws.sub_cnt = (uint8_t *)(w + off[1]);
+    ws.tile_start = (uint32_t *)(w + off[2]);
+    ws.tile_exit = (uint32_t *)(w + off[3]);
+    ws.tile_cnt = (uint32_t *)(w + off[4]);
+    ws.tile_off = (unsigned long long *)(w + off[5]);
+    FastWorkspace fw;
+    fw.mismatch = (int32_t *)(w + 16);
+    fw.sub_info = (uint16_t *)(w + off[6]);
+    fw.seg_cnt = (uint32_t *)(w + off[7]);
+    fw.seg_assumed = (uint32_t *)(w + off[8]);
+    fw.seg_exit = (uint32_t *)(w + off[9]);
+    fw.seg_off = (unsigned long long *)(w + off[10]);
+    const unsigned long long end = bit_start + nbits;
+    const unsigned long long nwt = (nsub + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
+    const unsigned long long sms = (unsigned long long)sm_count();
+
+    // the table must be usable before any bit is interpreted
+    int32_t tmeta[10];
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (tmeta[8] != DC_OK) return tmeta[8];
+    if (tmeta[1] == 0) return DC_ERR_RADIX;
+
+    const int force = decode_force_mode();
+    if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
+
+    const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
+        decode_fast_sync_kernel<<<(unsigned int)(want < sms * 8 ? want : sms * 8), kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table,
+                                                                                                       fw, nsub, nwt, nseg);
+    }
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status);
+    }
+    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * (kF_TileWords + kF_Halo) * 4 +
+                         (size_t)kF_Warps * kF_StageBytes;
+    static bool attr3 = false;
+    if (!attr3) {
+        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        attr3 = true;
+    }
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
+        decode_fast_write_kernel<<<(unsigned int)(want < sms * 4 ? want : sms * 4), kF_Threads, smem3, st>>>(
+            d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
+    }
+    DC_CUDA_TRY(cudaGetLastError());
+    // did every segment start on a code boundary?  (blocking read of one flag)
+    int32_t mismatch = 0;
+    DC_CUDA_TRY(cudaMemcpyAsync(&mismatch, fw.mismatch, sizeof mismatch, cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (mismatch || force == 2) {
+        if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+        return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
+    }
+    return DC_OK;
 }

@@ -78,6 +78,11 @@ typedef struct dc_huff_table {
     uint32_t len_offset[32];
     uint16_t sorted[DC_NSLOTS + 1]; /* symbols in (length, value) order */
     uint16_t lut[1 << DC_LUT_BITS]; /* index = next 12 bits: nbits << 8 | symbol; 0 = escape (longer/unused) */
+    /* multi-symbol tables, same index: every code that lies completely inside the 12 bits.
+     *   lut_count: total bits | count << 16 | first code's bits << 24            (0 = escape)
+     *   lut_pair : symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | count(1..2) << 22 | first bits << 24 */
+    uint32_t lut_count[1 << DC_LUT_BITS];
+    uint32_t lut_pair[1 << DC_LUT_BITS];
 } dc_huff_table;
 
 /* ------------------------------------------------------------------------- library */
@@ -105,6 +110,9 @@ enum dc_kernel_id {
     DC_K_DECODE_HANDOFF,
     DC_K_DECODE_SCAN,
     DC_K_DECODE_WRITE,
+    DC_K_DECODE_FAST_SYNC,
+    DC_K_DECODE_FAST_SCAN,
+    DC_K_DECODE_FAST_WRITE,
     DC_K_NYBBLE_PACK,
     DC_K_NYBBLE_UNPACK,
     DC_K_NYBBLE_TAIL,

@@ -222,6 +222,36 @@ def test_decode_matches_oracle_on_oracle_stream(dc, oracle):
             assert np.array_equal(oracle.unpack(payload, phase, bits, ln, n_ary, data.size), data)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_decode_robust_path(dc, oracle, mode):
+    """mode 1: the iterative hand-off kernels alone; mode 2: fast path first, then forced fallback."""
+    old = dc.lib().dc_debug_decode_mode(mode)
+    try:
+        for n_ary in PACKABLE:
+            data = _zipf(dc, 200003, seed=8 + n_ary)
+            table = dc.huff_build(dc.histogram(data), n_ary)
+            for phase in (0, 5):
+                res = dc.huff_encode(data, table, bit_phase=phase)
+                out, status = dc.huff_decode(res.payload, res.bits(), table, data.numel(), bit_start=phase)
+                assert int(status.item()) == 0 and torch.equal(out, data), (mode, n_ary, phase)
+    finally:
+        dc.lib().dc_debug_decode_mode(old)
+
+
+def test_decode_fixed_length_codes_with_phase(dc, oracle):
+    """256 equiprobable bytes -> 8/9-bit codes that barely self-synchronise; a shard phase shifts every code
+    off the subsequence grid.  Whatever path is taken, the result must be exact."""
+    rng = np.random.default_rng(12)
+    data = rng.integers(0, 256, size=300000, dtype=np.uint8)
+    d = _dev(data)
+    for n_ary in PACKABLE:
+        table = dc.huff_build(dc.histogram(d), n_ary)
+        for phase in (0, 3, 4):
+            res = dc.huff_encode(d, table, bit_phase=phase)
+            out, status = dc.huff_decode(res.payload, res.bits(), table, data.size, bit_start=phase)
+            assert int(status.item()) == 0 and torch.equal(out, d), (n_ary, phase)
+
+
 def test_decode_reports_corruption(dc, oracle):
     data = _zipf(dc, 100000, seed=6)
     table = dc.huff_build(dc.histogram(data), 2)
