@@ -224,8 +224,13 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             count++;
             if (count <= 2) used2 = used;
         }
-        tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : 0u;
-        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | ((count < 2 ? count : 2u) << 22) | (first << 24)) : 0u;
+        // an unused code slot (the dummy leaves): when every code fits the index it gets a real entry -- advance one
+        // digit, no symbol, flagged -- so the decoders need no escape branch; with longer codes 0 = escape
+        const bool total_lut = bpd != 0 && max_len * bpd <= DC_LUT_BITS;
+        const unsigned int dead = (unsigned int)bpd;
+        tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : 0u);
+        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | ((count < 2 ? count : 2u) << 22) | (first << 24))
+                                 : (total_lut ? ((dead << 16) | (dead << 24) | 0x80000000u) : 0u);
     }
     if (tid == 0) {
         tab->n_ary = n_ary;

@@ -335,8 +335,6 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(const uint8_t
 
 constexpr int kF_Threads = 256;
 constexpr int kF_Warps = kF_Threads / 32;
-constexpr int kF_TileWords = 32 * kSubBits / 32;   // 128 words = 512 B per warp tile
-constexpr int kF_Halo = 8;
 constexpr int kF_SegTiles = 32;                    // 16 KB of bitstream per warp
 constexpr int kF_StageBytes = 32 * kMaxSymPerSub + 32;
 
@@ -376,78 +374,110 @@ __device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *
     return 0;
 }
 
-__device__ __forceinline__ uint32_t peek32(const uint32_t *words, uint32_t p) {
-    return __funnelshift_l(words[(p >> 5) + 1], words[p >> 5], p & 31);
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
 }
 
-// count-only decode of bits [p, lim) of the warp tile (positions relative to the tile); lut = lut_count
-__device__ __forceinline__ void sync_decode(const FastTables *t, const uint32_t *words, uint32_t p, uint32_t lim,
+// One lane's subsequence lives in registers: w[0..3] are its 128 bits (big-endian words), w[4] the 32 bits
+// that follow.  Positions are relative to the subsequence; word k is indexed statically.
+// ESC = the table has codes longer than the 12 index bits (entry 0 = escape to the canonical search);
+// otherwise every entry is valid and the loops carry no escape branch.
+//
+// count-only decode of bits [p, lim), lim <= 128; lut = shared address of lut_count
+template <bool ESC>
+__device__ __forceinline__ void sync_decode(const FastTables *t, uint32_t lut, const uint32_t (&w)[5], uint32_t p, uint32_t lim,
                                             uint32_t *p_end, uint32_t *count) {
-    uint32_t c = 0;
-    while ((int)p <= (int)lim - DC_LUT_BITS) {  // every code inside the 12-bit window starts before lim
-        const uint32_t w = peek32(words, p);
-        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
-        if (e) {
-            p += e & 0xFFu;
-            c += (e >> 16) & 0xFFu;
-        } else {
-            int sym;
-            const int nb = decode_escape(t, w, &sym);
-            p += nb ? nb : t->bpd;
-            c += nb ? 1u : 0u;
+    uint32_t csum = 0;  // bits 16..23 accumulate the symbol count (the field above it only carries upwards)
+    const int multi_lim = (int)lim - DC_LUT_BITS;  // every code inside the 12-bit window starts before lim
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int stop = min(32 * (k + 1) - 1, multi_lim);
+        while ((int)p <= stop) {
+            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
+            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+            if (ESC && e == 0) {
+                int sym;
+                const int nb = decode_escape(t, x, &sym);
+                p += nb ? nb : t->bpd;
+                csum += nb ? 0x10000u : 0u;
+            } else {
+                p += e & 0xFFu;
+                csum += e;
+            }
         }
     }
-    while (p < lim) {  // the last few bits: one code at a time
-        const uint32_t w = peek32(words, p);
-        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
-        if (e) {
-            p += e >> 24;
-            c += 1u;
-        } else {
-            int sym;
-            const int nb = decode_escape(t, w, &sym);
-            p += nb ? nb : t->bpd;
-            c += nb ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // the last few bits: one code at a time
+        const int stop = min(32 * (k + 1), (int)lim) - 1;
+        while ((int)p <= stop) {
+            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
+            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+            if (ESC && e == 0) {
+                int sym;
+                const int nb = decode_escape(t, x, &sym);
+                p += nb ? nb : t->bpd;
+                csum += nb ? 0x10000u : 0u;
+            } else {
+                p += e >> 24;
+                csum += (e & 0x00FF0000u) ? 0x10000u : 0u;
+            }
         }
     }
     *p_end = p;
-    *count = c;
+    *count = (csum >> 16) & 0xFFu;
 }
 
-// decode bits [p, lim) into dst; lut = lut_pair (two symbols per look-up)
-__device__ __forceinline__ void write_decode(const FastTables *t, const uint32_t *words, uint32_t p, uint32_t lim, uint8_t *dst,
-                                             uint32_t *p_end, uint32_t *count, bool *corrupt) {
-    uint32_t c = 0;
-    while ((int)p <= (int)lim - DC_LUT_BITS) {
-        const uint32_t w = peek32(words, p);
-        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
-        if (e) {
-            dst[c] = (uint8_t)e;
-            if (e & (2u << 22)) dst[c + 1] = (uint8_t)(e >> 8);
-            p += (e >> 16) & 0x3Fu;
-            c += (e >> 22) & 3u;
-        } else {
-            int sym = 0;
-            const int nb = decode_escape(t, w, &sym);
-            if (nb) dst[c++] = (uint8_t)sym; else *corrupt = true;
-            p += nb ? nb : t->bpd;
+// decode bits [p, lim) into dst; lut = shared address of lut_pair (two symbols per look-up)
+template <bool ESC>
+__device__ __forceinline__ void write_decode(const FastTables *t, uint32_t lut, const uint32_t (&w)[5], uint32_t p, uint32_t lim,
+                                             uint8_t *dst0, uint32_t *p_end, uint32_t *count, bool *corrupt) {
+    uint8_t *dst = dst0;
+    uint32_t flags = 0;
+    const int multi_lim = (int)lim - DC_LUT_BITS;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int stop = min(32 * (k + 1) - 1, multi_lim);
+        while ((int)p <= stop) {
+            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
+            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+            if (ESC && e == 0) {
+                int sym = 0;
+                const int nb = decode_escape(t, x, &sym);
+                if (nb) *dst++ = (uint8_t)sym; else flags = 0x80000000u;
+                p += nb ? nb : t->bpd;
+            } else {
+                dst[0] = (uint8_t)e;
+                if (e & (2u << 22)) dst[1] = (uint8_t)(e >> 8);
+                p += (e >> 16) & 0x3Fu;
+                dst += (e >> 22) & 3u;
+                flags |= e;
+            }
         }
     }
-    while (p < lim) {
-        const uint32_t w = peek32(words, p);
-        const uint32_t e = t->lut[w >> (32 - DC_LUT_BITS)];
-        if (e) {
-            dst[c++] = (uint8_t)e;
-            p += e >> 24;
-        } else {
-            int sym = 0;
-            const int nb = decode_escape(t, w, &sym);
-            if (nb) dst[c++] = (uint8_t)sym; else *corrupt = true;
-            p += nb ? nb : t->bpd;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int stop = min(32 * (k + 1), (int)lim) - 1;
+        while ((int)p <= stop) {
+            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
+            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+            if (ESC && e == 0) {
+                int sym = 0;
+                const int nb = decode_escape(t, x, &sym);
+                if (nb) *dst++ = (uint8_t)sym; else flags = 0x80000000u;
+                p += nb ? nb : t->bpd;
+            } else {
+                dst[0] = (uint8_t)e;
+                p += (e >> 24) & 0x3Fu;
+                dst += (e >> 31) ^ 1u;  // a flagged (unused) slot yields no symbol
+                flags |= e;
+            }
         }
     }
+    if (flags & 0x80000000u) *corrupt = true;
     *p_end = p;
-    *count = c;
+    *count = (uint32_t)(dst - dst0);
 }
 
 struct FastWorkspace {
@@ -457,54 +487,77 @@ struct FastWorkspace {
     int32_t *mismatch;                               // F2: some segment started on a wrong guess
 };
 
-// warp-cooperative load of warp tile `tile` (+halo) as big-endian words
-__device__ __forceinline__ void load_warp_tile(uint32_t *words, const uint8_t *__restrict__ d_bits, unsigned long long tile,
-                                               unsigned long long nvec, int lane) {
-    const uint4 *v = (const uint4 *)d_bits;
-    const unsigned long long gv = tile * 32 + lane;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (gv < nvec) x = ldg_stream(v + gv);
-    uint4 y = make_uint4(bswap32(x.x), bswap32(x.y), bswap32(x.z), bswap32(x.w));
-    ((uint4 *)words)[lane] = y;
-    if (lane < kF_Halo / 4) {
-        const unsigned long long hv = tile * 32 + 32 + lane;
-        uint4 h = make_uint4(0, 0, 0, 0);
-        if (hv < nvec) h = ldg_stream(v + hv);
-        ((uint4 *)words)[32 + lane] = make_uint4(bswap32(h.x), bswap32(h.y), bswap32(h.z), bswap32(h.w));
+// A warp's view of its segment: 32-bit positions relative to the segment start, tiles streamed through
+// registers one 16-byte load per lane ahead.
+struct SegCursor {
+    const uint4 *src;      // this lane's vector of the NEXT tile to fetch
+    uint32_t vec_left;     // vectors of the stream from the segment start on (clamped)
+    uint32_t bits_left;    // bits of the stream from the segment start on (clamped)
+    uint4 next;            // prefetched vector (little-endian words as loaded)
+    uint32_t fetched;      // tiles fetched so far
+    int lane;
+
+    __device__ __forceinline__ void init(const uint8_t *d_bits, unsigned long long first_tile, unsigned long long nvec,
+                                         unsigned long long end, int lane_) {
+        lane = lane_;
+        const unsigned long long vec0 = first_tile * 32, bit0 = first_tile * (unsigned long long)(32 * kSubBits);
+        src = (const uint4 *)d_bits + vec0 + lane;
+        const unsigned long long vl = nvec > vec0 ? nvec - vec0 : 0, bl = end > bit0 ? end - bit0 : 0;
+        vec_left = vl > 0x40000000ull ? 0x40000000u : (uint32_t)vl;
+        bits_left = bl > 0x40000000ull ? 0x40000000u : (uint32_t)bl;
+        fetched = 0;
+        fetch();
     }
-}
+    __device__ __forceinline__ void fetch() {
+        next = make_uint4(0, 0, 0, 0);
+        if (fetched * 32 + lane < vec_left) next = ldg_stream(src);
+        src += 32;
+        fetched++;
+    }
+    // words of tile number `fetched - 1` for this lane + the 32 bits that follow; prefetches the tile after it
+    __device__ __forceinline__ void take(uint32_t (&w)[5]) {
+        const uint4 cur = next;
+        fetch();
+        w[0] = bswap32(cur.x); w[1] = bswap32(cur.y); w[2] = bswap32(cur.z); w[3] = bswap32(cur.w);
+        const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+        const uint32_t wrap = __shfl_sync(0xFFFFFFFFu, bswap32(next.x), 0);
+        w[4] = lane == 31 ? wrap : right;
+    }
+};
 
 // ------------------------------------------------------------------------------------------ F1
+template <bool ESC>
 __global__ void __launch_bounds__(kF_Threads) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
                                                                       unsigned long long end, const dc_huff_table *__restrict__ tab,
                                                                       FastWorkspace ws, unsigned long long nsub,
                                                                       unsigned long long ntiles, unsigned long long nseg) {
     __shared__ FastTables s_t;
-    __shared__ __align__(16) uint32_t s_words[kF_Warps][kF_TileWords + kF_Halo];
     load_fast_tables(&s_t, tab, tab->lut_count);
     __syncthreads();
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *words = s_words[warp];
     const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
     const uint32_t guess = (uint32_t)(bit_start & 7);  // fixed-length-like codes keep the stream's phase
     for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
          seg += (unsigned long long)gridDim.x * kF_Warps) {
-        const unsigned long long tile0 = seg * kF_SegTiles;
+        const int warm = seg == 0 ? 0 : 1;  // walk the last tile of the previous segment first to find our first code
+        const unsigned long long tile0 = seg * kF_SegTiles - warm;
+        SegCursor cur;
+        cur.init(d_bits, tile0, nvec, end, lane);
+        const uint32_t ntile = (uint32_t)min((unsigned long long)(kF_SegTiles + warm), ntiles - tile0);
+        uint16_t *info = ws.sub_info + tile0 * 32 + lane;
+        const unsigned long long sub0 = tile0 * 32;
+        const uint32_t sub_left = nsub - sub0 > 0x40000000ull ? 0x40000000u : (uint32_t)(nsub - sub0);
         uint32_t carry = seg == 0 ? (uint32_t)bit_start : guess, assumed = carry, total = 0;
-        for (int tt = seg == 0 ? 0 : -1; tt < kF_SegTiles; tt++) {  // tt == -1: the warm-up tile of the previous segment
-            const unsigned long long tile = tile0 + tt;
-            if (tile >= ntiles) break;
-            __syncwarp();
-            load_warp_tile(words, d_bits, tile, nvec, lane);
-            __syncwarp();
-            const unsigned long long tile_bit0 = tile * (unsigned long long)(32 * kSubBits);
-            const uint32_t sub_lo = lane * kSubBits;
-            const bool active = tile_bit0 + sub_lo < end;
-            const unsigned long long rest = end - tile_bit0;  // > 0 for every launched tile
-            const uint32_t lim = rest < sub_lo + kSubBits ? (uint32_t)rest : sub_lo + kSubBits;
-            uint32_t start = lane == 0 ? carry : guess, p_end = sub_lo + kSubBits, cnt = 0;
-            if (active) sync_decode(&s_t, words, sub_lo + start, lim, &p_end, &cnt);
-            uint32_t my_exit = p_end >= sub_lo + kSubBits ? p_end - (sub_lo + kSubBits) : 0u;
+        for (uint32_t tt = 0; tt < ntile; tt++, info += 32) {
+            uint32_t w[5];
+            cur.take(w);
+            const uint32_t sub_bit0 = (tt * 32 + lane) * kSubBits;             // relative to tile0
+            const bool active = sub_bit0 < cur.bits_left;
+            const uint32_t lim = active ? min((uint32_t)kSubBits, cur.bits_left - sub_bit0) : 0u;
+            uint32_t start = lane == 0 ? carry : guess, p_end = kSubBits, cnt = 0;
+            if (active) sync_decode<ESC>(&s_t, lut, w, start, lim, &p_end, &cnt);
+            uint32_t my_exit = p_end >= (uint32_t)kSubBits ? p_end - kSubBits : 0u;
             while (true) {
                 uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, my_exit, 1);
                 if (lane == 0) ns = start;
@@ -512,16 +565,15 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_sync_kernel(const uint
                 if (!__any_sync(0xFFFFFFFFu, redo)) break;
                 if (redo) {
                     start = ns;
-                    sync_decode(&s_t, words, sub_lo + start, lim, &p_end, &cnt);
-                    my_exit = p_end >= sub_lo + kSubBits ? p_end - (sub_lo + kSubBits) : 0u;
+                    sync_decode<ESC>(&s_t, lut, w, start, lim, &p_end, &cnt);
+                    my_exit = p_end >= (uint32_t)kSubBits ? p_end - kSubBits : 0u;
                 }
             }
             carry = __shfl_sync(0xFFFFFFFFu, my_exit, 31);
-            if (tt < 0) {
+            if (tt < (uint32_t)warm) {
                 assumed = carry;
             } else {
-                const unsigned long long sidx = tile * 32 + lane;
-                if (sidx < nsub) ws.sub_info[sidx] = (uint16_t)(start | (cnt << 8));
+                if (tt * 32 + lane < sub_left) *info = (uint16_t)(start | (cnt << 8));
                 total += cnt;
             }
         }
@@ -585,6 +637,7 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
 }
 
 // ------------------------------------------------------------------------------------------ F3
+template <bool ESC>
 __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
                                                                        const dc_huff_table *__restrict__ tab, FastWorkspace ws,
                                                                        unsigned long long nsub, unsigned long long ntiles,
@@ -592,27 +645,33 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
                                                                        unsigned long long n_out, int32_t *__restrict__ d_status) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
     FastTables *s_t = (FastTables *)fast_smem;
-    uint32_t *s_words = (uint32_t *)(fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15));
-    uint8_t *s_stage = (uint8_t *)(s_words + kF_Warps * (kF_TileWords + kF_Halo));
+    uint8_t *s_stage = fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15);
     if (*ws.mismatch) return;  // the robust path redoes the stream
     load_fast_tables(s_t, tab, tab->lut_pair);
     __syncthreads();
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *words = s_words + warp * (kF_TileWords + kF_Halo);
     uint8_t *stage = s_stage + warp * kF_StageBytes;
     const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
     bool corrupt = false;
     for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
          seg += (unsigned long long)gridDim.x * kF_Warps) {
+        const unsigned long long tile0 = seg * kF_SegTiles;
+        SegCursor cur;
+        cur.init(d_bits, tile0, nvec, end, lane);
+        const uint32_t ntile = (uint32_t)min((unsigned long long)kF_SegTiles, ntiles - tile0);
+        const uint16_t *info = ws.sub_info + tile0 * 32 + lane;
+        const unsigned long long sub0 = tile0 * 32;
+        const uint32_t sub_left = nsub - sub0 > 0x40000000ull ? 0x40000000u : (uint32_t)(nsub - sub0);
         unsigned long long ob = ws.seg_off[seg];
-        for (int tt = 0; tt < kF_SegTiles; tt++) {
-            const unsigned long long tile = seg * kF_SegTiles + tt;
-            if (tile >= ntiles) break;
-            __syncwarp();
-            load_warp_tile(words, d_bits, tile, nvec, lane);
-            const unsigned long long sidx = tile * 32 + lane;
-            const uint32_t info = sidx < nsub ? ws.sub_info[sidx] : 0u;
-            const uint32_t start = info & 0xFFu, my_cnt = info >> 8;
+        uint32_t next_info = lane < sub_left ? *info : 0u;
+        for (uint32_t tt = 0; tt < ntile; tt++) {
+            uint32_t w[5];
+            cur.take(w);
+            const uint32_t my_info = next_info;
+            info += 32;
+            next_info = (tt + 1 < ntile && (tt + 1) * 32 + lane < sub_left) ? *info : 0u;
+            const uint32_t start = my_info & 0xFFu, my_cnt = my_info >> 8;
             uint32_t incl = my_cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -621,15 +680,13 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
             }
             const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const uint32_t a = (uint32_t)(((uintptr_t)out + ob) & 15);
-            __syncwarp();
-            const unsigned long long tile_bit0 = tile * (unsigned long long)(32 * kSubBits);
-            const uint32_t sub_lo = lane * kSubBits;
-            if (tile_bit0 + sub_lo < end && sidx < nsub) {
-                const unsigned long long rest = end - tile_bit0;
-                const uint32_t lim = rest < sub_lo + kSubBits ? (uint32_t)rest : sub_lo + kSubBits;
+            const uint32_t sub_bit0 = (tt * 32 + lane) * kSubBits;
+            __syncwarp();  // the previous tile's copy-out has read the staging buffer
+            if (sub_bit0 < cur.bits_left && tt * 32 + lane < sub_left) {
+                const uint32_t lim = min((uint32_t)kSubBits, cur.bits_left - sub_bit0);
                 uint32_t p_end, c;
-                write_decode(s_t, words, sub_lo + start, lim, stage + a + (incl - my_cnt), &p_end, &c, &corrupt);
-                if (c != my_cnt || tile_bit0 + p_end > end) corrupt = true;
+                write_decode<ESC>(s_t, lut, w, start, lim, stage + a + (incl - my_cnt), &p_end, &c, &corrupt);
+                if (c != my_cnt || p_end > cur.bits_left - sub_bit0) corrupt = true;
             }
             __syncwarp();
             // copy-out: staging byte i <-> out[ob - a + i]; 16-byte words are aligned on both sides
@@ -782,30 +839,33 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
 
+    const bool esc = tmeta[7] > DC_LUT_BITS;  // max_bits: codes longer than the LUT index need the escape path
     const int force = decode_force_mode();
     if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
-        decode_fast_sync_kernel<<<(unsigned int)(want < sms * 8 ? want : sms * 8), kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table,
-                                                                                                       fw, nsub, nwt, nseg);
+        const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
+        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsub, nwt, nseg);
+        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsub, nwt, nseg);
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
         decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status);
     }
-    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * (kF_TileWords + kF_Halo) * 4 +
-                         (size_t)kF_Warps * kF_StageBytes;
+    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * kF_StageBytes;
     static bool attr3 = false;
     if (!attr3) {
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         attr3 = true;
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
-        decode_fast_write_kernel<<<(unsigned int)(want < sms * 4 ? want : sms * 4), kF_Threads, smem3, st>>>(
-            d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
+        const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
+        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
+        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
     }
     DC_CUDA_TRY(cudaGetLastError());
     // did every segment start on a code boundary?  (blocking read of one flag)
