@@ -691,15 +691,18 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
             __syncwarp();
             // copy-out: staging byte i <-> out[ob - a + i]; 16-byte words are aligned on both sides
             const uint32_t span = a + tile_total;
-            for (uint32_t j = lane; j * 16 < span; j += 32) {
-                const uint32_t lo = j * 16, hi = lo + 16;
-                const unsigned long long g = ob - a + lo;
-                if (lo >= a && hi <= span && g + 16 <= n_out) {
-                    stg_stream((uint4 *)(out + g), *(const uint4 *)(stage + lo));
-                } else {
-                    for (uint32_t k = lo < a ? a : lo; k < hi && k < span; k++)
-                        if (ob - a + k < n_out) out[ob - a + k] = stage[k];
-                }
+            if (ob + tile_total <= n_out) {
+                const uint32_t jfull = span >> 4;  // staging vectors [head, jfull) are complete
+                const uint32_t head = a ? 1u : 0u;
+                for (uint32_t j = head + lane; j < jfull; j += 32)
+                    stg_stream((uint4 *)(out + (ob - a)) + j, *(const uint4 *)(stage + j * 16));
+                // ragged edges, one byte per lane: lanes 0..15 the first vector, lanes 16..31 the last one
+                const uint32_t k = lane < 16 ? (uint32_t)lane : jfull * 16 + (lane - 16);
+                const bool edge = lane < 16 ? (a != 0 || jfull == 0) : (jfull != 0);
+                if (edge && k >= a && k < span) out[ob - a + k] = stage[k];
+            } else {  // more symbols than the caller expects (corrupt stream): clamp every byte
+                for (uint32_t k = a + lane; k < span; k += 32)
+                    if (ob - a + k < n_out) out[ob - a + k] = stage[k];
             }
             ob += tile_total;
         }
