@@ -1,0 +1,195 @@
+"""Multi-GPU shard layer: one process per GPU, torch.distributed for the plumbing.
+
+Both paths shard naturally; the only data-path exchanges are tiny:
+
+  encode   contiguous byte ranges per rank
+           local histogram --all_reduce(259 x i64)--> one global code table (every rank builds it, identically)
+           local bit total = dot(local histogram, global lengths)   (no data pass)
+           --all_gather(1 x i64)--> exclusive scan = this rank's global bit offset O_r
+           the rank encodes at phase O_r mod 8 into its own buffer; the byte a shard shares with its
+           neighbour is OR-combined (--all_gather(2 bytes)--), so the concatenation of the shard buffers at
+           byte offsets O_r // 8 IS the single-stream payload, bit for bit
+  decode   every rank decodes the codes that start in its shard (start phase and bit count are the encoder's
+           side information), no exchange at all; symbol counts are all-gathered for the output offsets
+
+The compute backend is injected: the default is the CUDA library (no CPU fallback); the CPU tests in
+tests/ pass a CPU stand-in of their own so the arithmetic of this layer is exercised with gloo, world_size 2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+class CudaBackend:
+    """The product backend: every call lands in libdc_b200.so."""
+
+    def __init__(self):
+        from . import api
+        self.api = api
+
+    def histogram(self, data):
+        return self.api.histogram(data)
+
+    def build(self, hist, n_ary):
+        return self.api.huff_build(hist, n_ary)
+
+    def bits_for_hist(self, hist, table):
+        return self.api.huff_bits_for_hist(hist, table)
+
+    def encode(self, data, table, bit_phase, nbits_hint):
+        cap = (nbits_hint + bit_phase + 7) // 8 + 64
+        out = torch.empty(cap, dtype=torch.uint8, device=data.device)
+        res = self.api.huff_encode(data, table, out=out, bit_phase=bit_phase)
+        return res.payload, res.total_bits, res.status
+
+    def decode(self, payload, nbits, table, n_out, bit_start):
+        out, status = self.api.huff_decode(payload, nbits, table, n_out, bit_start=bit_start)
+        return out, status
+
+
+@dataclass
+class ShardedPayload:
+    payload: torch.Tensor       # this rank's bytes [bit_offset // 8, ceil((bit_offset + nbits) / 8)) of the stream
+    nbits: int                  # code bits of this shard
+    bit_offset: int             # O_r: global bit offset of the shard's first code
+    total_bits: int             # bits of the whole stream
+    n_symbols: int              # symbols of this shard
+    table: object               # the global code table
+    shard_bits: list            # bits of every shard (the side information a container would carry)
+
+    @property
+    def bit_phase(self) -> int:
+        return self.bit_offset % 8
+
+    @property
+    def byte_offset(self) -> int:
+        return self.bit_offset // 8
+
+    @property
+    def nbytes(self) -> int:
+        return (self.bit_phase + self.nbits + 7) // 8 if self.nbits else 0
+
+
+def exclusive_offsets(bits_per_rank):
+    """O_r = sum of the bit totals of the ranks before r (pure function: tested on CPU)."""
+    off, out = 0, []
+    for b in bits_per_rank:
+        out.append(off)
+        off += int(b)
+    return out, off
+
+
+def merge_boundary_bytes(my_rank, first_last, byte_ranges):
+    """Given every rank's (first byte value, last byte value) and global byte range [lo, hi) of its buffer,
+    return the values this rank's first and last bytes must take so that shared bytes agree everywhere.
+    A byte can be shared by more than two shards when shards are tiny."""
+    lo, hi = byte_ranges[my_rank]
+    if hi <= lo:
+        return None, None
+    first, last = first_last[my_rank]
+    for q, (qlo, qhi) in enumerate(byte_ranges):
+        if q == my_rank or qhi <= qlo:
+            continue
+        qf, ql = first_last[q]
+        for idx, val in ((qlo, qf), (qhi - 1, ql)):
+            if idx == lo:
+                first |= val
+            if idx == hi - 1:
+                last |= val
+    if hi - lo == 1:
+        first = last = first | last
+    return first, last
+
+
+class ShardedHuffman:
+    def __init__(self, group=None, backend=None, device=None):
+        self.group = group
+        self.backend = backend or CudaBackend()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device
+
+    # --- collectives on tiny tensors
+    def _all_reduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def _all_gather_list(self, t):
+        if self.world == 1:
+            return [t]
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t, group=self.group)
+        return outs
+
+    def encode(self, local: torch.Tensor, n_ary: int) -> ShardedPayload:
+        be = self.backend
+        hist = be.histogram(local)
+        ghist = self._all_reduce(hist.clone())
+        table = be.build(ghist, n_ary)
+        my_bits = be.bits_for_hist(hist, table)
+        bits = [int(t.item()) for t in self._all_gather_list(my_bits)]
+        offsets, total = exclusive_offsets(bits)
+        off = offsets[self.rank]
+        payload, d_bits, d_status = be.encode(local, table, off % 8, bits[self.rank])
+        st = int(d_status.item())
+        if st != 0:
+            from ._lib import DcError
+            raise DcError(st, "sharded encode")
+        assert int(d_bits.item()) == bits[self.rank], "dot(local histogram, lengths) disagrees with the encoder"
+        sp = ShardedPayload(payload, bits[self.rank], off, total, local.numel(), table, bits)
+        sp.payload = payload[: sp.nbytes]
+        self._merge_boundaries(sp, offsets, bits)
+        return sp
+
+    def _merge_boundaries(self, sp: ShardedPayload, offsets, bits) -> None:
+        if self.world == 1:
+            return
+        ranges = []
+        for o, b in zip(offsets, bits):
+            ranges.append((o // 8, (o + b + 7) // 8 if b else o // 8))
+        mine = torch.zeros(2, dtype=torch.uint8, device=sp.payload.device)
+        if sp.nbytes:
+            mine[0] = sp.payload[0]
+            mine[1] = sp.payload[sp.nbytes - 1]
+        allb = [tuple(int(x) for x in t.cpu()) for t in self._all_gather_list(mine)]
+        first, last = merge_boundary_bytes(self.rank, allb, ranges)
+        if first is not None:
+            sp.payload[0] = first
+            sp.payload[sp.nbytes - 1] = last
+
+    def decode(self, sp: ShardedPayload) -> torch.Tensor:
+        out, status = self.backend.decode(sp.payload, sp.nbits, sp.table, sp.n_symbols, sp.bit_phase)
+        st = int(status.item())
+        if st != 0:
+            from ._lib import DcError
+            raise DcError(st, "sharded decode")
+        return out
+
+    def symbol_offsets(self, n_local: int):
+        """Exclusive scan of the per-rank symbol counts (the decode side's output offsets)."""
+        t = torch.tensor([n_local], dtype=torch.int64, device=self.device or "cpu")
+        counts = [int(x.item()) for x in self._all_gather_list(t)]
+        return exclusive_offsets(counts)
+
+    def gather_stream(self, sp: ShardedPayload):
+        """Rank 0 gets the whole logical bitstream (test/verification helper: moves C bytes)."""
+        sizes = [int(x.item()) for x in self._all_gather_list(torch.tensor([sp.nbytes], dtype=torch.int64,
+                                                                           device=sp.payload.device))]
+        offs = [int(x.item()) for x in self._all_gather_list(torch.tensor([sp.byte_offset], dtype=torch.int64,
+                                                                          device=sp.payload.device))]
+        cap = max(sizes) if sizes else 0
+        buf = torch.zeros(max(cap, 1), dtype=torch.uint8, device=sp.payload.device)
+        buf[: sp.nbytes] = sp.payload[: sp.nbytes]
+        parts = self._all_gather_list(buf)
+        if self.rank != 0:
+            return None
+        total_bytes = (sp.total_bits + 7) // 8
+        out = torch.zeros(total_bytes, dtype=torch.uint8, device=sp.payload.device)
+        for p, sz, o in zip(parts, sizes, offs):
+            if sz:
+                out[o: o + sz] |= p[:sz]
+        return out
