@@ -48,12 +48,13 @@ def _peaks():
 # --------------------------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons through NVML while the timed region runs (the recipe's
-    `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.*` line, read in-process every 50 ms)."""
+    """Samples SM clocks / throttle reasons through NVML (the recipe's `nvidia-smi --query-gpu=clocks.sm,...,
+    clocks_event_reasons.*` line, read in-process every 4 ms).  The thread is started before warm-up (nvmlInit takes
+    longer than a short timed region); begin()/stop() bracket the timed region and only its samples are reported."""
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], set(), False, None, None
-        self.err = None
+        self.gpu, self.samples, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], False, None, None
+        self.err, self.t_begin, self.t_end, self.ready = None, None, None, threading.Event()
 
     def _loop(self):
         try:
@@ -63,33 +64,34 @@ class ClockSampler:
             idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {
-                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            }
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = int(get_reasons(h))
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.05)
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                time.sleep(0.004)
         except Exception as e:  # noqa: BLE001 - the bench must not die because NVML is unavailable
             self.err = repr(e)
+            self.ready.set()
 
     def start(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
+    def begin(self):
+        self.ready.wait(timeout=10)
+        self.t_begin = time.perf_counter()
+
     def stop(self) -> dict:
+        self.t_end = time.perf_counter()
+        time.sleep(0.01)
         self.stop_flag = True
         if self.thread is not None:
             self.thread.join(timeout=2)
-        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-               "samples": len(self.samples), "reasons": sorted(self.reasons)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        inside = [x for x in self.samples if self.t_begin is not None and self.t_begin <= x[0] <= self.t_end + 0.005]
+        reasons = sorted({name for _, _, r in inside for bit, name in names.items() if r & bit})
+        out = {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(inside), "reasons": reasons}
         if self.err:
             out["error"] = self.err
         return out
@@ -239,6 +241,10 @@ def run_ours(args) -> None:
         dc.huff_decode(payload, state["nbits"], table, n, bit_start=state["phase"], out=decoded, workspace=state["dec_ws"],
                        status=dec_status)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # first pass: learn the bit count (side information a container header carries), check the round trip
     res = encode_path()
     if state["nbits"] is None:
@@ -260,11 +266,10 @@ def run_ours(args) -> None:
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     L.dc_profile_reset(); L.dc_profile_enable(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = dc.launch_count()
     barrier()
+    if rank == 0:
+        sampler.begin()
     ev[0].record()
     for s in range(args.steps):
         encode_path()
@@ -363,7 +368,7 @@ def run_ours(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-ary", type=int, default=4)

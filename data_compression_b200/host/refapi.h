@@ -1,0 +1,64 @@
+/*
+ * refapi.h -- the reference's own function names on top of libdc_b200.so.
+ *
+ * carycode/data_compression has no plugin/FFI layer: a C caller links the non-static functions of
+ * n_ary_huffman.c / nybble_compression.c directly.  This header declares those functions with the
+ * reference's signatures (file:line cited per function); refapi.c implements each one as a call into the
+ * dc_host_* entry points of include/dc_b200.h, i.e. H2D copy -> sm_100a kernels -> D2H copy.  There is no
+ * CPU implementation behind them.
+ *
+ * Error behaviour mirrors the reference: where the reference would assert() and abort, these print one
+ * line to stderr and abort() too (dc_refapi_set_abort(0) turns that into a return of the dc_status).
+ */
+#ifndef DC_REFAPI_H
+#define DC_REFAPI_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* n_ary_huffman.c:461-493 -- counts bytes of a NUL-terminated text into h[0..max_symbol_value] */
+void histogram(const char *text, const int max_symbol_value, int h[]);
+
+/* n_ary_huffman.c:1161-1208 -- n-ary Huffman code lengths (digits), as-written dummy rule */
+void huffman(const int max_leaf_value, const int symbol_frequencies[], const int compressed_symbols, int lengths[]);
+
+/* n_ary_huffman.c:1382-1612 -- canonical code values for the lengths */
+void convert_lengths_to_encode_table(const int max_symbol_value, const int canonical_lengths[],
+                                     const int compressed_symbols, int encode_length_table[],
+                                     unsigned int encode_value_table[]);
+
+/* n_ary_huffman.c:1621-1678 -- append the codes of original_text[0..original_length) to
+ * compressed_text[start...]; returns the number of bytes written.  (A stub in the reference; the payload
+ * layout is the one DESIGN.md defines.)  n in {2,4,16}. */
+int represent_items_with_codes(const int max_symbol_value, int canonical_lengths[], const int compressed_symbols,
+                               const int bufsize, const int original_length, char original_text[], int start,
+                               char compressed_text[]);
+
+/* the decoder the reference leaves as assert(0) (n_ary_huffman.c:2081-2089): inverse of
+ * represent_items_with_codes; writes n_symbols bytes + a terminating NUL; returns n_symbols */
+int decode_items_with_codes(const int max_symbol_value, const int canonical_lengths[], const int compressed_symbols,
+                            const uint64_t total_bits, const char compressed_text[], const int n_symbols,
+                            char decompressed_text[]);
+
+/* bits emitted by the last represent_items_with_codes() call (the reference's signature has no slot for it) */
+uint64_t represent_items_last_total_bits(void);
+
+/* stream forms of write_nybble() nybble_compression.c:1091-1114 and of the split at :767-769.
+ * (write_nybble itself stores ONE nibble into a host byte; there is nothing to offload in that.) */
+void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned char *packed);
+void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigned char *symbols);
+
+/* 1 (default): abort() on a device error, like the reference's assert(); 0: record it and return */
+void dc_refapi_set_abort(int on);
+/* dc_status of the last call made through this header */
+int dc_refapi_last_status(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DC_REFAPI_H */

@@ -1,0 +1,68 @@
+"""The C host side (data_compression_b200/host): refapi library exports the reference's function names, and
+the CLI shims named after the reference binaries behave like them -- `Successful test.` per round trip on a
+GPU box, a loud abort (never a CPU fallback) without a device."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HOST = os.path.join(ROOT, "data_compression_b200", "host")
+REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
+REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
+             "decode_items_with_codes", "nybble_pack_stream", "nybble_unpack_stream"]
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_refapi_exports_reference_names(built):
+    L = ctypes.CDLL(REFAPI)
+    missing = [n for n in REF_NAMES if not hasattr(L, n)]
+    assert not missing, missing
+    assert os.access(os.path.join(HOST, "n_ary_huffman"), os.X_OK)
+    assert os.access(os.path.join(HOST, "nybble_compression"), os.X_OK)
+
+
+def test_cli_aborts_without_device(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-device behaviour")
+    r = subprocess.run([os.path.join(HOST, "n_ary_huffman")], input=b"abc", capture_output=True)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr
+    r = subprocess.run([os.path.join(HOST, "nybble_compression")], capture_output=True)
+    assert r.returncode != 0 and b"Successful" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radix,expect", [(None, 3), (2, 2), (4, 2), (16, 2)])
+def test_n_ary_huffman_cli(built, radix, expect):
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_7bit_spec()
+    text = synth.host_stream(300000, 11, thr, base).tobytes()   # 7-bit, no NUL: what the reference accepts
+    args = [os.path.join(HOST, "n_ary_huffman")] + (["--n", str(radix)] if radix else [])
+    r = subprocess.run(args, input=text, capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    out = r.stdout.decode(errors="replace")
+    assert out.count("Successful test.") == expect
+    if radix:
+        assert "# compressed: 300000 ->" in out and "pass-through" not in out.split("Starting next block")[1]
+    else:
+        assert "pass-through raw data" in out.split("Starting next block")[1]   # n=3: table only, like the reference
+    q = subprocess.run(args + ["--quiet"], input=text, capture_output=True, timeout=120)
+    assert q.returncode == 0 and set(q.stdout.decode().split("\n")) <= {"Successful test.", ""}
+
+
+@pytest.mark.gpu
+def test_nybble_compression_cli(built):
+    r = subprocess.run([os.path.join(HOST, "nybble_compression")], capture_output=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.decode().count("Successful test.") == 1
+    data = np.random.default_rng(3).integers(0, 256, size=1 << 20, dtype=np.uint8).tobytes()
+    r = subprocess.run([os.path.join(HOST, "nybble_compression"), "-"], input=data, capture_output=True, timeout=60)
+    assert r.returncode == 0 and b"Successful test." in r.stdout
