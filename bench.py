@@ -297,7 +297,8 @@ def run_ours(args) -> None:
         if cnt.value:
             kern[L.dc_profile_kernel_name(kid).decode()] = {"ms_total": ms.value, "launches": cnt.value,
                                                             "ms_avg": ms.value / cnt.value}
-    alg_bytes = {"histogram": n, "encode": n + c_bytes, "decode_sync": c_bytes, "decode_write": c_bytes + n}
+    alg_bytes = {"histogram": n, "encode_count": n, "encode": n + c_bytes, "decode_sync": c_bytes, "decode_write": c_bytes + n,
+                 "decode_fast_sync": c_bytes, "decode_fast_write": c_bytes + n}
     peak, peak_src = _peaks()
     dom = max((k for k in kern if k in alg_bytes), key=lambda k: kern[k]["ms_total"])
     achieved = alg_bytes[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9

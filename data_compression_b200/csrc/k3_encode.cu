@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t
     __shared__ uint32_t s_len[256];
     __shared__ uint32_t s_chunk[kEncWarps];
     if (!table_usable(tab, d_status)) return;
+    if (tab->max_bits <= kNarrowBits) return;  // narrow tables take the single-pass kernel
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_len[tid] = (uint32_t)(tab->enc64[tid] >> 32);
     __syncthreads();
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kScanThreads) encode_scan_kernel(const dc_huff
     __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ok = tab->status == DC_OK && tab->bits_per_digit != 0;
+    if (tab->max_bits <= kNarrowBits) return;  // narrow tables take the single-pass kernel
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (unsigned int base = 0; base < nruns; base += kScanThreads * kScanItems) {
@@ -394,18 +396,308 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
     }
 }
 
-static size_t enc_ws_layout(size_t n, size_t off[6]) {
+
+// ================================================================================================ single pass
+// Narrow tables (every code <= 16 bits): ONE launch, one read of the input.  A CTA takes a ticket for a
+// 32 KB run; each of its 8 warps encodes one 4 KB chunk into its own shared-memory staging buffer at
+// chunk-local bit offsets, so the chunk's bit count is known when the staging is complete.  Warp 0 publishes
+// the run's bit count in a descriptor and obtains the run's bit offset by decoupled look-back over the
+// descriptors of earlier runs (tickets make every predecessor a running or finished CTA, so the wait is
+// deadlock-free; looking back over runs, not chunks, keeps the walk to the resolved frontier short).  Every
+// warp then copies its staging buffer out, funnel-shifted to the global bit alignment, with 16-byte
+// streaming stores.  The 16-byte word shared by two chunks is merged by the second arrival.
+constexpr int kSpZeroPrefix = 4;                                            // words of zeros in front of the data
+constexpr int kSpTightBits = 12;                                          // tables up to this run 4 CTAs per SM
+__host__ __device__ constexpr int sp_stage_words(int max_bits) { return kSpZeroPrefix + kChunkBytes * max_bits / 32 + 12; }  // per warp
+constexpr unsigned long long kDescAggregate = 1ull << 62, kDescInclusive = 2ull << 62, kDescValue = (1ull << 62) - 1;
+
+struct SpWorkspace {
+    unsigned int *ticket;          // [1]          next run to hand out
+    unsigned long long *desc;      // [nruns]      status << 62 | bits of the run
+    uint32_t *bstate;              // [nchunks+1]  arrivals at the boundary word between chunk b-1 and chunk b
+    uint4 *bleft, *bright;         // [nchunks+1]
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+
+// The 16-byte word shared by the last chunk of one run and the first chunk of the next: both sides deposit
+// their half (big-endian word domain) and bump a counter; the second arrival stores the word.  `ends` != 0
+// (right side only): the stream ends inside this word and only that many of its bytes exist.
+__device__ __forceinline__ void sp_boundary_merge(const SpWorkspace &ws, unsigned int b, bool left_side, uint4 mine, uint32_t ends,
+                                                  uint8_t *__restrict__ out, unsigned long long vec, size_t out_cap) {
+    uint4 *my_slot = left_side ? ws.bleft + b : ws.bright + b;
+    const uint4 *other_slot = left_side ? ws.bright + b : ws.bleft + b;
+    *my_slot = mine;
+    __threadfence();
+    const uint32_t old = atomicAdd(&ws.bstate[b], 1u + (ends << 8));
+    if ((old & 0xFFu) == 1u) {
+        __threadfence();
+        const uint4 o = ld_cg_u128(other_slot);
+        uint4 rr;
+        rr.x = bswap32(mine.x | o.x);
+        rr.y = bswap32(mine.y | o.y);
+        rr.z = bswap32(mine.z | o.z);
+        rr.w = bswap32(mine.w | o.w);
+        const uint32_t nbytes = (old >> 8) | ends;  // 0 = the whole word
+        if (nbytes == 0 && (vec + 1) * 16 <= out_cap) {
+            stg_stream((uint4 *)out + vec, rr);
+        } else {
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            const size_t end = min((size_t)out_cap, (size_t)vec * 16 + (nbytes ? nbytes : 16u));
+            for (size_t i = vec * 16; i < end; i++) out[i] = (uint8_t)(rw[(i & 15) >> 2] >> (8 * (i & 3)));
+        }
+    }
+}
+
+// one sub-tile (32 lanes x 16 symbols) appended to the warp's staging buffer at bit position `bitpos`
+template <bool FULL>
+__device__ __forceinline__ void sp_subtile(uint32_t *stage, const uint32_t *s_enc, const uint32_t (&w)[4], int valid, int lane,
+                                           uint32_t &bitpos, uint32_t &flags) {
+    constexpr int kItems = kEncPerThread / 2;
+    uint32_t item_val[kItems], item_len[kItems];
+    uint32_t my_bits = 0;
+#pragma unroll
+    for (int k = 0; k < kEncPerThread; k += 2) {
+        uint32_t e0 = s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+        uint32_t e1 = s_enc[(w[k >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu];
+        if (!FULL && k >= valid) e0 = 1u << 31;       // not a symbol: no bits, not "missing"
+        if (!FULL && k + 1 >= valid) e1 = 1u << 31;
+        flags &= e0 & e1;                             // bit 31 survives only if every entry has a code
+        e0 &= 0x7FFFFFFFu;
+        e1 &= 0x7FFFFFFFu;
+        const uint32_t l1 = e1 & 63u;
+        item_val[k / 2] = ((e0 >> 6) << l1) | (e1 >> 6);
+        item_len[k / 2] = (e0 & 63u) + l1;
+        my_bits += (e0 & 63u) + l1;
+    }
+    uint32_t incl = my_bits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += x;
+    }
+    const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const bool fast = __all_sync(0xFFFFFFFFu, my_bits >= 32u);
+    const uint32_t pos = bitpos + incl - my_bits;
+    uint32_t wi = pos >> 5, nb = pos & 31, hi = 0, lo = 0;
+    if (fast) {
+        // plain stores: a lane writes every word it completes.  The leading `lead` bits of its first word are
+        // its left neighbour's trailing bits (lane 0: the previous sub-tile's, already in the buffer)
+        const uint32_t first_wi = wi, lead = nb;
+        uint32_t left_tail = (lane == 0 && lead != 0) ? stage[first_wi] : 0u;
+#pragma unroll
+        for (int k = 0; k < kItems; k++) emit_bits_owned(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
+        const uint32_t my_tail = nb ? lo << (32u - nb) : 0u;
+        const uint32_t lt = __shfl_up_sync(0xFFFFFFFFu, my_tail, 1);
+        if (lane != 0) left_tail = lt;
+        if (lead != 0) stage[first_wi] |= left_tail;
+        if (lane == 31) stage[wi] = my_tail;
+    } else {
+        // word bitpos >> 5 holds the previous sub-tile's trailing bits (or zeros); clear everything behind it
+        const uint32_t z0 = (bitpos >> 5) + 1, z1 = ((bitpos + tile_bits) >> 5) + 1;
+        for (uint32_t i = z0 + lane; i <= z1; i += 32) stage[i] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kItems; k++) emit_bits(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
+        stage_or_if(stage + wi, lo << ((32u - nb) & 31u), nb != 0u);
+    }
+    __syncwarp();
+    bitpos += tile_bits;
+}
+
+template <int MAXBITS>
+__global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) encode_single_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                       const dc_huff_table *__restrict__ tab,
+                                                                       uint8_t *__restrict__ out, size_t out_cap, unsigned phase,
+                                                                       SpWorkspace ws, unsigned int nruns,
+                                                                       unsigned long long *__restrict__ d_total_bits,
+                                                                       int32_t *__restrict__ d_status) {
+    extern __shared__ __align__(16) uint32_t sp_smem[];
+    __shared__ uint32_t s_enc[256];
+    __shared__ unsigned int s_run;
+    __shared__ uint32_t s_bits[kEncWarps];
+    __shared__ unsigned long long s_run_excl;
+    if (!table_usable(tab, d_status)) return;
+    constexpr int kSpStageWords = sp_stage_words(MAXBITS);
+    {   // this instantiation's tables: (12, 16] or [1, 12]; wide tables take the three-launch path
+        const int mb = tab->max_bits;
+        if (mb > MAXBITS || (MAXBITS > kSpTightBits && mb <= kSpTightBits)) return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint32_t e = tab->enc[tid];
+        s_enc[tid] = e ? (e | (1u << 31)) : 0u;  // bit 31 = "has a code"
+    }
+    if (tid == 0) s_run = atomicAdd(ws.ticket, 1u);
+    __syncthreads();
+    const unsigned int run = s_run;
+    if (run >= nruns) return;
+    uint32_t *stage = sp_smem + warp * kSpStageWords;
+    const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
+    const size_t chunk = (size_t)run * kEncWarps + warp;
+    const bool have_chunk = chunk < nchunks;  // the last run may be short of chunks; its idle warps still join the barriers
+    const size_t chunk_base = chunk * kChunkBytes;
+    const size_t chunk_len = have_chunk ? min((size_t)kChunkBytes, n - chunk_base) : 0;
+    const bool last_chunk = chunk == nchunks - 1;
+
+    // ---- 1. encode the chunk into the staging buffer (chunk-local bit offsets behind a zero prefix)
+    if (lane <= kSpZeroPrefix) stage[lane] = 0;
+    uint32_t bitpos = 32u * kSpZeroPrefix, flags = 0xFFFFFFFFu;
+    if (chunk_len == (size_t)kChunkBytes) {
+        uint4 v[kChunkSubs];
+        const uint4 *src = (const uint4 *)(in + chunk_base) + lane;
+#pragma unroll
+        for (int t = 0; t < kChunkSubs; t++) v[t] = ldg_stream(src + t * 32);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < kChunkSubs; t++) {
+            const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+            sp_subtile<true>(stage, s_enc, w, kEncPerThread, lane, bitpos, flags);
+        }
+    } else {  // the ragged last chunk of the stream (or no chunk at all)
+        __syncwarp();
+        const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
+#pragma unroll 1
+        for (int t = 0; t < nsub; t++) {
+            const size_t base = chunk_base + (size_t)t * kSubTile + (size_t)lane * kEncPerThread;
+            const int valid = base < n ? (int)min((size_t)kEncPerThread, n - base) : 0;
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
+            sp_subtile<false>(stage, s_enc, w, valid, lane, bitpos, flags);
+        }
+    }
+    if (lane < 8) stage[(bitpos >> 5) + 1 + lane] = 0;  // the copy-out reads up to 5 words past the last bit
+    const uint32_t chunk_bits = bitpos - 32u * kSpZeroPrefix;
+    if ((flags >> 31) == 0u) set_status(d_status, DC_ERR_SYMBOL);
+
+    // ---- 2. bit offset of the run by decoupled look-back over RUN descriptors (warp 0), of the chunk by a sum in the CTA
+    if (lane == 0) s_bits[warp] = chunk_bits;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t run_bits = 0;
+#pragma unroll
+        for (int w = 0; w < kEncWarps; w++) run_bits += s_bits[w];
+        unsigned long long excl = 0;
+        if (run > 0) {
+            if (lane == 0) st_relaxed_u64(ws.desc + run, kDescAggregate | run_bits);
+            long long base = (long long)run - 1;
+            while (true) {
+                const long long idx = base - lane;
+                unsigned long long d;
+                do {
+                    d = idx >= 0 ? ld_relaxed_u64(ws.desc + idx) : kDescInclusive;
+                } while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0));
+                const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 32;  // nearest predecessor with an inclusive prefix
+                unsigned long long part = lane <= stop ? (d & kDescValue) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                excl += part;
+                if (incl_mask) break;
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed_u64(ws.desc + run, kDescInclusive | (excl + run_bits));
+            s_run_excl = excl;
+        }
+    }
+    __syncthreads();
+    if (!have_chunk) return;
+    unsigned long long excl = s_run_excl;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; w++) excl += w < warp ? s_bits[w] : 0u;
+
+    // ---- 3. copy-out at the global alignment
+    const unsigned long long g = (unsigned long long)phase + excl, gend = g + chunk_bits;
+    const size_t stream_bytes_here = (size_t)((gend + 7) >> 3);
+    if (last_chunk && lane == 0 && d_total_bits) *d_total_bits = excl + chunk_bits;
+    if (stream_bytes_here > out_cap) {
+        if (lane == 0) set_status(d_status, DC_ERR_CAPACITY);
+        return;
+    }
+    const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this chunk
+    const uint32_t r = (uint32_t)(g & 127), t = (uint32_t)(gend & 127);
+    const bool shared_first = chunk != 0 && r != 0;           // first word also holds the previous chunk's bits
+    if (v1 == v0 && !last_chunk) return;                       // < 128 bits from 4096 symbols: symbols without codes (reported)
+    const uint32_t nvec = (uint32_t)(v1 - v0);
+    const uint32_t sbit0 = 32u * kSpZeroPrefix - r;            // staging bit of the first bit of 16-byte word v0
+    const uint32_t sbit1 = nvec * 128u + sbit0;                // ... of 16-byte word v1
+
+    // 3a. the two 16-byte words this chunk shares with its neighbours.  Inside the CTA the LEFT chunk owns the
+    // shared word: it reads the right chunk's leading bits straight from that warp's staging buffer (complete
+    // since the barrier).  Across CTAs both sides deposit their half and the second arrival stores the word.
+    // These go first, so that their fences do not wait for the bulk stores below.
+    if (shared_first && warp == 0 && lane == 8) {
+        const uint4 m = make_uint4(stage_word(stage, sbit0), stage_word(stage, sbit0 + 32), stage_word(stage, sbit0 + 64),
+                                   stage_word(stage, sbit0 + 96));
+        // if the stream ends inside this word (a tiny last chunk), say how many of its bytes exist
+        const uint32_t ends = (last_chunk && v1 == v0) ? (uint32_t)(stream_bytes_here - v0 * 16) : 0u;
+        sp_boundary_merge(ws, (unsigned int)chunk, false, m, ends, out, v0, out_cap);
+    }
+    if (t != 0 && !(shared_first && v1 == v0)) {
+        if (last_chunk) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
+            const uint32_t rem_bytes = (t + 7) >> 3;
+            if (lane < (int)rem_bytes) out[v1 * 16 + lane] = (uint8_t)(stage_word(stage, sbit1 + 8u * lane) >> 24);
+        } else if (warp == kEncWarps - 1) {
+            if (lane == 16) {
+                const uint4 m = make_uint4(stage_word(stage, sbit1), stage_word(stage, sbit1 + 32), stage_word(stage, sbit1 + 64),
+                                           stage_word(stage, sbit1 + 96));
+                sp_boundary_merge(ws, (unsigned int)chunk + 1, true, m, 0u, out, v1, out_cap);
+            }
+        } else if (lane < 16) {
+            // own trailing t bits | the right chunk's first 128 - t bits (its staging starts with 128 zero bits)
+            const uint32_t *right = stage + kSpStageWords;
+            const uint32_t rbit = 32u * kSpZeroPrefix - t;
+            const uint32_t word = stage_word(stage, sbit1 + 32u * (lane >> 2)) | stage_word(right, rbit + 32u * (lane >> 2));
+            // the right chunk may be the last of the stream and end inside this word
+            const unsigned long long rend = gend + s_bits[warp + 1];
+            size_t limit = out_cap;
+            if (chunk + 1 == nchunks - 1) limit = min(limit, (size_t)((rend + 7) >> 3));
+            const size_t byte = (size_t)v1 * 16 + lane;
+            if (byte < limit) out[byte] = (uint8_t)(word >> (24 - 8 * (lane & 3)));
+        }
+    }
+    // 3b. the words that are this chunk's alone
+    {
+        uint4 *dst = (uint4 *)out + v0;
+        const uint32_t sh = sbit0 & 31;
+        const uint32_t *sw = stage + (sbit0 >> 5);
+        for (uint32_t j = (shared_first ? 1u : 0u) + lane; j < nvec; j += 32) {
+            const uint32_t *p = sw + 4 * j;
+            const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4];
+            uint4 o;
+            o.x = bswap32(__funnelshift_l(a1, a0, sh));
+            o.y = bswap32(__funnelshift_l(a2, a1, sh));
+            o.z = bswap32(__funnelshift_l(a3, a2, sh));
+            o.w = bswap32(__funnelshift_l(a4, a3, sh));
+            stg_stream(dst + j, o);
+        }
+    }
+}
+
+static size_t enc_ws_layout(size_t n, size_t off[8]) {
     const size_t nruns = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o[6];
-    o[0] = take(nruns * 4);              // run_bits
-    o[1] = take(nruns * kEncWarps * 4);  // chunk_rel
-    o[2] = take((nruns + 1) * 8);        // run_off
-    o[3] = take((nchunks + 1) * 4);      // bstate
+    size_t o[8];
+    o[0] = take(nruns * 4);              // run_bits                  (wide path)
+    o[1] = take(nruns * kEncWarps * 4);  // chunk_rel                 (wide path)
+    o[2] = take((nruns + 1) * 8);        // run_off                   (wide path)
+    o[3] = take((nchunks + 1) * 4 + 64); // bstate, then the ticket   (zeroed together)
+    o[6] = o[3] + (nchunks + 1) * 4;     // ticket (4-byte aligned, inside the bstate block)
+    o[7] = take(nchunks * 8);            // desc                      (single pass; zeroed)
     o[4] = take((nchunks + 1) * 16);     // bleft
     o[5] = take((nchunks + 1) * 16);     // bright
-    if (off) for (int i = 0; i < 6; i++) off[i] = o[i];
+    if (off) for (int i = 0; i < 8; i++) off[i] = o[i];
     return p;
 }
 
@@ -424,7 +716,7 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     if (d_total_bits) DC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), st));
     if (n == 0) return DC_OK;
-    size_t off[6];
+    size_t off[8];
     const size_t need = enc_ws_layout(n, off);
     if (workspace_bytes < need) return DC_ERR_CAPACITY;
     const size_t nruns64 = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
@@ -438,8 +730,36 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     ws.bstate = (uint32_t *)(w + off[3]);
     ws.bleft = (uint4 *)(w + off[4]);
     ws.bright = (uint4 *)(w + off[5]);
-    DC_CUDA_TRY(cudaMemsetAsync(ws.bstate, 0, (nchunks + 1) * 4, st));
+    // bstate + ticket and (contiguous, see enc_ws_layout) the look-back descriptors are zeroed in one memset
+    DC_CUDA_TRY(cudaMemsetAsync(w + off[3], 0, (off[7] - off[3]) + nchunks * 8, st));
     const unsigned int sms = (unsigned int)sm_count();
+    {
+        SpWorkspace sp;
+        sp.ticket = (unsigned int *)(w + off[6]);
+        sp.desc = (unsigned long long *)(w + off[7]);
+        sp.bstate = ws.bstate;
+        sp.bleft = ws.bleft;
+        sp.bright = ws.bright;
+        const size_t smem12 = (size_t)kEncWarps * sp_stage_words(kSpTightBits) * 4, smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
+        static bool attr = false;
+        if (!attr) {
+            DC_CUDA_TRY(cudaFuncSetAttribute(encode_single_kernel<kSpTightBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12));
+            DC_CUDA_TRY(cudaFuncSetAttribute(encode_single_kernel<kNarrowBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            attr = true;
+        }
+        {   // the instantiation that does not match the table returns before it takes a ticket
+            LaunchScope ls(DC_K_ENCODE, st);
+            encode_single_kernel<kSpTightBits><<<nruns, kEncThreads, smem12, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
+                                                                                  nruns, (unsigned long long *)d_total_bits, d_status);
+        }
+        {
+            LaunchScope ls(DC_K_ENCODE_MID, st);
+            encode_single_kernel<kNarrowBits><<<nruns, kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
+                                                                                 nruns, (unsigned long long *)d_total_bits, d_status);
+        }
+    }
+    // tables with codes longer than 16 bits: count + scan + 64-bit-entry encode; for all others these three
+    // launches return at once
     {
         LaunchScope ls(DC_K_ENCODE_COUNT, st);
         encode_count_kernel<<<min(nruns, sms * 8u), kEncThreads, 0, st>>>(d_in, n, d_table, ws, nruns, d_status);
@@ -447,11 +767,6 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     {
         LaunchScope ls(DC_K_ENCODE_SCAN, st);
         encode_scan_kernel<<<1, kScanThreads, 0, st>>>(d_table, ws, nruns, (unsigned long long *)d_total_bits);
-    }
-    {
-        LaunchScope ls(DC_K_ENCODE, st);
-        encode_run_kernel<false><<<min(nruns, sms * 32u), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
-                                                                              ws, nruns, d_status);
     }
     {
         // tables with codes longer than 16 bits take the 64-bit-entry instantiation; for all others this

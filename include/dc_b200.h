@@ -105,6 +105,7 @@ enum dc_kernel_id {
     DC_K_ENCODE_COUNT,
     DC_K_ENCODE_SCAN,
     DC_K_ENCODE,
+    DC_K_ENCODE_MID,
     DC_K_ENCODE_WIDE,
     DC_K_DECODE_SYNC,
     DC_K_DECODE_HANDOFF,
