@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         const bool total_lut = bpd != 0 && max_len * bpd <= DC_LUT_BITS;
         const unsigned int dead = (unsigned int)bpd;
         tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : 0u);
-        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | ((count < 2 ? count : 2u) << 22) | (first << 24))
-                                 : (total_lut ? ((dead << 16) | (dead << 24) | 0x80000000u) : 0u);
+        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
+                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
     }
     if (tid == 0) {
         tab->n_ary = n_ary;

@@ -335,8 +335,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_write_kernel(const uint8_t
 
 constexpr int kF_Threads = 256;
 constexpr int kF_Warps = kF_Threads / 32;
-constexpr int kF_SegTiles = 32;                    // 16 KB of bitstream per warp
-constexpr int kF_StageBytes = 32 * kMaxSymPerSub + 32;
+constexpr int kF_SubBits = 256;                    // one lane's subsequence
+constexpr int kF_SubWords = kF_SubBits / 32;
+constexpr int kF_TileVecs = 32 * kF_SubBits / 128; // 16-byte vectors per warp tile (1 KB)
+constexpr int kF_SegTiles = 16;                    // 16 KB of bitstream per warp
 
 struct FastTables {  // shared-memory copy: one multi-symbol LUT + the canonical arrays for the escape path
     uint32_t lut[1 << DC_LUT_BITS];
@@ -379,129 +381,130 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
     return v;
 }
-
-// One lane's subsequence lives in registers: w[0..3] are its 128 bits (big-endian words), w[4] the 32 bits
-// that follow.  Positions are relative to the subsequence; word k is indexed statically.
-// ESC = the table has codes longer than the 12 index bits (entry 0 = escape to the canonical search);
-// otherwise every entry is valid and the loops carry no escape branch.
-//
-// count-only decode of bits [p, lim), lim <= 128; lut = shared address of lut_count
-template <bool ESC>
-__device__ __forceinline__ void sync_decode(const FastTables *t, uint32_t lut, const uint32_t (&w)[5], uint32_t p, uint32_t lim,
-                                            uint32_t *p_end, uint32_t *count) {
-    uint32_t csum = 0;  // bits 16..23 accumulate the symbol count (the field above it only carries upwards)
-    const int multi_lim = (int)lim - DC_LUT_BITS;  // every code inside the 12-bit window starts before lim
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int stop = min(32 * (k + 1) - 1, multi_lim);
-        while ((int)p <= stop) {
-            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
-            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
-            if (ESC && e == 0) {
-                int sym;
-                const int nb = decode_escape(t, x, &sym);
-                p += nb ? nb : t->bpd;
-                csum += nb ? 0x10000u : 0u;
-            } else {
-                p += e & 0xFFu;
-                csum += e;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {  // the last few bits: one code at a time
-        const int stop = min(32 * (k + 1), (int)lim) - 1;
-        while ((int)p <= stop) {
-            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
-            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
-            if (ESC && e == 0) {
-                int sym;
-                const int nb = decode_escape(t, x, &sym);
-                p += nb ? nb : t->bpd;
-                csum += nb ? 0x10000u : 0u;
-            } else {
-                p += e >> 24;
-                csum += (e & 0x00FF0000u) ? 0x10000u : 0u;
-            }
-        }
-    }
-    *p_end = p;
-    *count = (csum >> 16) & 0xFFu;
+__device__ __forceinline__ void ldg_256(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+// c + byte `b` of e (IDP.4A: one instruction instead of shift + mask + add); b is a compile-time constant after unrolling
+__device__ __forceinline__ uint32_t add_byte(uint32_t e, int b, uint32_t c) { return __dp4a(e, 1u << (8 * b), c); }
+// replace byte `b` of word with the low byte of v (PRMT)
+__device__ __forceinline__ uint32_t put_byte(uint32_t word, int b, uint32_t v) {
+    return __byte_perm(word, v, (0x3210u & ~(0xFu << (4 * b))) | (0x4u << (4 * b)));
 }
 
-// decode bits [p, lim) into dst; lut = shared address of lut_pair (two symbols per look-up)
+// One lane's subsequence lives in registers: w[0..7] are its 256 bits (big-endian words), w[8] the 32 bits that
+// follow.  Positions are relative to the subsequence; word k is indexed statically, so the walk is one loop per
+// word.  ESC = the table has codes longer than the 12 index bits (entry 0 = escape to the canonical search).
+//
+// What a walk leaves behind (the lane's record of its current path):
+//   chk   byte k = low 8 bits of the position after the multi-symbol loop of word k
+//   wc    byte k = symbols counted in word k (word 7 also holds the single-code steps at the end)
+//   exit  bits by which the last code overhangs the subsequence
+// A re-walk from a corrected start updates the record word by word and stops at the first word whose end
+// position equals the recorded one: from there on the two paths are the same path, and the rest of the record
+// (and the exit) stands.  The symbol count is the sum of the wc bytes.
+struct SyncRecord {
+    uint32_t chk[2], wc[2], exit;
+    __device__ __forceinline__ uint32_t count() const { return __dp4a(wc[0], 0x01010101u, __dp4a(wc[1], 0x01010101u, 0u)); }
+};
+
 template <bool ESC>
-__device__ __forceinline__ void write_decode(const FastTables *t, uint32_t lut, const uint32_t (&w)[5], uint32_t p, uint32_t lim,
-                                             uint8_t *dst0, uint32_t *p_end, uint32_t *count, bool *corrupt) {
-    uint8_t *dst = dst0;
-    uint32_t flags = 0;
-    const int multi_lim = (int)lim - DC_LUT_BITS;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int stop = min(32 * (k + 1) - 1, multi_lim);
-        while ((int)p <= stop) {
-            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
-            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
-            if (ESC && e == 0) {
-                int sym = 0;
-                const int nb = decode_escape(t, x, &sym);
-                if (nb) *dst++ = (uint8_t)sym; else flags = 0x80000000u;
-                p += nb ? nb : t->bpd;
-            } else {
-                dst[0] = (uint8_t)e;
-                if (e & (2u << 22)) dst[1] = (uint8_t)(e >> 8);
-                p += (e >> 16) & 0x3Fu;
-                dst += (e >> 22) & 3u;
-                flags |= e;
-            }
-        }
+__device__ __forceinline__ void sync_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &csum) {
+    const uint32_t x = __funnelshift_l(lo, hi, p);
+    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    if (ESC && e == 0) {
+        int sym;
+        const int nb = decode_escape(t, x, &sym);
+        p += nb ? nb : t->bpd;
+        csum += nb ? 0x10000u : 0u;
+    } else {
+        p = add_byte(e, 0, p);  // bits of every code inside the window
+        csum += e;              // byte 2 accumulates their number (byte 0 only carries into the unused byte 1)
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int stop = min(32 * (k + 1), (int)lim) - 1;
-        while ((int)p <= stop) {
-            const uint32_t x = __funnelshift_l(w[k + 1], w[k], p);
-            const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
-            if (ESC && e == 0) {
-                int sym = 0;
-                const int nb = decode_escape(t, x, &sym);
-                if (nb) *dst++ = (uint8_t)sym; else flags = 0x80000000u;
-                p += nb ? nb : t->bpd;
-            } else {
-                dst[0] = (uint8_t)e;
-                p += (e >> 24) & 0x3Fu;
-                dst += (e >> 31) ^ 1u;  // a flagged (unused) slot yields no symbol
-                flags |= e;
-            }
-        }
+}
+template <bool ESC>
+__device__ __forceinline__ void sync_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
+    const uint32_t x = __funnelshift_l(lo, hi, p);
+    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    if (ESC && e == 0) {
+        int sym;
+        const int nb = decode_escape(t, x, &sym);
+        p += nb ? nb : t->bpd;
+        scnt += nb ? 1u : 0u;
+    } else {
+        p += e >> 24;                            // the first code only
+        scnt += (e & 0x00FF0000u) ? 1u : 0u;     // an unused slot counts nothing
     }
-    if (flags & 0x80000000u) *corrupt = true;
-    *p_end = p;
-    *count = (uint32_t)(dst - dst0);
+}
+
+// FIRST: walk the whole subsequence and write the record.  !FIRST: re-walk from `p` until the path merges
+// with the recorded one (`merged` lanes take no part; the warp leaves as soon as every lane has merged).
+// FULL: lim == 256 for every lane of the warp (all tiles but the stream's last).
+template <bool ESC, bool FIRST, bool FULL>
+__device__ __forceinline__ void sync_walk(const FastTables *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t p, uint32_t lim,
+                                          bool merged, SyncRecord &r) {
+    const int multi_lim = (int)lim - DC_LUT_BITS;  // every code inside the 12-bit window then starts before lim
+#pragma unroll
+    for (int k = 0; k < kF_SubWords; k++) {
+        if (!FIRST && !__any_sync(0xFFFFFFFFu, !merged)) return;
+        uint32_t csum = 0;
+        if (FIRST || !merged) {
+            const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - DC_LUT_BITS : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
+            while ((int)p <= stop) sync_lookup_multi<ESC>(t, lut, w[k], w[k + 1], p, csum);
+        }
+        if (k == kF_SubWords - 1 && (FIRST || !merged)) {
+            // the last few bits: one code at a time (in a short subsequence they may begin in any word)
+            uint32_t scnt = 0;
+            if (FULL) {
+                while (p < (uint32_t)kF_SubBits) sync_lookup_single<ESC>(t, lut, w[k], w[k + 1], p, scnt);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kF_SubWords; j++) {
+                    const int stop1 = min(32 * (j + 1), (int)lim) - 1;
+                    while ((int)p <= stop1) sync_lookup_single<ESC>(t, lut, w[j], w[j + 1], p, scnt);
+                }
+            }
+            csum += scnt << 16;
+        }
+        const uint32_t cw = csum >> 16;  // byte 2 (byte 3 stays empty: at most 44 symbols per word)
+        if (FIRST) {
+            if (k < 4) { r.chk[0] = put_byte(r.chk[0], k & 3, p); r.wc[0] = put_byte(r.wc[0], k & 3, cw); }
+            else       { r.chk[1] = put_byte(r.chk[1], k & 3, p); r.wc[1] = put_byte(r.wc[1], k & 3, cw); }
+        } else if (!merged) {
+            const uint32_t old = k < 4 ? r.chk[0] : r.chk[1];
+            const uint32_t neu = put_byte(old, k & 3, p);
+            if (k < 4) { r.chk[0] = neu; r.wc[0] = put_byte(r.wc[0], k & 3, cw); }
+            else       { r.chk[1] = neu; r.wc[1] = put_byte(r.wc[1], k & 3, cw); }
+            // same position at the end of word k => same path from here on (the last word always updates the exit)
+            if (k < kF_SubWords - 1 && neu == old) merged = true;
+        }
+        if (k == kF_SubWords - 1 && (FIRST || !merged)) r.exit = p >= (uint32_t)kF_SubBits ? p - kF_SubBits : 0u;
+    }
 }
 
 struct FastWorkspace {
-    uint16_t *sub_info;                              // [nsub] start offset | symbol count << 8
+    uint16_t *sub_info;                              // [nsub] start offset (7 bits) | symbol count << 7
     uint32_t *seg_cnt, *seg_assumed, *seg_exit;      // [nseg]
     unsigned long long *seg_off;                     // [nseg]
     int32_t *mismatch;                               // F2: some segment started on a wrong guess
 };
 
 // A warp's view of its segment: 32-bit positions relative to the segment start, tiles streamed through
-// registers one 16-byte load per lane ahead.
+// registers one 32-byte load per lane ahead.
 struct SegCursor {
-    const uint4 *src;      // this lane's vector of the NEXT tile to fetch
+    const uint4 *src;      // this lane's two vectors of the NEXT tile to fetch
     uint32_t vec_left;     // vectors of the stream from the segment start on (clamped)
     uint32_t bits_left;    // bits of the stream from the segment start on (clamped)
-    uint4 next;            // prefetched vector (little-endian words as loaded)
+    uint4 n0, n1;          // prefetched vectors (little-endian words as loaded)
     uint32_t fetched;      // tiles fetched so far
     int lane;
 
     __device__ __forceinline__ void init(const uint8_t *d_bits, unsigned long long first_tile, unsigned long long nvec,
                                          unsigned long long end, int lane_) {
         lane = lane_;
-        const unsigned long long vec0 = first_tile * 32, bit0 = first_tile * (unsigned long long)(32 * kSubBits);
-        src = (const uint4 *)d_bits + vec0 + lane;
+        const unsigned long long vec0 = first_tile * kF_TileVecs, bit0 = first_tile * (unsigned long long)(32 * kF_SubBits);
+        src = (const uint4 *)d_bits + vec0 + 2 * lane;
         const unsigned long long vl = nvec > vec0 ? nvec - vec0 : 0, bl = end > bit0 ? end - bit0 : 0;
         vec_left = vl > 0x40000000ull ? 0x40000000u : (uint32_t)vl;
         bits_left = bl > 0x40000000ull ? 0x40000000u : (uint32_t)bl;
@@ -509,19 +512,23 @@ struct SegCursor {
         fetch();
     }
     __device__ __forceinline__ void fetch() {
-        next = make_uint4(0, 0, 0, 0);
-        if (fetched * 32 + lane < vec_left) next = ldg_stream(src);
-        src += 32;
+        n0 = make_uint4(0, 0, 0, 0);
+        n1 = make_uint4(0, 0, 0, 0);
+        const uint32_t i = fetched * kF_TileVecs + 2 * lane;
+        if (i + 1 < vec_left) ldg_256(src, n0, n1);
+        else if (i < vec_left) n0 = ldg_stream(src);
+        src += kF_TileVecs;
         fetched++;
     }
     // words of tile number `fetched - 1` for this lane + the 32 bits that follow; prefetches the tile after it
-    __device__ __forceinline__ void take(uint32_t (&w)[5]) {
-        const uint4 cur = next;
+    __device__ __forceinline__ void take(uint32_t (&w)[kF_SubWords + 1]) {
+        const uint4 c0 = n0, c1 = n1;
         fetch();
-        w[0] = bswap32(cur.x); w[1] = bswap32(cur.y); w[2] = bswap32(cur.z); w[3] = bswap32(cur.w);
+        w[0] = bswap32(c0.x); w[1] = bswap32(c0.y); w[2] = bswap32(c0.z); w[3] = bswap32(c0.w);
+        w[4] = bswap32(c1.x); w[5] = bswap32(c1.y); w[6] = bswap32(c1.z); w[7] = bswap32(c1.w);
         const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-        const uint32_t wrap = __shfl_sync(0xFFFFFFFFu, bswap32(next.x), 0);
-        w[4] = lane == 31 ? wrap : right;
+        const uint32_t wrap = __shfl_sync(0xFFFFFFFFu, bswap32(n0.x), 0);
+        w[8] = lane == 31 ? wrap : right;
     }
 };
 
@@ -550,30 +557,32 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_sync_kernel(const uint
         const uint32_t sub_left = nsub - sub0 > 0x40000000ull ? 0x40000000u : (uint32_t)(nsub - sub0);
         uint32_t carry = seg == 0 ? (uint32_t)bit_start : guess, assumed = carry, total = 0;
         for (uint32_t tt = 0; tt < ntile; tt++, info += 32) {
-            uint32_t w[5];
+            uint32_t w[kF_SubWords + 1];
             cur.take(w);
-            const uint32_t sub_bit0 = (tt * 32 + lane) * kSubBits;             // relative to tile0
+            const uint32_t sub_bit0 = (tt * 32 + lane) * kF_SubBits;             // relative to tile0
             const bool active = sub_bit0 < cur.bits_left;
-            const uint32_t lim = active ? min((uint32_t)kSubBits, cur.bits_left - sub_bit0) : 0u;
-            uint32_t start = lane == 0 ? carry : guess, p_end = kSubBits, cnt = 0;
-            if (active) sync_decode<ESC>(&s_t, lut, w, start, lim, &p_end, &cnt);
-            uint32_t my_exit = p_end >= (uint32_t)kSubBits ? p_end - kSubBits : 0u;
+            const uint32_t lim = active ? min((uint32_t)kF_SubBits, cur.bits_left - sub_bit0) : 0u;
+            const bool full = (tt + 1) * 32 * kF_SubBits <= cur.bits_left;       // warp-uniform: every lane has 256 bits
+            uint32_t start = lane == 0 ? carry : guess;
+            SyncRecord r;
+            r.chk[0] = r.chk[1] = r.wc[0] = r.wc[1] = r.exit = 0;
+            if (full) sync_walk<ESC, true, true>(&s_t, lut, w, start, lim, false, r);
+            else if (active) sync_walk<ESC, true, false>(&s_t, lut, w, start, lim, false, r);
             while (true) {
-                uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, my_exit, 1);
+                uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, r.exit, 1);
                 if (lane == 0) ns = start;
                 const bool redo = active && ns != start;
                 if (!__any_sync(0xFFFFFFFFu, redo)) break;
-                if (redo) {
-                    start = ns;
-                    sync_decode<ESC>(&s_t, lut, w, start, lim, &p_end, &cnt);
-                    my_exit = p_end >= (uint32_t)kSubBits ? p_end - kSubBits : 0u;
-                }
+                start = ns;
+                if (full) sync_walk<ESC, false, true>(&s_t, lut, w, start, lim, !redo, r);
+                else sync_walk<ESC, false, false>(&s_t, lut, w, start, lim, !redo, r);
             }
-            carry = __shfl_sync(0xFFFFFFFFu, my_exit, 31);
+            carry = __shfl_sync(0xFFFFFFFFu, r.exit, 31);
             if (tt < (uint32_t)warm) {
                 assumed = carry;
             } else {
-                if (tt * 32 + lane < sub_left) *info = (uint16_t)(start | (cnt << 8));
+                const uint32_t cnt = r.count();
+                if (tt * 32 + lane < sub_left) *info = (uint16_t)(start | (cnt << 7));
                 total += cnt;
             }
         }
@@ -637,12 +646,84 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
 }
 
 // ------------------------------------------------------------------------------------------ F3
+// lut_pair entry: symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | first code's bits << 24 (5 bits)
+//                 | unused-slot flag << 29 | number of symbols (0..2) << 30
+constexpr uint32_t kPairUnused = 1u << 29;
+
+template <bool ESC>
+__device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
+                                                   uint32_t &flags) {
+    const uint32_t x = __funnelshift_l(lo, hi, p);
+    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    if (ESC && e == 0) {
+        int sym = 0;
+        const int nb = decode_escape(t, x, &sym);
+        if (nb) {
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(sym) : "memory");
+            dst++;
+        } else {
+            flags |= kPairUnused;
+        }
+        p += nb ? nb : t->bpd;
+    } else {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(e) : "memory");
+        if ((int)e < 0) asm volatile("st.shared.u8 [%0+1], %1;" ::"r"(dst), "r"(e >> 8) : "memory");  // two symbols
+        p = add_byte(e, 2, p);
+        dst += e >> 30;
+        flags |= e;
+    }
+}
+template <bool ESC>
+__device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
+                                                    uint32_t &flags) {
+    const uint32_t x = __funnelshift_l(lo, hi, p);
+    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    if (ESC && e == 0) {
+        int sym = 0;
+        const int nb = decode_escape(t, x, &sym);
+        if (nb) {
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(sym) : "memory");
+            dst++;
+        } else {
+            flags |= kPairUnused;
+        }
+        p += nb ? nb : t->bpd;
+    } else {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(e) : "memory");
+        p += (e >> 24) & 31u;                 // the first code only
+        dst += (e >> 30) ? 1u : 0u;           // an unused slot yields no symbol
+        flags |= e;
+    }
+}
+
+// decode bits [p, lim) of the lane's subsequence into shared memory at dst (a shared-space byte address)
+template <bool ESC, bool FULL>
+__device__ __forceinline__ void write_walk(const FastTables *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t &p, uint32_t lim,
+                                           uint32_t &dst, uint32_t &flags) {
+    const int multi_lim = (int)lim - DC_LUT_BITS;
+#pragma unroll
+    for (int k = 0; k < kF_SubWords; k++) {
+        const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - DC_LUT_BITS : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
+        while ((int)p <= stop) write_lookup_multi<ESC>(t, lut, w[k], w[k + 1], p, dst, flags);
+    }
+    if (FULL) {
+        while (p < (uint32_t)kF_SubBits) write_lookup_single<ESC>(t, lut, w[kF_SubWords - 1], w[kF_SubWords], p, dst, flags);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kF_SubWords; j++) {
+            const int stop1 = min(32 * (j + 1), (int)lim) - 1;
+            while ((int)p <= stop1) write_lookup_single<ESC>(t, lut, w[j], w[j + 1], p, dst, flags);
+        }
+    }
+}
+
 template <bool ESC>
 __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
                                                                        const dc_huff_table *__restrict__ tab, FastWorkspace ws,
                                                                        unsigned long long nsub, unsigned long long ntiles,
                                                                        unsigned long long nseg, uint8_t *__restrict__ out,
-                                                                       unsigned long long n_out, int32_t *__restrict__ d_status) {
+                                                                       unsigned long long n_out, uint32_t stage_bytes,
+                                                                       int32_t *__restrict__ d_status) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
     FastTables *s_t = (FastTables *)fast_smem;
     uint8_t *s_stage = fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15);
@@ -651,7 +732,8 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
     __syncthreads();
     const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *stage = s_stage + warp * kF_StageBytes;
+    uint8_t *stage = s_stage + (size_t)warp * stage_bytes;  // 16-byte aligned: stage_bytes is a multiple of 16
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
     const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
     bool corrupt = false;
     for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
@@ -666,12 +748,12 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
         unsigned long long ob = ws.seg_off[seg];
         uint32_t next_info = lane < sub_left ? *info : 0u;
         for (uint32_t tt = 0; tt < ntile; tt++) {
-            uint32_t w[5];
+            uint32_t w[kF_SubWords + 1];
             cur.take(w);
             const uint32_t my_info = next_info;
             info += 32;
             next_info = (tt + 1 < ntile && (tt + 1) * 32 + lane < sub_left) ? *info : 0u;
-            const uint32_t start = my_info & 0xFFu, my_cnt = my_info >> 8;
+            const uint32_t start = my_info & 0x7Fu, my_cnt = my_info >> 7;
             uint32_t incl = my_cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -680,18 +762,27 @@ __global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uin
             }
             const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             const uint32_t a = (uint32_t)(((uintptr_t)out + ob) & 15);
-            const uint32_t sub_bit0 = (tt * 32 + lane) * kSubBits;
+            const uint32_t sub_bit0 = (tt * 32 + lane) * kF_SubBits;
+            const bool full = (tt + 1) * 32 * kF_SubBits <= cur.bits_left && (tt + 1) * 32 <= sub_left;  // warp-uniform
+            // a record that cannot be true (more symbols than the staging tile holds) must not be walked
+            const bool sane = a + tile_total + 2 <= stage_bytes;
             __syncwarp();  // the previous tile's copy-out has read the staging buffer
-            if (sub_bit0 < cur.bits_left && tt * 32 + lane < sub_left) {
-                const uint32_t lim = min((uint32_t)kSubBits, cur.bits_left - sub_bit0);
-                uint32_t p_end, c;
-                write_decode<ESC>(s_t, lut, w, start, lim, stage + a + (incl - my_cnt), &p_end, &c, &corrupt);
-                if (c != my_cnt || p_end > cur.bits_left - sub_bit0) corrupt = true;
+            if (!sane) {
+                corrupt = true;
+            } else if (sub_bit0 < cur.bits_left && tt * 32 + lane < sub_left) {
+                const uint32_t lim = min((uint32_t)kF_SubBits, cur.bits_left - sub_bit0);
+                const uint32_t dst0 = stage_addr + a + (incl - my_cnt);
+                uint32_t p = start, dst = dst0, flags = 0;
+                if (full) write_walk<ESC, true>(s_t, lut, w, p, lim, dst, flags);
+                else write_walk<ESC, false>(s_t, lut, w, p, lim, dst, flags);
+                if ((flags & kPairUnused) || dst - dst0 != my_cnt || p > cur.bits_left - sub_bit0) corrupt = true;
             }
             __syncwarp();
             // copy-out: staging byte i <-> out[ob - a + i]; 16-byte words are aligned on both sides
             const uint32_t span = a + tile_total;
-            if (ob + tile_total <= n_out) {
+            if (!sane) {
+                // nothing to copy
+            } else if (ob + tile_total <= n_out) {
                 const uint32_t jfull = span >> 4;  // staging vectors [head, jfull) are complete
                 const uint32_t head = a ? 1u : 0u;
                 for (uint32_t j = head + lane; j < jfull; j += 32)
@@ -715,7 +806,8 @@ static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbi
     const unsigned long long end = bit_start + nbits;
     const unsigned long long nsub = (end + kSubBits - 1) / kSubBits;
     const unsigned long long ntiles = (nsub + kTileSubs - 1) / kTileSubs;        // robust path: 256 subsequences
-    const unsigned long long nwt = (nsub + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;  // fast path
+    const unsigned long long nsubf = (end + kF_SubBits - 1) / kF_SubBits;                              // fast path: 256-bit subsequences
+    const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
     size_t o[12];
@@ -725,7 +817,7 @@ static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbi
     o[3] = take(ntiles * 4);      // tile_exit
     o[4] = take(ntiles * 4);      // tile_cnt
     o[5] = take(ntiles * 8);      // tile_off
-    o[6] = take(nsub * 2);        // fast: sub_info
+    o[6] = take(nwt * 32 * 2);    // fast: sub_info
     o[7] = take(nseg * 4);        // fast: seg_cnt
     o[8] = take(nseg * 4);        // fast: seg_assumed
     o[9] = take(nseg * 4);        // fast: seg_exit
@@ -832,7 +924,8 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     fw.seg_exit = (uint32_t *)(w + off[9]);
     fw.seg_off = (unsigned long long *)(w + off[10]);
     const unsigned long long end = bit_start + nbits;
-    const unsigned long long nwt = (nsub + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
+    const unsigned long long nsubf = (end + kF_SubBits - 1) / kF_SubBits;
+    const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
     const unsigned long long sms = (unsigned long long)sm_count();
 
     // the table must be usable before any bit is interpreted
@@ -850,25 +943,28 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
         const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
-        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsub, nwt, nseg);
-        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsub, nwt, nseg);
+        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg);
+        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg);
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
         decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status);
     }
-    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * kF_StageBytes;
-    static bool attr3 = false;
-    if (!attr3) {
+    // staging tile per warp: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
+    const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
+    const uint32_t stage_bytes = (uint32_t)((32 * (kF_SubBits / min_bits + 2) + 64 + 15) & ~15);
+    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
+    static size_t attr3 = 0;
+    if (smem3 > attr3) {
         DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        attr3 = true;
+        attr3 = smem3;
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
         const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
-        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsub, nwt, nseg, d_out, n_out, d_status);
+        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
     }
     DC_CUDA_TRY(cudaGetLastError());
     // did every segment start on a code boundary?  (blocking read of one flag)

@@ -80,7 +80,8 @@ typedef struct dc_huff_table {
     uint16_t lut[1 << DC_LUT_BITS]; /* index = next 12 bits: nbits << 8 | symbol; 0 = escape (longer/unused) */
     /* multi-symbol tables, same index: every code that lies completely inside the 12 bits.
      *   lut_count: total bits | count << 16 | first code's bits << 24            (0 = escape)
-     *   lut_pair : symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | count(1..2) << 22 | first bits << 24 */
+     *   lut_pair : symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | first code's bits << 24 (5 bits)
+ *              | unused-slot flag << 29 | count(0..2) << 30                                     (0 = escape) */
     uint32_t lut_count[1 << DC_LUT_BITS];
     uint32_t lut_pair[1 << DC_LUT_BITS];
 } dc_huff_table;
