@@ -534,7 +534,7 @@ struct SegCursor {
 
 // ------------------------------------------------------------------------------------------ F1
 template <bool ESC>
-__global__ void __launch_bounds__(kF_Threads) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
+__global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
                                                                       unsigned long long end, const dc_huff_table *__restrict__ tab,
                                                                       FastWorkspace ws, unsigned long long nsub,
                                                                       unsigned long long ntiles, unsigned long long nseg) {
@@ -718,7 +718,7 @@ __device__ __forceinline__ void write_walk(const FastTables *t, uint32_t lut, co
 }
 
 template <bool ESC>
-__global__ void __launch_bounds__(kF_Threads) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
+__global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
                                                                        const dc_huff_table *__restrict__ tab, FastWorkspace ws,
                                                                        unsigned long long nsub, unsigned long long ntiles,
                                                                        unsigned long long nseg, uint8_t *__restrict__ out,
