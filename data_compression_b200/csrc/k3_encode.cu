@@ -536,12 +536,18 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
         const uint32_t e = tab->enc[tid];
         s_enc[tid] = e ? (e | (1u << 31)) : 0u;  // bit 31 = "has a code"
     }
+    uint32_t *stage = sp_smem + warp * kSpStageWords;
+    const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
+    // one ticket = one run.  The 12-bit instantiation (the hot one) is launched with one CTA per run -- measured
+    // faster than a persistent loop, whose extra barrier keeps a CTA's warps in lockstep across runs; the 16-bit one
+    // loops over tickets so that it costs next to nothing when the table is not its own.
+    constexpr bool kPersistent = MAXBITS > kSpTightBits;
+    while (true) {
+    __syncthreads();  // the previous run's s_run / s_bits / s_run_excl have been read by every warp
     if (tid == 0) s_run = atomicAdd(ws.ticket, 1u);
     __syncthreads();
     const unsigned int run = s_run;
     if (run >= nruns) return;
-    uint32_t *stage = sp_smem + warp * kSpStageWords;
-    const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
     const size_t chunk = (size_t)run * kEncWarps + warp;
     const bool have_chunk = chunk < nchunks;  // the last run may be short of chunks; its idle warps still join the barriers
     const size_t chunk_base = chunk * kChunkBytes;
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
         }
     }
     __syncthreads();
-    if (!have_chunk) return;
+    if (!have_chunk) { if (kPersistent) continue; return; }
     unsigned long long excl = s_run_excl;
 #pragma unroll
     for (int w = 0; w < kEncWarps; w++) excl += w < warp ? s_bits[w] : 0u;
@@ -622,12 +628,13 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
     if (last_chunk && lane == 0 && d_total_bits) *d_total_bits = excl + chunk_bits;
     if (stream_bytes_here > out_cap) {
         if (lane == 0) set_status(d_status, DC_ERR_CAPACITY);
+        if (kPersistent) continue;
         return;
     }
     const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this chunk
     const uint32_t r = (uint32_t)(g & 127), t = (uint32_t)(gend & 127);
     const bool shared_first = chunk != 0 && r != 0;           // first word also holds the previous chunk's bits
-    if (v1 == v0 && !last_chunk) return;                       // < 128 bits from 4096 symbols: symbols without codes (reported)
+    if (v1 == v0 && !last_chunk) { if (kPersistent) continue; return; }                   // < 128 bits from 4096 symbols: symbols without codes (reported)
     const uint32_t nvec = (uint32_t)(v1 - v0);
     const uint32_t sbit0 = 32u * kSpZeroPrefix - r;            // staging bit of the first bit of 16-byte word v0
     const uint32_t sbit1 = nvec * 128u + sbit0;                // ... of 16-byte word v1
@@ -682,6 +689,8 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
             stg_stream(dst + j, o);
         }
     }
+    if (!kPersistent) return;
+    }  // next ticket
 }
 
 static size_t enc_ws_layout(size_t n, size_t off[8]) {
@@ -754,7 +763,7 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
         }
         {
             LaunchScope ls(DC_K_ENCODE_MID, st);
-            encode_single_kernel<kNarrowBits><<<nruns, kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
+            encode_single_kernel<kNarrowBits><<<min(nruns, sms * 3u), kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
                                                                                  nruns, (unsigned long long *)d_total_bits, d_status);
         }
     }

@@ -184,6 +184,40 @@ def test_wide_codes_up_to_30_bits(dc, oracle):
     assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
 
 
+@pytest.mark.parametrize("n_ary,depths", [(2, 14), (2, 15), (4, 7), (4, 8), (16, 4)])
+def test_mid_codes_13_to_16_bits(dc, oracle, n_ary, depths):
+    """Tables whose longest code is 13..16 bits: the 16-bit instantiation of the single-pass encoder and the escape
+    path of the decoder (codes longer than the 12 LUT index bits).  Skewed data so the long codes are rare but present,
+    plus one ragged tail."""
+    ln = np.zeros(259, dtype=np.int32)
+    sym = 1
+    for depth in range(1, depths):           # n-1 symbols at each depth, n at the last: a complete code
+        for _ in range(n_ary - 1):
+            if sym < 250:
+                ln[sym] = depth; sym += 1
+    for _ in range(n_ary):
+        if sym < 256:
+            ln[sym] = depths; sym += 1
+    bpd = oracle.bits_per_digit(n_ary)
+    el, ev, st = oracle.convert_lengths_to_encode_table(ln, n_ary)
+    assert st == 0
+    table = dc.huff_table_from_lengths(_dev(ln), n_ary)
+    t = table.download()
+    assert t.status == 0 and 12 < t.max_bits <= 16, t.max_bits
+    rng = np.random.default_rng(depths * 31 + n_ary)
+    used = np.flatnonzero(ln)
+    w = 0.5 ** (ln[used] * bpd / 2.0)
+    for size in (200003, 4096 * 8 * 3 + 17):
+        data = rng.choice(used, size=size, p=w / w.sum()).astype(np.uint8)
+        res = dc.huff_encode(_dev(data), table, out=torch.empty(data.size * 2 + 64, dtype=torch.uint8, device="cuda"))
+        nbits = res.bits()
+        want, wbits = oracle.pack(data, el, ev, bpd)
+        assert nbits == wbits
+        assert np.array_equal(res.payload[: (nbits + 7) // 8].cpu().numpy(), want)
+        out, status = dc.huff_decode(res.payload, nbits, table, data.size)
+        assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
+
+
 def test_degenerate_alphabets(dc, oracle):
     # one distinct symbol: 1-bit codes (binary), 128 symbols per 128-bit subsequence
     for n_ary in PACKABLE:
