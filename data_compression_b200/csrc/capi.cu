@@ -325,10 +325,16 @@ extern "C" int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bi
     dc_huff_table *d_tab = (dc_huff_table *)g_arena.take(sizeof(dc_huff_table));
     int32_t *d_len = (int32_t *)g_arena.take(DC_NSLOTS * 4);
     int32_t *d_status = (int32_t *)g_arena.take(4);
-    if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_bits, payload, nbytes, cudaMemcpyHostToDevice, 0));
     DC_CUDA_TRY(cudaMemcpyAsync(d_len, lens, DC_NSLOTS * 4, cudaMemcpyHostToDevice, 0));
     rc = dc_huff_table_from_lengths(d_len, compressed_symbols, d_tab, nullptr);
     if (rc != DC_OK) return rc;
+    // large streams: chunked, with the upload, the decode and the download overlapping
+    rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status);
+    if (rc <= 0) return rc;
+    if (rc != 1 && nbytes) return DC_ERR_CUDA;
+    // one-shot path.  (After a pipelined attempt that fell back the payload is on the device already; copying it
+    // again keeps this path independent of that.)
+    if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_bits, payload, nbytes, cudaMemcpyHostToDevice, 0));
     rc = dc_huff_decode(d_bits, 0, total_bits, d_tab, d_out, n_out, d_status, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
     int32_t st = 0;

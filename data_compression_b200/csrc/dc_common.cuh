@@ -45,6 +45,11 @@ struct TableRaw {
 int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
                  TableRaw raw, cudaStream_t st);
 
+// pipelined form of dc_host_huff_decompress (k4_decode.cu): DC_OK / negative dc_status / +1 = use the one-shot path
+int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
+                              uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
+                              int32_t *d_status);
+
 // ---------------------------------------------------------------- device helpers
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }

@@ -598,9 +598,11 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
             while (true) {
                 const long long idx = base - lane;
                 unsigned long long d;
-                do {
+                while (true) {
                     d = idx >= 0 ? ld_relaxed_u64(ws.desc + idx) : kDescInclusive;
-                } while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0));
+                    if (!__any_sync(0xFFFFFFFFu, (d >> 62) == 0)) break;
+                    __nanosleep(200);  // back off: hundreds of CTAs poll the same few lines that their predecessors must write
+                }
                 const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
                 const int stop = incl_mask ? __ffs(incl_mask) - 1 : 32;  // nearest predecessor with an inclusive prefix
                 unsigned long long part = lane <= stop ? (d & kDescValue) : 0ull;

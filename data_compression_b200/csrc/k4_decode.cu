@@ -24,6 +24,8 @@
 // advance by one digit and produce no symbol -- and are reported as DC_ERR_CORRUPT on the true path.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "dc_common.cuh"
 
 namespace dc {
@@ -483,6 +485,13 @@ __device__ __forceinline__ void sync_walk(const FastTables *t, uint32_t lut, con
     }
 }
 
+// Decoding a stream in several launches (a chunk of the bitstream each, in order): what one chunk hands to the next.
+struct DecodeChain {
+    unsigned long long base;   // symbols decoded by the chunks before this one = output offset of this chunk
+    uint32_t next_start;       // bit offset, relative to the first bit of the next chunk, of that chunk's first code
+    int32_t mismatch;          // sticky: some segment of some chunk started on a wrong guess
+};
+
 struct FastWorkspace {
     uint16_t *sub_info;                              // [nsub] start offset (7 bits) | symbol count << 7
     uint32_t *seg_cnt, *seg_assumed, *seg_exit;      // [nseg]
@@ -537,10 +546,12 @@ template <bool ESC>
 __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
                                                                       unsigned long long end, const dc_huff_table *__restrict__ tab,
                                                                       FastWorkspace ws, unsigned long long nsub,
-                                                                      unsigned long long ntiles, unsigned long long nseg) {
+                                                                      unsigned long long ntiles, unsigned long long nseg,
+                                                                      const DecodeChain *__restrict__ chain) {
     __shared__ FastTables s_t;
     load_fast_tables(&s_t, tab, tab->lut_count);
     __syncthreads();
+    if (chain) bit_start = chain->next_start;  // a later chunk of a stream: its first code starts where the previous chunk's last one ended
     const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
@@ -598,12 +609,13 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
 
 // ------------------------------------------------------------------------------------------ F2
 __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
-                                                                int32_t *__restrict__ d_status) {
+                                                                int32_t *__restrict__ d_status, DecodeChain *__restrict__ chain,
+                                                                int last_chunk) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_bad = 0; }
+    if (tid == 0) { s_carry = chain ? chain->base : 0ull; s_bad = 0; }
     __syncthreads();
     constexpr int kItems = 4;
     for (unsigned long long base = 0; base < nseg; base += 1024 * kItems) {
@@ -641,7 +653,12 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
     }
     if (tid == 0) {
         *ws.mismatch = s_bad;
-        if (!s_bad && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
+        if (chain) {
+            chain->base = s_carry;
+            chain->next_start = ws.seg_exit[nseg - 1];
+            chain->mismatch |= s_bad;
+        }
+        if (!s_bad && last_chunk && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
     }
 }
 
@@ -877,6 +894,47 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
     return cuda_status(cudaGetLastError());
 }
 
+
+// staging tile per warp of the write kernel: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
+static uint32_t fast_stage_bytes(const int32_t *tmeta) {
+    const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
+    return (uint32_t)((32 * (kF_SubBits / min_bits + 2) + 64 + 15) & ~15);
+}
+
+// F1 + F2 + F3 over `ntiles` warp tiles of the bitstream at d_bits (`end` = end of the STREAM in bits from d_bits; a chunk that
+// is not the last one may read a few bytes of the next chunk).  chain == nullptr: a whole stream that starts at bit_start.
+static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
+                       unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out,
+                       size_t n_out, int32_t *d_status, bool esc, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
+                       cudaStream_t st) {
+    const unsigned long long sms = (unsigned long long)sm_count();
+    const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
+        const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
+        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain);
+        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain);
+    }
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk);
+    }
+    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
+    static size_t attr3 = 0;
+    if (smem3 > attr3) {
+        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        attr3 = smem3;
+    }
+    {
+        LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
+        const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
+        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+    }
+    return cuda_status(cudaGetLastError());
+}
+
 // test hook: 1 = always take the robust path, 2 = pretend the fast path's guess failed after running it
 static int g_decode_force = -1;
 static int decode_force_mode() {
@@ -939,34 +997,11 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     const int force = decode_force_mode();
     if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
-    const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    const uint32_t stage_bytes = fast_stage_bytes(tmeta);
     {
-        LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
-        const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
-        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg);
-        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg);
+        const int rc = launch_fast(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, nullptr, 1, st);
+        if (rc != DC_OK) return rc;
     }
-    {
-        LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status);
-    }
-    // staging tile per warp: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
-    const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
-    const uint32_t stage_bytes = (uint32_t)((32 * (kF_SubBits / min_bits + 2) + 64 + 15) & ~15);
-    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
-    static size_t attr3 = 0;
-    if (smem3 > attr3) {
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        attr3 = smem3;
-    }
-    {
-        LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
-        const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
-        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
-    }
-    DC_CUDA_TRY(cudaGetLastError());
     // did every segment start on a code boundary?  (blocking read of one flag)
     int32_t mismatch = 0;
     DC_CUDA_TRY(cudaMemcpyAsync(&mismatch, fw.mismatch, sizeof mismatch, cudaMemcpyDeviceToHost, st));
@@ -977,3 +1012,138 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     }
     return DC_OK;
 }
+
+// ================================================================================================ pipelined host decompress
+// dc_host_huff_decompress on a large stream: the payload goes up in 32 MiB chunks, each chunk is decoded as soon as the
+// chunk after it has arrived (its last code may cross into it) and its symbols go back down while the next chunks are
+// still coming up, so the two PCIe directions overlap.  Chunks are chained on the device (DecodeChain: first code's bit
+// offset, output offset); the host reads the 16-byte chain state after every chunk's scan only to learn how many bytes
+// to copy back.  Returns DC_OK, a negative dc_status, or +1 = "not taken, use the one-shot path" (small streams, test
+// hooks, or a stream that did not self-synchronise -- everything is then on the device already).
+namespace dc {
+
+constexpr unsigned long long kPipeChunkTiles = 32768;  // 32 MiB of bitstream; a multiple of kF_SegTiles
+
+struct PipeState {
+    cudaStream_t up = nullptr, cp = nullptr, dn = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_f2, ev_f3;
+    DecodeChain *h_ring = nullptr;
+    size_t ring = 0;
+    int ensure(size_t k) {
+        if (!up) {
+            DC_CUDA_TRY(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+            DC_CUDA_TRY(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+            DC_CUDA_TRY(cudaStreamCreateWithFlags(&dn, cudaStreamNonBlocking));
+        }
+        while (ev_up.size() < k) {
+            cudaEvent_t a, b, c;
+            DC_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            DC_CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            DC_CUDA_TRY(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+            ev_up.push_back(a); ev_f2.push_back(b); ev_f3.push_back(c);
+        }
+        if (ring < k) {
+            if (h_ring) cudaFreeHost(h_ring);
+            h_ring = nullptr; ring = 0;
+            DC_CUDA_TRY(cudaMallocHost((void **)&h_ring, k * sizeof(DecodeChain)));
+            ring = k;
+        }
+        return DC_OK;
+    }
+};
+static PipeState g_pipe;
+
+int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
+                              uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
+                              int32_t *d_status) {
+    const size_t nbytes = (size_t)((total_bits + 7) / 8);
+    const unsigned long long chunk_bytes = kPipeChunkTiles * (kF_TileVecs * 16ull);
+    const size_t nchunk = (size_t)((nbytes + chunk_bytes - 1) / chunk_bytes);
+    if (nchunk < 3 || decode_force_mode() != 0) return 1;
+    size_t off[12];
+    unsigned long long nsub, ntiles;
+    if (workspace_bytes < dec_ws_layout(0, total_bits, off, &nsub, &ntiles)) return DC_ERR_CAPACITY;
+    if (g_pipe.ensure(nchunk) != DC_OK) return DC_ERR_CUDA;
+    char *w = (char *)d_workspace;
+    FastWorkspace fw;
+    fw.mismatch = (int32_t *)(w + 16);
+    fw.sub_info = (uint16_t *)(w + off[6]);
+    fw.seg_cnt = (uint32_t *)(w + off[7]);
+    fw.seg_assumed = (uint32_t *)(w + off[8]);
+    fw.seg_exit = (uint32_t *)(w + off[9]);
+    fw.seg_off = (unsigned long long *)(w + off[10]);
+    DecodeChain *d_chain = (DecodeChain *)(w + 32);
+
+    // the table (built on the legacy stream by the caller) must be usable before any bit is interpreted
+    int32_t tmeta[10];
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, 0));
+    DC_CUDA_TRY(cudaStreamSynchronize(0));
+    if (tmeta[8] != DC_OK) return tmeta[8];
+    if (tmeta[1] == 0) return DC_ERR_RADIX;
+    const bool esc = tmeta[7] > DC_LUT_BITS;
+    const uint32_t stage_bytes = fast_stage_bytes(tmeta);
+
+    cudaStream_t up = g_pipe.up, cp = g_pipe.cp, dn = g_pipe.dn;
+    for (size_t k = 0; k < nchunk; k++) {
+        const size_t o = (size_t)(k * chunk_bytes), len = (size_t)min((unsigned long long)(nbytes - o), chunk_bytes);
+        DC_CUDA_TRY(cudaMemcpyAsync(d_bits + o, h_payload + o, len, cudaMemcpyHostToDevice, up));
+        DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_up[k], up));
+    }
+    DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), cp));
+    DC_CUDA_TRY(cudaMemsetAsync(d_chain, 0, sizeof(DecodeChain), cp));  // base 0, first code at bit 0, no mismatch
+    unsigned long long base = 0;
+    bool fallback = false;
+    for (size_t k = 0; k < nchunk; k++) {
+        const unsigned long long bit0 = k * chunk_bytes * 8ull;
+        const unsigned long long end_rel = total_bits - bit0;                    // stream end, from this chunk's first bit
+        const unsigned long long bits_here = min(end_rel, chunk_bytes * 8ull);   // bits that belong to this chunk
+        const unsigned long long nsubf = (bits_here + kF_SubBits - 1) / kF_SubBits;
+        const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
+        const int last = k + 1 == nchunk;
+        DC_CUDA_TRY(cudaStreamWaitEvent(cp, g_pipe.ev_up[last ? k : k + 1], 0));
+        // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
+        const unsigned long long sms = (unsigned long long)sm_count(), want = (nseg + kF_Warps - 1) / kF_Warps;
+        const uint8_t *bits_k = d_bits + k * chunk_bytes;
+        {
+            LaunchScope ls(DC_K_DECODE_FAST_SYNC, cp);
+            const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
+            if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, cp>>>(bits_k, 0, end_rel, d_table, fw, nsubf, nwt, nseg, d_chain);
+            else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, cp>>>(bits_k, 0, end_rel, d_table, fw, nsubf, nwt, nseg, d_chain);
+        }
+        {
+            LaunchScope ls(DC_K_DECODE_FAST_SCAN, cp);
+            decode_fast_scan_kernel<<<1, 1024, 0, cp>>>(fw, nseg, n_out, d_status, d_chain, last);
+        }
+        DC_CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_ring[k], d_chain, sizeof(DecodeChain), cudaMemcpyDeviceToHost, cp));
+        DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f2[k], cp));
+        {
+            const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
+            DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            LaunchScope ls(DC_K_DECODE_FAST_WRITE, cp);
+            const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
+            if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, cp>>>(bits_k, end_rel, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+            else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, cp>>>(bits_k, end_rel, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+        }
+        DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f3[k], cp));
+        DC_CUDA_TRY(cudaGetLastError());
+        DC_CUDA_TRY(cudaEventSynchronize(g_pipe.ev_f2[k]));  // how many symbols did this chunk hold?
+        const DecodeChain c = g_pipe.h_ring[k];
+        if (c.mismatch) { fallback = true; break; }
+        const unsigned long long hi = min((unsigned long long)n_out, c.base);
+        if (hi > base) {
+            DC_CUDA_TRY(cudaStreamWaitEvent(dn, g_pipe.ev_f3[k], 0));
+            DC_CUDA_TRY(cudaMemcpyAsync(h_out + base, d_out + base, (size_t)(hi - base), cudaMemcpyDeviceToHost, dn));
+        }
+        base = c.base > base ? c.base : base;
+    }
+    DC_CUDA_TRY(cudaStreamSynchronize(up));
+    DC_CUDA_TRY(cudaStreamSynchronize(cp));
+    DC_CUDA_TRY(cudaStreamSynchronize(dn));
+    if (fallback) return 1;
+    int32_t stt = 0;
+    DC_CUDA_TRY(cudaMemcpy(&stt, d_status, sizeof stt, cudaMemcpyDeviceToHost));
+    return stt;
+}
+
+}  // namespace dc

@@ -73,6 +73,35 @@ def test_compress_decompress_host(dc, oracle):
         assert np.array_equal(dc.hostapi.huff_decompress(payload, bits, lengths, n, data.size), data)
 
 
+@pytest.mark.parametrize("n_ary", [2, 16])
+def test_decompress_host_pipelined(dc, oracle, n_ary):
+    """A stream of more than three 32 MiB chunks takes the chunked, overlapped path of dc_host_huff_decompress: the
+    chunks are chained on the device (first-code offset, output offset) and must reassemble the input exactly; a
+    wrong symbol count and a truncated stream are still reported."""
+    import torch
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_bytes_spec()
+    n = 150 * (1 << 20) + 12345
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(d, 991, synth.device_thresholds(thr, "cuda"), base)
+    data = d.cpu().numpy()
+    del d
+    payload, bits, lengths = dc.hostapi.huff_compress(data, n_ary)
+    assert payload.size > 3 * (32 << 20)
+    # spot-check the payload against the oracle on the first MiB of symbols (same table, prefix of the stream)
+    ln, el, ev, st = oracle.build_tables(oracle.histogram_u8(data), n_ary)
+    assert np.array_equal(lengths, ln)
+    want, wbits = oracle.pack(data[: 1 << 20], el, ev, oracle.bits_per_digit(n_ary))
+    assert np.array_equal(payload[: wbits // 8], want[: wbits // 8])
+    back = dc.hostapi.huff_decompress(payload, bits, lengths, n_ary, n)
+    assert np.array_equal(back, data)
+    with pytest.raises(dc.DcError) as e:
+        dc.hostapi.huff_decompress(payload, bits, lengths, n_ary, n - 1)
+    assert e.value.status in (dc.DC_ERR_CAPACITY, dc.DC_ERR_CORRUPT)
+    with pytest.raises(dc.DcError):
+        dc.hostapi.huff_decompress(payload, bits - 4099, lengths, n_ary, n)
+
+
 def test_nybble_host(dc, oracle):
     for c in load_golden("nybble.json")["write_nybble"]:
         s = np.array(c["symbols"], dtype=np.uint8)
