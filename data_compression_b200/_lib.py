@@ -67,6 +67,9 @@ SYMBOLS = [
     ("dc_huff_decode", _i, [_vp, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_nybble_pack", _i, [_vp, _sz, _vp, _vp, _vp]),
     ("dc_nybble_unpack", _i, [_vp, _sz, _vp, _vp]),
+    ("dc_nybble_text_workspace_bytes", _sz, [_sz]),
+    ("dc_nybble_text_compress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    ("dc_nybble_text_decompress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     ("dc_synth_fill", _i, [_vp, _sz, _u64, _vp, _i, _i, _vp]),
     ("dc_host_histogram", _i, [C.c_char_p, _i, _ip]),
     ("dc_host_histogram_u8", _i, [_vp, _sz, _u64p]),
@@ -76,6 +79,8 @@ SYMBOLS = [
     ("dc_host_represent_items_with_codes", _i, [_i, _ip, _i, _i, _i, _vp, _i, _vp, _u64p]),
     ("dc_host_huff_compress", C.c_longlong, [_vp, _sz, _i, _vp, _sz, _ip, _u64p]),
     ("dc_host_huff_decompress", _i, [_vp, _u64, _ip, _i, _vp, _sz]),
+    ("dc_host_compress_bytestring", C.c_longlong, [C.c_char_p, _vp, _i]),
+    ("dc_host_decompress_bytestring", C.c_longlong, [C.c_char_p, _vp, _i]),
     ("dc_host_nybble_pack", _i, [_vp, _sz, _vp]),
     ("dc_host_nybble_unpack", _i, [_vp, _sz, _vp]),
 ]

@@ -179,6 +179,29 @@ def nybble_unpack(packed: torch.Tensor, n_sym: int, out: torch.Tensor | None = N
     return out
 
 
+def _nybble_text(fn_name: str, src: torch.Tensor, cap: int):
+    _need_cuda(src, "src")
+    n = src.numel()
+    out = torch.empty(cap + 16, dtype=torch.uint8, device=src.device)
+    ws = torch.empty(max(lib().dc_nybble_text_workspace_bytes(n), 16), dtype=torch.uint8, device=src.device)
+    out_len = torch.empty(1, dtype=torch.int64, device=src.device)
+    status = torch.empty(1, dtype=torch.int32, device=src.device)
+    check(getattr(lib(), fn_name)(src.data_ptr(), n, out.data_ptr(), cap, out_len.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), _stream()), fn_name)
+    return out, out_len, status
+
+
+def nybble_text_compress(src: torch.Tensor):
+    """compress_bytestring(src, dst, false) nybble_compression.c:887 (static " etaoins" table) on a CUDA byte tensor.
+    Returns (buffer, 1 x int64 length, 1 x int32 status); nothing blocks."""
+    return _nybble_text("dc_nybble_text_compress", src, src.numel() + 2)
+
+
+def nybble_text_decompress(src: torch.Tensor):
+    """decompress_bytestring(src, dst, false) nybble_compression.c:734.  Returns (buffer, length, status)."""
+    return _nybble_text("dc_nybble_text_decompress", src, 2 * src.numel() + 2)
+
+
 def synth_fill(out: torch.Tensor, seed: int, thresholds: torch.Tensor, value_base: int) -> torch.Tensor:
     """Fill `out` (uint8, CUDA) with the counter-based synthetic stream (see synth.py)."""
     _need_cuda(out, "out")

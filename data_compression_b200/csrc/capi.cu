@@ -136,7 +136,7 @@ extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
 }
 extern "C" const char *dc_profile_kernel_name(int id) {
     static const char *names[DC_K_COUNT] = {"histogram", "table", "bits_for_hist", "encode_count", "encode_scan", "encode", "encode_mid", "encode_wide", "decode_sync", "decode_handoff",
-                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "synth"};
+                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "synth"};
     return id >= 0 && id < DC_K_COUNT ? names[id] : "?";
 }
 
@@ -375,4 +375,38 @@ extern "C" int dc_host_nybble_unpack(const uint8_t *packed, size_t n_sym, uint8_
     if (n_sym) DC_CUDA_TRY(cudaMemcpyAsync(sym, d_sym, n_sym, cudaMemcpyDeviceToHost, 0));
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ static-table nybble compressor
+
+static long long host_text(const char *source, char *dest, int modify, bool compress) {
+    if (!source || !dest || modify) return DC_ERR_ARG;  // the adaptive (move-to-front) table is a serial chain: not offloaded
+    const size_t n = strlen(source);
+    const size_t cap = compress ? n + 2 : 2 * n + 2, ws_bytes = dc_nybble_text_workspace_bytes(n);
+    int rc = g_arena.reserve(Arena::pad(n + 16) + Arena::pad(cap + 16) + Arena::pad(ws_bytes) + 512);
+    if (rc != DC_OK) return rc;
+    uint8_t *d_src = (uint8_t *)g_arena.take(n + 16), *d_dst = (uint8_t *)g_arena.take(cap + 16);
+    void *d_ws = g_arena.take(ws_bytes);
+    uint64_t *d_len = (uint64_t *)g_arena.take(8);
+    int32_t *d_status = (int32_t *)g_arena.take(4);
+    if (n) DC_CUDA_TRY(cudaMemcpyAsync(d_src, source, n, cudaMemcpyHostToDevice, 0));
+    rc = compress ? dc_nybble_text_compress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr)
+                  : dc_nybble_text_decompress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr);
+    if (rc != DC_OK) return rc;
+    uint64_t len = 0;
+    int32_t st = 0;
+    DC_CUDA_TRY(cudaMemcpyAsync(&len, d_len, 8, cudaMemcpyDeviceToHost, 0));
+    DC_CUDA_TRY(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, 0));
+    DC_CUDA_TRY(cudaStreamSynchronize(0));
+    if (st != DC_OK) return st;
+    if (len) DC_CUDA_TRY(cudaMemcpy(dest, d_dst, (size_t)len, cudaMemcpyDeviceToHost));
+    dest[len] = '\0';
+    return (long long)len;
+}
+
+extern "C" long long dc_host_compress_bytestring(const char *source, char *dest, int modify) {
+    return host_text(source, dest, modify, true);
+}
+extern "C" long long dc_host_decompress_bytestring(const char *source, char *dest, int modify) {
+    return host_text(source, dest, modify, false);
 }

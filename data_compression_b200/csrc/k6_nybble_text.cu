@@ -1,0 +1,464 @@
+// k6_nybble_text.cu -- K6: the static-table nybble compressor / decompressor.
+//
+// Replaces compress_bytestring(src, dst, false) (nybble_compression.c:887-1038, with compress_byte_index :819-884)
+// and decompress_bytestring(src, dst, false) (:734-817, with decompress_nybble :643-663).  With modify == false the
+// 16 contexts all hold " etaoins" (initialize_dictionary :546-562) and never change, so the coder is a two-state
+// transducer over the input and both directions are exact parallel scans:
+//
+//   compress    state q = parity of the run of table hits that ends just before the byte.
+//               hit : q == 1 -> emit the pair byte ((8|i_prev) << 4) | (8|i), q = 0;   q == 0 -> q = 1
+//               miss: q == 1 -> emit the previous byte as a literal (the reference rewrites its half-written
+//                               byte, :855-857), then this byte;  q == 0 -> emit this byte;   q = 0
+//               end : q == 1 -> emit the last byte as a literal (:1000-1009)
+//               stream = 0xAF, src[0], body, NUL (:903-905); if that is not shorter than the source: ' ' + source (:1018-1037)
+//   decompress  units are nibbles, high first (:767-773); state q = 1 inside a literal.
+//               nibble with bit 3: q == 0 -> letter[nibble & 7], q == 1 -> literal ((prev & 7) << 4) + nibble;   q = 0
+//               nibble without  : q == 0 -> q = 1 (first half of a literal), q == 1 -> literal as above, q = 0
+//               end : q == 1 -> the dangling half literal is completed with a zero nibble
+//               type byte 0xAF as above, ' ' = copy the rest (:799-805), anything else = copy everything (:806-812)
+//
+// A block of units is summarised by its transfer function over the two states: symbols emitted and next state, for
+// each entry state.  Functions compose associatively, so: S1 one function per 8 KB tile, S2 a one-CTA scan of the
+// tile functions (exclusive output offset and entry state of every tile, total length, the fall-back decision),
+// S3 every tile re-derives its threads' entry states, emits into shared memory and copies out with aligned
+// 16-byte stores.  HBM traffic 2N + C.
+#include "dc_common.cuh"
+
+namespace dc {
+
+constexpr int kTxThreads = 256;
+constexpr int kTxVec = 2;                      // 16-byte vectors per thread
+constexpr int kTxPer = 16 * kTxVec;            // input bytes per thread
+constexpr int kTxTile = kTxThreads * kTxPer;   // 8 KB per CTA step
+constexpr int kTxWarps = kTxThreads / 32;
+
+// ---- transfer functions, packed: e0 [0,15) | e1 [15,30) | next state from 0 (bit 30) | next state from 1 (bit 31)
+__device__ __forceinline__ uint32_t fn_pack(uint32_t e0, uint32_t e1, uint32_t q0, uint32_t q1) {
+    return e0 | (e1 << 15) | (q0 << 30) | (q1 << 31);
+}
+__device__ __forceinline__ uint32_t fn_emit(uint32_t f, uint32_t q) { return (f >> (15 * q)) & 0x7FFFu; }
+__device__ __forceinline__ uint32_t fn_next(uint32_t f, uint32_t q) { return (f >> (30 + q)) & 1u; }
+__device__ __forceinline__ uint32_t fn_compose(uint32_t a, uint32_t b) {  // a, then b
+    const uint32_t a0 = fn_next(a, 0), a1 = fn_next(a, 1);
+    return fn_pack(fn_emit(a, 0) + fn_emit(b, a0), fn_emit(a, 1) + fn_emit(b, a1), fn_next(b, a0), fn_next(b, a1));
+}
+constexpr uint32_t kFnIdentity = 1u << 31;  // emits nothing, keeps the state
+
+// " etaoins" (initialize_dictionary :552-559).  letter_of: byte i of the eight letters (one PRMT).
+// The inverse is a 128-entry table in shared memory (8 = not a letter), filled by fill_letter_table().
+__device__ __forceinline__ uint32_t letter_of(uint32_t i) { return __byte_perm(0x61746520u, 0x736e696fu, i & 7u) & 0xFFu; }
+__device__ __forceinline__ void fill_letter_table(uint8_t *lut) {
+    for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+        uint32_t idx = 8;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++)
+            if (letter_of(i) == (uint32_t)c) idx = i;
+        lut[c] = (uint8_t)idx;
+    }
+}
+
+struct TxWorkspace {
+    uint32_t *tile_fn;                 // [ntiles]  S1
+    unsigned long long *tile_off;      // [ntiles]  S2: symbols emitted by the tiles before this one
+    uint8_t *tile_q;                   // [ntiles]  S2: entry state
+    unsigned long long *out_len;       // [1] bytes of the output (without the NUL)
+    int32_t *mode;                     // [1] compress: 1 = fall back to ' ' + raw; decompress: 0 = 0xAF, 1 = ' ', 2 = other; -1 = do nothing
+};
+
+// bytes [base, base + 16) of the input as 16 values (0 beyond n); prev = byte base - 1 (0 at the start)
+__device__ __forceinline__ void load_block(const uint8_t *__restrict__ in, size_t n, size_t base, uint32_t (&c)[kTxPer], uint32_t &prev) {
+    if (base + kTxPer <= n && ((uintptr_t)(in + base) & 15) == 0) {
+        uint4 v[kTxVec];
+#pragma unroll
+        for (int j = 0; j < kTxVec; j++) v[j] = ldg_stream((const uint4 *)(in + base) + j);
+#pragma unroll
+        for (int j = 0; j < kTxVec; j++) {
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) c[16 * j + k] = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kTxPer; k++) c[k] = base + k < n ? in[base + k] : 0u;
+    }
+    prev = base > 0 && base - 1 < n ? in[base - 1] : 0u;
+}
+
+// transfer function of the thread's block.  COMPRESS: units are bytes (byte 0 of the stream is the verbatim first
+// byte: it emits nothing and leaves q = 0).  else: units are the two nibbles of every byte from index 2 on.
+template <bool COMPRESS, bool FULL>
+__device__ __forceinline__ uint32_t block_fn_impl(const uint8_t *lut, const uint32_t (&c)[kTxPer], int valid, int skip, bool &bad) {
+    uint32_t e0 = 0, e1 = 0, q0 = 0, q1 = 1;
+#pragma unroll
+    for (int k = 0; k < kTxPer; k++) {
+        if (!FULL && k >= valid) break;
+        if (!FULL && k < skip) { q0 = q1 = 0; e0 = e1 = 0; continue; }
+        if (COMPRESS) {
+            bad |= c[k] == 0 || c[k] >= 0x80u;  // assert( source[i] < 0x80 ) :910; 0x00 would end the C string
+            const uint32_t hit = lut[c[k] & 0x7Fu] < 8 ? 1u : 0u;
+            e0 += hit ? q0 : 1 + q0;
+            e1 += hit ? q1 : 1 + q1;
+            q0 = hit & (q0 ^ 1u);
+            q1 = hit & (q1 ^ 1u);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t x = h == 0 ? c[k] >> 4 : c[k] & 0xFu, hb = x >> 3;
+                e0 += hb | q0;
+                e1 += hb | q1;
+                q0 = (hb | q0) ^ 1u;
+                q1 = (hb | q1) ^ 1u;
+            }
+        }
+    }
+    return fn_pack(e0, e1, q0, q1);
+}
+template <bool COMPRESS>
+__device__ __forceinline__ uint32_t block_fn(const uint8_t *lut, const uint32_t (&c)[kTxPer], size_t base, size_t n, bool &bad) {
+    // 32-bit bookkeeping: how many of the block's bytes exist, and how many leading bytes are the stream's header
+    const int valid = (int)min((size_t)kTxPer, n - base);
+    const int skip = base == 0 ? (COMPRESS ? 1 : 2) : 0;
+    if (valid == kTxPer && skip == 0) return block_fn_impl<COMPRESS, true>(lut, c, valid, skip, bad);
+    return block_fn_impl<COMPRESS, false>(lut, c, valid, skip, bad);
+}
+
+// ------------------------------------------------------------------------------------------ S1
+template <bool COMPRESS>
+__global__ void __launch_bounds__(kTxThreads) tx_summary_kernel(const uint8_t *__restrict__ in, size_t n, TxWorkspace ws, size_t ntiles,
+                                                                int32_t *__restrict__ d_status) {
+    __shared__ uint32_t s_warp[kTxWarps];
+    __shared__ uint8_t s_lut[128];
+    fill_letter_table(s_lut);
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool bad = false;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t base = tile * kTxTile + (size_t)tid * kTxPer;
+        uint32_t f = kFnIdentity;
+        if (base < n) {
+            uint32_t c[kTxPer], prev;
+            load_block(in, n, base, c, prev);
+            f = block_fn<COMPRESS>(s_lut, c, base, n, bad);
+        }
+        // ordered reduction over the warp, then over the CTA's warps
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t g = __shfl_down_sync(0xFFFFFFFFu, f, d);
+            if ((lane & (2 * d - 1)) == 0) f = fn_compose(f, g);
+        }
+        if (lane == 0) s_warp[warp] = f;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = s_warp[0];
+#pragma unroll
+            for (int w = 1; w < kTxWarps; w++) t = fn_compose(t, s_warp[w]);
+            ws.tile_fn[tile] = t;
+        }
+        __syncthreads();
+    }
+    if (COMPRESS && bad) set_status(d_status, DC_ERR_SYMBOL);
+}
+
+// ------------------------------------------------------------------------------------------ S2
+// the same functions with 64-bit counts, for the scan over all tiles
+struct Fn64 {
+    unsigned long long e0, e1;
+    uint32_t q;  // bit 0: next from 0, bit 1: next from 1
+};
+__device__ __forceinline__ Fn64 fn64_of(uint32_t f) { return Fn64{fn_emit(f, 0), fn_emit(f, 1), (f >> 30) & 3u}; }
+__device__ __forceinline__ Fn64 fn64_compose(const Fn64 &a, const Fn64 &b) {
+    const uint32_t a0 = a.q & 1u, a1 = (a.q >> 1) & 1u;
+    Fn64 r;
+    r.e0 = a.e0 + (a0 ? b.e1 : b.e0);
+    r.e1 = a.e1 + (a1 ? b.e1 : b.e0);
+    r.q = ((b.q >> a0) & 1u) | (((b.q >> a1) & 1u) << 1);
+    return r;
+}
+
+constexpr int kTxScanThreads = 1024;
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(kTxScanThreads) tx_scan_kernel(const uint8_t *__restrict__ in, size_t n, TxWorkspace ws, size_t ntiles,
+                                                                 uint8_t *__restrict__ out, size_t out_cap,
+                                                                 unsigned long long *__restrict__ d_out_len, int32_t *__restrict__ d_status) {
+    __shared__ Fn64 s_warp[32];
+    __shared__ unsigned long long s_off;
+    __shared__ uint32_t s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_off = 0; s_q = 0; }  // the stream starts in state 0 with nothing emitted
+    __syncthreads();
+    // blocks of 1024 x 8 tiles: a thread composes its 8 consecutive tiles, the CTA scans the 1024 results by
+    // composition, and every thread walks its tiles again from its now known entry state and offset
+    constexpr int kPer = 8;
+    for (size_t blk = 0; blk < ntiles; blk += (size_t)kTxScanThreads * kPer) {
+        const size_t t0 = blk + (size_t)tid * kPer;
+        uint32_t f[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) f[k] = t0 + k < ntiles ? ws.tile_fn[t0 + k] : kFnIdentity;
+        Fn64 mine = fn64_of(f[0]);
+#pragma unroll
+        for (int k = 1; k < kPer; k++) mine = fn64_compose(mine, fn64_of(f[k]));
+        Fn64 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Fn64 g;
+            g.e0 = __shfl_up_sync(0xFFFFFFFFu, incl.e0, d);
+            g.e1 = __shfl_up_sync(0xFFFFFFFFu, incl.e1, d);
+            g.q = __shfl_up_sync(0xFFFFFFFFu, incl.q, d);
+            if (lane >= d) incl = fn64_compose(g, incl);
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        // entry of this thread = (block entry) through the earlier warps, then the earlier lanes of this warp
+        unsigned long long off = s_off;
+        uint32_t q = s_q;
+        for (int w = 0; w < warp; w++) {
+            const Fn64 g = s_warp[w];
+            off += q ? g.e1 : g.e0;
+            q = (g.q >> q) & 1u;
+        }
+        {
+            Fn64 g;
+            g.e0 = __shfl_up_sync(0xFFFFFFFFu, incl.e0, 1);
+            g.e1 = __shfl_up_sync(0xFFFFFFFFu, incl.e1, 1);
+            g.q = __shfl_up_sync(0xFFFFFFFFu, incl.q, 1);
+            if (lane != 0) {
+                off += q ? g.e1 : g.e0;
+                q = (g.q >> q) & 1u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            if (t0 + k < ntiles) {
+                ws.tile_off[t0 + k] = off;
+                ws.tile_q[t0 + k] = (uint8_t)q;
+            }
+            off += fn_emit(f[k], q);
+            q = fn_next(f[k], q);
+        }
+        __syncthreads();
+        if (tid == kTxScanThreads - 1) { s_off = off; s_q = q; }  // the last thread's exit = the block's exit
+        __syncthreads();
+    }
+    const unsigned long long off = s_off;
+    const uint32_t q = s_q;
+    if (tid == kTxScanThreads - 1) {
+        // the thread that owns the last tile (or none: then off/q are the whole stream's) finishes the stream
+        const unsigned long long body = off + q;  // a pending half (compress: odd hit; decompress: half literal) is one more symbol
+        unsigned long long len;
+        int32_t mode;
+        if (COMPRESS) {
+            len = 2 + body;                   // 0xAF, first byte, body
+            mode = 0;
+            if (len >= n) { len = n + 1; mode = 1; }   // not shorter: ' ' + raw copy (:1018-1037)
+        } else {
+            const uint32_t type = in[0];
+            if (type == 0xAFu) { len = n >= 2 ? 1 + body : 0; mode = 0; }
+            else if (type == ' ') { len = n - 1; mode = 1; }
+            else { len = n; mode = 2; }
+        }
+        if (len > out_cap) {
+            set_status(d_status, DC_ERR_CAPACITY);
+            mode = -1;
+        } else if (len < out_cap) {
+            out[len] = 0;  // the reference's strings are NUL-terminated (:1011, :814)
+        }
+        *ws.out_len = len;
+        *ws.mode = mode;
+        if (d_out_len) *d_out_len = len;
+    }
+}
+
+// emit the symbols of the thread's block from entry state q into shared memory at dst
+template <bool COMPRESS, bool FULL>
+__device__ __forceinline__ void emit_block(const uint8_t *s_lut, const uint32_t (&c)[kTxPer], int valid, int skip, bool ends_here, uint32_t q,
+                                           uint32_t prev, uint8_t *dst) {
+    uint32_t pli = s_lut[prev & 0x7Fu];  // table index of the previous byte
+#pragma unroll
+    for (int k = 0; k < kTxPer; k++) {
+        if (!FULL && k >= valid) break;
+        if (COMPRESS) {
+            if (!FULL && k < skip) { q = 0; prev = c[k]; pli = 8; continue; }
+            // predicated stores, no branches (a byte past the thread's own range belongs to the next thread)
+            const uint32_t li = s_lut[c[k] & 0x7Fu], hit = li < 8 ? 1u : 0u;
+            const uint32_t pair = ((8u | pli) << 4) | (8u | li);
+            const uint32_t b0 = hit ? pair : (q ? prev : c[k]);
+            const uint32_t n_emit = hit ? q : 1u + q;
+            if (n_emit >= 1) dst[0] = (uint8_t)b0;
+            if (n_emit == 2) dst[1] = (uint8_t)c[k];
+            dst += n_emit;
+            q = hit & (q ^ 1u);
+            prev = c[k];
+            pli = li;
+            if (!FULL && ends_here && k == valid - 1 && q) *dst++ = (uint8_t)c[k];  // trailing half byte -> literal
+        } else {
+            if (!FULL && k < skip) { q = 0; prev = c[k] & 0xFu; continue; }
+            uint32_t pn = prev & 0xFu;  // the nibble before this byte's high nibble
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t x = h == 0 ? c[k] >> 4 : c[k] & 0xFu, emit = (x >> 3) | q;
+                if (emit) dst[0] = (uint8_t)(q ? ((pn & 7u) << 4) + x : letter_of(x));
+                dst += emit;
+                q = emit ^ 1u;
+                pn = x;
+            }
+            prev = c[k];
+            if (!FULL && ends_here && k == valid - 1 && q) *dst++ = (uint8_t)((pn & 7u) << 4);  // dangling half literal + zero nibble
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ S3
+constexpr int kTxStageBytes = kTxThreads * 2 * kTxPer + 48;  // decompress: two symbols per byte; + alignment slack
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__restrict__ in, size_t n, TxWorkspace ws, size_t ntiles,
+                                                             uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t s_stage[kTxStageBytes];
+    __shared__ uint32_t s_warp[kTxWarps];
+    __shared__ uint8_t s_lut[128];
+    fill_letter_table(s_lut);
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t mode = *ws.mode;
+    if (mode < 0) return;
+    const bool raw = COMPRESS ? mode == 1 : mode != 0;
+    const size_t raw_shift = COMPRESS ? 0 : (mode == 1 ? 1 : 0);  // decompress: skip the type byte of a LITERAL block
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t base = tile * kTxTile + (size_t)tid * kTxPer;
+        if (raw) {
+            if (COMPRESS && base == 0) out[0] = ' ';
+            for (int k = 0; k < kTxPer; k++) {
+                const size_t i = base + k;
+                if (i < n && i + 1 > raw_shift) out[i - raw_shift + (COMPRESS ? 1 : 0)] = in[i];
+            }
+            continue;
+        }
+        uint32_t c[kTxPer], prev = 0, f = kFnIdentity;
+        bool bad = false;
+        if (base < n) {
+            load_block(in, n, base, c, prev);
+            f = block_fn<COMPRESS>(s_lut, c, base, n, bad);
+        }
+        // inclusive scan over the warp by composition, warp totals to shared memory
+        uint32_t incl = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t g = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl = fn_compose(g, incl);
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();  // also: the previous tile's copy-out has read the staging buffer
+        uint32_t q = ws.tile_q[tile], off = 0;
+        for (int w = 0; w < warp; w++) {
+            const uint32_t g = s_warp[w];
+            off += fn_emit(g, q);
+            q = fn_next(g, q);
+        }
+        const uint32_t total_q_in = q;  // entry state of this warp
+        {
+            const uint32_t g = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane != 0) { off += fn_emit(g, total_q_in); q = fn_next(g, total_q_in); }
+        }
+        // tile totals (every thread computes them the same way: needed for the copy-out)
+        uint32_t tq = ws.tile_q[tile], tile_total = 0;
+        for (int w = 0; w < kTxWarps; w++) {
+            const uint32_t g = s_warp[w];
+            tile_total += fn_emit(g, tq);
+            tq = fn_next(g, tq);
+        }
+        const bool last_tile = tile == ntiles - 1;
+        if (last_tile) tile_total += tq;  // the pending half symbol at the end of the stream
+        const unsigned long long ob = (COMPRESS ? 2ull : 1ull) + ws.tile_off[tile];
+        const uint32_t a = (uint32_t)(((uintptr_t)out + ob) & 15);
+        uint8_t *dst = s_stage + a + off;
+        if (base < n) {
+            const int valid = (int)min((size_t)kTxPer, n - base);
+            const int skip = base == 0 ? (COMPRESS ? 1 : 2) : 0;
+            const bool ends_here = base + kTxPer >= n;  // this block holds the last byte of the stream
+            if (valid == kTxPer && skip == 0 && !ends_here) emit_block<COMPRESS, true>(s_lut, c, valid, skip, false, q, prev, dst);
+            else emit_block<COMPRESS, false>(s_lut, c, valid, skip, ends_here, q, prev, dst);
+        }
+        if (tile == 0 && tid == 0) {
+            if (COMPRESS) { out[0] = 0xAF; out[1] = in[0]; }   // :903, :905
+            else if (n >= 2) out[0] = in[1];                      // :750
+        }
+        __syncthreads();
+        // copy-out: staging byte i <-> out[ob - a + i]; 16-byte words are aligned on both sides
+        const uint32_t span = a + tile_total;
+        const uint32_t jfull = span >> 4, head = a ? 1u : 0u;
+        for (uint32_t j = head + tid; j < jfull; j += kTxThreads) stg_stream((uint4 *)(out + (ob - a)) + j, *(const uint4 *)(s_stage + j * 16));
+        if (tid < 16) {
+            if ((a != 0 || jfull == 0) && (uint32_t)tid >= a && (uint32_t)tid < span) out[ob - a + tid] = s_stage[tid];
+        } else if (tid < 32) {
+            const uint32_t k = jfull * 16 + (tid - 16);
+            if (jfull != 0 && k >= a && k < span) out[ob - a + k] = s_stage[k];
+        }
+    }
+}
+
+static size_t tx_ws_layout(size_t n, size_t off[5]) {
+    const size_t ntiles = (n + kTxTile - 1) / kTxTile;
+    size_t p = 64;
+    auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
+    size_t o[5];
+    o[0] = take(ntiles * 4);   // tile_fn
+    o[1] = take(ntiles * 8);   // tile_off
+    o[2] = take(ntiles);       // tile_q
+    o[3] = 0;                  // out_len (header)
+    o[4] = 8;                  // mode (header)
+    if (off) for (int i = 0; i < 5; i++) off[i] = o[i];
+    return p;
+}
+
+template <bool COMPRESS>
+static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, uint64_t *d_out_len, int32_t *d_status, void *d_ws,
+                  size_t ws_bytes, cudaStream_t st) {
+    if ((n && (!d_src || !d_dst || !d_ws)) || ((uintptr_t)d_ws & 15)) return DC_ERR_ARG;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    if (d_out_len) DC_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(uint64_t), st));
+    if (n == 0) {
+        if (cap && d_dst) DC_CUDA_TRY(cudaMemsetAsync(d_dst, 0, 1, st));  // the empty string
+        return DC_OK;
+    }
+    size_t off[5];
+    if (ws_bytes < tx_ws_layout(n, off)) return DC_ERR_CAPACITY;
+    char *w = (char *)d_ws;
+    TxWorkspace ws;
+    ws.tile_fn = (uint32_t *)(w + off[0]);
+    ws.tile_off = (unsigned long long *)(w + off[1]);
+    ws.tile_q = (uint8_t *)(w + off[2]);
+    ws.out_len = (unsigned long long *)(w + off[3]);
+    ws.mode = (int32_t *)(w + off[4]);
+    const size_t ntiles = (n + kTxTile - 1) / kTxTile;
+    const unsigned int grid = (unsigned int)min(ntiles, (size_t)sm_count() * 8);
+    {
+        LaunchScope ls(DC_K_TEXT_SUMMARY, st);
+        tx_summary_kernel<COMPRESS><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_status);
+    }
+    {
+        LaunchScope ls(DC_K_TEXT_SCAN, st);
+        tx_scan_kernel<COMPRESS><<<1, kTxScanThreads, 0, st>>>(d_src, n, ws, ntiles, d_dst, cap, (unsigned long long *)d_out_len, d_status);
+    }
+    {
+        LaunchScope ls(DC_K_TEXT_EMIT, st);
+        tx_emit_kernel<COMPRESS><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_dst);
+    }
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" size_t dc_nybble_text_workspace_bytes(size_t n) { return tx_ws_layout(n, nullptr); }
+
+extern "C" int dc_nybble_text_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                       int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return tx_run<true>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dc_nybble_text_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                         int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return tx_run<false>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}

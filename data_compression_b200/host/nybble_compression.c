@@ -6,8 +6,12 @@
  * GPU: the split of every byte into (high, low) nibbles (:767-769) and write_nybble()'s packing order
  * (:1091-1114), through refapi.h -> libdc_b200.so.
  *
+ * and for the static-table compressor compress_bytestring(text, c, false) / decompress_bytestring (:1160-1166),
+ * including the reference's `assert(strlen(compressed) <= 70)` (:1162).  The adaptive-table round trips of the
+ * reference's main() (:1176-1215) are a serial move-to-front chain and are not offloaded.
+ *
  *   ./nybble_compression            fixed text, as the reference
- *   ./nybble_compression - < file   the same round trip over stdin
+ *   ./nybble_compression - < file   the nibble round trip over stdin (and the compressor, if the file is 7-bit text)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,6 +50,26 @@ static void round_trip(const unsigned char *bytes, size_t n) {
     free(packed);
 }
 
+static void text_round_trip(const char *text, size_t limit) {
+    const size_t n = strlen(text);
+    char *c = malloc(n + 2), *d = malloc(2 * n + 2);
+    if (!c || !d) abort();
+    compress_bytestring(text, c, false);
+    printf("# compressed %zu -> %zu bytes (static table)\n", n, strlen(c));
+    if (limit && strlen(c) > limit) {
+        printf("Error: compressed text longer than %zu bytes.\n", limit);
+        abort();
+    }
+    decompress_bytestring(c, d, false);
+    if (strlen(d) != n || memcmp(text, d, n) != 0) {
+        printf("Error: decompressed text doesn't match original text.\n");
+        abort();
+    }
+    printf("Successful test.\n");
+    free(c);
+    free(d);
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "-")) {
         size_t cap = 1 << 16, used = 0;
@@ -60,11 +84,20 @@ int main(int argc, char **argv) {
         }
         printf("# %zu bytes -> %zu nybbles -> %zu bytes\n", used, 2 * used, used);
         if (used) round_trip(buf, used);
+        int is_text = used > 0;
+        for (size_t i = 0; i < used && is_text; i++) is_text = buf[i] != 0 && buf[i] < 0x80;
+        if (is_text) {
+            buf = realloc(buf, used + 1);
+            if (!buf) abort();
+            buf[used] = 0;
+            text_round_trip((const char *)buf, 0);
+        }
         free(buf);
         return 0;
     }
     const char *text = "Hello, world. This is a test. This is only a test. Banana banana banana banana. ";
     printf("# %zu bytes -> %zu nybbles -> %zu bytes\n", strlen(text), 2 * strlen(text), strlen(text));
     round_trip((const unsigned char *)text, strlen(text));
+    text_round_trip(text, 70);
     return 0;
 }

@@ -66,3 +66,13 @@ void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned
 void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigned char *symbols) {
     done("nybble_unpack_stream", dc_host_nybble_unpack(packed, n_symbols, symbols));
 }
+
+void compress_bytestring(const char *source, char *dest, bool modify) {
+    const long long rc = dc_host_compress_bytestring(source, dest, modify ? 1 : 0);
+    done("compress_bytestring", rc < 0 ? (int)rc : DC_OK);
+}
+
+void decompress_bytestring(const char *source, char *dest, bool modify) {
+    const long long rc = dc_host_decompress_bytestring(source, dest, modify ? 1 : 0);
+    done("decompress_bytestring", rc < 0 ? (int)rc : DC_OK);
+}

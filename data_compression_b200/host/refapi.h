@@ -53,6 +53,12 @@ uint64_t represent_items_last_total_bits(void);
 void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned char *packed);
 void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigned char *symbols);
 
+/* nybble_compression.c:887-1038 / :734-817 -- the static-table mode (modify == false) runs on the GPU.  The adaptive
+ * move-to-front mode (modify == true, what nybble_compress()/nybble_decompress() :1134/:1117 use) is a serial chain
+ * over the whole string; it is not offloaded and is refused (DC_ERR_ARG, i.e. abort like a failed assert). */
+void compress_bytestring(const char *source, char *dest, bool modify);
+void decompress_bytestring(const char *source, char *dest, bool modify);
+
 /* 1 (default): abort() on a device error, like the reference's assert(); 0: record it and return */
 void dc_refapi_set_abort(int on);
 /* dc_status of the last call made through this header */

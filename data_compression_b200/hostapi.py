@@ -124,3 +124,22 @@ def nybble_unpack(packed, n_sym: int, out: np.ndarray | None = None) -> np.ndarr
         out = np.zeros(n_sym, dtype=np.uint8)
     check(lib().dc_host_nybble_unpack(p.ctypes.data, n_sym, out.ctypes.data), "dc_host_nybble_unpack")
     return out
+
+
+def compress_bytestring(source: bytes, modify: bool = False) -> bytes:
+    """compress_bytestring(source, dest, modify) nybble_compression.c:887 -- the static-table mode runs on the GPU;
+    modify=True (adaptive move-to-front table) is a serial chain and raises DcError(DC_ERR_ARG)."""
+    dest = C.create_string_buffer(len(source) + 2)
+    n = lib().dc_host_compress_bytestring(bytes(source), C.addressof(dest), int(modify))
+    if n < 0:
+        raise DcError(int(n), "dc_host_compress_bytestring")
+    return dest.raw[:n]
+
+
+def decompress_bytestring(source: bytes, modify: bool = False) -> bytes:
+    """decompress_bytestring(source, dest, modify) nybble_compression.c:734 (static table)."""
+    dest = C.create_string_buffer(2 * len(source) + 2)
+    n = lib().dc_host_decompress_bytestring(bytes(source), C.addressof(dest), int(modify))
+    if n < 0:
+        raise DcError(int(n), "dc_host_decompress_bytestring")
+    return dest.raw[:n]

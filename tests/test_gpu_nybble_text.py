@@ -1,0 +1,87 @@
+"""GPU: the static-table nybble compressor / decompressor against the golden vectors generated
+from the unmodified compress_bytestring()/decompress_bytestring() and against the oracle on text-like data."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(b: bytes) -> torch.Tensor:
+    return torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+
+
+def _run(fn, src: bytes):
+    buf, n, st = fn(_dev(src) if src else torch.empty(0, dtype=torch.uint8, device="cuda"))
+    return bytes(buf[: int(n.item())].cpu().numpy()), int(st.item()), buf, int(n.item())
+
+
+def _textlike(rng, n, p_letter):
+    letters = np.frombuffer(b" etaoins", dtype=np.uint8)
+    others = np.array([c for c in range(1, 128) if c not in letters], dtype=np.uint8)
+    pick = rng.random(n) < p_letter
+    return np.where(pick, rng.choice(letters, n), rng.choice(others, n)).astype(np.uint8).tobytes()
+
+
+def test_reference_golden_vectors(dc):
+    for c in load_golden("nybble.json")["static"]:
+        text, comp = bytes.fromhex(c["text"]), bytes.fromhex(c["compressed"])
+        if not text:
+            continue
+        got, st, buf, n = _run(dc.nybble_text_compress, text)
+        assert st == 0 and got == comp
+        assert int(buf[n].item()) == 0                      # NUL-terminated like the reference's strings
+        back, st, _, _ = _run(dc.nybble_text_decompress, comp)
+        assert st == 0 and back == text
+        assert dc.hostapi.compress_bytestring(text) == comp
+        assert dc.hostapi.decompress_bytestring(comp) == text
+    main = bytes.fromhex(load_golden("nybble.json")["static"][0]["text"])
+    assert len(dc.hostapi.compress_bytestring(main)) <= 70  # nybble_compression.c:1162
+
+
+@pytest.mark.parametrize("p_letter", [0.0, 0.3, 0.62, 0.95, 1.0])
+@pytest.mark.parametrize("n", [1, 2, 3, 15, 16, 17, 4095, 4096, 4097, 70001, 1 << 20])
+def test_matches_oracle(dc, oracle, n, p_letter):
+    rng = np.random.default_rng(n * 7 + int(p_letter * 100))
+    text = _textlike(rng, n, p_letter)
+    want = oracle.nybble_static_compress(text)
+    got, st, _, _ = _run(dc.nybble_text_compress, text)
+    assert st == 0 and got == want, (n, p_letter)
+    back, st, _, _ = _run(dc.nybble_text_decompress, want)
+    assert st == 0 and back == oracle.nybble_static_decompress(want) == text
+
+
+def test_long_runs_cross_tiles(dc, oracle):
+    # hit runs longer than a 4 KB tile, odd and even, so the parity state crosses tile and warp boundaries
+    for run in (4097, 8192, 12289):
+        text = b"X" + b"e" * run + b"Q" + b"t" * (run + 1) + b"Z" * 3 + b" " * 7
+        want = oracle.nybble_static_compress(text)
+        got, st, _, _ = _run(dc.nybble_text_compress, text)
+        assert st == 0 and got == want
+        back, st, _, _ = _run(dc.nybble_text_decompress, want)
+        assert st == 0 and back == text
+
+
+def test_decoder_accepts_nibble_granular_literals(dc, oracle):
+    # streams the compressor never writes but the reference decoder parses: literals that start on a low nibble,
+    # a dangling half literal at the end, the ' ' (raw) type and an unknown type byte
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 9, 100, 5000, 70000):
+        body = rng.integers(1, 256, size=n, dtype=np.uint8).tobytes()
+        for head in (b"\xafA", b" ", b"Q"):
+            comp = head + body
+            want = oracle.nybble_static_decompress(comp)
+            got, st, _, _ = _run(dc.nybble_text_decompress, comp)
+            assert st == 0 and got == want, (n, head)
+
+
+def test_errors(dc):
+    got, st, _, _ = _run(dc.nybble_text_compress, b"abc\x80def")
+    assert st == dc.DC_ERR_SYMBOL                              # assert( source[i] < 0x80 ) :910
+    with pytest.raises(dc.DcError) as e:
+        dc.hostapi.compress_bytestring(b"hello", modify=True)  # adaptive mode is serial: not offloaded
+    assert e.value.status == dc.DC_ERR_ARG
+    assert dc.hostapi.compress_bytestring(b"") == b""
+    assert dc.hostapi.decompress_bytestring(b"") == b""

@@ -13,7 +13,8 @@ from conftest import ROOT
 HOST = os.path.join(ROOT, "data_compression_b200", "host")
 REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
 REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
-             "decode_items_with_codes", "nybble_pack_stream", "nybble_unpack_stream"]
+             "decode_items_with_codes", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
+             "decompress_bytestring"]
 
 
 @pytest.fixture(scope="module")
@@ -62,7 +63,8 @@ def test_n_ary_huffman_cli(built, radix, expect):
 @pytest.mark.gpu
 def test_nybble_compression_cli(built):
     r = subprocess.run([os.path.join(HOST, "nybble_compression")], capture_output=True, timeout=60)
-    assert r.returncode == 0 and r.stdout.decode().count("Successful test.") == 1
+    assert r.returncode == 0 and r.stdout.decode().count("Successful test.") == 2
+    assert b"compressed 80 -> 57 bytes" in r.stdout           # the reference's own result on its fixed text
     data = np.random.default_rng(3).integers(0, 256, size=1 << 20, dtype=np.uint8).tobytes()
     r = subprocess.run([os.path.join(HOST, "nybble_compression"), "-"], input=data, capture_output=True, timeout=60)
     assert r.returncode == 0 and b"Successful test." in r.stdout

@@ -1,0 +1,20 @@
+import ctypes as C, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import data_compression_b200 as dc
+dev = torch.device("cuda:0"); n = 1 << 30
+g = torch.Generator(device=dev); g.manual_seed(7)
+letters = torch.tensor(list(b" etaoins"), dtype=torch.uint8, device=dev)
+others = torch.tensor([c for c in range(33, 127) if c not in b" etaoins"], dtype=torch.uint8, device=dev)
+pick = torch.rand(n, device=dev, generator=g) < 0.62
+text = torch.where(pick, letters[torch.randint(0, 8, (n,), device=dev, generator=g)], others[torch.randint(0, others.numel(), (n,), device=dev, generator=g)])
+del pick
+L = dc.lib()
+buf, ln, st = dc.nybble_text_compress(text); clen = int(ln.item()); comp = buf[:clen].clone(); del buf
+L.dc_profile_reset(); L.dc_profile_enable(1)
+for _ in range(3):
+    dc.nybble_text_compress(text); dc.nybble_text_decompress(comp)
+torch.cuda.synchronize(); L.dc_profile_enable(0)
+for kid in range(40):
+    ms, cnt = C.c_double(0), C.c_uint64(0)
+    L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+    if cnt.value: print(L.dc_profile_kernel_name(kid).decode(), round(ms.value / cnt.value, 4), cnt.value)
