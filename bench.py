@@ -179,7 +179,7 @@ def run_reference(args) -> None:
                          "decode_gbs": sample.size * args.steps / td / 1e9, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -361,12 +361,31 @@ def run_ours(args) -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(n_ary)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1), so
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+def _emit(line: dict) -> None:
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
+_OUT = sys.stdout
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
