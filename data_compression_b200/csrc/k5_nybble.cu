@@ -73,6 +73,15 @@ __global__ void nybble_pack_bytes_kernel(const uint8_t *__restrict__ sym, size_t
     }
 }
 
+// one 32-byte store: a thread's two output vectors are contiguous, and two separate 16-byte stores would each write half
+// of every 32-byte sector the warp touches
+__device__ __forceinline__ void stg_stream_256(uint4 *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
+template <bool WIDE>  // WIDE: the symbol buffer is 32-byte aligned
 __global__ void __launch_bounds__(kNybThreads) nybble_unpack_kernel(const uint4 *__restrict__ packed, size_t nvec_in,
                                                                     uint4 *__restrict__ sym) {
     const size_t stride = (size_t)gridDim.x * kNybThreads;
@@ -92,8 +101,12 @@ __global__ void __launch_bounds__(kNybThreads) nybble_unpack_kernel(const uint4 
             hi.y = unpack_half(p[u].z, 0x3322);
             hi.z = unpack_half(p[u].w, 0x1100);
             hi.w = unpack_half(p[u].w, 0x3322);
-            stg_stream(sym + 2 * (i + u * stride), lo);
-            stg_stream(sym + 2 * (i + u * stride) + 1, hi);
+            if (WIDE) {
+                stg_stream_256(sym + 2 * (i + u * stride), lo, hi);
+            } else {
+                stg_stream(sym + 2 * (i + u * stride), lo);
+                stg_stream(sym + 2 * (i + u * stride) + 1, hi);
+            }
         }
     }
     for (; i < nvec_in; i += stride) {
@@ -159,7 +172,8 @@ extern "C" int dc_nybble_unpack(const uint8_t *d_packed, size_t n_sym, uint8_t *
     const size_t nvec = aligned ? n_sym / 32 : 0;
     if (nvec) {
         LaunchScope ls(DC_K_NYBBLE_UNPACK, st);
-        nybble_unpack_kernel<<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_packed, nvec, (uint4 *)d_sym);
+        if (((uintptr_t)d_sym & 31) == 0) nybble_unpack_kernel<true><<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_packed, nvec, (uint4 *)d_sym);
+        else nybble_unpack_kernel<false><<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_packed, nvec, (uint4 *)d_sym);
     }
     const size_t done = nvec * 32;
     if (done < n_sym) {
