@@ -901,6 +901,18 @@ static uint32_t fast_stage_bytes(const int32_t *tmeta) {
     return (uint32_t)((32 * (kF_SubBits / min_bits + 2) + 64 + 15) & ~15);
 }
 
+// the write kernel's dynamic shared memory limit only ever grows (the attribute is a limit, not a request: setting it
+// lower for one table would make the next launch for a table with shorter codes fail)
+static cudaError_t ensure_write_smem(size_t smem3) {
+    static size_t limit = 0;
+    if (smem3 <= limit) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e == cudaSuccess) limit = smem3;
+    return e;
+}
+
 // F1 + F2 + F3 over `ntiles` warp tiles of the bitstream at d_bits (`end` = end of the STREAM in bits from d_bits; a chunk that
 // is not the last one may read a few bytes of the next chunk).  chain == nullptr: a whole stream that starts at bit_start.
 static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
@@ -920,12 +932,7 @@ static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsi
         decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk);
     }
     const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
-    static size_t attr3 = 0;
-    if (smem3 > attr3) {
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        attr3 = smem3;
-    }
+    DC_CUDA_TRY(ensure_write_smem(smem3));
     {
         LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
         const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
@@ -1118,8 +1125,7 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f2[k], cp));
         {
             const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
-            DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            DC_CUDA_TRY(cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            DC_CUDA_TRY(ensure_write_smem(smem3));
             LaunchScope ls(DC_K_DECODE_FAST_WRITE, cp);
             const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
             if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, cp>>>(bits_k, end_rel, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
