@@ -378,6 +378,13 @@ __device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *
     return 0;
 }
 
+// LUT entry for the window in the top 12 bits of x: base + (x >> 20) * 4 as one shift and one multiply-add (written in
+// PTX so that it is not canonicalised back into shift, mask and add) in front of the LDS
+__device__ __forceinline__ uint32_t lds_lut(uint32_t lut, uint32_t x) {
+    uint32_t v;
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" : "=r"(v) : "r"(x >> (32 - DC_LUT_BITS)), "r"(lut));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
@@ -414,7 +421,7 @@ struct SyncRecord {
 template <bool ESC>
 __device__ __forceinline__ void sync_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &csum) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    const uint32_t e = lds_lut(lut, x);
     if (ESC && e == 0) {
         int sym;
         const int nb = decode_escape(t, x, &sym);
@@ -428,7 +435,7 @@ __device__ __forceinline__ void sync_lookup_multi(const FastTables *t, uint32_t 
 template <bool ESC>
 __device__ __forceinline__ void sync_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    const uint32_t e = lds_lut(lut, x);
     if (ESC && e == 0) {
         int sym;
         const int nb = decode_escape(t, x, &sym);
@@ -552,7 +559,8 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
     load_fast_tables(&s_t, tab, tab->lut_count);
     __syncthreads();
     if (chain) bit_start = chain->next_start;  // a later chunk of a stream: its first code starts where the previous chunk's last one ended
-    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
+    uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
+    asm volatile("" : "+r"(lut));  // keep the table's address in a register: otherwise it is re-derived (S2R + LEA) in every word loop
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long nvec = ((end + 7) / 8 + 15) / 16;
     const uint32_t guess = (uint32_t)(bit_start & 7);  // fixed-length-like codes keep the stream's phase
@@ -671,7 +679,7 @@ template <bool ESC>
 __device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
                                                    uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    const uint32_t e = lds_lut(lut, x);
     if (ESC && e == 0) {
         int sym = 0;
         const int nb = decode_escape(t, x, &sym);
@@ -694,7 +702,7 @@ template <bool ESC>
 __device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
                                                     uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_u32(lut + ((x >> (30 - DC_LUT_BITS)) & (((1u << DC_LUT_BITS) - 1u) << 2)));
+    const uint32_t e = lds_lut(lut, x);
     if (ESC && e == 0) {
         int sym = 0;
         const int nb = decode_escape(t, x, &sym);
@@ -747,7 +755,8 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const 
     if (*ws.mismatch) return;  // the robust path redoes the stream
     load_fast_tables(s_t, tab, tab->lut_pair);
     __syncthreads();
-    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
+    uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
+    asm volatile("" : "+r"(lut));  // as in F1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = s_stage + (size_t)warp * stage_bytes;  // 16-byte aligned: stage_bytes is a multiple of 16
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
