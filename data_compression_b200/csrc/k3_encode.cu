@@ -7,23 +7,30 @@
 // concatenated in input order, MSB-first within each byte; the final byte is zero-padded.
 //
 // The input is cut into CHUNKS of 4 KB (one warp each); 8 chunks form a 32 KB RUN (one CTA).
-// Three launches, no spin-waits, no CTA-wide barriers in the hot kernel:
+//
+// SINGLE PASS (tables whose longest code is <= 16 bits; see "single pass" below): one launch, one read of the
+// input.  A warp stages its whole chunk in shared memory at chunk-local bit offsets, the run's bit offset comes
+// from a decoupled look-back over run descriptors, and the staging buffer is copied out funnel-shifted to the
+// global bit alignment.  HBM traffic = N + C.
+//
+// THREE LAUNCHES (tables with codes up to 32 bits; the kernels directly below):
 //   E1 count   : bits per chunk = sum of code lengths (one streaming read of the input); per run the
 //                exclusive offsets of its 8 chunks and the run total
 //   E2 scan    : exclusive scan of the run totals -> global bit offset of every run, total bit count
 //   E3 encode  : every WARP walks its chunk in 8 sub-tiles of 512 symbols (32 lanes x 16 symbols):
-//        A. 16 code look-ups from a shared-memory copy of the table, combined pairwise in registers
+//        A. 16 code look-ups from a shared-memory copy of the table (64-bit entries)
 //        B. warp-wide exclusive scan of the per-lane bit totals (shuffles)
-//        C. every lane streams its 8 code pairs through a 64-bit accumulator into the warp's staging
-//           buffer at its bit offset.  When every lane holds >= 32 bits each staging word is shared by at
-//           most two neighbouring lanes, so words are written with plain stores and the one shared partial
-//           word travels by shuffle; otherwise (very compressible or ragged data) shared-memory OR is used
+//        C. every lane streams its codes through a 64-bit accumulator into the warp's staging buffer at its
+//           bit offset.  When every lane holds >= 32 bits each staging word is shared by at most two
+//           neighbouring lanes, so words are written with plain stores and the one shared partial word
+//           travels by shuffle; otherwise (very compressible or ragged data) shared-memory OR is used
 //        D. coalesced copy-out: staging words are funnel-shifted to the global bit alignment and stored
 //           as 16-byte words.  The partial 16-byte word at the end of a sub-tile is carried into the next
 //           one in registers; the one shared between two CHUNKS is merged by whichever warp arrives
 //           second (both sides deposit their half in the workspace and bump a counter), so every output
 //           byte is written exactly once, in any scheduling order, with no pre-zeroed output.
-// HBM traffic = 2N (count + encode reads) + C (write).
+//   HBM traffic = 2N (count + encode reads) + C (write).
+// Both paths share the sub-tile steps A-C (lookup_items, emit_bits*, the shuffle scan).
 #include "dc_common.cuh"
 
 namespace dc {

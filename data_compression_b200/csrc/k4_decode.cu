@@ -5,21 +5,25 @@
 // layout of k3_encode.cu from the bitstream alone -- no side information besides the code lengths, the
 // bit count and the symbol count.
 //
-// The stream is cut into 128-bit subsequences (one per lane), 32 of them form a warp tile (512 B) and 32
-// tiles a segment (16 KB, one warp).  FAST PATH (three launches, no spin-waits):
-//   F1 synchronise+count: a warp walks its segment tile by tile.  Every lane decodes its subsequence from
-//      a guessed start as if a code began there, then restarts from the exit point of its left
-//      neighbour (shuffle) until no start changes; codes self-synchronise after a few symbols, so this is
-//      ~2 rounds.  Multi-symbol look-ups (every code that lies inside the next 12 bits) keep a round at
-//      ~0.5 table reads per symbol.  Per subsequence the exact start offset and symbol count are stored
-//      (2 bytes per 16 bytes of bitstream); per segment the symbol count.  The first code of a segment is
-//      found by synchronising over the LAST tile of the previous segment (1/32 extra work); that is an
-//      assumption, so F2 checks it: assumed start of segment s == exit of segment s-1, for every s.
+// FAST PATH (three launches, no spin-waits).  The stream is cut into 256-bit subsequences (one per lane, held in
+// registers), 32 of them form a warp tile (1 KB) and 16 tiles a segment (16 KB, one warp):
+//   F1 synchronise+count: a warp walks its segment tile by tile.  Every lane walks its subsequence from a
+//      guessed start as if a code began there, recording the position at the end of every 32-bit word; then it
+//      takes the exit point of its left neighbour (shuffle) as its start and re-walks only until its position at
+//      a word end equals the recorded one -- codes self-synchronise after a few symbols, so the re-walks cost a
+//      fifth of the first walk.  Multi-symbol look-ups (every code that lies inside the next 12 bits) keep a walk
+//      at ~0.6 table reads per symbol.  Per subsequence the exact start offset and symbol count are stored
+//      (2 bytes per 32 bytes of bitstream); per segment the symbol count.  The first code of a segment is found
+//      by synchronising over the LAST tile of the previous segment (1/16 extra work); that is an assumption, so
+//      F2 checks it: assumed start of segment s == exit of segment s-1, for every s.
 //   F2 verify + exclusive scan of the segment counts -> output offsets; total checked against n_out.
 //   F3 decode+write: a warp re-walks its segment with exact starts, decodes two symbols per look-up into a
 //      shared-memory staging tile and copies it out with aligned 16-byte stores.
-// ROBUST PATH (the v1 kernels D1..D4 below): used when F2's check fails (a stream whose codes do not
-// self-synchronise within 4096 bits); hands the tile starts over iteratively, always terminates.
+// A stream can also be decoded chunk by chunk (DecodeChain): the pipelined host entry point at the end of this
+// file uploads, decodes and downloads 32 MiB chunks concurrently.
+// ROBUST PATH (the v1 kernels D1..D4 directly below, 128-bit subsequences): used when F2's check fails (a
+// stream whose codes do not self-synchronise within 8192 bits); hands the tile starts over iteratively, always
+// terminates.
 // Unused code slots (the reference's dummy leaves) are legal on speculative paths -- they
 // advance by one digit and produce no symbol -- and are reported as DC_ERR_CORRUPT on the true path.
 #include <stdlib.h>
