@@ -1077,7 +1077,13 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
                               uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
                               int32_t *d_status) {
     const size_t nbytes = (size_t)((total_bits + 7) / 8);
-    const unsigned long long chunk_bytes = kPipeChunkTiles * (kF_TileVecs * 16ull);
+    static unsigned long long chunk_tiles = 0;
+    if (chunk_tiles == 0) {  // DC_PIPE_CHUNK_MIB: tuning knob (a multiple of the 16 KB segment either way)
+        const char *e = getenv("DC_PIPE_CHUNK_MIB");
+        const unsigned long long mib = e ? strtoull(e, nullptr, 10) : 0;
+        chunk_tiles = mib >= 1 && mib <= 1024 ? mib * 1024 : kPipeChunkTiles;
+    }
+    const unsigned long long chunk_bytes = chunk_tiles * (kF_TileVecs * 16ull);
     const size_t nchunk = (size_t)((nbytes + chunk_bytes - 1) / chunk_bytes);
     if (nchunk < 3 || decode_force_mode() != 0) return 1;
     size_t off[12];

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t block_fn_impl(const uint8_t *lut, const uint
     uint32_t e0 = 0, e1 = 0, q0 = 0, q1 = 1;
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
-        if (!FULL && k >= valid) break;
+        if (!FULL && k >= valid) continue;  // (no break: the loop must unroll completely or c[] lands in local memory)
         if (!FULL && k < skip) { q0 = q1 = 0; e0 = e1 = 0; continue; }
         if (COMPRESS) {
             bad |= c[k] == 0 || c[k] >= 0x80u;  // assert( source[i] < 0x80 ) :910; 0x00 would end the C string
@@ -276,7 +276,7 @@ __device__ __forceinline__ void emit_block(const uint8_t *s_lut, const uint32_t 
     uint32_t pli = s_lut[prev & 0x7Fu];  // table index of the previous byte
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
-        if (!FULL && k >= valid) break;
+        if (!FULL && k >= valid) continue;  // (no break: see block_fn_impl)
         if (COMPRESS) {
             if (!FULL && k < skip) { q = 0; prev = c[k]; pli = 8; continue; }
             // predicated stores, no branches (a byte past the thread's own range belongs to the next thread)
