@@ -44,6 +44,12 @@ class HuffTableStruct(C.Structure):
 
 TABLE_BYTES = C.sizeof(HuffTableStruct)
 
+
+class ShardSummaryStruct(C.Structure):
+    """Mirror of ``struct dc_shard_summary`` (include/dc_b200.h)."""
+    _fields_ = [("symbols", C.c_uint64), ("exit", C.c_uint32), ("resync", C.c_int32), ("assumed_start", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
 # every symbol include/dc_b200.h declares: (name, restype, argtypes)
 _vp, _sz, _u64, _i, _u = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint
 _ip, _up, _u64p = C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_uint64)
@@ -65,6 +71,8 @@ SYMBOLS = [
     ("dc_huff_encode", _i, [_vp, _sz, _vp, _vp, _sz, _u, _vp, _vp, _vp, _sz, _vp]),
     ("dc_huff_decode_workspace_bytes", _sz, [_u64, _u64]),
     ("dc_huff_decode", _i, [_vp, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
+    ("dc_huff_decode_shard_sync", _i, [_vp, _i, _u, _u64, _u64, _vp, _vp, _vp, _sz, _vp]),
+    ("dc_huff_decode_shard_write", _i, [_vp, _i, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_nybble_pack", _i, [_vp, _sz, _vp, _vp, _vp]),
     ("dc_nybble_unpack", _i, [_vp, _sz, _vp, _vp]),
     ("dc_nybble_text_workspace_bytes", _sz, [_sz]),

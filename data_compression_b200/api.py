@@ -141,6 +141,49 @@ def huff_decode(bits: torch.Tensor, nbits: int, table: HuffTable, n_out: int, bi
     return out[:n_out], status
 
 
+SHARD_ALIGN = 1024  # a longer stream is cut into shards at multiples of this many bytes
+
+
+class ShardDecoder:
+    """One contiguous byte range of a longer bitstream (dc_huff_decode_shard_sync / _write).
+
+    `buf` holds [1024 bytes of the previous shard's tail | the shard | >= 16 bytes of the next shard]; the halo in front
+    is ignored for the stream's first shard."""
+
+    def __init__(self, buf: torch.Tensor, shard_bytes: int, shard_bits: int, stream_bits_left: int, table: HuffTable):
+        _need_cuda(buf, "buf")
+        if buf.data_ptr() % 16 or buf.numel() < SHARD_ALIGN + shard_bytes + 16:
+            raise ValueError("buf: 16-byte aligned, 1024-byte halo + shard + 16 bytes")
+        self.buf, self.table = buf, table
+        self.shard_bits, self.left = shard_bits, stream_bits_left
+        self.ptr = buf.data_ptr() + SHARD_ALIGN
+        need = lib().dc_huff_decode_workspace_bytes(0, shard_bits + 8 * SHARD_ALIGN)
+        self.ws = torch.empty(max(need, 16), dtype=torch.uint8, device=buf.device)
+        self.summary = torch.empty(3, dtype=torch.int64, device=buf.device)   # 24 bytes: dc_shard_summary
+        self.has_halo = 0
+
+    def sync(self, has_halo: bool, first_code_bit: int = 0) -> torch.Tensor:
+        """Phase 1.  Returns the device-resident summary as int64[3] (symbols, exit | resync << 32, assumed | 0)."""
+        self.has_halo = 1 if has_halo else 0
+        check(lib().dc_huff_decode_shard_sync(self.ptr, self.has_halo, first_code_bit, self.shard_bits, self.left, self.table.ptr,
+                                              self.summary.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()),
+              "dc_huff_decode_shard_sync")
+        return self.summary
+
+    @staticmethod
+    def unpack(summary_i64) -> dict:
+        s = [int(x) for x in summary_i64]
+        return {"symbols": s[0], "exit": s[1] & 0xFFFFFFFF, "resync": (s[1] >> 32) & 0xFFFFFFFF, "assumed_start": s[2] & 0xFFFFFFFF}
+
+    def write(self, n_out: int):
+        out = torch.empty(max(n_out, 1), dtype=torch.uint8, device=self.buf.device)
+        status = torch.empty(1, dtype=torch.int32, device=self.buf.device)
+        check(lib().dc_huff_decode_shard_write(self.ptr, self.has_halo, self.shard_bits, self.left, self.table.ptr, out.data_ptr(),
+                                               n_out, status.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()),
+              "dc_huff_decode_shard_write")
+        return out[:n_out], status
+
+
 def huff_compress(data: torch.Tensor, n_ary: int):
     """histogram -> table -> encode on one GPU.  Returns (payload tensor, total_bits int, HuffTable)."""
     hist = histogram(data)

@@ -501,7 +501,10 @@ struct DecodeChain {
     unsigned long long base;   // symbols decoded by the chunks before this one = output offset of this chunk
     uint32_t next_start;       // bit offset, relative to the first bit of the next chunk, of that chunk's first code
     int32_t mismatch;          // sticky: some segment of some chunk started on a wrong guess
+    uint32_t first_assumed;    // the start the chunk's first segment assumed (== its given start unless it had a lead tile)
+    uint32_t reserved;
 };
+static_assert(sizeof(DecodeChain) == sizeof(dc_shard_summary), "dc_shard_summary is the public face of DecodeChain");
 
 struct FastWorkspace {
     uint16_t *sub_info;                              // [nsub] start offset (7 bits) | symbol count << 7
@@ -558,7 +561,9 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
                                                                       unsigned long long end, const dc_huff_table *__restrict__ tab,
                                                                       FastWorkspace ws, unsigned long long nsub,
                                                                       unsigned long long ntiles, unsigned long long nseg,
-                                                                      const DecodeChain *__restrict__ chain) {
+                                                                      const DecodeChain *__restrict__ chain, int lead) {
+    // lead = 1: tile 0 of d_bits is the last tile of the PREVIOUS shard of a longer stream; the first code of this
+    // shard is unknown and segment 0 finds it like every other segment does, by synchronising over the tile in front
     __shared__ FastTables s_t;
     load_fast_tables(&s_t, tab, tab->lut_count);
     __syncthreads();
@@ -570,15 +575,16 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
     const uint32_t guess = (uint32_t)(bit_start & 7);  // fixed-length-like codes keep the stream's phase
     for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
          seg += (unsigned long long)gridDim.x * kF_Warps) {
-        const int warm = seg == 0 ? 0 : 1;  // walk the last tile of the previous segment first to find our first code
-        const unsigned long long tile0 = seg * kF_SegTiles - warm;
+        const bool exact = seg == 0 && lead == 0;  // the stream's (or chunk's) first segment starts where it was told
+        const int warm = exact ? 0 : 1;            // the others walk the tile in front of them first to find their first code
+        const unsigned long long tile0 = (unsigned long long)lead + seg * kF_SegTiles - warm;
         SegCursor cur;
         cur.init(d_bits, tile0, nvec, end, lane);
         const uint32_t ntile = (uint32_t)min((unsigned long long)(kF_SegTiles + warm), ntiles - tile0);
         uint16_t *info = ws.sub_info + tile0 * 32 + lane;
         const unsigned long long sub0 = tile0 * 32;
         const uint32_t sub_left = nsub - sub0 > 0x40000000ull ? 0x40000000u : (uint32_t)(nsub - sub0);
-        uint32_t carry = seg == 0 ? (uint32_t)bit_start : guess, assumed = carry, total = 0;
+        uint32_t carry = exact ? (uint32_t)bit_start : guess, assumed = carry, total = 0;
         for (uint32_t tt = 0; tt < ntile; tt++, info += 32) {
             uint32_t w[kF_SubWords + 1];
             cur.take(w);
@@ -669,6 +675,7 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
             chain->base = s_carry;
             chain->next_start = ws.seg_exit[nseg - 1];
             chain->mismatch |= s_bad;
+            chain->first_assumed = ws.seg_assumed[0];
         }
         if (!s_bad && last_chunk && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
     }
@@ -752,7 +759,7 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const 
                                                                        unsigned long long nsub, unsigned long long ntiles,
                                                                        unsigned long long nseg, uint8_t *__restrict__ out,
                                                                        unsigned long long n_out, uint32_t stage_bytes,
-                                                                       int32_t *__restrict__ d_status) {
+                                                                       int32_t *__restrict__ d_status, int lead) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
     FastTables *s_t = (FastTables *)fast_smem;
     uint8_t *s_stage = fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15);
@@ -768,7 +775,7 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const 
     bool corrupt = false;
     for (unsigned long long seg = (unsigned long long)blockIdx.x * kF_Warps + warp; seg < nseg;
          seg += (unsigned long long)gridDim.x * kF_Warps) {
-        const unsigned long long tile0 = seg * kF_SegTiles;
+        const unsigned long long tile0 = (unsigned long long)lead + seg * kF_SegTiles;
         SegCursor cur;
         cur.init(d_bits, tile0, nvec, end, lane);
         const uint32_t ntile = (uint32_t)min((unsigned long long)kF_SegTiles, ntiles - tile0);
@@ -926,33 +933,48 @@ static cudaError_t ensure_write_smem(size_t smem3) {
     return e;
 }
 
-// F1 + F2 + F3 over `ntiles` warp tiles of the bitstream at d_bits (`end` = end of the STREAM in bits from d_bits; a chunk that
-// is not the last one may read a few bytes of the next chunk).  chain == nullptr: a whole stream that starts at bit_start.
-static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
-                       unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out,
-                       size_t n_out, int32_t *d_status, bool esc, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
-                       cudaStream_t st) {
+// F1 + F2, then F3, over `nwt` warp tiles of the bitstream at d_bits (`end` = end of the STREAM in bits from d_bits; a chunk
+// that is not the last one may read a few bytes of the next chunk).  chain == nullptr: a whole stream that starts at
+// bit_start.  lead = 1: tile 0 belongs to the previous shard (see F1); nwt and nsubf count it, nseg does not.
+static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
+                            unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw,
+                            size_t n_out, int32_t *d_status, bool esc, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
         const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
-        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain);
-        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain);
+        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead);
+        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead);
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
         decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk);
     }
+    return cuda_status(cudaGetLastError());
+}
+
+static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
+                             unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out, size_t n_out,
+                             int32_t *d_status, bool esc, uint32_t stage_bytes, int lead, cudaStream_t st) {
+    const unsigned long long sms = (unsigned long long)sm_count();
+    const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
     DC_CUDA_TRY(ensure_write_smem(smem3));
-    {
-        LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
-        const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-        if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
-        else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
-    }
+    LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
+    const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
+    if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead);
+    else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead);
     return cuda_status(cudaGetLastError());
+}
+
+static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
+                       unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out,
+                       size_t n_out, int32_t *d_status, bool esc, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
+                       cudaStream_t st) {
+    const int rc = launch_fast_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, n_out, d_status, esc, chain, last_chunk, 0, st);
+    if (rc != DC_OK) return rc;
+    return launch_fast_write(d_bits, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, 0, st);
 }
 
 // test hook: 1 = always take the robust path, 2 = pretend the fast path's guess failed after running it
@@ -1031,6 +1053,83 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
         return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
     }
     return DC_OK;
+}
+
+// ================================================================================================ shards of a longer stream
+
+namespace {
+struct ShardGeom {
+    const uint8_t *base;              // d_bits, or d_bits - 1024 with a halo
+    unsigned long long end, nsubf, nwt, nseg;
+    int lead;
+    FastWorkspace fw;
+    DecodeChain *chain;
+    bool esc;
+    uint32_t stage_bytes;
+};
+}  // namespace
+
+static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bits, uint64_t stream_bits_left,
+                          const dc_huff_table *d_table, void *d_workspace, size_t workspace_bytes, cudaStream_t st, ShardGeom *g) {
+    if (!d_bits || !d_table || !d_workspace || shard_bits == 0 || stream_bits_left < shard_bits) return DC_ERR_ARG;
+    if ((((uintptr_t)d_bits | (uintptr_t)d_workspace) & 15) != 0) return DC_ERR_ARG;
+    const unsigned long long tile_bits = 32ull * kF_SubBits;
+    if (stream_bits_left > shard_bits && shard_bits % tile_bits != 0) return DC_ERR_ARG;  // only the last shard is ragged
+    g->lead = has_halo ? 1 : 0;
+    g->base = d_bits - (size_t)g->lead * (tile_bits / 8);
+    g->end = stream_bits_left + (unsigned long long)g->lead * tile_bits;          // stream end, in bits from g->base
+    const unsigned long long own = shard_bits + (unsigned long long)g->lead * tile_bits;
+    g->nsubf = (own + kF_SubBits - 1) / kF_SubBits;                               // subsequences incl. the lead tile
+    g->nwt = (g->nsubf + 31) / 32;
+    g->nseg = (g->nwt - g->lead + kF_SegTiles - 1) / kF_SegTiles;
+    size_t off[12];
+    unsigned long long nsub, ntiles;
+    if (workspace_bytes < dec_ws_layout(0, own, off, &nsub, &ntiles)) return DC_ERR_CAPACITY;
+    char *w = (char *)d_workspace;
+    g->fw.mismatch = (int32_t *)(w + 16);
+    g->fw.sub_info = (uint16_t *)(w + off[6]);
+    g->fw.seg_cnt = (uint32_t *)(w + off[7]);
+    g->fw.seg_assumed = (uint32_t *)(w + off[8]);
+    g->fw.seg_exit = (uint32_t *)(w + off[9]);
+    g->fw.seg_off = (unsigned long long *)(w + off[10]);
+    g->chain = (DecodeChain *)(w + 32);
+    int32_t tmeta[10];
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (tmeta[8] != DC_OK) return tmeta[8];
+    if (tmeta[1] == 0) return DC_ERR_RADIX;
+    g->esc = tmeta[7] > DC_LUT_BITS;
+    g->stage_bytes = fast_stage_bytes(tmeta);
+    return DC_OK;
+}
+
+extern "C" int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, unsigned first_code_bit, uint64_t shard_bits,
+                                         uint64_t stream_bits_left, const dc_huff_table *d_table, dc_shard_summary *d_summary,
+                                         void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!d_summary || (!has_halo && first_code_bit >= (unsigned)kSubBits)) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    ShardGeom g;
+    int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
+    if (rc != DC_OK) return rc;
+    DecodeChain init = {0ull, has_halo ? 0u : first_code_bit, 0, 0u, 0u};
+    DC_CUDA_TRY(cudaMemcpyAsync(g.chain, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    // (F2 never checks the symbol total here: last_chunk = 0; the caller checks the sum over all shards)
+    rc = launch_fast_sync(g.base, first_code_bit, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, 0, nullptr, g.esc, g.chain, 0, g.lead, st);
+    if (rc != DC_OK) return rc;
+    DC_CUDA_TRY(cudaMemcpyAsync(d_summary, g.chain, sizeof(DecodeChain), cudaMemcpyDeviceToDevice, st));
+    return DC_OK;
+}
+
+extern "C" int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, uint64_t shard_bits, uint64_t stream_bits_left,
+                                          const dc_huff_table *d_table, uint8_t *d_out, size_t n_out, int32_t *d_status,
+                                          void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (n_out && !d_out) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    ShardGeom g;
+    int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
+    if (rc != DC_OK) return rc;
+    return launch_fast_write(g.base, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, d_out, n_out, d_status, g.esc, g.stage_bytes, g.lead, st);
 }
 
 // ================================================================================================ pipelined host decompress
@@ -1128,27 +1227,16 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         const int last = k + 1 == nchunk;
         DC_CUDA_TRY(cudaStreamWaitEvent(cp, g_pipe.ev_up[last ? k : k + 1], 0));
         // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
-        const unsigned long long sms = (unsigned long long)sm_count(), want = (nseg + kF_Warps - 1) / kF_Warps;
         const uint8_t *bits_k = d_bits + k * chunk_bytes;
         {
-            LaunchScope ls(DC_K_DECODE_FAST_SYNC, cp);
-            const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
-            if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, cp>>>(bits_k, 0, end_rel, d_table, fw, nsubf, nwt, nseg, d_chain);
-            else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, cp>>>(bits_k, 0, end_rel, d_table, fw, nsubf, nwt, nseg, d_chain);
-        }
-        {
-            LaunchScope ls(DC_K_DECODE_FAST_SCAN, cp);
-            decode_fast_scan_kernel<<<1, 1024, 0, cp>>>(fw, nseg, n_out, d_status, d_chain, last);
+            const int rc = launch_fast_sync(bits_k, 0, end_rel, nsubf, nwt, nseg, d_table, fw, n_out, d_status, esc, d_chain, last, 0, cp);
+            if (rc != DC_OK) return rc;
         }
         DC_CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_ring[k], d_chain, sizeof(DecodeChain), cudaMemcpyDeviceToHost, cp));
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f2[k], cp));
         {
-            const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
-            DC_CUDA_TRY(ensure_write_smem(smem3));
-            LaunchScope ls(DC_K_DECODE_FAST_WRITE, cp);
-            const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-            if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, cp>>>(bits_k, end_rel, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
-            else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, cp>>>(bits_k, end_rel, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status);
+            const int rc = launch_fast_write(bits_k, end_rel, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, 0, cp);
+            if (rc != DC_OK) return rc;
         }
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f3[k], cp));
         DC_CUDA_TRY(cudaGetLastError());

@@ -169,6 +169,66 @@ class ShardedHuffman:
             raise DcError(st, "sharded decode")
         return out
 
+    def decode_stream(self, part: torch.Tensor, part_bytes: int, total_bits: int, table, n_total: int):
+        """Decode ONE bitstream that is cut into equal byte ranges over the ranks (BASELINE config 5): rank r holds bytes
+        [r * part_bytes, ...) of the payload in `part`; part_bytes is a multiple of 1024 (the last rank's part may be
+        shorter).  No side information about code boundaries: every rank finds its first code by synchronising over the
+        last 1024 bytes of its left neighbour, the ranks compare what they assumed with where their neighbours really
+        ended (an all-gather of 24 bytes), and the symbol counts become output offsets.  Returns (symbols, offset)."""
+        from . import api
+        if part_bytes % api.SHARD_ALIGN:
+            raise ValueError("part_bytes must be a multiple of 1024")
+        dev = part.device
+        r, G = self.rank, self.world
+        total_bytes = (total_bits + 7) // 8
+        lo = min(r * part_bytes, total_bytes)
+        hi = min(lo + part_bytes, total_bytes)
+        mine = hi - lo
+        # halos: the last 1024 bytes and the first 1024 bytes of every part
+        edge = torch.zeros(2 * api.SHARD_ALIGN, dtype=torch.uint8, device=dev)
+        if mine:
+            k = min(mine, api.SHARD_ALIGN)
+            edge[:k] = part[:k]
+            edge[2 * api.SHARD_ALIGN - k:] = part[mine - k: mine]
+        edges = self._all_gather_list(edge)
+        buf = torch.zeros(api.SHARD_ALIGN + mine + api.SHARD_ALIGN, dtype=torch.uint8, device=dev)
+        if r > 0:
+            buf[: api.SHARD_ALIGN] = edges[r - 1][api.SHARD_ALIGN:]
+        buf[api.SHARD_ALIGN: api.SHARD_ALIGN + mine] = part[:mine]
+        if r + 1 < G:
+            buf[api.SHARD_ALIGN + mine:] = edges[r + 1][: api.SHARD_ALIGN]
+        left = total_bits - 8 * lo if mine else 0
+        my_bits = min(8 * mine, left)
+        dec = api.ShardDecoder(buf, mine, my_bits, left, table) if my_bits > 0 else None
+        summ = dec.sync(has_halo=r > 0) if dec else torch.zeros(3, dtype=torch.int64, device=dev)
+        for _ in range(G + 1):
+            infos = [api.ShardDecoder.unpack(t.cpu()) for t in self._all_gather_list(summ)]
+            active = [g for g in range(G) if min(8 * part_bytes, max(total_bits - 8 * g * part_bytes, 0)) > 0]
+            if any(infos[g]["resync"] for g in active):
+                raise RuntimeError("the stream does not self-synchronise within 8192 bits; decode it on one device")
+            # where does every shard's first code really start?  (the previous active shard's exit; 0 for the first)
+            wrong = [g for i, g in enumerate(active) if i > 0 and infos[g]["assumed_start"] != infos[active[i - 1]]["exit"]]
+            if not wrong:
+                break
+            if r in wrong and dec:
+                prev = active[active.index(r) - 1]
+                summ = dec.sync(has_halo=False, first_code_bit=infos[prev]["exit"])
+        else:
+            raise RuntimeError("shard starts did not settle")
+        counts = [infos[g]["symbols"] if g in active else 0 for g in range(G)]
+        offsets, total = exclusive_offsets(counts)
+        if total != n_total:
+            from ._lib import DC_ERR_CORRUPT, DcError
+            raise DcError(DC_ERR_CORRUPT, f"sharded decode: {total} symbols, expected {n_total}")
+        if not dec:
+            return torch.empty(0, dtype=torch.uint8, device=dev), offsets[r]
+        out, status = dec.write(counts[r])
+        st = int(status.item())
+        if st != 0:
+            from ._lib import DcError
+            raise DcError(st, "sharded decode")
+        return out, offsets[r]
+
     def symbol_offsets(self, n_local: int):
         """Exclusive scan of the per-rank symbol counts (the decode side's output offsets)."""
         t = torch.tensor([n_local], dtype=torch.int64, device=self.device or "cpu")

@@ -192,6 +192,39 @@ int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, co
                    uint8_t *d_out, size_t n_out, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
                    void *stream);
 
+/* ---- one contiguous byte range ("shard") of a longer bitstream, e.g. one GPU's part (BASELINE config 5)
+ *
+ * The stream is cut at multiples of 1024 bytes.  A shard does not know where its first code begins; it finds it the way
+ * every 16 KB segment inside a stream does, by walking the last 1024 bytes of the PREVIOUS shard until the codes have
+ * self-synchronised, and reports what it assumed and where its own last code ends.  The caller exchanges the summaries
+ * (an all-gather of 24 bytes per shard), checks assumed_start[g] == exit[g-1] for every g, turns the symbol counts into
+ * output offsets with an exclusive scan, and calls the write phase.  A shard whose assumption was wrong (a stream that
+ * does not self-synchronise within 8192 bits) is re-run with has_halo = 0 and first_code_bit = exit[g-1].
+ *
+ * Geometry, the same for both calls:
+ *   d_bits            first byte of the shard, 16-byte aligned, at a multiple of 1024 bytes of the stream
+ *   has_halo          != 0: the 1024 bytes in front of d_bits are readable and hold the previous shard's tail
+ *   first_code_bit    has_halo == 0 only: exact bit offset (< 128) of the first code that starts in the shard
+ *   shard_bits        bits of the stream that belong to this shard (a multiple of 8192 for all but the last shard)
+ *   stream_bits_left  bits from d_bits to the end of the stream (>= shard_bits; up to 8 bytes past the shard are read)
+ */
+typedef struct dc_shard_summary {
+    uint64_t symbols;        /* codes that START in the shard */
+    uint32_t exit;           /* bits by which the shard's last code reaches into the next shard */
+    int32_t resync;          /* != 0: some 16 KB segment inside the shard did not self-synchronise; decode the stream whole */
+    uint32_t assumed_start;  /* bit offset of the first code the shard assumed (== first_code_bit without a halo) */
+    uint32_t reserved;
+} dc_shard_summary;
+
+int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, unsigned first_code_bit, uint64_t shard_bits,
+                              uint64_t stream_bits_left, const dc_huff_table *d_table, dc_shard_summary *d_summary,
+                              void *d_workspace, size_t workspace_bytes, void *stream);
+/* writes the shard's symbols to d_out[0 .. n_out); n_out must equal the summary's symbol count.  Uses the workspace
+ * the sync phase left behind. */
+int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, uint64_t shard_bits, uint64_t stream_bits_left,
+                               const dc_huff_table *d_table, uint8_t *d_out, size_t n_out, int32_t *d_status,
+                               void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------- K5 nybble */
 
 /*

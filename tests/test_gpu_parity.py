@@ -345,3 +345,33 @@ def test_shard_bit_totals(dc, oracle):
         want = dc.huff_encode(data[lo:hi].clone(), table).bits()
         got = int(dc.huff_bits_for_hist(dc.histogram(data[lo:hi].clone()), table).item())
         assert got == want
+
+
+@pytest.mark.parametrize("n_ary", PACKABLE)
+def test_shard_decoder_halo_and_exact_start_agree(dc, oracle, n_ary):
+    """A shard of a longer stream decoded (a) by synchronising over its neighbour's last 1024 bytes and (b) from the
+    exact first-code offset the neighbour reports: same assumption, same symbols -- and together with shard 0 the input."""
+    data = _zipf(dc, 900001, seed=n_ary)
+    host = data.cpu().numpy()
+    ln, el, ev, st = oracle.build_tables(oracle.histogram_u8(host), n_ary)
+    payload, total_bits = oracle.pack(host, el, ev, oracle.bits_per_digit(n_ary))
+    table = dc.huff_table_from_lengths(_dev(ln.astype(np.int32)), n_ary)
+    cut = (payload.size // 2) // 1024 * 1024
+    pad = np.zeros(1024, dtype=np.uint8)
+    buf0 = _dev(np.concatenate([pad, payload[:cut], payload[cut: cut + 1024]]))
+    buf1 = _dev(np.concatenate([payload[cut - 1024: cut], payload[cut:], pad]))
+    d0 = dc.ShardDecoder(buf0, cut, 8 * cut, total_bits, table)
+    s0 = dc.ShardDecoder.unpack(d0.sync(has_halo=False, first_code_bit=0).cpu())
+    d1 = dc.ShardDecoder(buf1, payload.size - cut, total_bits - 8 * cut, total_bits - 8 * cut, table)
+    s1 = dc.ShardDecoder.unpack(d1.sync(has_halo=True).cpu())
+    assert s0["resync"] == 0 and s1["resync"] == 0
+    assert s1["assumed_start"] == s0["exit"]
+    assert s0["symbols"] + s1["symbols"] == host.size
+    out0, st0 = d0.write(s0["symbols"])
+    out1, st1 = d1.write(s1["symbols"])
+    assert int(st0.item()) == 0 and int(st1.item()) == 0
+    assert np.array_equal(np.concatenate([out0.cpu().numpy(), out1.cpu().numpy()]), host)
+    s1x = dc.ShardDecoder.unpack(d1.sync(has_halo=False, first_code_bit=s0["exit"]).cpu())
+    assert s1x["symbols"] == s1["symbols"] and s1x["exit"] == s1["exit"] and s1x["assumed_start"] == s0["exit"]
+    out1x, st1x = d1.write(s1x["symbols"])
+    assert int(st1x.item()) == 0 and torch.equal(out1x, out1)

@@ -70,3 +70,45 @@ def test_sharded_cuda_encode_equals_single_stream(n_ary, sizes):
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n_ary, sizes, results), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world)), dict(results)
+
+
+def _stream_worker(rank, world, port, n_ary, n, results):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import data_compression_b200 as dc
+        from data_compression_b200 import synth
+        from data_compression_b200.shard import ShardedHuffman
+        from oracle import pyoracle as O
+        O.build()
+        thr, base = synth.zipf_bytes_spec()
+        stream = synth.host_stream(n, 1234 + n_ary, thr, base)
+        # the bitstream comes from the ORACLE (BASELINE config 5: "reference-produced"), and is cut blindly into byte ranges
+        lengths, el, ev, st = O.build_tables(O.histogram_u8(stream), n_ary)
+        payload, total_bits = O.pack(stream, el, ev, O.bits_per_digit(n_ary))
+        part_bytes = ((payload.size + world - 1) // world + 1023) // 1024 * 1024
+        lo = min(rank * part_bytes, payload.size)
+        part = torch.from_numpy(payload[lo: lo + part_bytes].copy()).to(dev)
+        table = dc.huff_table_from_lengths(torch.from_numpy(lengths.astype(np.int32)).to(dev), n_ary)
+        sh = ShardedHuffman(device=dev)
+        out, off = sh.decode_stream(part, part_bytes, total_bits, table, n)
+        ok = bool(np.array_equal(out.cpu().numpy(), stream[off: off + out.numel()]))
+        sizes = [int(x.item()) for x in sh._all_gather_list(torch.tensor([out.numel()], dtype=torch.int64, device=dev))]
+        ok &= sum(sizes) == n and off == sum(sizes[:rank])
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_ary,n,world", [(2, 700001, 2), (4, 300000, 2), (16, 123457, 2), (2, 5000, 2), (4, 2000000, 4)])
+def test_one_stream_cut_blindly_over_ranks(n_ary, n, world):
+    """Config 5: one oracle-produced bitstream, byte ranges per rank, first codes found by boundary synchronisation."""
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_stream_worker, args=(world, _free_port(), n_ary, n, results), nprocs=world, join=True)
+    assert all(results.get(r) for r in range(world)), dict(results)
