@@ -59,6 +59,18 @@ int decode_items_with_codes(const int max_symbol_value, const int canonical_leng
     return done("decode_items_with_codes", rc) < 0 ? rc : n_symbols;
 }
 
+void write_nybble(const int nybble, char *dest, bool nybble_offset) {
+    if (nybble < 0 || nybble >= 0x10 || !dest) {  /* assert( nybble < 0x10 ) :1093 */
+        done("write_nybble", DC_ERR_SYMBOL);
+        return;
+    }
+    const unsigned char old = (unsigned char)*dest;
+    unsigned char sym[2], packed = 0;
+    sym[0] = nybble_offset ? (unsigned char)(old >> 4) : (unsigned char)nybble;
+    sym[1] = nybble_offset ? (unsigned char)nybble : (unsigned char)(old & 0x0F);
+    if (done("write_nybble", dc_host_nybble_pack(sym, 2, &packed)) == DC_OK) *dest = (char)packed;
+}
+
 void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned char *packed) {
     done("nybble_pack_stream", dc_host_nybble_pack(symbols, n_symbols, packed));
 }

@@ -48,8 +48,12 @@ int decode_items_with_codes(const int max_symbol_value, const int canonical_leng
 /* bits emitted by the last represent_items_with_codes() call (the reference's signature has no slot for it) */
 uint64_t represent_items_last_total_bits(void);
 
-/* stream forms of write_nybble() nybble_compression.c:1091-1114 and of the split at :767-769.
- * (write_nybble itself stores ONE nibble into a host byte; there is nothing to offload in that.) */
+/* nybble_compression.c:1091-1114, verbatim signature: store one nibble into *dest, offset 0 = the HIGH nibble.
+ * One nibble per call is no work for a GPU; it is here so that a caller of the reference links unchanged (it goes
+ * through the same pack kernel as the stream form below, which is the one to use). */
+void write_nybble(const int nybble, char *dest, bool nybble_offset);
+
+/* stream forms of write_nybble() and of the decoder's split at :767-769 */
 void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned char *packed);
 void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigned char *symbols);
 

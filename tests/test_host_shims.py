@@ -13,7 +13,7 @@ from conftest import ROOT
 HOST = os.path.join(ROOT, "data_compression_b200", "host")
 REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
 REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
-             "decode_items_with_codes", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
+             "decode_items_with_codes", "write_nybble", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
              "decompress_bytestring"]
 
 
@@ -68,3 +68,16 @@ def test_nybble_compression_cli(built):
     data = np.random.default_rng(3).integers(0, 256, size=1 << 20, dtype=np.uint8).tobytes()
     r = subprocess.run([os.path.join(HOST, "nybble_compression"), "-"], input=data, capture_output=True, timeout=60)
     assert r.returncode == 0 and b"Successful test." in r.stdout
+
+
+@pytest.mark.gpu
+def test_write_nybble_verbatim_signature(built):
+    """write_nybble(nybble, dest, offset) nybble_compression.c:1091-1114: offset 0 replaces the high nibble, 1 the low."""
+    L = ctypes.CDLL(REFAPI)
+    L.write_nybble.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_bool]
+    L.write_nybble.restype = None
+    b = ctypes.create_string_buffer(b"\x5a", 1)
+    L.write_nybble(0xC, b, False)
+    assert b.raw == b"\xca"
+    L.write_nybble(0x3, b, True)
+    assert b.raw == b"\xc3"
