@@ -65,61 +65,126 @@ struct TxWorkspace {
     int32_t *mode;                     // [1] compress: 1 = fall back to ' ' + raw; decompress: 0 = 0xAF, 1 = ' ', 2 = other; -1 = do nothing
 };
 
-// bytes [base, base + 16) of the input as 16 values (0 beyond n); prev = byte base - 1 (0 at the start)
-__device__ __forceinline__ void load_block(const uint8_t *__restrict__ in, size_t n, size_t base, uint32_t (&c)[kTxPer], uint32_t &prev) {
+// ---- a thread's block as bit masks.  Units are bytes (compress, 32 per block) or nibbles in stream order
+// (decompress, 64 per block); bit j of a mask = unit j.
+//   T  units that toggle the state: table hits (compress) / nibbles without bit 3 (decompress)
+//   V  units that take part: they exist and are not the stream's header (byte 0 when compressing, bytes 0-1 when
+//      decompressing); a unit outside T resets the state to 0
+// The state before every unit follows from T alone: inside a run of T units it alternates, starting from 0 after a
+// reset (or from the block's entry state for the run that begins at unit 0).  E = units at an even offset inside
+// their run (after such a unit the state is 1); the usual carry trick finds it without a loop.
+template <typename M> struct TxBlock {
+    M T, V;
+    int units;       // units present in the block (header included)
+};
+
+template <typename M> __device__ __forceinline__ M even_mask();
+template <> __device__ __forceinline__ uint32_t even_mask<uint32_t>() { return 0x55555555u; }
+template <> __device__ __forceinline__ unsigned long long even_mask<unsigned long long>() { return 0x5555555555555555ull; }
+__device__ __forceinline__ int popcnt(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popcnt(unsigned long long x) { return __popcll(x); }
+
+// E for entry state 0, and the leading run F (the only part the entry state changes)
+template <typename M>
+__device__ __forceinline__ void run_parity(M T, M &E, M &F) {
+    const M even = even_mask<M>();
+    const M S = T & ~(T << 1);                       // run starts
+    const M Re = ((T + (S & even)) ^ T) & T;         // runs that start on an even unit
+    E = (Re & even) | (T & ~Re & ~even);
+    F = T & ~(T + 1);                                // the run that begins at unit 0
+}
+template <typename M> __device__ __forceinline__ M low_bits(int k) { return k >= (int)(8 * sizeof(M)) ? ~(M)0 : (((M)1 << k) - 1); }
+
+// the two 16-byte vectors of the block (0 beyond n), unpacked; prev = the byte in front of the block (0 at the start)
+// byte k of the block (k is a compile-time constant after unrolling: one shift and one mask, no array of bytes kept live)
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[kTxPer / 4], int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xFFu; }
+
+__device__ __forceinline__ void load_block(const uint8_t *__restrict__ in, size_t n, size_t base, uint32_t &prev, uint32_t (&w)[kTxPer / 4]) {
     if (base + kTxPer <= n && ((uintptr_t)(in + base) & 15) == 0) {
         uint4 v[kTxVec];
 #pragma unroll
         for (int j = 0; j < kTxVec; j++) v[j] = ldg_stream((const uint4 *)(in + base) + j);
 #pragma unroll
-        for (int j = 0; j < kTxVec; j++) {
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-            for (int k = 0; k < 16; k++) c[16 * j + k] = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-        }
+        for (int j = 0; j < kTxVec; j++) { w[4 * j] = v[j].x; w[4 * j + 1] = v[j].y; w[4 * j + 2] = v[j].z; w[4 * j + 3] = v[j].w; }
     } else {
 #pragma unroll
-        for (int k = 0; k < kTxPer; k++) c[k] = base + k < n ? in[base + k] : 0u;
+        for (int j = 0; j < kTxPer / 4; j++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) x |= (base + 4 * j + k < n ? (uint32_t)in[base + 4 * j + k] : 0u) << (8 * k);
+            w[j] = x;
+        }
     }
     prev = base > 0 && base - 1 < n ? in[base - 1] : 0u;
 }
 
-// transfer function of the thread's block.  COMPRESS: units are bytes (byte 0 of the stream is the verbatim first
-// byte: it emits nothing and leaves q = 0).  else: units are the two nibbles of every byte from index 2 on.
-template <bool COMPRESS, bool FULL>
-__device__ __forceinline__ uint32_t block_fn_impl(const uint8_t *lut, const uint32_t (&c)[kTxPer], int valid, int skip, bool &bad) {
-    uint32_t e0 = 0, e1 = 0, q0 = 0, q1 = 1;
+// masks of a compress block: T = table hits.  li[k] = table index of byte k (8 = not in the table)
+__device__ __forceinline__ void compress_masks(const uint8_t *lut, const uint32_t (&w)[kTxPer / 4], size_t base, size_t n, TxBlock<uint32_t> &b,
+                                               uint32_t (&li)[kTxPer], bool &bad) {
+    const int valid = (int)min((size_t)kTxPer, n - base), skip = base == 0 ? 1 : 0;
+    b.units = valid;
+    b.V = low_bits<uint32_t>(valid) & ~low_bits<uint32_t>(skip);
+    uint32_t miss = 0;
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
-        if (!FULL && k >= valid) continue;  // (no break: the loop must unroll completely or c[] lands in local memory)
-        if (!FULL && k < skip) { q0 = q1 = 0; e0 = e1 = 0; continue; }
-        if (COMPRESS) {
-            bad |= c[k] == 0 || c[k] >= 0x80u;  // assert( source[i] < 0x80 ) :910; 0x00 would end the C string
-            const uint32_t hit = lut[c[k] & 0x7Fu] < 8 ? 1u : 0u;
-            e0 += hit ? q0 : 1 + q0;
-            e1 += hit ? q1 : 1 + q1;
-            q0 = hit & (q0 ^ 1u);
-            q1 = hit & (q1 ^ 1u);
-        } else {
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t x = h == 0 ? c[k] >> 4 : c[k] & 0xFu, hb = x >> 3;
-                e0 += hb | q0;
-                e1 += hb | q1;
-                q0 = (hb | q0) ^ 1u;
-                q1 = (hb | q1) ^ 1u;
-            }
-        }
+        li[k] = lut[byte_of(w, k) & 0x7Fu];
+        miss |= k >= 3 ? (li[k] & 8u) << (k - 3) : (li[k] & 8u) >> (3 - k);
     }
-    return fn_pack(e0, e1, q0, q1);
+    b.T = ~miss & b.V;
+    // assert( source[i] < 0x80 ) :910, and 0x00 would end the C string: a zero byte or a byte with bit 7 among the valid ones
+    uint32_t flag = 0;
+#pragma unroll
+    for (int j = 0; j < kTxPer / 4; j++) {
+        const uint32_t x = w[j];
+        uint32_t f = (x | ((x - 0x01010101u) & ~x)) & 0x80808080u;   // bit 7 of every byte that is 0 or >= 0x80
+        const int nb = valid - 4 * j;                                  // bytes of this word that exist
+        if (nb < 4) f &= nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb)));
+        if (j == 0 && skip) f &= ~0xFFu;                               // the verbatim first byte is not looked at
+        flag |= f;
+    }
+    bad |= flag != 0;
 }
-template <bool COMPRESS>
-__device__ __forceinline__ uint32_t block_fn(const uint8_t *lut, const uint32_t (&c)[kTxPer], size_t base, size_t n, bool &bad) {
-    // 32-bit bookkeeping: how many of the block's bytes exist, and how many leading bytes are the stream's header
-    const int valid = (int)min((size_t)kTxPer, n - base);
-    const int skip = base == 0 ? (COMPRESS ? 1 : 2) : 0;
-    if (valid == kTxPer && skip == 0) return block_fn_impl<COMPRESS, true>(lut, c, valid, skip, bad);
-    return block_fn_impl<COMPRESS, false>(lut, c, valid, skip, bad);
+
+// masks of a decompress block: T = nibbles WITHOUT bit 3 (first or second halves of literals), in stream order
+__device__ __forceinline__ void decompress_masks(const uint32_t (&w)[kTxPer / 4], size_t base, size_t n, TxBlock<unsigned long long> &b) {
+    const int valid = (int)min((size_t)kTxPer, n - base), skip = base == 0 ? 2 : 0;
+    b.units = 2 * valid;
+    b.V = low_bits<unsigned long long>(2 * valid) & ~low_bits<unsigned long long>(2 * min(skip, valid));
+    unsigned long long hmask = 0;
+#pragma unroll
+    for (int j = 0; j < kTxPer / 4; j++) {
+        // bit 3 of the 8 nibbles of word j -> 8 consecutive bits, low nibble of byte 0 first; then swap pairs: the stream
+        // has the HIGH nibble of every byte first (:767-773)
+        uint32_t y = (w[j] >> 3) & 0x11111111u;
+        y = (y | (y >> 3)) & 0x03030303u;
+        y = (y | (y >> 6)) & 0x000F000Fu;
+        y = (y | (y >> 12)) & 0xFFu;
+        y = ((y & 0x55u) << 1) | ((y & 0xAAu) >> 1);
+        hmask |= (unsigned long long)y << (8 * j);
+    }
+    b.T = ~hmask & b.V;
+}
+
+// transfer function of a block from its masks.  COMPRESS: a hit emits the pending pair (state 1), a miss emits itself and,
+// in state 1, the stranded hit in front of it.  else: every nibble emits, except the first half of a literal.
+template <bool COMPRESS, typename M>
+__device__ __forceinline__ uint32_t block_fn_of(const TxBlock<M> &b) {
+    if (b.units == 0) return kFnIdentity;
+    M E, F;
+    run_parity(b.T, E, F);
+    const M E1 = E ^ F;
+    const M Q0 = E << 1, Q1 = (E1 << 1) | (M)1;
+    uint32_t e0, e1;
+    if (COMPRESS) {
+        const int misses = popcnt(b.V & ~b.T);
+        e0 = (uint32_t)(misses + popcnt(Q0 & b.V));
+        e1 = (uint32_t)(misses + popcnt(Q1 & b.V));
+    } else {
+        e0 = (uint32_t)popcnt(b.V & (~b.T | Q0));
+        e1 = (uint32_t)popcnt(b.V & (~b.T | Q1));
+    }
+    const int last = b.units - 1;
+    return fn_pack(e0, e1, (uint32_t)(E >> last) & 1u, (uint32_t)(E1 >> last) & 1u);
 }
 
 // ------------------------------------------------------------------------------------------ S1
@@ -136,9 +201,18 @@ __global__ void __launch_bounds__(kTxThreads) tx_summary_kernel(const uint8_t *_
         const size_t base = tile * kTxTile + (size_t)tid * kTxPer;
         uint32_t f = kFnIdentity;
         if (base < n) {
-            uint32_t c[kTxPer], prev;
-            load_block(in, n, base, c, prev);
-            f = block_fn<COMPRESS>(s_lut, c, base, n, bad);
+            uint32_t prev, w[kTxPer / 4];
+            load_block(in, n, base, prev, w);
+            if (COMPRESS) {
+                TxBlock<uint32_t> b;
+                uint32_t li[kTxPer];
+                compress_masks(s_lut, w, base, n, b, li, bad);
+                f = block_fn_of<true>(b);
+            } else {
+                TxBlock<unsigned long long> b;
+                decompress_masks(w, base, n, b);
+                f = block_fn_of<false>(b);
+            }
         }
         // ordered reduction over the warp, then over the CTA's warps
 #pragma unroll
@@ -269,42 +343,52 @@ __global__ void __launch_bounds__(kTxScanThreads) tx_scan_kernel(const uint8_t *
     }
 }
 
-// emit the symbols of the thread's block from entry state q into shared memory at dst
-template <bool COMPRESS, bool FULL>
-__device__ __forceinline__ void emit_block(const uint8_t *s_lut, const uint32_t (&c)[kTxPer], int valid, int skip, bool ends_here, uint32_t q,
-                                           uint32_t prev, uint8_t *dst) {
-    uint32_t pli = s_lut[prev & 0x7Fu];  // table index of the previous byte
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// emit the symbols of a compress block from entry state q_in into shared memory at dst (a shared-space address).
+// Every byte knows the state in front of it (Q) and its output offset (a popcount), so nothing is carried along.
+__device__ __forceinline__ void emit_compress(const TxBlock<uint32_t> &b, const uint32_t (&w)[kTxPer / 4], const uint32_t (&li)[kTxPer], uint32_t prev,
+                                              uint32_t prev_li, uint32_t q_in, uint32_t dst, bool ends_here) {
+    uint32_t E, F;
+    run_parity(b.T, E, F);
+    if (q_in) E ^= F;
+    const uint32_t Q = (E << 1) | q_in;
+    const uint32_t A = Q & b.V;        // a byte in front of which a hit is pending: a hit completes the pair, a miss strands it
+    const uint32_t Mm = b.V & ~b.T;    // misses: literals
+    const uint32_t pairs = A & b.T, strand = A & Mm;
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
-        if (!FULL && k >= valid) continue;  // (no break: see block_fn_impl)
-        if (COMPRESS) {
-            if (!FULL && k < skip) { q = 0; prev = c[k]; pli = 8; continue; }
-            // predicated stores, no branches (a byte past the thread's own range belongs to the next thread)
-            const uint32_t li = s_lut[c[k] & 0x7Fu], hit = li < 8 ? 1u : 0u;
-            const uint32_t pair = ((8u | pli) << 4) | (8u | li);
-            const uint32_t b0 = hit ? pair : (q ? prev : c[k]);
-            const uint32_t n_emit = hit ? q : 1u + q;
-            if (n_emit >= 1) dst[0] = (uint8_t)b0;
-            if (n_emit == 2) dst[1] = (uint8_t)c[k];
-            dst += n_emit;
-            q = hit & (q ^ 1u);
-            prev = c[k];
-            pli = li;
-            if (!FULL && ends_here && k == valid - 1 && q) *dst++ = (uint8_t)c[k];  // trailing half byte -> literal
-        } else {
-            if (!FULL && k < skip) { q = 0; prev = c[k] & 0xFu; continue; }
-            uint32_t pn = prev & 0xFu;  // the nibble before this byte's high nibble
+        const uint32_t bit = 1u << k, below = bit - 1u;
+        const uint32_t off = dst + __popc(A & below) + __popc(Mm & below);
+        const uint32_t ck = byte_of(w, k), pc = k ? byte_of(w, k ? k - 1 : 0) : prev, pl = k ? li[k ? k - 1 : 0] : prev_li;
+        if (pairs & bit) sts8(off, ((8u | pl) << 4) | (8u | li[k]));
+        if (strand & bit) sts8(off, pc);
+        if (Mm & bit) sts8(off + ((Q >> k) & 1u), ck);
+        if (ends_here && k == b.units - 1 && (E & bit)) sts8(dst + __popc(A) + __popc(Mm), ck);  // trailing half byte -> literal
+    }
+}
+
+// the same for a decompress block: 64 nibbles, in two halves of 32 so that the masks stay 32-bit
+__device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long> &b, const uint32_t (&w)[kTxPer / 4], uint32_t prev, uint32_t q_in,
+                                                uint32_t dst, bool ends_here) {
+    unsigned long long E, F;
+    run_parity(b.T, E, F);
+    if (q_in) E ^= F;
+    const unsigned long long Q = (E << 1) | q_in;
+    const unsigned long long Em = b.V & (~b.T | Q);  // every nibble emits, except the first half of a literal
+    const uint32_t em[2] = {(uint32_t)Em, (uint32_t)(Em >> 32)}, qq[2] = {(uint32_t)Q, (uint32_t)(Q >> 32)};
+    const uint32_t ee[2] = {(uint32_t)E, (uint32_t)(E >> 32)};
+    const uint32_t base1 = __popc(em[0]);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t x = h == 0 ? c[k] >> 4 : c[k] & 0xFu, emit = (x >> 3) | q;
-                if (emit) dst[0] = (uint8_t)(q ? ((pn & 7u) << 4) + x : letter_of(x));
-                dst += emit;
-                q = emit ^ 1u;
-                pn = x;
-            }
-            prev = c[k];
-            if (!FULL && ends_here && k == valid - 1 && q) *dst++ = (uint8_t)((pn & 7u) << 4);  // dangling half literal + zero nibble
-        }
+    for (int j = 0; j < 2 * kTxPer; j++) {
+        const int h = j >> 5;
+        const uint32_t bit = 1u << (j & 31), below = bit - 1u;
+        const uint32_t off = dst + (h ? base1 : 0u) + __popc(em[h] & below);
+        const uint32_t cj = byte_of(w, j >> 1);
+        const uint32_t x = (j & 1) ? (cj & 0xFu) : (cj >> 4);
+        const uint32_t pn = j == 0 ? (prev & 0xFu) : ((j & 1) ? (cj >> 4) : (byte_of(w, j ? (j >> 1) - 1 : 0) & 0xFu));
+        if (em[h] & bit) sts8(off, (qq[h] & bit) ? ((pn & 7u) << 4) + x : letter_of(x));
+        if (ends_here && j == b.units - 1 && (ee[h] & bit)) sts8(dst + base1 + __popc(em[1]), (x & 7u) << 4);  // dangling half literal
     }
 }
 
@@ -334,11 +418,21 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
             }
             continue;
         }
-        uint32_t c[kTxPer], prev = 0, f = kFnIdentity;
+        uint32_t prev = 0, w[kTxPer / 4], f = kFnIdentity;
+        uint32_t li[COMPRESS ? kTxPer : 1];
+        TxBlock<uint32_t> bc;
+        TxBlock<unsigned long long> bd;
+        bc.units = bd.units = 0;
         bool bad = false;
         if (base < n) {
-            load_block(in, n, base, c, prev);
-            f = block_fn<COMPRESS>(s_lut, c, base, n, bad);
+            load_block(in, n, base, prev, w);
+            if (COMPRESS) {
+                compress_masks(s_lut, w, base, n, bc, (uint32_t(&)[kTxPer])li, bad);
+                f = block_fn_of<true>(bc);
+            } else {
+                decompress_masks(w, base, n, bd);
+                f = block_fn_of<false>(bd);
+            }
         }
         // inclusive scan over the warp by composition, warp totals to shared memory
         uint32_t incl = f;
@@ -371,13 +465,11 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
         if (last_tile) tile_total += tq;  // the pending half symbol at the end of the stream
         const unsigned long long ob = (COMPRESS ? 2ull : 1ull) + ws.tile_off[tile];
         const uint32_t a = (uint32_t)(((uintptr_t)out + ob) & 15);
-        uint8_t *dst = s_stage + a + off;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + a + off;
         if (base < n) {
-            const int valid = (int)min((size_t)kTxPer, n - base);
-            const int skip = base == 0 ? (COMPRESS ? 1 : 2) : 0;
             const bool ends_here = base + kTxPer >= n;  // this block holds the last byte of the stream
-            if (valid == kTxPer && skip == 0 && !ends_here) emit_block<COMPRESS, true>(s_lut, c, valid, skip, false, q, prev, dst);
-            else emit_block<COMPRESS, false>(s_lut, c, valid, skip, ends_here, q, prev, dst);
+            if (COMPRESS) emit_compress(bc, w, (const uint32_t(&)[kTxPer])li, prev, s_lut[prev & 0x7Fu], q, dst, ends_here);
+            else emit_decompress(bd, w, prev, q, dst, ends_here);
         }
         if (tile == 0 && tid == 0) {
             if (COMPRESS) { out[0] = 0xAF; out[1] = in[0]; }   // :903, :905
