@@ -348,37 +348,42 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("
 // emit the symbols of a compress block from entry state q_in into shared memory at dst (a shared-space address).
 // Every byte knows the state in front of it (Q) and its output offset (a popcount), so nothing is carried along.
 __device__ __forceinline__ void emit_compress(const TxBlock<uint32_t> &b, const uint32_t (&w)[kTxPer / 4], const uint32_t (&li)[kTxPer], uint32_t prev,
-                                              uint32_t prev_li, uint32_t q_in, uint32_t dst, bool ends_here) {
+                                              uint32_t prev_li, uint32_t q_in, uint32_t dst, bool ends_here, const uint8_t *__restrict__ in,
+                                              size_t n) {
     uint32_t E, F;
     run_parity(b.T, E, F);
     if (q_in) E ^= F;
     const uint32_t Q = (E << 1) | q_in;
     const uint32_t A = Q & b.V;        // a byte in front of which a hit is pending: a hit completes the pair, a miss strands it
     const uint32_t Mm = b.V & ~b.T;    // misses: literals
-    const uint32_t pairs = A & b.T, strand = A & Mm;
+    // a byte writes at most two output bytes: "first" (the pair it completes, or the stranded hit in front of it) and
+    // "second" (itself, if it is a miss).  Two predicated stores per byte, offsets by popcount.
+    uint32_t pc = prev, pl8 = 8u | prev_li;
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
         const uint32_t bit = 1u << k, below = bit - 1u;
         const uint32_t off = dst + __popc(A & below) + __popc(Mm & below);
-        const uint32_t ck = byte_of(w, k), pc = k ? byte_of(w, k ? k - 1 : 0) : prev, pl = k ? li[k ? k - 1 : 0] : prev_li;
-        if (pairs & bit) sts8(off, ((8u | pl) << 4) | (8u | li[k]));
-        if (strand & bit) sts8(off, pc);
-        if (Mm & bit) sts8(off + ((Q >> k) & 1u), ck);
-        if (ends_here && k == b.units - 1 && (E & bit)) sts8(dst + __popc(A) + __popc(Mm), ck);  // trailing half byte -> literal
+        const uint32_t ck = byte_of(w, k), l8 = 8u | li[k];
+        if (A & bit) sts8(off, (b.T & bit) ? ((pl8 << 4) | l8) : pc);
+        if (Mm & bit) sts8(off + ((A >> k) & 1u), ck);
+        pc = ck;
+        pl8 = l8;
     }
+    // trailing half byte -> literal (:1000-1009): one thread of the whole grid
+    if (ends_here && b.units > 0 && ((E >> (b.units - 1)) & 1u)) sts8(dst + __popc(A) + __popc(Mm), in[n - 1]);
 }
 
 // the same for a decompress block: 64 nibbles, in two halves of 32 so that the masks stay 32-bit
 __device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long> &b, const uint32_t (&w)[kTxPer / 4], uint32_t prev, uint32_t q_in,
-                                                uint32_t dst, bool ends_here) {
+                                                uint32_t dst, bool ends_here, const uint8_t *__restrict__ in, size_t n) {
     unsigned long long E, F;
     run_parity(b.T, E, F);
     if (q_in) E ^= F;
     const unsigned long long Q = (E << 1) | q_in;
     const unsigned long long Em = b.V & (~b.T | Q);  // every nibble emits, except the first half of a literal
     const uint32_t em[2] = {(uint32_t)Em, (uint32_t)(Em >> 32)}, qq[2] = {(uint32_t)Q, (uint32_t)(Q >> 32)};
-    const uint32_t ee[2] = {(uint32_t)E, (uint32_t)(E >> 32)};
     const uint32_t base1 = __popc(em[0]);
+    uint32_t pn = prev & 0xFu;
 #pragma unroll
     for (int j = 0; j < 2 * kTxPer; j++) {
         const int h = j >> 5;
@@ -386,10 +391,11 @@ __device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long
         const uint32_t off = dst + (h ? base1 : 0u) + __popc(em[h] & below);
         const uint32_t cj = byte_of(w, j >> 1);
         const uint32_t x = (j & 1) ? (cj & 0xFu) : (cj >> 4);
-        const uint32_t pn = j == 0 ? (prev & 0xFu) : ((j & 1) ? (cj >> 4) : (byte_of(w, j ? (j >> 1) - 1 : 0) & 0xFu));
         if (em[h] & bit) sts8(off, (qq[h] & bit) ? ((pn & 7u) << 4) + x : letter_of(x));
-        if (ends_here && j == b.units - 1 && (ee[h] & bit)) sts8(dst + base1 + __popc(em[1]), (x & 7u) << 4);  // dangling half literal
+        pn = x;
     }
+    // a dangling half literal at the very end is completed with a zero nibble: one thread of the whole grid
+    if (ends_here && b.units > 0 && ((E >> (b.units - 1)) & 1ull)) sts8(dst + base1 + __popc(em[1]), ((uint32_t)in[n - 1] & 7u) << 4);
 }
 
 // ------------------------------------------------------------------------------------------ S3
@@ -468,8 +474,8 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + a + off;
         if (base < n) {
             const bool ends_here = base + kTxPer >= n;  // this block holds the last byte of the stream
-            if (COMPRESS) emit_compress(bc, w, (const uint32_t(&)[kTxPer])li, prev, s_lut[prev & 0x7Fu], q, dst, ends_here);
-            else emit_decompress(bd, w, prev, q, dst, ends_here);
+            if (COMPRESS) emit_compress(bc, w, (const uint32_t(&)[kTxPer])li, prev, s_lut[prev & 0x7Fu], q, dst, ends_here, in, n);
+            else emit_decompress(bd, w, prev, q, dst, ends_here, in, n);
         }
         if (tile == 0 && tid == 0) {
             if (COMPRESS) { out[0] = 0xAF; out[1] = in[0]; }   // :903, :905

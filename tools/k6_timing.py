@@ -10,11 +10,12 @@ text = torch.where(pick, letters[torch.randint(0, 8, (n,), device=dev, generator
 del pick
 L = dc.lib()
 buf, ln, st = dc.nybble_text_compress(text); clen = int(ln.item()); comp = buf[:clen].clone(); del buf
-L.dc_profile_reset(); L.dc_profile_enable(1)
-for _ in range(3):
-    dc.nybble_text_compress(text); dc.nybble_text_decompress(comp)
-torch.cuda.synchronize(); L.dc_profile_enable(0)
-for kid in range(40):
-    ms, cnt = C.c_double(0), C.c_uint64(0)
-    L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
-    if cnt.value: print(L.dc_profile_kernel_name(kid).decode(), round(ms.value / cnt.value, 4), cnt.value)
+for name, fn in (("compress", lambda: dc.nybble_text_compress(text)), ("decompress", lambda: dc.nybble_text_decompress(comp))):
+    L.dc_profile_reset(); L.dc_profile_enable(1)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(); L.dc_profile_enable(0)
+    for kid in range(40):
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+        if cnt.value: print(name, L.dc_profile_kernel_name(kid).decode(), round(ms.value / cnt.value, 4), cnt.value)
