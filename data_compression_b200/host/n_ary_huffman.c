@@ -37,100 +37,6 @@ static void fail(const char *what) {
     abort();
 }
 
-static int packable(int n) { return n == 2 || n == 4 || n == 16; }
-
-/* ---- block writer: returns bytes written to out */
-static size_t compress_block(int n, const int lengths[NSLOTS], char *text, size_t text_len, char *out, size_t out_cap) {
-    char *d = out;
-    int header_ok = packable(n) && text_len > 0 && text_len <= (size_t)INT32_MAX - 64 && out_cap <= (size_t)INT32_MAX;
-    for (int i = 0; i < NSLOTS && header_ok; i++) header_ok = lengths[i] < 16;
-    if (header_ok) {
-        SAY("# %d : compressed_symbols.\n# header ....\n", n);
-        const int table_len = 2 + 3 + 1 + NSLOTS; /* "\nX" "258" ":" digits */
-        d += sprintf(d, "%d:\nX%d:", table_len, MAX_SYMBOL_VALUE);
-        for (int i = 0; i < NSLOTS; i++) *d++ = "0123456789ABCDEF"[lengths[i]];
-        d += sprintf(d, ",\n");
-        SAY("# data ....\n");
-        /* payload first (at a scratch position behind the largest possible prefix), then the netstring around it */
-        char *scratch = d + 64;
-        int lens[NSLOTS];
-        memcpy(lens, lengths, sizeof lens);
-        const int bufsize = (int)(out_cap - 1);
-        const int nbytes = represent_items_with_codes(MAX_SYMBOL_VALUE, lens, n, bufsize, (int)text_len, text,
-                                                      (int)(scratch - out), out);
-        const uint64_t bits = represent_items_last_total_bits();
-        char meta[64];
-        const int meta_len = sprintf(meta, "\nZ%zu %llu\n", text_len, (unsigned long long)bits);
-        const size_t coded = (size_t)(d - out) + 24 + (size_t)meta_len + (size_t)nbytes;
-        if (coded < text_len) {
-            d += sprintf(d, "%zu:%s", (size_t)meta_len + (size_t)nbytes, meta);
-            memmove(d, scratch, (size_t)nbytes);
-            d += nbytes;
-            d += sprintf(d, ",\n");
-            SAY("# compressed: %zu -> %zu bytes (%llu bits).\n", text_len, (size_t)(d - out), (unsigned long long)bits);
-            return (size_t)(d - out);
-        }
-        d = out; /* no saving: fall through to the raw block, as the reference does (:1801-1814) */
-    }
-    SAY("# pass-through raw data.\n");
-    d += sprintf(d, "%zu:\n\n", text_len + 2);
-    memcpy(d, text, text_len);
-    d += text_len;
-    d += sprintf(d, ",\n");
-    return (size_t)(d - out);
-}
-
-/* ---- block reader: returns the decompressed length */
-static size_t decompress_blocks(int n, const char *in, size_t in_len, char *out, size_t out_cap) {
-    const char *s = in, *end = in + in_len;
-    int lengths[NSLOTS];
-    int have_table = 0;
-    size_t produced = 0;
-    while (s < end) {
-        char *colon = NULL;
-        const unsigned long long len = strtoull(s, &colon, 10);
-        if (!colon || *colon != ':' || colon + 1 + len + 2 > end) fail("malformed netstring");
-        const char *body = colon + 1, *after = body + len;
-        if (after[0] != ',' || after[1] != '\n' || len < 2 || body[0] != '\n') fail("malformed block");
-        const char type = body[1];
-        const char *data = body + 2;
-        const size_t data_len = (size_t)len - 2;
-        if (type == '\n') {
-            SAY("# raw data:\n");
-            if (produced + data_len + 1 > out_cap) fail("output buffer too small");
-            memcpy(out + produced, data, data_len);
-            produced += data_len;
-        } else if (type == '#') {
-            SAY("# skipping metadata.\n");
-        } else if (type == 'X') {
-            int msv = 0, used = 0;
-            if (sscanf(data, "%d:%n", &msv, &used) != 1 || msv != MAX_SYMBOL_VALUE || data_len != (size_t)used + NSLOTS)
-                fail("unsupported table block");
-            for (int i = 0; i < NSLOTS; i++) {
-                const char c = data[used + i];
-                lengths[i] = c >= '0' && c <= '9' ? c - '0' : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1;
-                if (lengths[i] < 0) fail("bad length digit");
-            }
-            have_table = 1;
-        } else if (type == 'Z') {
-            if (!have_table) fail("data block before its table");
-            size_t nsym = 0;
-            unsigned long long bits = 0;
-            int used = 0;
-            if (sscanf(data, "%zu %llu\n%n", &nsym, &bits, &used) != 2) fail("bad data block");
-            if (produced + nsym + 1 > out_cap || nsym > (size_t)INT32_MAX) fail("output buffer too small");
-            if ((bits + 7) / 8 != data_len - (size_t)used) fail("data block length mismatch");
-            decode_items_with_codes(MAX_SYMBOL_VALUE, lengths, n, bits, data + used, (int)nsym, out + produced);
-            produced += nsym;
-        } else {
-            fail("unknown block type");
-        }
-        s = after + 2;
-    }
-    out[produced] = '\0';
-    return produced;
-}
-
 /* ---- one block through the whole path */
 static void round_trip(int n, char *text, size_t text_len) {
     int freqs[NSLOTS], lengths[NSLOTS];
@@ -154,9 +60,9 @@ static void round_trip(int n, char *text, size_t text_len) {
     char *compressed = malloc(cap + 1), *decompressed = malloc(text_len + 2);
     if (!compressed || !decompressed) fail("out of memory");
     SAY("# compressing text.\n");
-    const size_t clen = compress_block(n, lengths, text, text_len, compressed, cap);
+    const size_t clen = dc_container_compress(n, lengths, text, text_len, compressed, cap);
     SAY("# decompressing text.\n");
-    const size_t dlen = decompress_blocks(n, compressed, clen, decompressed, text_len + 2);
+    const size_t dlen = dc_container_decompress(n, compressed, clen, decompressed, text_len + 2);
     if (dlen != text_len || memcmp(text, decompressed, text_len) != 0) {
         printf("Error: decompressed text doesn't match original text.\n");
         fflush(stdout);
@@ -225,6 +131,7 @@ int main(int argc, char **argv) {
         }
     }
     if (n < 2) fail("radix must be >= 2");
+    dc_container_set_verbose(!quiet);
     test_convert_lengths_to_encode_table();
     test_huffman_known_answers();
     SAY("# embedded text ...\n");

@@ -63,6 +63,14 @@ void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigne
 void compress_bytestring(const char *source, char *dest, bool modify);
 void decompress_bytestring(const char *source, char *dest, bool modify);
 
+/* the netstring block container of n_ary_huffman.c:1705-1814 / :2014-2094 (container.c): table block 'X', data block
+ * 'Z', raw block.  compress() / decompress() are static in the reference; these are their linkable counterparts.
+ * Return the number of bytes written, (size_t)-1 on a malformed container. */
+size_t dc_container_compress(int compressed_symbols, const int canonical_lengths[259], char *text, size_t text_len, char *out,
+                             size_t out_cap);
+size_t dc_container_decompress(int compressed_symbols, const char *in, size_t in_len, char *out, size_t out_cap);
+void dc_container_set_verbose(int on);
+
 /* 1 (default): abort() on a device error, like the reference's assert(); 0: record it and return */
 void dc_refapi_set_abort(int on);
 /* dc_status of the last call made through this header */

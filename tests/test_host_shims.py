@@ -14,7 +14,7 @@ HOST = os.path.join(ROOT, "data_compression_b200", "host")
 REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
 REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
              "decode_items_with_codes", "write_nybble", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
-             "decompress_bytestring"]
+             "decompress_bytestring", "dc_container_compress", "dc_container_decompress"]
 
 
 @pytest.fixture(scope="module")
@@ -81,3 +81,36 @@ def test_write_nybble_verbatim_signature(built):
     assert b.raw == b"\xca"
     L.write_nybble(0x3, b, True)
     assert b.raw == b"\xc3"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radix", [2, 4, 16, 3])
+def test_container_blocks(built, radix):
+    """The netstring container (n_ary_huffman.c:1705-1814 / :2014-2094): table block in the reference's own text form,
+    data block, raw fall-back; written and read back through the library."""
+    import numpy as np
+    from data_compression_b200 import hostapi, synth
+    L = ctypes.CDLL(REFAPI)
+    L.dc_container_compress.restype = ctypes.c_size_t
+    L.dc_container_compress.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t,
+                                        ctypes.c_char_p, ctypes.c_size_t]
+    L.dc_container_decompress.restype = ctypes.c_size_t
+    L.dc_container_decompress.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    thr, base = synth.zipf_7bit_spec()
+    text = synth.host_stream(200001, 21, thr, base).tobytes()
+    h = hostapi.histogram(text)
+    lengths = hostapi.huffman(h, radix).astype(np.int32)
+    cap = len(text) + len(text) // 4 + 4096
+    out = ctypes.create_string_buffer(cap + 1)
+    n = L.dc_container_compress(radix, lengths.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), text, len(text), out, cap)
+    blob = out.raw[:n]
+    if radix == 3:      # no payload packing for this radix: the raw block, like the reference
+        assert blob == b"%d:\n\n" % (len(text) + 2) + text + b",\n"
+    else:
+        digits = "".join("0123456789ABCDEF"[int(x)] for x in lengths)
+        assert blob.startswith(b"265:\nX258:" + digits.encode() + b",\n")   # the reference's table block (:1727-1747)
+        assert n < len(text)
+    back = ctypes.create_string_buffer(len(text) + 2)
+    m = L.dc_container_decompress(radix, blob, n, back, len(text) + 2)
+    assert m == len(text) and back.raw[:m] == text
+    assert L.dc_container_decompress(radix, blob[:-3], n - 3, back, len(text) + 2) == ctypes.c_size_t(-1).value   # truncated
