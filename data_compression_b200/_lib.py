@@ -32,13 +32,14 @@ class HuffTableStruct(C.Structure):
     _fields_ = [
         ("n_ary", C.c_int32), ("bits_per_digit", C.c_int32), ("max_symbol_value", C.c_int32),
         ("nonzero_symbols", C.c_int32), ("dummy_nodes", C.c_int32), ("min_len", C.c_int32), ("max_len", C.c_int32),
-        ("max_bits", C.c_int32), ("status", C.c_int32), ("reserved0", C.c_int32),
+        ("max_bits", C.c_int32), ("status", C.c_int32), ("packed_radix", C.c_int32),
         ("total_symbols", C.c_uint64), ("total_bits", C.c_uint64),
         ("lengths", C.c_int32 * (DC_NSLOTS + 1)), ("values", C.c_uint32 * (DC_NSLOTS + 1)),
         ("enc", C.c_uint32 * 256), ("enc64", C.c_uint64 * 256),
         ("first_code", C.c_uint32 * 32), ("len_count", C.c_uint32 * 32), ("len_offset", C.c_uint32 * 32),
         ("sorted", C.c_uint16 * (DC_NSLOTS + 1)), ("lut", C.c_uint16 * (1 << DC_LUT_BITS)),
         ("lut_count", C.c_uint32 * (1 << DC_LUT_BITS)), ("lut_pair", C.c_uint32 * (1 << DC_LUT_BITS)),
+        ("lut2", C.c_uint16 * (256 * 16)), ("lut2_used", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -75,6 +76,8 @@ SYMBOLS = [
     ("dc_huff_decode_shard_write", _i, [_vp, _i, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_nybble_pack", _i, [_vp, _sz, _vp, _vp, _vp]),
     ("dc_nybble_unpack", _i, [_vp, _sz, _vp, _vp]),
+    ("dc_trit_pack", _i, [_vp, _u64, _vp, _vp, _vp]),
+    ("dc_trit_unpack", _i, [_vp, _u64, _vp, _vp, _vp]),
     ("dc_nybble_text_workspace_bytes", _sz, [_sz]),
     ("dc_nybble_text_compress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     ("dc_nybble_text_decompress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),

@@ -222,6 +222,27 @@ def nybble_unpack(packed: torch.Tensor, n_sym: int, out: torch.Tensor | None = N
     return out
 
 
+def trit_pack(t2: torch.Tensor, ntrits: int, out: torch.Tensor | None = None):
+    """Radix 3: the kernels' 2-bit-per-trit stream -> the 5-trits-per-byte payload (n_ary_huffman.c:745-748).
+    Returns (payload[: ceil(ntrits / 5)], status)."""
+    _need_cuda(t2, "t2")
+    nb = (ntrits + 4) // 5
+    if out is None:
+        out = torch.empty(max(nb, 1) + 16, dtype=torch.uint8, device=t2.device)
+    status = torch.empty(1, dtype=torch.int32, device=t2.device)
+    check(lib().dc_trit_pack(t2.data_ptr(), ntrits, out.data_ptr(), status.data_ptr(), _stream()), "dc_trit_pack")
+    return out[:nb], status
+
+
+def trit_unpack(payload: torch.Tensor, ntrits: int):
+    """Inverse of trit_pack.  Returns (t2 stream with slack for dc_huff_decode's vector loads, status)."""
+    _need_cuda(payload, "payload")
+    t2 = torch.empty((2 * ntrits + 7) // 8 + 64, dtype=torch.uint8, device=payload.device)
+    status = torch.empty(1, dtype=torch.int32, device=payload.device)
+    check(lib().dc_trit_unpack(payload.data_ptr(), ntrits, t2.data_ptr(), status.data_ptr(), _stream()), "dc_trit_unpack")
+    return t2, status
+
+
 def _nybble_text(fn_name: str, src: torch.Tensor, cap: int):
     _need_cuda(src, "src")
     n = src.numel()

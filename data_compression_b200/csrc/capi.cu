@@ -136,7 +136,7 @@ extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
 }
 extern "C" const char *dc_profile_kernel_name(int id) {
     static const char *names[DC_K_COUNT] = {"histogram", "table", "bits_for_hist", "encode_count", "encode_scan", "encode", "encode_mid", "encode_wide", "decode_sync", "decode_handoff",
-                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "synth"};
+                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "synth"};
     return id >= 0 && id < DC_K_COUNT ? names[id] : "?";
 }
 
@@ -232,7 +232,8 @@ extern "C" int dc_host_convert_lengths_to_encode_table(int max_symbol_value, con
 
 static int encode_from_table(const uint8_t *h_in, size_t n, dc_huff_table *d_tab, uint8_t *h_out, size_t out_capacity,
                              uint64_t *total_bits, size_t *bytes_written, uint8_t *d_in, uint8_t *d_out, size_t d_cap,
-                             void *d_ws, size_t ws_bytes, uint64_t *d_bits, int32_t *d_status, bool input_resident) {
+                             void *d_ws, size_t ws_bytes, uint64_t *d_bits, int32_t *d_status, bool input_resident, bool trits,
+                             uint8_t *d_packed) {
     if (!input_resident && n) DC_CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, 0));
     int rc = dc_huff_encode(d_in, n, d_tab, d_out, d_cap, 0, d_bits, d_status, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
@@ -242,18 +243,29 @@ static int encode_from_table(const uint8_t *h_in, size_t n, dc_huff_table *d_tab
     DC_CUDA_TRY(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, 0));
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     if (st != DC_OK) return st;
-    const size_t nbytes = (size_t)((bits + 7) / 8);
+    // radix 3: the kernels wrote one 2-bit field per trit; the payload holds 5 trits per byte (K7)
+    const uint8_t *d_payload = d_out;
+    size_t nbytes = (size_t)((bits + 7) / 8);
+    if (trits) {
+        const uint64_t ntrits = bits / 2;
+        rc = dc_trit_pack(d_out, ntrits, d_packed, d_status, nullptr);
+        if (rc != DC_OK) return rc;
+        d_payload = d_packed;
+        nbytes = (size_t)((ntrits + 4) / 5);
+    }
     if (nbytes > out_capacity) return DC_ERR_CAPACITY;
-    if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, nbytes, cudaMemcpyDeviceToHost, 0));
+    if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(h_out, d_payload, nbytes, cudaMemcpyDeviceToHost, 0));
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     if (total_bits) *total_bits = bits;
     *bytes_written = nbytes;
     return DC_OK;
 }
 
-static size_t device_out_capacity(size_t n, size_t host_capacity) {
+static size_t device_out_capacity(size_t n, size_t host_capacity, bool trits) {
     const size_t worst = n * 4 + 64;  // 32 bits per symbol
-    return ((host_capacity < worst ? host_capacity : worst) + 15) & ~(size_t)15;
+    // (radix 3: the intermediate 2-bit-per-trit stream is 1.25 x the payload the host buffer is sized for)
+    const size_t want = trits ? host_capacity + host_capacity / 4 + 64 : host_capacity;
+    return ((want < worst ? want : worst) + 15) & ~(size_t)15;
 }
 
 // represent_items_with_codes(...) n_ary_huffman.c:1621-1678
@@ -264,12 +276,14 @@ extern "C" int dc_host_represent_items_with_codes(int max_symbol_value, const in
         start > bufsize || original_length > bufsize)
         return DC_ERR_ARG;
     const size_t n = (size_t)original_length, host_cap = (size_t)(bufsize + 1 - start);
-    const size_t d_cap = device_out_capacity(n, host_cap), ws_bytes = dc_huff_encode_workspace_bytes(n);
-    int rc = g_arena.reserve(Arena::pad(n) + Arena::pad(d_cap) + Arena::pad(ws_bytes) + Arena::pad(sizeof(dc_huff_table)) +
+    const bool trits = compressed_symbols == 3;
+    const size_t d_cap = device_out_capacity(n, host_cap, trits), ws_bytes = dc_huff_encode_workspace_bytes(n);
+    int rc = g_arena.reserve(Arena::pad(n) + 2 * Arena::pad(d_cap) + Arena::pad(ws_bytes) + Arena::pad(sizeof(dc_huff_table)) +
                              Arena::pad(DC_NSLOTS * 4) + 512);
     if (rc != DC_OK) return rc;
     uint8_t *d_in = (uint8_t *)g_arena.take(n);
     uint8_t *d_out = (uint8_t *)g_arena.take(d_cap);
+    uint8_t *d_packed = (uint8_t *)g_arena.take(d_cap);
     void *d_ws = g_arena.take(ws_bytes);
     dc_huff_table *d_tab = (dc_huff_table *)g_arena.take(sizeof(dc_huff_table));
     int32_t *d_len = (int32_t *)g_arena.take(DC_NSLOTS * 4);
@@ -280,19 +294,21 @@ extern "C" int dc_host_represent_items_with_codes(int max_symbol_value, const in
     if (rc != DC_OK) return rc;
     size_t written = 0;
     rc = encode_from_table((const uint8_t *)text, n, d_tab, (uint8_t *)out + start, host_cap, total_bits, &written, d_in, d_out,
-                           d_cap, d_ws, ws_bytes, d_bits, d_status, false);
+                           d_cap, d_ws, ws_bytes, d_bits, d_status, false, trits, d_packed);
     return rc != DC_OK ? rc : (int)written;
 }
 
 extern "C" long long dc_host_huff_compress(const uint8_t *in, size_t n, int compressed_symbols, uint8_t *out, size_t out_capacity,
                                            int lengths_out[DC_NSLOTS], uint64_t *total_bits) {
     if ((!in && n) || (!out && out_capacity) || !lengths_out) return DC_ERR_ARG;
-    const size_t d_cap = device_out_capacity(n, out_capacity), ws_bytes = dc_huff_encode_workspace_bytes(n);
-    int rc = g_arena.reserve(Arena::pad(n) + Arena::pad(d_cap) + Arena::pad(ws_bytes) + Arena::pad(sizeof(dc_huff_table)) +
-                             Arena::pad(DC_NSLOTS * 8) + 512);
+    const bool trits = compressed_symbols == 3;
+    const size_t d_cap = device_out_capacity(n, out_capacity, trits), ws_bytes = dc_huff_encode_workspace_bytes(n);
+    int rc = g_arena.reserve(Arena::pad(n) + (trits ? 2 : 1) * Arena::pad(d_cap) + Arena::pad(ws_bytes) +
+                             Arena::pad(sizeof(dc_huff_table)) + Arena::pad(DC_NSLOTS * 8) + 512);
     if (rc != DC_OK) return rc;
     uint8_t *d_in = (uint8_t *)g_arena.take(n);
     uint8_t *d_out = (uint8_t *)g_arena.take(d_cap);
+    uint8_t *d_packed = trits ? (uint8_t *)g_arena.take(d_cap) : nullptr;
     void *d_ws = g_arena.take(ws_bytes);
     dc_huff_table *d_tab = (dc_huff_table *)g_arena.take(sizeof(dc_huff_table));
     uint64_t *d_hist = (uint64_t *)g_arena.take(DC_NSLOTS * 8);
@@ -305,7 +321,7 @@ extern "C" long long dc_host_huff_compress(const uint8_t *in, size_t n, int comp
     if (rc != DC_OK) return rc;
     size_t written = 0;
     rc = encode_from_table(in, n, d_tab, out, out_capacity, total_bits, &written, d_in, d_out, d_cap, d_ws, ws_bytes, d_bits,
-                           d_status, true);
+                           d_status, true, trits, d_packed);
     if (rc != DC_OK) return rc;
     DC_CUDA_TRY(cudaMemcpy(lengths_out, (const char *)d_tab + offsetof(dc_huff_table, lengths), DC_NSLOTS * 4,
                            cudaMemcpyDeviceToHost));
@@ -315,11 +331,15 @@ extern "C" long long dc_host_huff_compress(const uint8_t *in, size_t n, int comp
 extern "C" int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bits, const int lens[DC_NSLOTS],
                                        int compressed_symbols, uint8_t *out, size_t n_out) {
     if ((!payload && total_bits) || !lens || (!out && n_out)) return DC_ERR_ARG;
+    const bool trits = compressed_symbols == 3;   // payload = 5 trits per byte; total_bits = 2 * trits (K7)
+    const uint64_t ntrits = total_bits / 2;
     const size_t nbytes = (size_t)((total_bits + 7) / 8), ws_bytes = dc_huff_decode_workspace_bytes(0, total_bits);
-    int rc = g_arena.reserve(Arena::pad(nbytes + 64) + Arena::pad(n_out + 16) + Arena::pad(ws_bytes) +
+    const size_t pbytes = trits ? (size_t)((ntrits + 4) / 5) : 0;
+    int rc = g_arena.reserve(Arena::pad(nbytes + 64) + Arena::pad(pbytes + 64) + Arena::pad(n_out + 16) + Arena::pad(ws_bytes) +
                              Arena::pad(sizeof(dc_huff_table)) + Arena::pad(DC_NSLOTS * 4) + 512);
     if (rc != DC_OK) return rc;
     uint8_t *d_bits = (uint8_t *)g_arena.take(nbytes + 64);
+    uint8_t *d_packed = (uint8_t *)g_arena.take(pbytes + 64);
     uint8_t *d_out = (uint8_t *)g_arena.take(n_out + 16);
     void *d_ws = g_arena.take(ws_bytes);
     dc_huff_table *d_tab = (dc_huff_table *)g_arena.take(sizeof(dc_huff_table));
@@ -328,13 +348,23 @@ extern "C" int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bi
     DC_CUDA_TRY(cudaMemcpyAsync(d_len, lens, DC_NSLOTS * 4, cudaMemcpyHostToDevice, 0));
     rc = dc_huff_table_from_lengths(d_len, compressed_symbols, d_tab, nullptr);
     if (rc != DC_OK) return rc;
-    // large streams: chunked, with the upload, the decode and the download overlapping
-    rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status);
-    if (rc <= 0) return rc;
-    if (rc != 1 && nbytes) return DC_ERR_CUDA;
-    // one-shot path.  (After a pipelined attempt that fell back the payload is on the device already; copying it
-    // again keeps this path independent of that.)
-    if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_bits, payload, nbytes, cudaMemcpyHostToDevice, 0));
+    if (trits) {
+        if (total_bits & 1) return DC_ERR_ARG;
+        if (pbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_packed, payload, pbytes, cudaMemcpyHostToDevice, 0));
+        rc = dc_trit_unpack(d_packed, ntrits, d_bits, d_status, nullptr);
+        if (rc != DC_OK) return rc;
+        int32_t st0 = 0;
+        DC_CUDA_TRY(cudaMemcpy(&st0, d_status, 4, cudaMemcpyDeviceToHost));
+        if (st0 != DC_OK) return st0;
+    } else {
+        // large streams: chunked, with the upload, the decode and the download overlapping
+        rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status);
+        if (rc <= 0) return rc;
+        if (rc != 1 && nbytes) return DC_ERR_CUDA;
+        // one-shot path.  (After a pipelined attempt that fell back the payload is on the device already; copying it
+        // again keeps this path independent of that.)
+        if (nbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_bits, payload, nbytes, cudaMemcpyHostToDevice, 0));
+    }
     rc = dc_huff_decode(d_bits, 0, total_bits, d_tab, d_out, n_out, d_status, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
     int32_t st = 0;

@@ -22,7 +22,27 @@ namespace dc {
 constexpr int kTabThreads = 1024;
 constexpr int kTabCap = 1040;  // >= DC_MAX_LEAVES + max dummy leaves (n_ary <= 512)
 
-__device__ __forceinline__ int bits_per_digit_of(int n) { return n == 2 ? 1 : n == 4 ? 2 : n == 16 ? 4 : 0; }
+// bits a digit occupies in the stream the encode / decode kernels work on.  n = 3 (the reference's default radix) is
+// handled as 2 bits per trit -- an intermediate "T2" stream that dc_trit_pack() turns into the 5-trits-per-byte payload
+// (tab->packed_radix = 3 marks such a table); every other radix without a power-of-two digit has tables only.
+__device__ __forceinline__ int bits_per_digit_of(int n) { return n == 2 ? 1 : n == 4 ? 2 : n == 16 ? 4 : n == 3 ? 2 : 0; }
+// a base-3 numeral of `len` digits rewritten with one 2-bit field per digit (most significant first)
+__device__ __forceinline__ unsigned int trits_to_t2(unsigned int v, int len) {
+    unsigned int r = 0;
+    for (int k = 0; k < len; k++) { r |= (v % 3u) << (2 * k); v /= 3u; }
+    return r;
+}
+// the first `len` 2-bit digits of a left-aligned window as a base-3 value; false if one of them is 3 (no trit)
+__device__ __forceinline__ bool t2_to_trits(unsigned int window, int window_bits, int len, unsigned int *v) {
+    unsigned int r = 0;
+    for (int k = 0; k < len; k++) {
+        const unsigned int d = (window >> (window_bits - 2 * (k + 1))) & 3u;
+        if (d == 3u) return false;
+        r = r * 3u + d;
+    }
+    *v = r;
+    return true;
+}
 
 __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long long *__restrict__ d_hist,
                                                             const int32_t *__restrict__ d_lengths_in, int nsym,
@@ -171,14 +191,17 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     if (!tab) return;
     const int bpd = bits_per_digit_of(n_ary);
     const int nbits = my_len * bpd;
+    const bool t2 = n_ary == 3;
+    // what the kernels emit / match for this symbol: the canonical value itself, or its trits as 2-bit fields
+    const unsigned int my_stream_value = (t2 && assigned && my_len <= 16) ? trits_to_t2(my_value, my_len) : my_value;
     if (tid <= DC_NSLOTS) {
         tab->lengths[tid] = tid < nsym ? my_len : 0;
         tab->values[tid] = tid < nsym ? my_value : 0u;
         tab->sorted[tid] = 0;
     }
     if (tid < 256) {
-        tab->enc[tid] = (assigned && nbits <= 26) ? ((my_value << 6) | (unsigned int)nbits) : 0u;
-        tab->enc64[tid] = assigned ? ((unsigned long long)my_value | ((unsigned long long)nbits << 32)) : 0ull;
+        tab->enc[tid] = (assigned && nbits <= 26) ? ((my_stream_value << 6) | (unsigned int)nbits) : 0u;
+        tab->enc64[tid] = assigned ? ((unsigned long long)my_stream_value | ((unsigned long long)nbits << 32)) : 0ull;
     }
     if (tid < 32) {
         tab->first_code[tid] = s_first[tid];
@@ -200,7 +223,8 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             for (int l = min_len; l <= max_len && l < 32; l++) {
                 const int lb = l * bpd;
                 if (lb > DC_LUT_BITS) break;
-                const unsigned int v = (unsigned int)e >> (DC_LUT_BITS - lb);
+                unsigned int v = (unsigned int)e >> (DC_LUT_BITS - lb);
+                if (t2 && !t2_to_trits((unsigned int)e, DC_LUT_BITS, l, &v)) continue;  // a 2-bit field of 3 is no trit
                 if (s_lencount[l] && v >= s_first[l] && v - s_first[l] < s_lencount[l]) {
                     entry = ((unsigned int)lb << 8) | (unsigned int)(s_ssym[s_off[l] + (v - s_first[l])] & 0xFF);
                     break;
@@ -232,6 +256,52 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
                                  : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
     }
+    // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
+    {
+        __syncthreads();
+        unsigned char *s_flag = (unsigned char *)s_scnt;     // [4096] 1 = this window is the prefix of 13..16-bit codes
+        unsigned short *s_sub = (unsigned short *)s_icount;  // [4096] its subtable
+        const bool need2 = bpd != 0 && max_len * bpd > DC_LUT_BITS;
+        // the code (13..16 bits) that a left-aligned 16-bit window starts with; 0 if none
+        auto long_code = [&](unsigned int w16) -> unsigned int {
+            for (int l = min_len; l <= max_len && l < 32; l++) {
+                const int lb = l * bpd;
+                if (lb <= DC_LUT_BITS) continue;
+                if (lb > 16) break;
+                unsigned int v = w16 >> (16 - lb);
+                if (t2 && !t2_to_trits(w16, 16, l, &v)) continue;
+                if (s_lencount[l] && v >= s_first[l] && v - s_first[l] < s_lencount[l])
+                    return ((unsigned int)lb << 8) | (unsigned int)(s_ssym[s_off[l] + (v - s_first[l])] & 0xFF);
+            }
+            return 0u;
+        };
+        for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
+            unsigned int any = 0;
+            if (need2 && s_lut[e] == 0)
+                for (unsigned int sfx = 0; sfx < 16 && !any; sfx++) any = long_code(((unsigned int)e << 4) | sfx);
+            s_flag[e] = any ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {  // 4096 flags, a few microseconds: number the prefixes in index order
+            int nsub = 0;
+            for (int e = 0; e < (1 << DC_LUT_BITS); e++) {
+                s_sub[e] = 0xFFFF;
+                if (s_flag[e] && nsub < DC_LUT2_SUBTABLES) s_sub[e] = (unsigned short)nsub++;
+            }
+            tab->lut2_used = nsub;
+            tab->reserved1 = 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < DC_LUT2_SUBTABLES * 16; i += kTabThreads) tab->lut2[i] = 0;
+        __syncthreads();
+        for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
+            const unsigned int id = s_sub[e];
+            if (id == 0xFFFFu) continue;
+            for (unsigned int sfx = 0; sfx < 16; sfx++) tab->lut2[id * 16 + sfx] = (uint16_t)long_code(((unsigned int)e << 4) | sfx);
+            tab->lut_count[e] = 0xFF000000u | id;
+            tab->lut_pair[e] = 0x1F000000u | id;
+        }
+    }
     if (tid == 0) {
         tab->n_ary = n_ary;
         tab->bits_per_digit = bpd;
@@ -242,7 +312,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         tab->max_len = max_len;
         tab->max_bits = max_len * bpd;
         tab->status = (status == DC_OK && max_len * bpd > 32) ? DC_ERR_CODE_TOO_LONG : status;
-        tab->reserved0 = 0;
+        tab->packed_radix = t2 ? 3 : 0;
         tab->total_symbols = s_totsym;
         tab->total_bits = s_totbits;
     }

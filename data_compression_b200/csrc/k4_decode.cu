@@ -45,8 +45,21 @@ struct DecTables {  // shared-memory copy of the decode part of dc_huff_table
     uint16_t lut[1 << DC_LUT_BITS];
     uint32_t first_code[32], len_count[32], len_offset[32];
     uint16_t sorted[DC_NSLOTS + 1];
-    int bpd, min_len, max_len, max_bits;
+    int bpd, min_len, max_len, max_bits, t2;
 };
+
+// n = 3 tables (packed_radix == 3): the stream has one 2-bit field per trit.  The first `len` fields of the left-aligned
+// window w as a base-3 value, for the canonical search; false if a field is 3 (not a trit).
+__device__ __forceinline__ bool t2_window_value(uint32_t w, int len, uint32_t *v) {
+    uint32_t r = 0;
+    for (int k = 0; k < len && k < 16; k++) {
+        const uint32_t d = (w >> (30 - 2 * k)) & 3u;
+        if (d == 3u) return false;
+        r = r * 3u + d;
+    }
+    *v = r;
+    return true;
+}
 
 __device__ __forceinline__ void load_tables(DecTables *t, const dc_huff_table *__restrict__ tab) {
     for (int i = threadIdx.x; i < (1 << DC_LUT_BITS) / 2; i += blockDim.x)
@@ -62,6 +75,7 @@ __device__ __forceinline__ void load_tables(DecTables *t, const dc_huff_table *_
         t->min_len = tab->min_len;
         t->max_len = tab->max_len;
         t->max_bits = tab->max_bits;
+        t->t2 = tab->packed_radix == 3;
     }
 }
 
@@ -76,7 +90,8 @@ __device__ __forceinline__ int decode_one(const DecTables *t, uint32_t w, int *s
         for (int l = t->min_len; l <= t->max_len; l++) {
             const int lb = l * t->bpd;
             if (lb <= DC_LUT_BITS) continue;
-            const uint32_t v = lb >= 32 ? w : (w >> (32 - lb));
+            uint32_t v = lb >= 32 ? w : (w >> (32 - lb));
+            if (t->t2 && !t2_window_value(w, l, &v)) continue;
             const uint32_t f = t->first_code[l], c = t->len_count[l];
             if (c && v >= f && v - f < c) {
                 *sym = (int)t->sorted[t->len_offset[l] + (v - f)];
@@ -350,11 +365,17 @@ struct FastTables {  // shared-memory copy: one multi-symbol LUT + the canonical
     uint32_t lut[1 << DC_LUT_BITS];
     uint32_t first_code[32], len_count[32], len_offset[32];
     uint16_t sorted[DC_NSLOTS + 1];
-    int bpd, min_len, max_len;
+    int bpd, min_len, max_len, t2;
+    uint16_t lut2[DC_LUT2_SUBTABLES * 16];  // second level (codes of 13..16 bits); loaded, and allocated, for ESC kernels only
 };
+__host__ __device__ constexpr size_t fast_tables_bytes(bool esc) {
+    return ((esc ? sizeof(FastTables) : offsetof(FastTables, lut2)) + 15) & ~(size_t)15;
+}
 
-__device__ __forceinline__ void load_fast_tables(FastTables *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut) {
+__device__ __forceinline__ void load_fast_tables(FastTables *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut, bool esc) {
     for (int i = threadIdx.x; i < (1 << DC_LUT_BITS); i += blockDim.x) t->lut[i] = lut[i];
+    if (esc)
+        for (int i = threadIdx.x; i < DC_LUT2_SUBTABLES * 16 / 2; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
     for (int i = threadIdx.x; i < 32; i += blockDim.x) {
         t->first_code[i] = tab->first_code[i];
         t->len_count[i] = tab->len_count[i];
@@ -365,14 +386,31 @@ __device__ __forceinline__ void load_fast_tables(FastTables *t, const dc_huff_ta
         t->bpd = tab->bits_per_digit;
         t->min_len = tab->min_len;
         t->max_len = tab->max_len;
+        t->t2 = tab->packed_radix == 3;
     }
 }
 
-// escape path: canonical search over all lengths; returns the code's bits (0 = unused slot)
+// escape path: the 12-bit window holds no complete code.  Canonical search over the lengths LONGER than the LUT index
+// (a shorter code would have been in the LUT); returns the code's bits, 0 for an unused slot.
 __device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *sym) {
-    for (int l = t->min_len; l <= t->max_len; l++) {
-        const int lb = l * t->bpd;
-        const uint32_t v = lb >= 32 ? w : (w >> (32 - lb));
+    const int bpd = t->bpd;
+    int l = DC_LUT_BITS / bpd + 1;
+    if (l < t->min_len) l = t->min_len;
+    uint32_t v3 = 0;   // radix 3: the base-3 value of the first k two-bit fields, extended as l grows
+    int k = 0;
+    for (; l <= t->max_len; l++) {
+        const int lb = l * bpd;
+        uint32_t v;
+        if (t->t2) {
+            for (; k < l && k < 16; k++) {
+                const uint32_t d = (w >> (30 - 2 * k)) & 3u;
+                if (d == 3u) return 0;  // not a trit: no code of this or a greater length starts here
+                v3 = v3 * 3u + d;
+            }
+            v = v3;
+        } else {
+            v = lb >= 32 ? w : (w >> (32 - lb));
+        }
         const uint32_t f = t->first_code[l], c = t->len_count[l];
         if (c && v >= f && v - f < c) {
             *sym = (int)t->sorted[t->len_offset[l] + (v - f)];
@@ -381,6 +419,21 @@ __device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *
     }
     return 0;
 }
+
+// a look-up that did not resolve (ESC tables): e is 0 (canonical search) or the marker of a second-level table indexed by
+// the 4 bits behind the window.  Returns the code's bits (0 = unused slot).
+__device__ __forceinline__ int escape_code(const FastTables *t, uint32_t e, uint32_t x, int *sym) {
+    if (e) {
+        const uint32_t e2 = t->lut2[((e & 0xFFFFu) << 4) | ((x >> (28 - DC_LUT_BITS)) & 15u)];
+        if (e2) {
+            *sym = (int)(e2 & 0xFFu);
+            return (int)(e2 >> 8);
+        }
+    }
+    return decode_escape(t, x, sym);
+}
+__device__ __forceinline__ bool is_escape_count(uint32_t e) { return e == 0 || (e >> 24) == 0xFFu; }
+__device__ __forceinline__ bool is_escape_pair(uint32_t e) { return e == 0 || (e >> 24) == 0x1Fu; }
 
 // LUT entry for the window in the top 12 bits of x: base + (x >> 20) * 4 as one shift and one multiply-add (written in
 // PTX so that it is not canonicalised back into shift, mask and add) in front of the LDS
@@ -426,9 +479,9 @@ template <bool ESC>
 __device__ __forceinline__ void sync_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &csum) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
     const uint32_t e = lds_lut(lut, x);
-    if (ESC && e == 0) {
+    if (ESC && is_escape_count(e)) {
         int sym;
-        const int nb = decode_escape(t, x, &sym);
+        const int nb = escape_code(t, e, x, &sym);
         p += nb ? nb : t->bpd;
         csum += nb ? 0x10000u : 0u;
     } else {
@@ -440,9 +493,9 @@ template <bool ESC>
 __device__ __forceinline__ void sync_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
     const uint32_t e = lds_lut(lut, x);
-    if (ESC && e == 0) {
+    if (ESC && is_escape_count(e)) {
         int sym;
-        const int nb = decode_escape(t, x, &sym);
+        const int nb = escape_code(t, e, x, &sym);
         p += nb ? nb : t->bpd;
         scnt += nb ? 1u : 0u;
     } else {
@@ -565,7 +618,7 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
     // lead = 1: tile 0 of d_bits is the last tile of the PREVIOUS shard of a longer stream; the first code of this
     // shard is unknown and segment 0 finds it like every other segment does, by synchronising over the tile in front
     __shared__ FastTables s_t;
-    load_fast_tables(&s_t, tab, tab->lut_count);
+    load_fast_tables(&s_t, tab, tab->lut_count, ESC);
     __syncthreads();
     if (chain) bit_start = chain->next_start;  // a later chunk of a stream: its first code starts where the previous chunk's last one ended
     uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
@@ -691,9 +744,9 @@ __device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t
                                                    uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
     const uint32_t e = lds_lut(lut, x);
-    if (ESC && e == 0) {
+    if (ESC && is_escape_pair(e)) {
         int sym = 0;
-        const int nb = decode_escape(t, x, &sym);
+        const int nb = escape_code(t, e, x, &sym);
         if (nb) {
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(sym) : "memory");
             dst++;
@@ -714,9 +767,9 @@ __device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_
                                                     uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
     const uint32_t e = lds_lut(lut, x);
-    if (ESC && e == 0) {
+    if (ESC && is_escape_pair(e)) {
         int sym = 0;
-        const int nb = decode_escape(t, x, &sym);
+        const int nb = escape_code(t, e, x, &sym);
         if (nb) {
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(sym) : "memory");
             dst++;
@@ -762,9 +815,9 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const 
                                                                        int32_t *__restrict__ d_status, int lead) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
     FastTables *s_t = (FastTables *)fast_smem;
-    uint8_t *s_stage = fast_smem + ((sizeof(FastTables) + 15) & ~(size_t)15);
+    uint8_t *s_stage = fast_smem + fast_tables_bytes(ESC);
     if (*ws.mismatch) return;  // the robust path redoes the stream
-    load_fast_tables(s_t, tab, tab->lut_pair);
+    load_fast_tables(s_t, tab, tab->lut_pair, ESC);
     __syncthreads();
     uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
     asm volatile("" : "+r"(lut));  // as in F1
@@ -959,7 +1012,7 @@ static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsi
                              int32_t *d_status, bool esc, uint32_t stage_bytes, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
-    const size_t smem3 = ((sizeof(FastTables) + 15) & ~(size_t)15) + (size_t)kF_Warps * stage_bytes;
+    const size_t smem3 = fast_tables_bytes(esc) + (size_t)kF_Warps * stage_bytes;
     DC_CUDA_TRY(ensure_write_smem(smem3));
     LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
     const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);

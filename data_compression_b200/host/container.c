@@ -5,7 +5,7 @@
  *   block   = <decimal length> ':' '\n' <type> <data> ',' '\n'          (the length counts "\n" + type + data)
  *   type    '\n'  raw pass-through (:1801-1814)          '#'  metadata, skipped (:2076-2079)
  *           'X'   table: "258:" + one digit per length for symbols 0..258 (:1727-1744)
- *           'Z'   data : "<symbols> <bits>\n" + payload bytes
+ *           'Z'   data : "<symbols> <bits>\n" + payload bytes (radix 3: bits = 2 * trits, 5 trits per byte)
  * The reference prints every length with "%d", which only parses while all lengths are <= 9, and its 'Z' writer and
  * both Huffman readers are assert(0) stubs; here a length above 9 is one hex digit (its own limit is 15, :1414), the
  * data block carries the two counts a decoder needs, and block lengths are not capped at 32768 (:1826).  The radix is
@@ -31,7 +31,8 @@ static size_t fail(const char *what) {
     return (size_t)-1;
 }
 
-static int packable(int n) { return n == 2 || n == 4 || n == 16; }
+/* radices with a payload form: bit fields (2, 4, 16) and 5 trits per byte (3, the reference's default) */
+static int packable(int n) { return n == 2 || n == 3 || n == 4 || n == 16; }
 
 /* ---- block writer: returns bytes written to out (needs out_cap >= text_len + text_len / 4 + 4096) */
 size_t dc_container_compress(int n, const int lengths[NSLOTS], char *text, size_t text_len, char *out, size_t out_cap) {
@@ -115,7 +116,9 @@ size_t dc_container_decompress(int n, const char *in, size_t in_len, char *out, 
             if (sscanf(data, "%zu %llu%n", &nsym, &bits, &used) != 2 || data[used] != '\n') return fail("bad data block");
             used += 1;
             if (produced + nsym + 1 > out_cap || nsym > (size_t)INT32_MAX) return fail("output buffer too small");
-            if ((bits + 7) / 8 != data_len - (size_t)used) return fail("data block length mismatch");
+            /* payload bytes: bits / 8 rounded up; radix 3 counts 2 "bits" per trit and stores 5 trits per byte */
+            const unsigned long long want = n == 3 ? (bits / 2 + 4) / 5 : (bits + 7) / 8;
+            if (want != data_len - (size_t)used) return fail("data block length mismatch");
             decode_items_with_codes(MAX_SYMBOL_VALUE, lengths, n, bits, data + used, (int)nsym, out + produced);
             produced += nsym;
         } else {

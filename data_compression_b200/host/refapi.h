@@ -34,7 +34,8 @@ void convert_lengths_to_encode_table(const int max_symbol_value, const int canon
 
 /* n_ary_huffman.c:1621-1678 -- append the codes of original_text[0..original_length) to
  * compressed_text[start...]; returns the number of bytes written.  (A stub in the reference; the payload
- * layout is the one DESIGN.md defines.)  n in {2,4,16}. */
+ * layout is the one DESIGN.md defines.)  n in {2,4,16}: bit fields; n == 3: 5 trits per byte, and
+ * represent_items_last_total_bits() counts 2 per trit. */
 int represent_items_with_codes(const int max_symbol_value, int canonical_lengths[], const int compressed_symbols,
                                const int bufsize, const int original_length, char original_text[], int start,
                                char compressed_text[]);

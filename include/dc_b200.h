@@ -35,6 +35,7 @@ extern "C" {
 #define DC_NSLOTS 259           /* max_symbol_value + 1 histogram / length slots */
 #define DC_MAX_LEAVES 512       /* dc_host_huffman accepts max_leaf_value < DC_MAX_LEAVES */
 #define DC_LUT_BITS 12          /* decode look-up table index width */
+#define DC_LUT2_SUBTABLES 256   /* second-level tables of 16 entries (codes of 13..16 bits) */
 
 enum dc_status {
     DC_OK = 0,
@@ -57,7 +58,7 @@ enum dc_status {
  */
 typedef struct dc_huff_table {
     int32_t n_ary;            /* compressed_symbols */
-    int32_t bits_per_digit;   /* 1, 2, 4 for n = 2, 4, 16; 0 = table only (no payload packing) */
+    int32_t bits_per_digit;   /* 1, 2, 4 for n = 2, 4, 16; 2 for n = 3 (see packed_radix); 0 = table only (no payload packing) */
     int32_t max_symbol_value; /* 258 */
     int32_t nonzero_symbols;  /* :880-886 */
     int32_t dummy_nodes;      /* :900-903, as written */
@@ -65,7 +66,8 @@ typedef struct dc_huff_table {
     int32_t max_len;          /* digits (:1330-1352) */
     int32_t max_bits;         /* max_len * bits_per_digit */
     int32_t status;           /* DC_OK or DC_ERR_CODE_TOO_LONG / DC_ERR_RADIX */
-    int32_t reserved0;
+    int32_t packed_radix;     /* 0: the kernels' stream is the payload; 3: n = 3, the stream has 2 bits per trit and
+                               * dc_trit_pack() / dc_trit_unpack() convert it to / from the 5-trits-per-byte payload */
     uint64_t total_symbols;   /* sum of the histogram the table was built from (0 if from lengths) */
     uint64_t total_bits;      /* sum hist[s] * lengths[s] * bits_per_digit (0 if from lengths) */
     int32_t lengths[DC_NSLOTS + 1];
@@ -84,6 +86,13 @@ typedef struct dc_huff_table {
  *              | unused-slot flag << 29 | count(0..2) << 30                                     (0 = escape) */
     uint32_t lut_count[1 << DC_LUT_BITS];
     uint32_t lut_pair[1 << DC_LUT_BITS];
+    /* second level, for codes of 13..16 bits: a 12-bit window that is the prefix of such codes has the marker entry
+     *   lut_count = 0xFF000000 | subtable,  lut_pair = 0x1F000000 | subtable
+     * and lut2[subtable * 16 + next 4 bits] = code bits << 8 | symbol (0 = no code of <= 16 bits there).  Longer codes
+     * and unused slots keep the entry 0 = canonical search. */
+    uint16_t lut2[DC_LUT2_SUBTABLES * 16];
+    int32_t lut2_used;        /* subtables in use */
+    int32_t reserved1;
 } dc_huff_table;
 
 /* ------------------------------------------------------------------------- library */
@@ -121,6 +130,8 @@ enum dc_kernel_id {
     DC_K_TEXT_SUMMARY,
     DC_K_TEXT_SCAN,
     DC_K_TEXT_EMIT,
+    DC_K_TRIT_PACK,
+    DC_K_TRIT_UNPACK,
     DC_K_SYNTH,
     DC_K_COUNT
 };
@@ -236,6 +247,19 @@ int dc_nybble_pack(const uint8_t *d_sym, size_t n_sym, uint8_t *d_packed, int32_
 /* Inverse: the decoder's split nybble_compression.c:767-769 (high nibble first). */
 int dc_nybble_unpack(const uint8_t *d_packed, size_t n_sym, uint8_t *d_sym, void *stream);
 
+/* ------------------------------------------------------------------------- K7 trit payload (radix 3) */
+
+/*
+ * Radix 3 is the reference's default (n_ary_huffman.c:2529); its payload is sketched at :745-748: 5 trits per byte, byte =
+ * 1 + the group's base-3 value (most significant trit first), last group padded with zero trits.  For a table built
+ * with n_ary == 3 (packed_radix == 3) dc_huff_encode writes, and dc_huff_decode reads, an intermediate stream with one
+ * 2-bit field per trit ("T2": total_bits == 2 * trits); these two convert between that stream and the payload of
+ * ceil(trits / 5) bytes.  d_t2: 4-byte aligned (and, for dc_huff_decode, readable up to the next multiple of 16 bytes);
+ * d_payload: 16-byte aligned for dc_trit_pack.  *d_status = DC_ERR_CORRUPT for a field of 3 / a byte outside 1..243.
+ */
+int dc_trit_pack(const uint8_t *d_t2, uint64_t ntrits, uint8_t *d_payload, int32_t *d_status, void *stream);
+int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t *d_t2, int32_t *d_status, void *stream);
+
 /* ------------------------------------------------------------------------- K6 static-table nybble compressor */
 
 size_t dc_nybble_text_workspace_bytes(size_t n);
@@ -284,7 +308,9 @@ int dc_host_represent_items_with_codes(int max_symbol_value, const int canonical
                                        int bufsize, int original_length, const char original_text[], int start,
                                        char compressed_text[], uint64_t *total_bits);
 /* whole encode path on host buffers: histogram -> table -> payload.  lengths_out[259] and total_bits
- * are the side information a decoder needs.  Returns bytes written or a negative dc_status. */
+ * are the side information a decoder needs.  Returns bytes written or a negative dc_status.
+ * compressed_symbols in {2, 4, 16}: total_bits = payload bits.  compressed_symbols == 3: total_bits = 2 * trits and the
+ * payload is the 5-trits-per-byte form (K7), ceil(trits / 5) bytes. */
 long long dc_host_huff_compress(const uint8_t *in, size_t n, int compressed_symbols, uint8_t *out,
                                 size_t out_capacity, int lengths_out[DC_NSLOTS], uint64_t *total_bits);
 /* inverse on host buffers */

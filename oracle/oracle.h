@@ -74,6 +74,14 @@ int orc_unpack_mt(const uint8_t *bits, uint64_t bit_start, int max_symbol_value,
                   int compressed_symbols, uint8_t *out, size_t n, const uint64_t *block_bit_offsets,
                   size_t block_symbols, int threads);
 
+/* n = 3 (the reference's default radix, :2529): the trit payload sketched at n_ary_huffman.c:745-748 -- 5 trits per byte,
+ * byte = 1 + base-3 value of the group, most significant trit first, last group zero-padded.  PARITY UNPINNED like the
+ * bit payload (the reference has no packer).  The decoder is a plain O(alphabet) search per trit: small inputs only. */
+int orc_pack_trits(const uint8_t *in, size_t n, const int elen[], const unsigned int eval[], uint8_t *out,
+                   size_t out_capacity, uint64_t *total_trits);
+int orc_unpack_trits(const uint8_t *packed, uint64_t total_trits, int max_symbol_value, const int lengths[],
+                     uint8_t *out, size_t n_out_capacity, size_t *n_decoded);
+
 /* nybble_compression.c:1091-1114 (write_nybble, #else branches) and :767-773 (split): high nibble first. */
 void orc_nybble_pack(const uint8_t *sym, size_t n_sym, uint8_t *packed);
 void orc_nybble_unpack(const uint8_t *packed, size_t n_sym, uint8_t *sym);

@@ -454,3 +454,81 @@ int orc_unpack_mt(const uint8_t *bits, uint64_t bit_start, int max_symbol_value,
     dec_free(&d);
     return st;
 }
+
+/* ------------------------------------------------------------------ trit payload (n = 3; repo-defined, row N4) */
+
+/*
+ * The reference's default radix is 3 (n_ary_huffman.c:2529) and its author sketches the storage at :745-748: "grab 5
+ * trits at a time, convert into a number 1..243, and store as an 8-bit octet (which never uses byte 0 or 244..255)".
+ * Layout defined here: a code of `len` digits is the len-trit base-3 numeral of encode_value, most significant trit
+ * first (as for the power-of-two radices); codes are concatenated in input order; every 5 trits t0..t4 become the byte
+ * 1 + t0*81 + t1*27 + t2*9 + t3*3 + t4; the last group is padded with zero trits.
+ */
+int orc_pack_trits(const uint8_t *in, size_t n, const int elen[], const unsigned int eval[], uint8_t *out,
+                   size_t out_capacity, uint64_t *total_trits) {
+    uint64_t trits = 0;
+    unsigned group = 0;
+    int ng = 0;
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        const unsigned s = in[i];
+        const int l = elen[s];
+        if (l <= 0) return ORC_ERR_SYMBOL;
+        if (l > 20) return ORC_ERR_CODE_TOO_LONG;
+        unsigned digits[20];
+        unsigned v = eval[s];
+        for (int k = l - 1; k >= 0; k--) { digits[k] = v % 3u; v /= 3u; }
+        for (int k = 0; k < l; k++) {
+            group = group * 3u + digits[k];
+            if (++ng == 5) {
+                if (o >= out_capacity) return ORC_ERR_CAPACITY;
+                out[o++] = (uint8_t)(1u + group);
+                group = 0;
+                ng = 0;
+            }
+        }
+        trits += (uint64_t)l;
+    }
+    if (ng > 0) {
+        for (; ng < 5; ng++) group *= 3u;
+        if (o >= out_capacity) return ORC_ERR_CAPACITY;
+        out[o++] = (uint8_t)(1u + group);
+    }
+    if (total_trits) *total_trits = trits;
+    return ORC_OK;
+}
+
+/* sequential canonical decoder of the trit payload */
+int orc_unpack_trits(const uint8_t *packed, uint64_t total_trits, int max_symbol_value, const int lengths[],
+                     uint8_t *out, size_t n_out_capacity, size_t *n_decoded) {
+    if (max_symbol_value + 1 > 1024) return ORC_ERR_ARG;
+    int elen[1024];
+    unsigned int eval[1024];
+    const int st = orc_convert_lengths_to_encode_table(max_symbol_value, lengths, 3, elen, eval);
+    if (st != ORC_OK) return st;
+    size_t o = 0;
+    unsigned v = 0;
+    int l = 0;
+    for (uint64_t t = 0; t < total_trits; t++) {
+        const unsigned b = packed[t / 5];
+        if (b == 0 || b > 243) return ORC_ERR_CORRUPT;
+        static const unsigned p3[5] = {81, 27, 9, 3, 1};
+        const unsigned digit = ((b - 1u) / p3[t % 5]) % 3u;
+        v = v * 3u + digit;
+        l++;
+        int found = -1;
+        for (int s = 0; s <= max_symbol_value && found < 0; s++)
+            if (elen[s] == l && eval[s] == v) found = s;
+        if (found >= 0) {
+            if (o >= n_out_capacity) return ORC_ERR_CAPACITY;
+            out[o++] = (uint8_t)found;
+            v = 0;
+            l = 0;
+        } else if (l > 20) {
+            return ORC_ERR_CORRUPT;
+        }
+    }
+    if (l != 0) return ORC_ERR_CORRUPT;  /* the stream ends inside a code */
+    if (n_decoded) *n_decoded = o;
+    return ORC_OK;
+}

@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
         L.orc_convert_lengths_to_encode_table.argtypes = [C.c_int, i32p, C.c_int, i32p, u32p]
         L.orc_bits_per_digit.argtypes = [C.c_int]
         L.orc_pack.argtypes = [C.c_void_p, C.c_size_t, i32p, u32p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t, u64p]
+        L.orc_pack_trits.argtypes = [C.c_void_p, C.c_size_t, i32p, u32p, C.c_void_p, C.c_size_t, u64p]
+        L.orc_unpack_trits.argtypes = [C.c_void_p, C.c_uint64, C.c_int, i32p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_pack_mt.argtypes = [C.c_void_p, C.c_size_t, i32p, u32p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
                                   u64p, C.c_int, u64p, C.c_size_t]
         L.orc_unpack.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, i32p, C.c_int, C.c_void_p,
@@ -139,6 +141,31 @@ def pack(data, elen, evalue, bpd: int, bit_phase: int = 0):
         raise ValueError(f"orc_pack status {st}")
     nbytes = (bits.value + bit_phase + 7) // 8 if bits.value else 0
     return out[:nbytes].copy(), bits.value
+
+
+def pack_trits(data, elen, evalue):
+    """n = 3 payload: returns (payload bytes, total_trits)."""
+    d = _u8(data)
+    el = np.ascontiguousarray(elen, dtype=np.int32)
+    ev = np.ascontiguousarray(evalue, dtype=np.uint32)
+    cap = d.size * 4 + 16
+    out = np.zeros(cap, dtype=np.uint8)
+    trits = C.c_uint64(0)
+    st = lib().orc_pack_trits(d.ctypes.data, d.size, _p(el, C.c_int), _p(ev, C.c_uint), out.ctypes.data, cap, C.byref(trits))
+    if st != ORC_OK:
+        raise ValueError(f"orc_pack_trits status {st}")
+    return out[: (trits.value + 4) // 5].copy(), trits.value
+
+
+def unpack_trits(packed, total_trits: int, lengths, n_out: int) -> np.ndarray:
+    b = _u8(packed)
+    ln = np.ascontiguousarray(lengths, dtype=np.int32)
+    out = np.zeros(max(n_out, 1), dtype=np.uint8)
+    nd = C.c_size_t(0)
+    st = lib().orc_unpack_trits(b.ctypes.data, total_trits, ln.size - 1, _p(ln, C.c_int), out.ctypes.data, n_out, C.byref(nd))
+    if st != ORC_OK:
+        raise ValueError(f"orc_unpack_trits status {st}")
+    return out[: nd.value]
 
 
 def pack_mt(data, elen, evalue, bpd: int, bit_phase: int = 0, threads: int = 1, block_symbols: int = 1 << 16,

@@ -73,6 +73,20 @@ def test_compress_decompress_host(dc, oracle):
         assert np.array_equal(dc.hostapi.huff_decompress(payload, bits, lengths, n, data.size), data)
 
 
+def test_compress_decompress_host_radix3(dc, oracle):
+    """The reference's default radix through the host entry points: 5 trits per byte, against the oracle."""
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_7bit_spec()
+    for size in (1, 7, 4096, 300001):
+        data = synth.host_stream(size, synth.SEED_BASE + 9, thr, base)
+        payload, bits, lengths = dc.hostapi.huff_compress(data, 3)
+        ln, el, ev, st = oracle.build_tables(oracle.histogram_u8(data), 3)
+        want, wtrits = oracle.pack_trits(data, el, ev)
+        assert np.array_equal(lengths, ln) and bits == 2 * wtrits and np.array_equal(payload, want)
+        assert payload.min() >= 1 and payload.max() <= 243            # "never uses byte 0 or 244..255" (:748)
+        assert np.array_equal(dc.hostapi.huff_decompress(payload, bits, lengths, 3, data.size), data)
+
+
 @pytest.mark.parametrize("n_ary", [2, 16])
 def test_decompress_host_pipelined(dc, oracle, n_ary):
     """A stream of more than three 32 MiB chunks takes the chunked, overlapped path of dc_host_huff_decompress: the

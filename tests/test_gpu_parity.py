@@ -73,7 +73,8 @@ def test_tables_match_reference_golden(dc, oracle, table_cases):
                 assert t.status == 0
                 assert np.array_equal(np.array(t.values[:259], dtype=np.uint32), dense(rec["values"], dtype=np.uint32)), \
                     (case["name"], n)
-                bpd = oracle.bits_per_digit(n)
+                bpd = 2 if n == 3 else oracle.bits_per_digit(n)   # radix 3: one 2-bit field per trit in the kernels' stream
+                assert t.packed_radix == (3 if n == 3 else 0)
                 assert t.bits_per_digit == bpd and t.max_bits == int(want_len.max()) * bpd
                 assert t.total_bits == int((dense(case["hist"]) * want_len * bpd).sum())
             else:
@@ -307,7 +308,7 @@ def test_decode_reports_corruption(dc, oracle):
 
 def test_radix_without_packing_is_table_only(dc):
     data = _zipf(dc, 4096)
-    table = dc.huff_build(dc.histogram(data), 3)
+    table = dc.huff_build(dc.histogram(data), 5)
     assert table.download().bits_per_digit == 0
     res = dc.huff_encode(data, table)
     assert int(res.status.item()) == dc.DC_ERR_RADIX
@@ -375,3 +376,41 @@ def test_shard_decoder_halo_and_exact_start_agree(dc, oracle, n_ary):
     assert s1x["symbols"] == s1["symbols"] and s1x["exit"] == s1["exit"] and s1x["assumed_start"] == s0["exit"]
     out1x, st1x = d1.write(s1x["symbols"])
     assert int(st1x.item()) == 0 and torch.equal(out1x, out1)
+
+
+def test_radix3_trit_payload(dc, oracle):
+    """Row N4: radix 3 (the reference's default).  The kernels run on one 2-bit field per trit, K7 turns that into the
+    5-trits-per-byte payload the reference's author sketches (n_ary_huffman.c:745-748); everything against the oracle."""
+    for size, seed in ((1, 1), (4, 2), (5, 3), (79, 4), (80, 5), (81, 6), (70001, 7), ((1 << 20) + 3, 8)):
+        data = _zipf(dc, size, seed=seed)
+        host = data.cpu().numpy()
+        hist = dc.histogram(data)
+        table = dc.huff_build(hist, 3)
+        t = table.download()
+        ln, el, ev, st = oracle.build_tables(hist.cpu().numpy().astype(np.uint64), 3)
+        assert t.status == 0 and st == 0 and t.packed_radix == 3 and t.bits_per_digit == 2
+        assert np.array_equal(np.array(t.lengths[:259]), ln) and np.array_equal(np.array(t.values[:259], dtype=np.uint32), ev)
+        res = dc.huff_encode(data, table, out=torch.empty(size * 4 + 64, dtype=torch.uint8, device="cuda"))
+        nbits = res.bits()
+        want, wtrits = oracle.pack_trits(host, el, ev)
+        assert nbits == 2 * wtrits == t.total_bits
+        payload, pst = dc.trit_pack(res.payload, wtrits)
+        assert int(pst.item()) == 0 and np.array_equal(payload.cpu().numpy(), want), size
+        assert np.array_equal(oracle.unpack_trits(want, wtrits, ln, size), host) if size <= 70001 else True
+        t2, ust = dc.trit_unpack(torch.from_numpy(want).cuda(), wtrits)
+        assert int(ust.item()) == 0
+        nb = (nbits + 7) // 8
+        assert torch.equal(t2[: nb - 1], res.payload[: nb - 1])      # the same 2-bit stream (the last byte may differ in padding)
+        out, status = dc.huff_decode(t2, nbits, table, size)
+        assert int(status.item()) == 0 and torch.equal(out, data), size
+        if size == 70001:   # the robust decode path (tile hand-off) with the trit-aware canonical search
+            old = dc.lib().dc_debug_decode_mode(1)
+            try:
+                out, status = dc.huff_decode(t2, nbits, table, size)
+            finally:
+                dc.lib().dc_debug_decode_mode(old)
+            assert int(status.item()) == 0 and torch.equal(out, data)
+    # a payload byte outside 1..243 is reported
+    bad = torch.tensor([0, 5, 244], dtype=torch.uint8, device="cuda")
+    _, ust = dc.trit_unpack(bad, 15)
+    assert int(ust.item()) == dc.DC_ERR_CORRUPT

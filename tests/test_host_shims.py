@@ -42,7 +42,7 @@ def test_cli_aborts_without_device(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("radix,expect", [(None, 3), (2, 2), (4, 2), (16, 2)])
+@pytest.mark.parametrize("radix,expect", [(None, 3), (2, 2), (4, 2), (16, 2), (5, 2)])
 def test_n_ary_huffman_cli(built, radix, expect):
     from data_compression_b200 import synth
     thr, base = synth.zipf_7bit_spec()
@@ -52,10 +52,10 @@ def test_n_ary_huffman_cli(built, radix, expect):
     assert r.returncode == 0, r.stderr[-500:]
     out = r.stdout.decode(errors="replace")
     assert out.count("Successful test.") == expect
-    if radix:
+    if radix == 5:      # no payload form for this radix: tables on the GPU, raw block like the reference
+        assert "pass-through raw data" in out.split("Starting next block")[1]
+    else:               # the default is the reference's radix 3: 5 trits per byte
         assert "# compressed: 300000 ->" in out and "pass-through" not in out.split("Starting next block")[1]
-    else:
-        assert "pass-through raw data" in out.split("Starting next block")[1]   # n=3: table only, like the reference
     q = subprocess.run(args + ["--quiet"], input=text, capture_output=True, timeout=120)
     assert q.returncode == 0 and set(q.stdout.decode().split("\n")) <= {"Successful test.", ""}
 
@@ -84,7 +84,7 @@ def test_write_nybble_verbatim_signature(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("radix", [2, 4, 16, 3])
+@pytest.mark.parametrize("radix", [2, 4, 16, 3, 10])
 def test_container_blocks(built, radix):
     """The netstring container (n_ary_huffman.c:1705-1814 / :2014-2094): table block in the reference's own text form,
     data block, raw fall-back; written and read back through the library."""
@@ -104,7 +104,7 @@ def test_container_blocks(built, radix):
     out = ctypes.create_string_buffer(cap + 1)
     n = L.dc_container_compress(radix, lengths.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), text, len(text), out, cap)
     blob = out.raw[:n]
-    if radix == 3:      # no payload packing for this radix: the raw block, like the reference
+    if radix == 10:     # no payload packing for this radix: the raw block, like the reference
         assert blob == b"%d:\n\n" % (len(text) + 2) + text + b",\n"
     else:
         digits = "".join("0123456789ABCDEF"[int(x)] for x in lengths)

@@ -120,6 +120,44 @@ def test_pack_unpack_roundtrip_and_layout(oracle, n):
         assert np.array_equal(oracle.unpack_mt(payload, phase, lengths, n, data.size, offs, 777, 3), data)
 
 
+def test_trit_payload_layout_and_roundtrip(oracle):
+    """Radix 3 (the reference's default, n_ary_huffman.c:2529): 5 trits per octet, byte = 1 + base-3 value, the scheme the
+    author sketches at :745-748 ("never uses byte 0 or 244..255")."""
+    # hand vector: A x3, B x3, C once; the as-written dummy rule (:786) adds two dummies here, so C sits at depth 2
+    data = np.frombuffer(b"ABBAAB", dtype=np.uint8)
+    h = oracle.histogram_u8(np.frombuffer(b"ABBAABC", dtype=np.uint8))
+    lengths, el, ev, st = oracle.build_tables(h, 3)
+    assert st == 0 and [int(lengths[s]) for s in (65, 66, 67)] == [1, 1, 2]
+    payload, trits = oracle.pack_trits(data, el, ev)
+    assert trits == 6
+    t = [int(ev[b]) for b in data]
+    g0 = 1 + t[0] * 81 + t[1] * 27 + t[2] * 9 + t[3] * 3 + t[4]
+    g1 = 1 + t[5] * 81
+    assert payload.tolist() == [g0, g1]
+    assert oracle.unpack_trits(payload, trits, lengths, data.size).tobytes() == b"ABBAAB"
+
+    rng = np.random.default_rng(33)
+    for size in (1, 4, 5, 6, 4999):
+        data = rng.choice(np.arange(1, 60, dtype=np.uint8), size=size, p=np.arange(59, 0, -1) / 1770.0)
+        hist = oracle.histogram_u8(data)
+        hist[200] += 1  # keep at least two symbols
+        lengths, el, ev, st = oracle.build_tables(hist, 3)
+        assert st == 0
+        payload, trits = oracle.pack_trits(data, el, ev)
+        assert trits == int(sum(int(lengths[b]) for b in data))
+        assert payload.size == (trits + 4) // 5
+        assert payload.min() >= 1 and payload.max() <= 243
+        # independent construction: codes as base-3 numerals, MSB trit first
+        digits = []
+        for b in data:
+            v, L = int(ev[b]), int(lengths[b])
+            digits += [(v // 3 ** (L - 1 - k)) % 3 for k in range(L)]
+        digits += [0] * (-len(digits) % 5)
+        want = [1 + sum(d * 3 ** (4 - k) for k, d in enumerate(digits[i:i + 5])) for i in range(0, len(digits), 5)]
+        assert payload.tolist() == want
+        assert np.array_equal(oracle.unpack_trits(payload, trits, lengths, data.size), data)
+
+
 def test_unpack_flags_unused_slot(oracle):
     # binary always carries one dummy leaf (F2): its code slot must be reported, not decoded
     h = np.zeros(259, dtype=np.uint64); h[[97, 98, 99, 100]] = [1, 1, 2, 2]
