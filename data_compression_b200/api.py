@@ -247,7 +247,8 @@ def _nybble_text(fn_name: str, src: torch.Tensor, cap: int):
     _need_cuda(src, "src")
     n = src.numel()
     out = torch.empty(cap + 16, dtype=torch.uint8, device=src.device)
-    ws = torch.empty(max(lib().dc_nybble_text_workspace_bytes(n), 16), dtype=torch.uint8, device=src.device)
+    ws_fn = lib().dc_nybble_adaptive_workspace_bytes if "adaptive" in fn_name else lib().dc_nybble_text_workspace_bytes
+    ws = torch.empty(max(ws_fn(n), 16), dtype=torch.uint8, device=src.device)
     out_len = torch.empty(1, dtype=torch.int64, device=src.device)
     status = torch.empty(1, dtype=torch.int32, device=src.device)
     check(getattr(lib(), fn_name)(src.data_ptr(), n, out.data_ptr(), cap, out_len.data_ptr(), status.data_ptr(), ws.data_ptr(),
@@ -264,6 +265,18 @@ def nybble_text_compress(src: torch.Tensor):
 def nybble_text_decompress(src: torch.Tensor):
     """decompress_bytestring(src, dst, false) nybble_compression.c:734.  Returns (buffer, length, status)."""
     return _nybble_text("dc_nybble_text_decompress", src, 2 * src.numel() + 2)
+
+
+def nybble_adaptive_compress(src: torch.Tensor):
+    """nybble_compress() = compress_bytestring(src, dst, true) nybble_compression.c:1134: 16 move-to-front contexts.
+    Returns (buffer, 1 x int64 length, 1 x int32 status); nothing blocks."""
+    return _nybble_text("dc_nybble_adaptive_compress", src, src.numel() + 2)
+
+
+def nybble_adaptive_decompress(src: torch.Tensor):
+    """nybble_decompress() = decompress_bytestring(src, dst, true) :1117.  The hit nibbles are resolved by one serial
+    walk over the output on the device (the chain the format imposes).  Returns (buffer, length, status)."""
+    return _nybble_text("dc_nybble_adaptive_decompress", src, 2 * src.numel() + 2)
 
 
 def synth_fill(out: torch.Tensor, seed: int, thresholds: torch.Tensor, value_base: int) -> torch.Tensor:

@@ -136,7 +136,7 @@ extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
 }
 extern "C" const char *dc_profile_kernel_name(int id) {
     static const char *names[DC_K_COUNT] = {"histogram", "table", "bits_for_hist", "encode_count", "encode_scan", "encode", "encode_mid", "encode_wide", "decode_sync", "decode_handoff",
-                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "synth"};
+                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "mtf_walk", "mtf_scan", "mtf_resolve", "synth"};
     return id >= 0 && id < DC_K_COUNT ? names[id] : "?";
 }
 
@@ -407,12 +407,13 @@ extern "C" int dc_host_nybble_unpack(const uint8_t *packed, size_t n_sym, uint8_
     return DC_OK;
 }
 
-// ------------------------------------------------------------------------------------------ static-table nybble compressor
+// ------------------------------------------------------------------------------------------ nybble compressor (static table / adaptive contexts)
 
 static long long host_text(const char *source, char *dest, int modify, bool compress) {
-    if (!source || !dest || modify) return DC_ERR_ARG;  // the adaptive (move-to-front) table is a serial chain: not offloaded
+    if (!source || !dest) return DC_ERR_ARG;
     const size_t n = strlen(source);
-    const size_t cap = compress ? n + 2 : 2 * n + 2, ws_bytes = dc_nybble_text_workspace_bytes(n);
+    const size_t cap = compress ? n + 2 : 2 * n + 2;
+    const size_t ws_bytes = modify ? dc_nybble_adaptive_workspace_bytes(n) : dc_nybble_text_workspace_bytes(n);
     int rc = g_arena.reserve(Arena::pad(n + 16) + Arena::pad(cap + 16) + Arena::pad(ws_bytes) + 512);
     if (rc != DC_OK) return rc;
     uint8_t *d_src = (uint8_t *)g_arena.take(n + 16), *d_dst = (uint8_t *)g_arena.take(cap + 16);
@@ -420,8 +421,12 @@ static long long host_text(const char *source, char *dest, int modify, bool comp
     uint64_t *d_len = (uint64_t *)g_arena.take(8);
     int32_t *d_status = (int32_t *)g_arena.take(4);
     if (n) DC_CUDA_TRY(cudaMemcpyAsync(d_src, source, n, cudaMemcpyHostToDevice, 0));
-    rc = compress ? dc_nybble_text_compress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr)
-                  : dc_nybble_text_decompress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr);
+    if (modify)
+        rc = compress ? dc_nybble_adaptive_compress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr)
+                      : dc_nybble_adaptive_decompress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr);
+    else
+        rc = compress ? dc_nybble_text_compress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr)
+                      : dc_nybble_text_decompress(d_src, n, d_dst, cap, d_len, d_status, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
     uint64_t len = 0;
     int32_t st = 0;

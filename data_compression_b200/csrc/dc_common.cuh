@@ -50,6 +50,13 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
                               uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
                               int32_t *d_status);
 
+// K8 (k8_mtf.cu): the move-to-front contexts of the adaptive nybble compressor, used by K6
+size_t mtf_workspace_bytes(size_t n);
+// d_pos[i] = position of d_src[i] in its context's list just before it is touched (8 = absent; d_pos[0] = 8)
+int mtf_positions(const uint8_t *d_src, size_t n, uint8_t *d_pos, void *d_ws, cudaStream_t st);
+// d_buf[1..*d_len): bytes with bit 7 are 0x80 | position and are replaced by the letter they mean (only if *d_mode == 0)
+int mtf_resolve(uint8_t *d_buf, const unsigned long long *d_len, const int32_t *d_mode, cudaStream_t st);
+
 // ---------------------------------------------------------------- device helpers
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }

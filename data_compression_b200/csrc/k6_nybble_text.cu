@@ -118,16 +118,23 @@ __device__ __forceinline__ void load_block(const uint8_t *__restrict__ in, size_
     prev = base > 0 && base - 1 < n ? in[base - 1] : 0u;
 }
 
-// masks of a compress block: T = table hits.  li[k] = table index of byte k (8 = not in the table)
-__device__ __forceinline__ void compress_masks(const uint8_t *lut, const uint32_t (&w)[kTxPer / 4], size_t base, size_t n, TxBlock<uint32_t> &b,
-                                               uint32_t (&li)[kTxPer], bool &bad) {
+// masks of a compress block: T = table hits.  li[k] = table index of byte k (8 = not in the table).  ADAPT: the indices
+// are the move-to-front positions K8 computed (pos[i] for byte i of the string), not the static table's.
+template <bool ADAPT>
+__device__ __forceinline__ void compress_masks(const uint8_t *lut, const uint8_t *__restrict__ pos, const uint32_t (&w)[kTxPer / 4], size_t base,
+                                               size_t n, TxBlock<uint32_t> &b, uint32_t (&li)[kTxPer], bool &bad) {
     const int valid = (int)min((size_t)kTxPer, n - base), skip = base == 0 ? 1 : 0;
     b.units = valid;
     b.V = low_bits<uint32_t>(valid) & ~low_bits<uint32_t>(skip);
     uint32_t miss = 0;
+    uint32_t pw[kTxPer / 4];
+    if (ADAPT) {
+        uint32_t unused;
+        load_block(pos, n, base, unused, pw);
+    }
 #pragma unroll
     for (int k = 0; k < kTxPer; k++) {
-        li[k] = lut[byte_of(w, k) & 0x7Fu];
+        li[k] = ADAPT ? (k < valid ? byte_of(pw, k) & 0xFu : 8u) : lut[byte_of(w, k) & 0x7Fu];
         miss |= k >= 3 ? (li[k] & 8u) << (k - 3) : (li[k] & 8u) >> (3 - k);
     }
     b.T = ~miss & b.V;
@@ -188,9 +195,9 @@ __device__ __forceinline__ uint32_t block_fn_of(const TxBlock<M> &b) {
 }
 
 // ------------------------------------------------------------------------------------------ S1
-template <bool COMPRESS>
+template <bool COMPRESS, bool ADAPT>
 __global__ void __launch_bounds__(kTxThreads) tx_summary_kernel(const uint8_t *__restrict__ in, size_t n, TxWorkspace ws, size_t ntiles,
-                                                                int32_t *__restrict__ d_status) {
+                                                                int32_t *__restrict__ d_status, const uint8_t *__restrict__ pos) {
     __shared__ uint32_t s_warp[kTxWarps];
     __shared__ uint8_t s_lut[128];
     fill_letter_table(s_lut);
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kTxThreads) tx_summary_kernel(const uint8_t *_
             if (COMPRESS) {
                 TxBlock<uint32_t> b;
                 uint32_t li[kTxPer];
-                compress_masks(s_lut, w, base, n, b, li, bad);
+                compress_masks<ADAPT>(s_lut, pos, w, base, n, b, li, bad);
                 f = block_fn_of<true>(b);
             } else {
                 TxBlock<unsigned long long> b;
@@ -373,7 +380,9 @@ __device__ __forceinline__ void emit_compress(const TxBlock<uint32_t> &b, const 
     if (ends_here && b.units > 0 && ((E >> (b.units - 1)) & 1u)) sts8(dst + __popc(A) + __popc(Mm), in[n - 1]);
 }
 
-// the same for a decompress block: 64 nibbles, in two halves of 32 so that the masks stay 32-bit
+// the same for a decompress block: 64 nibbles, in two halves of 32 so that the masks stay 32-bit.  ADAPT: a hit nibble is
+// written as 0x80 | position (K8 resolves it, the letter depends on the bytes decoded before it)
+template <bool ADAPT>
 __device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long> &b, const uint32_t (&w)[kTxPer / 4], uint32_t prev, uint32_t q_in,
                                                 uint32_t dst, bool ends_here, const uint8_t *__restrict__ in, size_t n) {
     unsigned long long E, F;
@@ -391,7 +400,7 @@ __device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long
         const uint32_t off = dst + (h ? base1 : 0u) + __popc(em[h] & below);
         const uint32_t cj = byte_of(w, j >> 1);
         const uint32_t x = (j & 1) ? (cj & 0xFu) : (cj >> 4);
-        if (em[h] & bit) sts8(off, (qq[h] & bit) ? ((pn & 7u) << 4) + x : letter_of(x));
+        if (em[h] & bit) sts8(off, (qq[h] & bit) ? ((pn & 7u) << 4) + x : (ADAPT ? 0x80u | (x & 7u) : letter_of(x)));
         pn = x;
     }
     // a dangling half literal at the very end is completed with a zero nibble: one thread of the whole grid
@@ -401,9 +410,9 @@ __device__ __forceinline__ void emit_decompress(const TxBlock<unsigned long long
 // ------------------------------------------------------------------------------------------ S3
 constexpr int kTxStageBytes = kTxThreads * 2 * kTxPer + 48;  // decompress: two symbols per byte; + alignment slack
 
-template <bool COMPRESS>
+template <bool COMPRESS, bool ADAPT>
 __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__restrict__ in, size_t n, TxWorkspace ws, size_t ntiles,
-                                                             uint8_t *__restrict__ out) {
+                                                             uint8_t *__restrict__ out, const uint8_t *__restrict__ pos) {
     __shared__ __align__(16) uint8_t s_stage[kTxStageBytes];
     __shared__ uint32_t s_warp[kTxWarps];
     __shared__ uint8_t s_lut[128];
@@ -433,7 +442,7 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
         if (base < n) {
             load_block(in, n, base, prev, w);
             if (COMPRESS) {
-                compress_masks(s_lut, w, base, n, bc, (uint32_t(&)[kTxPer])li, bad);
+                compress_masks<ADAPT>(s_lut, pos, w, base, n, bc, (uint32_t(&)[kTxPer])li, bad);
                 f = block_fn_of<true>(bc);
             } else {
                 decompress_masks(w, base, n, bd);
@@ -474,8 +483,12 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + a + off;
         if (base < n) {
             const bool ends_here = base + kTxPer >= n;  // this block holds the last byte of the stream
-            if (COMPRESS) emit_compress(bc, w, (const uint32_t(&)[kTxPer])li, prev, s_lut[prev & 0x7Fu], q, dst, ends_here, in, n);
-            else emit_decompress(bd, w, prev, q, dst, ends_here, in, n);
+            if (COMPRESS) {
+                const uint32_t prev_li = ADAPT ? (base ? pos[base - 1] & 0xFu : 8u) : s_lut[prev & 0x7Fu];
+                emit_compress(bc, w, (const uint32_t(&)[kTxPer])li, prev, prev_li, q, dst, ends_here, in, n);
+            } else {
+                emit_decompress<ADAPT>(bd, w, prev, q, dst, ends_here, in, n);
+            }
         }
         if (tile == 0 && tid == 0) {
             if (COMPRESS) { out[0] = 0xAF; out[1] = in[0]; }   // :903, :905
@@ -495,21 +508,23 @@ __global__ void __launch_bounds__(kTxThreads) tx_emit_kernel(const uint8_t *__re
     }
 }
 
-static size_t tx_ws_layout(size_t n, size_t off[5]) {
+static size_t tx_ws_layout(size_t n, bool adapt_compress, size_t off[7]) {
     const size_t ntiles = (n + kTxTile - 1) / kTxTile;
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o[5];
+    size_t o[7];
     o[0] = take(ntiles * 4);   // tile_fn
     o[1] = take(ntiles * 8);   // tile_off
     o[2] = take(ntiles);       // tile_q
     o[3] = 0;                  // out_len (header)
     o[4] = 8;                  // mode (header)
-    if (off) for (int i = 0; i < 5; i++) off[i] = o[i];
+    o[5] = adapt_compress ? take(n + 16) : 0;                   // K8: move-to-front position of every byte
+    o[6] = adapt_compress ? take(mtf_workspace_bytes(n)) : 0;   // K8: lists per block / chunk
+    if (off) for (int i = 0; i < 7; i++) off[i] = o[i];
     return p;
 }
 
-template <bool COMPRESS>
+template <bool COMPRESS, bool ADAPT>
 static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, uint64_t *d_out_len, int32_t *d_status, void *d_ws,
                   size_t ws_bytes, cudaStream_t st) {
     if ((n && (!d_src || !d_dst || !d_ws)) || ((uintptr_t)d_ws & 15)) return DC_ERR_ARG;
@@ -519,8 +534,8 @@ static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, ui
         if (cap && d_dst) DC_CUDA_TRY(cudaMemsetAsync(d_dst, 0, 1, st));  // the empty string
         return DC_OK;
     }
-    size_t off[5];
-    if (ws_bytes < tx_ws_layout(n, off)) return DC_ERR_CAPACITY;
+    size_t off[7];
+    if (ws_bytes < tx_ws_layout(n, COMPRESS && ADAPT, off)) return DC_ERR_CAPACITY;
     char *w = (char *)d_ws;
     TxWorkspace ws;
     ws.tile_fn = (uint32_t *)(w + off[0]);
@@ -528,11 +543,17 @@ static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, ui
     ws.tile_q = (uint8_t *)(w + off[2]);
     ws.out_len = (unsigned long long *)(w + off[3]);
     ws.mode = (int32_t *)(w + off[4]);
+    const uint8_t *pos = nullptr;
+    if (COMPRESS && ADAPT) {
+        const int rc = mtf_positions(d_src, n, (uint8_t *)(w + off[5]), w + off[6], st);
+        if (rc != DC_OK) return rc;
+        pos = (const uint8_t *)(w + off[5]);
+    }
     const size_t ntiles = (n + kTxTile - 1) / kTxTile;
     const unsigned int grid = (unsigned int)min(ntiles, (size_t)sm_count() * 8);
     {
         LaunchScope ls(DC_K_TEXT_SUMMARY, st);
-        tx_summary_kernel<COMPRESS><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_status);
+        tx_summary_kernel<COMPRESS, COMPRESS && ADAPT><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_status, pos);
     }
     {
         LaunchScope ls(DC_K_TEXT_SCAN, st);
@@ -540,7 +561,11 @@ static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, ui
     }
     {
         LaunchScope ls(DC_K_TEXT_EMIT, st);
-        tx_emit_kernel<COMPRESS><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_dst);
+        tx_emit_kernel<COMPRESS, ADAPT><<<grid, kTxThreads, 0, st>>>(d_src, n, ws, ntiles, d_dst, pos);
+    }
+    if (!COMPRESS && ADAPT) {
+        const int rc = mtf_resolve(d_dst, ws.out_len, ws.mode, st);
+        if (rc != DC_OK) return rc;
     }
     return cuda_status(cudaGetLastError());
 }
@@ -549,14 +574,25 @@ static int tx_run(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t cap, ui
 
 using namespace dc;
 
-extern "C" size_t dc_nybble_text_workspace_bytes(size_t n) { return tx_ws_layout(n, nullptr); }
+extern "C" size_t dc_nybble_text_workspace_bytes(size_t n) { return tx_ws_layout(n, false, nullptr); }
+extern "C" size_t dc_nybble_adaptive_workspace_bytes(size_t n) { return tx_ws_layout(n, true, nullptr); }
 
 extern "C" int dc_nybble_text_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
                                        int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
-    return tx_run<true>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+    return tx_run<true, false>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dc_nybble_text_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
                                          int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
-    return tx_run<false>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+    return tx_run<false, false>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dc_nybble_adaptive_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                           int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return tx_run<true, true>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dc_nybble_adaptive_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                             int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return tx_run<false, true>(d_src, n, d_dst, dst_capacity, d_out_len, d_status, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -6,13 +6,14 @@
  * GPU: the split of every byte into (high, low) nibbles (:767-769) and write_nybble()'s packing order
  * (:1091-1114), through refapi.h -> libdc_b200.so.
  *
- * and for the static-table compressor compress_bytestring(text, c, false) / decompress_bytestring (:1160-1166),
- * including the reference's `assert(strlen(compressed) <= 70)` (:1162).  The adaptive-table round trips of the
- * reference's main() (:1176-1215) are a serial move-to-front chain and are not offloaded.
+ * and for the compressor: compress_bytestring(text, c, false) / decompress_bytestring (:1160-1166) with the static
+ * table, then nybble_compress() / nybble_decompress() (:1176-1215) with the adaptive contexts, each with the
+ * reference's `assert(strlen(compressed) <= 70)` (:1162, :1178).
  *
  *   ./nybble_compression            fixed text, as the reference
  *   ./nybble_compression - < file   the nibble round trip over stdin (and the compressor, if the file is 7-bit text)
  */
+#include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,17 +51,17 @@ static void round_trip(const unsigned char *bytes, size_t n) {
     free(packed);
 }
 
-static void text_round_trip(const char *text, size_t limit) {
+static void text_round_trip(const char *text, size_t limit, bool modify) {
     const size_t n = strlen(text);
     char *c = malloc(n + 2), *d = malloc(2 * n + 2);
     if (!c || !d) abort();
-    compress_bytestring(text, c, false);
-    printf("# compressed %zu -> %zu bytes (static table)\n", n, strlen(c));
+    compress_bytestring(text, c, modify);
+    printf("# compressed %zu -> %zu bytes (%s)\n", n, strlen(c), modify ? "adaptive contexts" : "static table");
     if (limit && strlen(c) > limit) {
         printf("Error: compressed text longer than %zu bytes.\n", limit);
         abort();
     }
-    decompress_bytestring(c, d, false);
+    decompress_bytestring(c, d, modify);
     if (strlen(d) != n || memcmp(text, d, n) != 0) {
         printf("Error: decompressed text doesn't match original text.\n");
         abort();
@@ -90,7 +91,8 @@ int main(int argc, char **argv) {
             buf = realloc(buf, used + 1);
             if (!buf) abort();
             buf[used] = 0;
-            text_round_trip((const char *)buf, 0);
+            text_round_trip((const char *)buf, 0, false);
+            text_round_trip((const char *)buf, 0, true);
         }
         free(buf);
         return 0;
@@ -98,6 +100,7 @@ int main(int argc, char **argv) {
     const char *text = "Hello, world. This is a test. This is only a test. Banana banana banana banana. ";
     printf("# %zu bytes -> %zu nybbles -> %zu bytes\n", strlen(text), 2 * strlen(text), strlen(text));
     round_trip((const unsigned char *)text, strlen(text));
-    text_round_trip(text, 70);
+    text_round_trip(text, 70, false);
+    text_round_trip(text, 70, true);
     return 0;
 }

@@ -88,3 +88,7 @@ void decompress_bytestring(const char *source, char *dest, bool modify) {
     const long long rc = dc_host_decompress_bytestring(source, dest, modify ? 1 : 0);
     done("decompress_bytestring", rc < 0 ? (int)rc : DC_OK);
 }
+
+void nybble_compress(const char *source, char *dest) { compress_bytestring(source, dest, true); }
+
+void nybble_decompress(const char *source, char *dest) { decompress_bytestring(source, dest, true); }

@@ -58,11 +58,13 @@ void write_nybble(const int nybble, char *dest, bool nybble_offset);
 void nybble_pack_stream(const unsigned char *symbols, size_t n_symbols, unsigned char *packed);
 void nybble_unpack_stream(const unsigned char *packed, size_t n_symbols, unsigned char *symbols);
 
-/* nybble_compression.c:887-1038 / :734-817 -- the static-table mode (modify == false) runs on the GPU.  The adaptive
- * move-to-front mode (modify == true, what nybble_compress()/nybble_decompress() :1134/:1117 use) is a serial chain
- * over the whole string; it is not offloaded and is refused (DC_ERR_ARG, i.e. abort like a failed assert). */
+/* nybble_compression.c:887-1038 / :734-817, both modes on the GPU: the static table (modify == false) and the 16
+ * adaptive move-to-front contexts (modify == true).  nybble_compress() / nybble_decompress() are the reference's
+ * modify == true wrappers (:1134, :1117). */
 void compress_bytestring(const char *source, char *dest, bool modify);
 void decompress_bytestring(const char *source, char *dest, bool modify);
+void nybble_compress(const char *source, char *dest);
+void nybble_decompress(const char *source, char *dest);
 
 /* the netstring block container of n_ary_huffman.c:1705-1814 / :2014-2094 (container.c): table block 'X', data block
  * 'Z', raw block.  compress() / decompress() are static in the reference; these are their linkable counterparts.

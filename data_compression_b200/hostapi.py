@@ -127,8 +127,8 @@ def nybble_unpack(packed, n_sym: int, out: np.ndarray | None = None) -> np.ndarr
 
 
 def compress_bytestring(source: bytes, modify: bool = False) -> bytes:
-    """compress_bytestring(source, dest, modify) nybble_compression.c:887 -- the static-table mode runs on the GPU;
-    modify=True (adaptive move-to-front table) is a serial chain and raises DcError(DC_ERR_ARG)."""
+    """compress_bytestring(source, dest, modify) nybble_compression.c:887 on the GPU: the static table, or with
+    modify=True the 16 adaptive move-to-front contexts (nybble_compress() :1134)."""
     dest = C.create_string_buffer(len(source) + 2)
     n = lib().dc_host_compress_bytestring(bytes(source), C.addressof(dest), int(modify))
     if n < 0:
@@ -137,7 +137,7 @@ def compress_bytestring(source: bytes, modify: bool = False) -> bytes:
 
 
 def decompress_bytestring(source: bytes, modify: bool = False) -> bytes:
-    """decompress_bytestring(source, dest, modify) nybble_compression.c:734 (static table)."""
+    """decompress_bytestring(source, dest, modify) nybble_compression.c:734 (modify=True: nybble_decompress() :1117)."""
     dest = C.create_string_buffer(2 * len(source) + 2)
     n = lib().dc_host_decompress_bytestring(bytes(source), C.addressof(dest), int(modify))
     if n < 0:

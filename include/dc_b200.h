@@ -132,6 +132,9 @@ enum dc_kernel_id {
     DC_K_TEXT_EMIT,
     DC_K_TRIT_PACK,
     DC_K_TRIT_UNPACK,
+    DC_K_MTF_WALK,
+    DC_K_MTF_SCAN,
+    DC_K_MTF_RESOLVE,
     DC_K_SYNTH,
     DC_K_COUNT
 };
@@ -265,9 +268,8 @@ int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t *d_t2, int
 size_t dc_nybble_text_workspace_bytes(size_t n);
 
 /*
- * Replaces compress_bytestring(source, dest, false) nybble_compression.c:887-1038 (static " etaoins" table, the
- * mode that is an exact parallel scan; the adaptive move-to-front mode, modify == true, is a serial chain and is not
- * offloaded).  Length-explicit: d_src[0..n) must hold bytes 0x01..0x7F (:910), else *d_status = DC_ERR_SYMBOL.
+ * Replaces compress_bytestring(source, dest, false) nybble_compression.c:887-1038 (static " etaoins" table; for
+ * modify == true see dc_nybble_adaptive_compress below).  Length-explicit: d_src[0..n) must hold bytes 0x01..0x7F (:910), else *d_status = DC_ERR_SYMBOL.
  * Output: 0xAF, src[0], body -- or ' ' + source when that is not shorter (:1018-1037) -- and a NUL when there is room.
  *   d_out_len  1 x u64: bytes written (without the NUL);  needs dst_capacity >= n + 1
  */
@@ -276,6 +278,22 @@ int dc_nybble_text_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size
 /* Replaces decompress_bytestring(source, dest, false) :734-817: type byte 0xAF / ' ' / anything else; at most 2n - 3 bytes. */
 int dc_nybble_text_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
                               int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- K6 + K8 adaptive nybble compressor */
+
+/*
+ * Replace compress_bytestring(source, dest, true) = nybble_compress() nybble_compression.c:1134 and
+ * decompress_bytestring(source, dest, true) = nybble_decompress() :1117: the same coder with 16 move-to-front
+ * contexts (byte_to_context :517, update_context :665-687) instead of the static table.  Same arguments, limits and
+ * status codes as the two functions above; the workspace is larger (dc_nybble_adaptive_workspace_bytes).
+ * Compress is a parallel scan (the contexts are known from the input).  Decompress resolves the hit nibbles with one
+ * serial walk over the output on the device -- the chain the format imposes; it is parallel only across strings.
+ */
+size_t dc_nybble_adaptive_workspace_bytes(size_t n);
+int dc_nybble_adaptive_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
+int dc_nybble_adaptive_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
+                                  int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- synthetic inputs (bench/tests) */
 
@@ -317,8 +335,8 @@ long long dc_host_huff_compress(const uint8_t *in, size_t n, int compressed_symb
 int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bits, const int lengths[DC_NSLOTS],
                             int compressed_symbols, uint8_t *out, size_t n_out);
 /* compress_bytestring(source, dest, modify) nybble_compression.c:887 / decompress_bytestring :734 on NUL-terminated
- * strings (dest must hold strlen(source) + 2, resp. 2 * strlen(source) + 1 bytes).  modify != 0 (the adaptive table) is
- * DC_ERR_ARG: that mode is a serial chain and stays on the host side of the caller.  Returns the output length. */
+ * strings (dest must hold strlen(source) + 2, resp. 2 * strlen(source) + 1 bytes).  modify != 0 selects the adaptive
+ * (move-to-front) contexts, as in nybble_compress() :1134 / nybble_decompress() :1117.  Returns the output length. */
 long long dc_host_compress_bytestring(const char *source, char *dest, int modify);
 long long dc_host_decompress_bytestring(const char *source, char *dest, int modify);
 int dc_host_nybble_pack(const uint8_t *sym, size_t n_sym, uint8_t *packed);

@@ -92,6 +92,9 @@ void orc_nybble_unpack_mt(const uint8_t *packed, size_t n_sym, uint8_t *sym, int
  * length-explicit.  Returns bytes written (excluding the terminating NUL it also writes). */
 size_t orc_nybble_static_compress(const uint8_t *src, size_t n, uint8_t *dst);
 size_t orc_nybble_static_decompress(const uint8_t *src, size_t n, uint8_t *dst);
+/* the same with modify=true: 16 move-to-front contexts (update_context :665-687). */
+size_t orc_nybble_adaptive_compress(const uint8_t *src, size_t n, uint8_t *dst);
+size_t orc_nybble_adaptive_decompress(const uint8_t *src, size_t n, uint8_t *dst);
 
 #ifdef __cplusplus
 }

@@ -132,3 +132,99 @@ size_t orc_nybble_static_decompress(const uint8_t *src, size_t n, uint8_t *dst) 
     dst[o] = 0;
     return o;
 }
+
+/* ---------------------------------------------------------------- adaptive compressor (row N3) */
+
+/*
+ * modify == true (nybble_compress :1134 / nybble_decompress :1117): 16 contexts, chosen by bits 3..6 of the
+ * previous byte (byte_to_context :517-523), each a move-to-front list of 8 letters that starts as
+ * " etaoins" (:546-562).  After every byte -- hit or miss, and on both sides -- the byte is moved to the
+ * front of its context's list (update_context :665-687): entries in front of its old position (or all
+ * but the last, if it was absent) shift back by one.  Emission is the static coder's (:819-884).
+ */
+typedef struct { uint8_t letter[16][8]; } orc_ctx_table;
+
+static void ctx_init(orc_ctx_table *t) {
+    for (int c = 0; c < 16; c++) memcpy(t->letter[c], k_letters, 8);
+}
+static int ctx_of(uint8_t prev) { return (prev >> 3) & 15; }
+static int ctx_find(const orc_ctx_table *t, int c, uint8_t s) {
+    for (int i = 0; i < 8; i++)
+        if (t->letter[c][i] == s) return i;
+    return -1;
+}
+static void ctx_touch(orc_ctx_table *t, int c, uint8_t s) {
+    int at = ctx_find(t, c, s);
+    if (at < 0) at = 7;
+    memmove(&t->letter[c][1], &t->letter[c][0], (size_t)at);
+    t->letter[c][0] = s;
+}
+
+size_t orc_nybble_adaptive_compress(const uint8_t *src, size_t n, uint8_t *dst) {
+    if (n == 0) { dst[0] = 0; return 0; }
+    orc_ctx_table t;
+    ctx_init(&t);
+    size_t o = 0;
+    dst[o++] = 0xAF;
+    dst[o++] = src[0];
+    int off = 0;
+    for (size_t i = 1; i < n; i++) {
+        const int c = ctx_of(src[i - 1]);
+        const int idx = ctx_find(&t, c, src[i]);
+        int used;
+        if (idx < 0) {
+            if (off == 0) { dst[o] = src[i]; used = 2; }
+            else { dst[o] = src[i - 1]; dst[o + 1] = src[i]; used = 3; }
+        } else {
+            const uint8_t nyb = (uint8_t)(idx | 0x8);
+            if (off == 0) dst[o] = (uint8_t)(nyb << 4);
+            else dst[o] |= nyb;
+            used = 1;
+        }
+        ctx_touch(&t, c, src[i]);
+        off += used;
+        if (off > 1) { o++; off -= 2; }
+        if (off > 1) { o++; off -= 2; }
+    }
+    if (off != 0) dst[o++] = src[n - 1];
+    dst[o] = 0;
+    if (o >= n) {
+        o = 0;
+        dst[o++] = ' ';
+        memcpy(dst + o, src, n);
+        o += n;
+        dst[o] = 0;
+    }
+    return o;
+}
+
+size_t orc_nybble_adaptive_decompress(const uint8_t *src, size_t n, uint8_t *dst) {
+    size_t o = 0;
+    if (n == 0) { dst[0] = 0; return 0; }
+    if (src[0] == 0xAF) {
+        if (n < 2) { dst[0] = 0; return 0; }
+        orc_ctx_table t;
+        ctx_init(&t);
+        dst[o++] = src[1];
+        size_t p = 2;
+        int off = 0;
+        while (p < n) {
+            const unsigned b = src[p], nb = p + 1 < n ? src[p + 1] : 0;
+            unsigned nyb, next;
+            if (off == 0) { nyb = (b >> 4) & 0xF; next = b & 0xF; }
+            else { nyb = b & 0xF; next = (nb >> 4) & 0xF; }
+            const int c = ctx_of(dst[o - 1]);
+            uint8_t out;
+            if (nyb & 0x8) { out = t.letter[c][nyb & 7]; off += 1; }
+            else { out = (uint8_t)(((nyb & 7) << 4) + next); off += 2; }
+            dst[o++] = out;
+            ctx_touch(&t, c, out);
+            if (off >= 2) { p++; off -= 2; }
+        }
+    } else {
+        size_t p = src[0] == ' ' ? 1 : 0;
+        while (p < n) dst[o++] = src[p++];
+    }
+    dst[o] = 0;
+    return o;
+}

@@ -67,7 +67,8 @@ def lib() -> C.CDLL:
         for f in ("orc_nybble_pack_mt", "orc_nybble_unpack_mt"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
             getattr(L, f).restype = None
-        for f in ("orc_nybble_static_compress", "orc_nybble_static_decompress"):
+        for f in ("orc_nybble_static_compress", "orc_nybble_static_decompress",
+                  "orc_nybble_adaptive_compress", "orc_nybble_adaptive_decompress"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
             getattr(L, f).restype = C.c_size_t
         _lib = L
@@ -247,6 +248,20 @@ def nybble_static_decompress(src: bytes) -> bytes:
     s = _u8(src)
     out = np.zeros(s.size * 2 + 8, dtype=np.uint8)
     n = lib().orc_nybble_static_decompress(s.ctypes.data, s.size, out.ctypes.data)
+    return out[:n].tobytes()
+
+
+def nybble_adaptive_compress(src: bytes) -> bytes:
+    s = _u8(src)
+    out = np.zeros(s.size * 2 + 8, dtype=np.uint8)
+    n = lib().orc_nybble_adaptive_compress(s.ctypes.data, s.size, out.ctypes.data)
+    return out[:n].tobytes()
+
+
+def nybble_adaptive_decompress(src: bytes) -> bytes:
+    s = _u8(src)
+    out = np.zeros(s.size * 2 + 8, dtype=np.uint8)
+    n = lib().orc_nybble_adaptive_decompress(s.ctypes.data, s.size, out.ctypes.data)
     return out[:n].tobytes()
 
 

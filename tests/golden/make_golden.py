@@ -119,8 +119,11 @@ def main():
         c = O.ref_compress_bytestring(t, False)
         assert O.ref_decompress_bytestring(c, False) == t
         ny["static"].append({"text": t.hex(), "compressed": c.hex()})
-    c = O.ref_compress_bytestring(text, True)
-    ny["adaptive"].append({"text": text.hex(), "compressed": c.hex()})
+    long_text = (text * 40)[:3001] + bytes(rng.choice(np.frombuffer(b" etaoinsrhldcu.,\nTHE", dtype=np.uint8), size=5000).tolist())
+    for t in texts + [long_text]:
+        c = O.ref_compress_bytestring(t, True)   # nybble_compress() :1134
+        assert O.ref_decompress_bytestring(c, True) == t
+        ny["adaptive"].append({"text": t.hex(), "compressed": c.hex()})
     for k in (0, 1, 2, 7, 32, 33, 95):
         s = rng.integers(0, 16, size=k).astype(np.uint8)
         ny["write_nybble"].append({"symbols": s.tolist(), "packed": O.ref_write_nybble_stream(s).tolist()})

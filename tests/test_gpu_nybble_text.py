@@ -1,5 +1,6 @@
-"""GPU: the static-table nybble compressor / decompressor against the golden vectors generated
-from the unmodified compress_bytestring()/decompress_bytestring() and against the oracle on text-like data."""
+"""GPU: the nybble compressor / decompressor -- static table and adaptive move-to-front contexts
+(row N3) -- against the golden vectors generated from the unmodified compress_bytestring()/decompress_bytestring()
+and against the oracle on text-like data."""
 import numpy as np
 import pytest
 import torch
@@ -80,8 +81,76 @@ def test_decoder_accepts_nibble_granular_literals(dc, oracle):
 def test_errors(dc):
     got, st, _, _ = _run(dc.nybble_text_compress, b"abc\x80def")
     assert st == dc.DC_ERR_SYMBOL                              # assert( source[i] < 0x80 ) :910
-    with pytest.raises(dc.DcError) as e:
-        dc.hostapi.compress_bytestring(b"hello", modify=True)  # adaptive mode is serial: not offloaded
-    assert e.value.status == dc.DC_ERR_ARG
+    got, st, _, _ = _run(dc.nybble_adaptive_compress, b"abc\x80def")
+    assert st == dc.DC_ERR_SYMBOL
     assert dc.hostapi.compress_bytestring(b"") == b""
     assert dc.hostapi.decompress_bytestring(b"") == b""
+
+
+# ------------------------------------------------------------------------------------------ adaptive contexts (row N3)
+
+def _english(rng, n):
+    words = [b"the", b"and", b"this", b"is", b"a", b"test", b"banana", b"Hello,", b"world.", b"only", b"of", b"to", b"in", b"it",
+             b"compression", b"nybble", b"context", b"Q", b"42", b"\n"]
+    out = bytearray()
+    while len(out) < n:
+        out += words[int(rng.integers(len(words)))] + b" "
+    return bytes(out[:n])
+
+
+def test_adaptive_reference_golden_vectors(dc):
+    g = load_golden("nybble.json")["adaptive"]
+    for c in g:
+        text, comp = bytes.fromhex(c["text"]), bytes.fromhex(c["compressed"])
+        got, st, buf, n = _run(dc.nybble_adaptive_compress, text)
+        assert st == 0 and got == comp, len(text)
+        assert int(buf[n].item()) == 0
+        back, st, _, _ = _run(dc.nybble_adaptive_decompress, comp)
+        assert st == 0 and back == text
+        assert dc.hostapi.compress_bytestring(text, modify=True) == comp          # nybble_compress() :1134
+        assert dc.hostapi.decompress_bytestring(comp, modify=True) == text        # nybble_decompress() :1117
+    assert len(dc.hostapi.compress_bytestring(bytes.fromhex(g[0]["text"]), modify=True)) <= 70   # :1178
+
+
+@pytest.mark.parametrize("kind", ["english", "letters", "uniform", "one_context"])
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 511, 512, 513, 1025, 32768, 32769, 70001, (1 << 20) + 5])
+def test_adaptive_matches_oracle(dc, oracle, n, kind):
+    rng = np.random.default_rng(n * 13 + len(kind))
+    if kind == "english":
+        text = _english(rng, n)
+    elif kind == "letters":
+        text = _textlike(rng, n, 0.7)
+    elif kind == "uniform":
+        text = rng.integers(1, 128, size=n, dtype=np.uint8).tobytes()   # every context, mostly misses
+    else:
+        text = rng.choice(np.frombuffer(b"abcdefg`", dtype=np.uint8), size=n).tobytes()  # one context, 8 letters: all hits soon
+    want = oracle.nybble_adaptive_compress(text)
+    got, st, _, _ = _run(dc.nybble_adaptive_compress, text)
+    assert st == 0 and got == want, (n, kind)
+    if n <= 70001:   # the decoder's resolve step is one serial walk
+        back, st, _, _ = _run(dc.nybble_adaptive_decompress, want)
+        assert st == 0 and back == oracle.nybble_adaptive_decompress(want) == text
+
+
+def test_adaptive_lists_cross_blocks_and_chunks(dc, oracle):
+    # a letter seen once, then 40 000 bytes of other contexts, then used again: its list position has to survive
+    # 78 blocks of 512 bytes and a chunk boundary (64 blocks); and a context that never appears in between
+    rng = np.random.default_rng(8)
+    filler = rng.choice(np.frombuffer(b"hijklmno", dtype=np.uint8), size=40000).tobytes()   # context 13 only
+    text = b"A~A~A~" + filler + b"A~A~" + filler[:700] + b"Az~"
+    want = oracle.nybble_adaptive_compress(text)
+    got, st, _, _ = _run(dc.nybble_adaptive_compress, text)
+    assert st == 0 and got == want
+    back, st, _, _ = _run(dc.nybble_adaptive_decompress, want)
+    assert st == 0 and back == text
+
+
+def test_adaptive_decoder_on_arbitrary_streams(dc, oracle):
+    rng = np.random.default_rng(6)
+    for n in (2, 3, 9, 100, 5000):
+        body = rng.integers(1, 256, size=n, dtype=np.uint8).tobytes()
+        for head in (b"\xafA", b" ", b"Q"):
+            comp = head + body
+            want = oracle.nybble_adaptive_decompress(comp)
+            got, st, _, _ = _run(dc.nybble_adaptive_decompress, comp)
+            assert st == 0 and got == want, (n, head)

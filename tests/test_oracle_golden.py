@@ -92,6 +92,11 @@ def test_nybble_golden(oracle):
         text, comp = bytes.fromhex(c["text"]), bytes.fromhex(c["compressed"])
         assert oracle.nybble_static_compress(text) == comp
         assert oracle.nybble_static_decompress(comp) == text
+    for c in g["adaptive"]:
+        text, comp = bytes.fromhex(c["text"]), bytes.fromhex(c["compressed"])
+        assert oracle.nybble_adaptive_compress(text) == comp
+        assert oracle.nybble_adaptive_decompress(comp) == text
+    assert len(bytes.fromhex(g["adaptive"][0]["compressed"])) <= 70  # nybble_compression.c:1187
     main_text = bytes.fromhex(g["static"][0]["text"])
     assert len(bytes.fromhex(g["static"][0]["compressed"])) <= 70  # nybble_compression.c:1162
     assert len(main_text) == 80

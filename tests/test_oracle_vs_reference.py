@@ -67,5 +67,13 @@ def test_nybble_differential(ref):
         assert ref.nybble_static_compress(text) == comp
         assert ref.nybble_static_decompress(comp) == text
         assert ref.ref_decompress_bytestring(comp, False) == text
+        # modify == true: nybble_compress() / nybble_decompress() (:1134, :1117), 16 move-to-front contexts
+        comp = ref.ref_compress_bytestring(text, True)
+        assert ref.nybble_adaptive_compress(text) == comp
+        assert ref.nybble_adaptive_decompress(comp) == text
+        assert ref.ref_decompress_bytestring(comp, True) == text
+    every = bytes(rng.permutation(np.arange(1, 128, dtype=np.uint8)).tolist()) * 3   # every context, every 7-bit byte
+    comp = ref.ref_compress_bytestring(every, True)
+    assert ref.nybble_adaptive_compress(every) == comp and ref.nybble_adaptive_decompress(comp) == every
     s = rng.integers(0, 16, size=257).astype(np.uint8)
     assert np.array_equal(ref.ref_write_nybble_stream(s), ref.nybble_pack(s))
