@@ -57,3 +57,52 @@ def test_config2_nybble_stream_equals_oracle(dc, oracle):
     want = oracle.nybble_pack(_host_of(sym), threads=threads)
     assert np.array_equal(_host_of(packed), want)
     assert torch.equal(dc.nybble_unpack(packed, N), sym)
+
+
+def test_radix3_quarter_gib_equals_oracle(dc, oracle):
+    """Row N4 at size: 256 MiB of Zipf(1.1) bytes, radix 3 (the reference's default).  The 5-trits-per-byte payload is compared
+    byte for byte with the oracle's (one host thread), and the oracle's payload is decoded back."""
+    from data_compression_b200 import synth
+    n = 1 << 28
+    thr, base = synth.zipf_bytes_spec()
+    data = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(data, synth.SEED_BASE + 2, synth.device_thresholds(thr, "cuda"), base)
+    host = _host_of(data)
+    hist = dc.histogram(data)
+    table = dc.huff_build(hist, 3)
+    ln, el, ev, st = oracle.build_tables(hist.cpu().numpy().astype(np.uint64), 3)
+    t = table.download()
+    assert st == 0 and t.status == 0 and np.array_equal(np.array(t.lengths[:259]), ln)
+    res = dc.huff_encode(data, table, out=torch.empty(n + n // 2 + 64, dtype=torch.uint8, device="cuda"))
+    want, wtrits = oracle.pack_trits(host, el, ev)
+    assert res.bits() == 2 * wtrits == t.total_bits
+    payload, pst = dc.trit_pack(res.payload, wtrits)
+    assert int(pst.item()) == 0 and np.array_equal(_host_of(payload), want)
+    del res, payload
+    t2, ust = dc.trit_unpack(torch.from_numpy(want).cuda(), wtrits)
+    out, status = dc.huff_decode(t2, 2 * wtrits, table, n)
+    assert int(ust.item()) == 0 and int(status.item()) == 0 and torch.equal(out, data)
+
+
+def test_adaptive_nybble_compressor_quarter_gib_equals_oracle(dc, oracle):
+    """Row N3 at size: 256 MiB of word-like 7-bit text through nybble_compress() (move-to-front contexts): the GPU scan must
+    give the oracle's bytes (the oracle is pinned against the unmodified reference in tests/test_oracle_vs_reference.py)."""
+    n = 1 << 28
+    rng = np.random.default_rng(1234)
+    words = [b"the ", b"and ", b"this ", b"is ", b"a ", b"test. ", b"banana ", b"Hello, ", b"world. ", b"only ", b"of ", b"to ",
+             b"compression ", b"nybble ", b"context ", b"Q", b"42 ", b"\n", b"entropy ", b"static "]
+    lens = np.array([len(w) for w in words])
+    picks = rng.integers(0, len(words), size=n // int(lens.mean()) + 1024)
+    table = np.frombuffer(b"".join(w.ljust(16, b"\0") for w in words), dtype=np.uint8).reshape(len(words), 16)
+    flat = table[picks].reshape(-1)
+    host = flat[flat != 0][:n].copy()
+    assert host.size == n
+    want = oracle.nybble_adaptive_compress(host)
+    buf, ln, st = dc.nybble_adaptive_compress(torch.from_numpy(host).cuda())
+    assert int(st.item()) == 0 and int(ln.item()) == len(want)
+    assert np.array_equal(_host_of(buf[: len(want)]), np.frombuffer(want, dtype=np.uint8))
+    # the decoder's resolve step is serial: round-trip the first MiB of text only
+    small = host[: 1 << 20]
+    comp = oracle.nybble_adaptive_compress(small)
+    back, bl, st = dc.nybble_adaptive_decompress(torch.from_numpy(np.frombuffer(comp, dtype=np.uint8).copy()).cuda())
+    assert int(st.item()) == 0 and np.array_equal(_host_of(back[: int(bl.item())]), small)
