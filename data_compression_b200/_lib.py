@@ -15,6 +15,7 @@ REFAPI_PATH = os.path.join(HERE, "libdc_b200_refapi.so")
 DC_NSLOTS = 259
 DC_MAX_SYMBOL_VALUE = 258
 DC_LUT_BITS = 12
+DC_LUT_ENTRIES = 6564   # max(2^12, 3^8) rounded up: the multi-symbol decode tables (radix 3 indexes them by 8 trits)
 
 DC_OK, DC_ERR_ARG, DC_ERR_CUDA, DC_ERR_CODE_TOO_LONG = 0, -1, -2, -3
 DC_ERR_CAPACITY, DC_ERR_CORRUPT, DC_ERR_SYMBOL, DC_ERR_RADIX = -4, -5, -6, -7
@@ -38,7 +39,7 @@ class HuffTableStruct(C.Structure):
         ("enc", C.c_uint32 * 256), ("enc64", C.c_uint64 * 256),
         ("first_code", C.c_uint32 * 32), ("len_count", C.c_uint32 * 32), ("len_offset", C.c_uint32 * 32),
         ("sorted", C.c_uint16 * (DC_NSLOTS + 1)), ("lut", C.c_uint16 * (1 << DC_LUT_BITS)),
-        ("lut_count", C.c_uint32 * (1 << DC_LUT_BITS)), ("lut_pair", C.c_uint32 * (1 << DC_LUT_BITS)),
+        ("lut_count", C.c_uint32 * DC_LUT_ENTRIES), ("lut_pair", C.c_uint32 * DC_LUT_ENTRIES),
         ("lut2", C.c_uint16 * (256 * 16)), ("lut2_used", C.c_int32), ("reserved1", C.c_int32),
     ]
 

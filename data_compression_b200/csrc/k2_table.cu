@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     }
     __syncthreads();
     // multi-symbol tables: greedily take every code that lies completely inside the 12 index bits
-    for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
+    for (int e = tid; e < (1 << DC_LUT_BITS) && !t2; e += kTabThreads) {
         unsigned int used = 0, count = 0, first = 0, sym0 = 0, sym1 = 0, used2 = 0;
         while (used < DC_LUT_BITS) {
             const unsigned int one = s_lut[((unsigned int)e << used) & ((1u << DC_LUT_BITS) - 1u)];
@@ -256,12 +256,45 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
                                  : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
     }
+    // radix 3: the same two tables indexed by the base-3 value of the next DC_TRIT_WINDOW trits (the kernels compute it from
+    // the 2-bit fields), so a look-up sees 8 trits instead of the 6 a 12-bit index would hold; bit counts are T2 bits
+    for (int e = tid; e < 6561 && t2; e += kTabThreads) {
+        unsigned int d[DC_TRIT_WINDOW];
+        {
+            unsigned int v = (unsigned int)e;
+            for (int k = DC_TRIT_WINDOW - 1; k >= 0; k--) { d[k] = v % 3u; v /= 3u; }
+        }
+        unsigned int used = 0, count = 0, first = 0, sym0 = 0, sym1 = 0, used2 = 0;   // used: trits
+        while (used < DC_TRIT_WINDOW) {
+            unsigned int val = 0, sym = 0;
+            int found = 0;
+            for (int l = 1; used + l <= DC_TRIT_WINDOW && l <= max_len; l++) {
+                val = val * 3u + d[used + l - 1];
+                if (l >= min_len && s_lencount[l] && val >= s_first[l] && val - s_first[l] < s_lencount[l]) {
+                    sym = (unsigned int)(s_ssym[s_off[l] + (val - s_first[l])] & 0xFF);
+                    found = l;
+                    break;
+                }
+            }
+            if (!found) break;
+            if (count == 0) { first = 2u * found; sym0 = sym; }
+            if (count == 1) sym1 = sym;
+            used += found;
+            count++;
+            if (count <= 2) used2 = 2u * used;
+        }
+        const bool total_lut = max_len <= DC_TRIT_WINDOW;
+        const unsigned int dead = 2u, ubits = 2u * used;
+        tab->lut_count[e] = count ? (ubits | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : 0u);
+        tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
+                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
+    }
     // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
     {
         __syncthreads();
         unsigned char *s_flag = (unsigned char *)s_scnt;     // [4096] 1 = this window is the prefix of 13..16-bit codes
         unsigned short *s_sub = (unsigned short *)s_icount;  // [4096] its subtable
-        const bool need2 = bpd != 0 && max_len * bpd > DC_LUT_BITS;
+        const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead
         // the code (13..16 bits) that a left-aligned 16-bit window starts with; 0 if none
         auto long_code = [&](unsigned int w16) -> unsigned int {
             for (int l = min_len; l <= max_len && l < 32; l++) {

@@ -361,40 +361,57 @@ constexpr int kF_SubWords = kF_SubBits / 32;
 constexpr int kF_TileVecs = 32 * kF_SubBits / 128; // 16-byte vectors per warp tile (1 KB)
 constexpr int kF_SegTiles = 16;                    // 16 KB of bitstream per warp
 
-struct FastTables {  // shared-memory copy: one multi-symbol LUT + the canonical arrays for the escape path
-    uint32_t lut[1 << DC_LUT_BITS];
+// decode modes of the fast path (the kernels' template parameter MODE)
+//   0  every code fits the 12-bit index: no escape branch
+//   1  ESC: codes of 13..16 bits through the second-level table, longer ones by canonical search
+//   2  T2 (radix 3, one 2-bit field per trit): the index is the base-3 value of the next 8 trits, every code fits
+//   3  T2 + ESC: codes of more than 8 trits by canonical search
+__host__ __device__ constexpr bool mode_esc(int m) { return (m & 1) != 0; }
+__host__ __device__ constexpr bool mode_t2(int m) { return (m & 2) != 0; }
+__host__ __device__ constexpr int mode_window(int m) { return mode_t2(m) ? 2 * DC_TRIT_WINDOW : DC_LUT_BITS; }  // bits a look-up sees
+constexpr int kTritLutEntries = 6561;  // 3^DC_TRIT_WINDOW
+
+struct FastHeader {  // the canonical arrays for the escape path
     uint32_t first_code[32], len_count[32], len_offset[32];
     uint16_t sorted[DC_NSLOTS + 1];
     int bpd, min_len, max_len, t2;
-    uint16_t lut2[DC_LUT2_SUBTABLES * 16];  // second level (codes of 13..16 bits); loaded, and allocated, for ESC kernels only
 };
-__host__ __device__ constexpr size_t fast_tables_bytes(bool esc) {
-    return ((esc ? sizeof(FastTables) : offsetof(FastTables, lut2)) + 15) & ~(size_t)15;
+template <int MODE>
+struct FastTables {  // shared-memory copy: one multi-symbol LUT (+ the second level for MODE 1) + the header
+    FastHeader h;
+    uint32_t lut[mode_t2(MODE) ? DC_LUT_ENTRIES : (1 << DC_LUT_BITS)];
+    uint16_t lut2[MODE == 1 ? DC_LUT2_SUBTABLES * 16 : 8];  // codes of 13..16 bits
+};
+static size_t fast_tables_bytes(int mode) {
+    const size_t b = mode == 0 ? sizeof(FastTables<0>) : mode == 1 ? sizeof(FastTables<1>) : mode == 2 ? sizeof(FastTables<2>) : sizeof(FastTables<3>);
+    return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ void load_fast_tables(FastTables *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut, bool esc) {
-    for (int i = threadIdx.x; i < (1 << DC_LUT_BITS); i += blockDim.x) t->lut[i] = lut[i];
-    if (esc)
+template <int MODE>
+__device__ __forceinline__ void load_fast_tables(FastTables<MODE> *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut) {
+    constexpr int kEntries = mode_t2(MODE) ? kTritLutEntries : (1 << DC_LUT_BITS);
+    for (int i = threadIdx.x; i < kEntries; i += blockDim.x) t->lut[i] = lut[i];
+    if (MODE == 1)
         for (int i = threadIdx.x; i < DC_LUT2_SUBTABLES * 16 / 2; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
     for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-        t->first_code[i] = tab->first_code[i];
-        t->len_count[i] = tab->len_count[i];
-        t->len_offset[i] = tab->len_offset[i];
+        t->h.first_code[i] = tab->first_code[i];
+        t->h.len_count[i] = tab->len_count[i];
+        t->h.len_offset[i] = tab->len_offset[i];
     }
-    for (int i = threadIdx.x; i <= DC_NSLOTS; i += blockDim.x) t->sorted[i] = tab->sorted[i];
+    for (int i = threadIdx.x; i <= DC_NSLOTS; i += blockDim.x) t->h.sorted[i] = tab->sorted[i];
     if (threadIdx.x == 0) {
-        t->bpd = tab->bits_per_digit;
-        t->min_len = tab->min_len;
-        t->max_len = tab->max_len;
-        t->t2 = tab->packed_radix == 3;
+        t->h.bpd = tab->bits_per_digit;
+        t->h.min_len = tab->min_len;
+        t->h.max_len = tab->max_len;
+        t->h.t2 = tab->packed_radix == 3;
     }
 }
 
-// escape path: the 12-bit window holds no complete code.  Canonical search over the lengths LONGER than the LUT index
+// escape path: the index window holds no complete code.  Canonical search over the lengths LONGER than the LUT index
 // (a shorter code would have been in the LUT); returns the code's bits, 0 for an unused slot.
-__device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *sym) {
+__device__ __noinline__ int decode_escape(const FastHeader *t, uint32_t w, int *sym) {
     const int bpd = t->bpd;
-    int l = DC_LUT_BITS / bpd + 1;
+    int l = (t->t2 ? DC_TRIT_WINDOW : DC_LUT_BITS / bpd) + 1;
     if (l < t->min_len) l = t->min_len;
     uint32_t v3 = 0;   // radix 3: the base-3 value of the first k two-bit fields, extended as l grows
     int k = 0;
@@ -422,24 +439,35 @@ __device__ __noinline__ int decode_escape(const FastTables *t, uint32_t w, int *
 
 // a look-up that did not resolve (ESC tables): e is 0 (canonical search) or the marker of a second-level table indexed by
 // the 4 bits behind the window.  Returns the code's bits (0 = unused slot).
-__device__ __forceinline__ int escape_code(const FastTables *t, uint32_t e, uint32_t x, int *sym) {
-    if (e) {
+template <int MODE>
+__device__ __forceinline__ int escape_code(const FastTables<MODE> *t, uint32_t e, uint32_t x, int *sym) {
+    if (MODE == 1 && e) {
         const uint32_t e2 = t->lut2[((e & 0xFFFFu) << 4) | ((x >> (28 - DC_LUT_BITS)) & 15u)];
         if (e2) {
             *sym = (int)(e2 & 0xFFu);
             return (int)(e2 >> 8);
         }
     }
-    return decode_escape(t, x, sym);
+    return decode_escape(&t->h, x, sym);
 }
 __device__ __forceinline__ bool is_escape_count(uint32_t e) { return e == 0 || (e >> 24) == 0xFFu; }
 __device__ __forceinline__ bool is_escape_pair(uint32_t e) { return e == 0 || (e >> 24) == 0x1Fu; }
 
 // LUT entry for the window in the top 12 bits of x: base + (x >> 20) * 4 as one shift and one multiply-add (written in
 // PTX so that it is not canonicalised back into shift, mask and add) in front of the LDS
+// T2: the window's top 16 bits are 8 two-bit trits; their base-3 value by three SWAR steps (pairs: 4a + b - a,
+// then 16a + b - 7a, then 256a + b - 175a), clamped so that a field of 3 (not a trit) cannot leave the table
+template <int MODE>
 __device__ __forceinline__ uint32_t lds_lut(uint32_t lut, uint32_t x) {
-    uint32_t v;
-    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" : "=r"(v) : "r"(x >> (32 - DC_LUT_BITS)), "r"(lut));
+    uint32_t v, idx;
+    if (mode_t2(MODE)) {
+        const uint32_t s1 = x - ((x >> 2) & 0x33330000u);
+        const uint32_t s2 = s1 - 7u * ((s1 >> 4) & 0x0F0F0000u);
+        idx = min((s2 >> 16) - 175u * (s2 >> 24), (uint32_t)(kTritLutEntries - 1));
+    } else {
+        idx = x >> (32 - DC_LUT_BITS);
+    }
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" : "=r"(v) : "r"(idx), "r"(lut));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
@@ -475,28 +503,28 @@ struct SyncRecord {
     __device__ __forceinline__ uint32_t count() const { return __dp4a(wc[0], 0x01010101u, __dp4a(wc[1], 0x01010101u, 0u)); }
 };
 
-template <bool ESC>
-__device__ __forceinline__ void sync_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &csum) {
+template <int MODE>
+__device__ __forceinline__ void sync_lookup_multi(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &csum) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_lut(lut, x);
-    if (ESC && is_escape_count(e)) {
+    const uint32_t e = lds_lut<MODE>(lut, x);
+    if (mode_esc(MODE) && is_escape_count(e)) {
         int sym;
         const int nb = escape_code(t, e, x, &sym);
-        p += nb ? nb : t->bpd;
+        p += nb ? nb : t->h.bpd;
         csum += nb ? 0x10000u : 0u;
     } else {
         p = add_byte(e, 0, p);  // bits of every code inside the window
         csum += e;              // byte 2 accumulates their number (byte 0 only carries into the unused byte 1)
     }
 }
-template <bool ESC>
-__device__ __forceinline__ void sync_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
+template <int MODE>
+__device__ __forceinline__ void sync_lookup_single(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_lut(lut, x);
-    if (ESC && is_escape_count(e)) {
+    const uint32_t e = lds_lut<MODE>(lut, x);
+    if (mode_esc(MODE) && is_escape_count(e)) {
         int sym;
         const int nb = escape_code(t, e, x, &sym);
-        p += nb ? nb : t->bpd;
+        p += nb ? nb : t->h.bpd;
         scnt += nb ? 1u : 0u;
     } else {
         p += e >> 24;                            // the first code only
@@ -507,28 +535,29 @@ __device__ __forceinline__ void sync_lookup_single(const FastTables *t, uint32_t
 // FIRST: walk the whole subsequence and write the record.  !FIRST: re-walk from `p` until the path merges
 // with the recorded one (`merged` lanes take no part; the warp leaves as soon as every lane has merged).
 // FULL: lim == 256 for every lane of the warp (all tiles but the stream's last).
-template <bool ESC, bool FIRST, bool FULL>
-__device__ __forceinline__ void sync_walk(const FastTables *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t p, uint32_t lim,
+template <int MODE, bool FIRST, bool FULL>
+__device__ __forceinline__ void sync_walk(const FastTables<MODE> *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t p, uint32_t lim,
                                           bool merged, SyncRecord &r) {
-    const int multi_lim = (int)lim - DC_LUT_BITS;  // every code inside the 12-bit window then starts before lim
+    constexpr int kWin = mode_window(MODE);
+    const int multi_lim = (int)lim - kWin;  // every code inside the index window then starts before lim
 #pragma unroll
     for (int k = 0; k < kF_SubWords; k++) {
         if (!FIRST && !__any_sync(0xFFFFFFFFu, !merged)) return;
         uint32_t csum = 0;
         if (FIRST || !merged) {
-            const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - DC_LUT_BITS : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
-            while ((int)p <= stop) sync_lookup_multi<ESC>(t, lut, w[k], w[k + 1], p, csum);
+            const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - kWin : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
+            while ((int)p <= stop) sync_lookup_multi<MODE>(t, lut, w[k], w[k + 1], p, csum);
         }
         if (k == kF_SubWords - 1 && (FIRST || !merged)) {
             // the last few bits: one code at a time (in a short subsequence they may begin in any word)
             uint32_t scnt = 0;
             if (FULL) {
-                while (p < (uint32_t)kF_SubBits) sync_lookup_single<ESC>(t, lut, w[k], w[k + 1], p, scnt);
+                while (p < (uint32_t)kF_SubBits) sync_lookup_single<MODE>(t, lut, w[k], w[k + 1], p, scnt);
             } else {
 #pragma unroll
                 for (int j = 0; j < kF_SubWords; j++) {
                     const int stop1 = min(32 * (j + 1), (int)lim) - 1;
-                    while ((int)p <= stop1) sync_lookup_single<ESC>(t, lut, w[j], w[j + 1], p, scnt);
+                    while ((int)p <= stop1) sync_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, scnt);
                 }
             }
             csum += scnt << 16;
@@ -564,6 +593,7 @@ struct FastWorkspace {
     uint32_t *seg_cnt, *seg_assumed, *seg_exit;      // [nseg]
     unsigned long long *seg_off;                     // [nseg]
     int32_t *mismatch;                               // F2: some segment started on a wrong guess
+    __host__ __device__ int32_t *bad_input() const { return mismatch + 2; }  // F1 (T2 streams): a 2-bit field of 3; zeroed per launch
 };
 
 // A warp's view of its segment: 32-bit positions relative to the segment start, tiles streamed through
@@ -609,16 +639,16 @@ struct SegCursor {
 };
 
 // ------------------------------------------------------------------------------------------ F1
-template <bool ESC>
-__global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
+template <int MODE>
+__global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast_sync_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start,
                                                                       unsigned long long end, const dc_huff_table *__restrict__ tab,
                                                                       FastWorkspace ws, unsigned long long nsub,
                                                                       unsigned long long ntiles, unsigned long long nseg,
                                                                       const DecodeChain *__restrict__ chain, int lead) {
     // lead = 1: tile 0 of d_bits is the last tile of the PREVIOUS shard of a longer stream; the first code of this
     // shard is unknown and segment 0 finds it like every other segment does, by synchronising over the tile in front
-    __shared__ FastTables s_t;
-    load_fast_tables(&s_t, tab, tab->lut_count, ESC);
+    __shared__ FastTables<MODE> s_t;
+    load_fast_tables(&s_t, tab, tab->lut_count);
     __syncthreads();
     if (chain) bit_start = chain->next_start;  // a later chunk of a stream: its first code starts where the previous chunk's last one ended
     uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
@@ -645,19 +675,29 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
             const bool active = sub_bit0 < cur.bits_left;
             const uint32_t lim = active ? min((uint32_t)kF_SubBits, cur.bits_left - sub_bit0) : 0u;
             const bool full = (tt + 1) * 32 * kF_SubBits <= cur.bits_left;       // warp-uniform: every lane has 256 bits
+            if (mode_t2(MODE)) {  // a 2-bit field of 3 is no trit: the robust path reports it (F2 reads the flag)
+                uint32_t bad3 = 0;
+#pragma unroll
+                for (int k = 0; k < kF_SubWords; k++) {
+                    const int left = (int)lim - 32 * k;
+                    const uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ~(0xFFFFFFFFu >> left));
+                    bad3 |= w[k] & (w[k] >> 1) & 0x55555555u & m;
+                }
+                if (bad3) *ws.bad_input() = 1;
+            }
             uint32_t start = lane == 0 ? carry : guess;
             SyncRecord r;
             r.chk[0] = r.chk[1] = r.wc[0] = r.wc[1] = r.exit = 0;
-            if (full) sync_walk<ESC, true, true>(&s_t, lut, w, start, lim, false, r);
-            else if (active) sync_walk<ESC, true, false>(&s_t, lut, w, start, lim, false, r);
+            if (full) sync_walk<MODE, true, true>(&s_t, lut, w, start, lim, false, r);
+            else if (active) sync_walk<MODE, true, false>(&s_t, lut, w, start, lim, false, r);
             while (true) {
                 uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, r.exit, 1);
                 if (lane == 0) ns = start;
                 const bool redo = active && ns != start;
                 if (!__any_sync(0xFFFFFFFFu, redo)) break;
                 start = ns;
-                if (full) sync_walk<ESC, false, true>(&s_t, lut, w, start, lim, !redo, r);
-                else sync_walk<ESC, false, false>(&s_t, lut, w, start, lim, !redo, r);
+                if (full) sync_walk<MODE, false, true>(&s_t, lut, w, start, lim, !redo, r);
+                else sync_walk<MODE, false, false>(&s_t, lut, w, start, lim, !redo, r);
             }
             carry = __shfl_sync(0xFFFFFFFFu, r.exit, 31);
             if (tt < (uint32_t)warm) {
@@ -681,7 +721,7 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_sync_kernel(const u
 // ------------------------------------------------------------------------------------------ F2
 __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
                                                                 int32_t *__restrict__ d_status, DecodeChain *__restrict__ chain,
-                                                                int last_chunk) {
+                                                                int last_chunk, int check_input) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
     __shared__ int s_bad;
@@ -723,6 +763,7 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
         __syncthreads();
     }
     if (tid == 0) {
+        if (check_input && *ws.bad_input()) s_bad = 1;
         *ws.mismatch = s_bad;
         if (chain) {
             chain->base = s_carry;
@@ -739,12 +780,12 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
 //                 | unused-slot flag << 29 | number of symbols (0..2) << 30
 constexpr uint32_t kPairUnused = 1u << 29;
 
-template <bool ESC>
-__device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
+template <int MODE>
+__device__ __forceinline__ void write_lookup_multi(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
                                                    uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_lut(lut, x);
-    if (ESC && is_escape_pair(e)) {
+    const uint32_t e = lds_lut<MODE>(lut, x);
+    if (mode_esc(MODE) && is_escape_pair(e)) {
         int sym = 0;
         const int nb = escape_code(t, e, x, &sym);
         if (nb) {
@@ -753,7 +794,7 @@ __device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t
         } else {
             flags |= kPairUnused;
         }
-        p += nb ? nb : t->bpd;
+        p += nb ? nb : t->h.bpd;
     } else {
         asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(e) : "memory");
         if ((int)e < 0) asm volatile("st.shared.u8 [%0+1], %1;" ::"r"(dst), "r"(e >> 8) : "memory");  // two symbols
@@ -762,12 +803,12 @@ __device__ __forceinline__ void write_lookup_multi(const FastTables *t, uint32_t
         flags |= e;
     }
 }
-template <bool ESC>
-__device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
+template <int MODE>
+__device__ __forceinline__ void write_lookup_single(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
                                                     uint32_t &flags) {
     const uint32_t x = __funnelshift_l(lo, hi, p);
-    const uint32_t e = lds_lut(lut, x);
-    if (ESC && is_escape_pair(e)) {
+    const uint32_t e = lds_lut<MODE>(lut, x);
+    if (mode_esc(MODE) && is_escape_pair(e)) {
         int sym = 0;
         const int nb = escape_code(t, e, x, &sym);
         if (nb) {
@@ -776,7 +817,7 @@ __device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_
         } else {
             flags |= kPairUnused;
         }
-        p += nb ? nb : t->bpd;
+        p += nb ? nb : t->h.bpd;
     } else {
         asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst), "r"(e) : "memory");
         p += (e >> 24) & 31u;                 // the first code only
@@ -786,38 +827,39 @@ __device__ __forceinline__ void write_lookup_single(const FastTables *t, uint32_
 }
 
 // decode bits [p, lim) of the lane's subsequence into shared memory at dst (a shared-space byte address)
-template <bool ESC, bool FULL>
-__device__ __forceinline__ void write_walk(const FastTables *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t &p, uint32_t lim,
+template <int MODE, bool FULL>
+__device__ __forceinline__ void write_walk(const FastTables<MODE> *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t &p, uint32_t lim,
                                            uint32_t &dst, uint32_t &flags) {
-    const int multi_lim = (int)lim - DC_LUT_BITS;
+    constexpr int kWin = mode_window(MODE);
+    const int multi_lim = (int)lim - kWin;
 #pragma unroll
     for (int k = 0; k < kF_SubWords; k++) {
-        const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - DC_LUT_BITS : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
-        while ((int)p <= stop) write_lookup_multi<ESC>(t, lut, w[k], w[k + 1], p, dst, flags);
+        const int stop = FULL ? (k == kF_SubWords - 1 ? kF_SubBits - kWin : 32 * (k + 1) - 1) : min(32 * (k + 1) - 1, multi_lim);
+        while ((int)p <= stop) write_lookup_multi<MODE>(t, lut, w[k], w[k + 1], p, dst, flags);
     }
     if (FULL) {
-        while (p < (uint32_t)kF_SubBits) write_lookup_single<ESC>(t, lut, w[kF_SubWords - 1], w[kF_SubWords], p, dst, flags);
+        while (p < (uint32_t)kF_SubBits) write_lookup_single<MODE>(t, lut, w[kF_SubWords - 1], w[kF_SubWords], p, dst, flags);
     } else {
 #pragma unroll
         for (int j = 0; j < kF_SubWords; j++) {
             const int stop1 = min(32 * (j + 1), (int)lim) - 1;
-            while ((int)p <= stop1) write_lookup_single<ESC>(t, lut, w[j], w[j + 1], p, dst, flags);
+            while ((int)p <= stop1) write_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, dst, flags);
         }
     }
 }
 
-template <bool ESC>
-__global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
+template <int MODE>
+__global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast_write_kernel(const uint8_t *__restrict__ d_bits, unsigned long long end,
                                                                        const dc_huff_table *__restrict__ tab, FastWorkspace ws,
                                                                        unsigned long long nsub, unsigned long long ntiles,
                                                                        unsigned long long nseg, uint8_t *__restrict__ out,
                                                                        unsigned long long n_out, uint32_t stage_bytes,
                                                                        int32_t *__restrict__ d_status, int lead) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
-    FastTables *s_t = (FastTables *)fast_smem;
-    uint8_t *s_stage = fast_smem + fast_tables_bytes(ESC);
+    FastTables<MODE> *s_t = (FastTables<MODE> *)fast_smem;
+    uint8_t *s_stage = fast_smem + ((sizeof(FastTables<MODE>) + 15) & ~(size_t)15);
     if (*ws.mismatch) return;  // the robust path redoes the stream
-    load_fast_tables(s_t, tab, tab->lut_pair, ESC);
+    load_fast_tables(s_t, tab, tab->lut_pair);
     __syncthreads();
     uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t->lut);
     asm volatile("" : "+r"(lut));  // as in F1
@@ -863,8 +905,8 @@ __global__ void __launch_bounds__(kF_Threads, 4) decode_fast_write_kernel(const 
                 const uint32_t lim = min((uint32_t)kF_SubBits, cur.bits_left - sub_bit0);
                 const uint32_t dst0 = stage_addr + a + (incl - my_cnt);
                 uint32_t p = start, dst = dst0, flags = 0;
-                if (full) write_walk<ESC, true>(s_t, lut, w, p, lim, dst, flags);
-                else write_walk<ESC, false>(s_t, lut, w, p, lim, dst, flags);
+                if (full) write_walk<MODE, true>(s_t, lut, w, p, lim, dst, flags);
+                else write_walk<MODE, false>(s_t, lut, w, p, lim, dst, flags);
                 if ((flags & kPairUnused) || dst - dst0 != my_cnt || p > cur.bits_left - sub_bit0) corrupt = true;
             }
             __syncwarp();
@@ -968,6 +1010,12 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 }
 
 
+// which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table)
+static int fast_mode(const int32_t *tmeta) {
+    if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
+    return tmeta[7] > DC_LUT_BITS ? 1 : 0;                          // max_bits against the 12-bit index
+}
+
 // staging tile per warp of the write kernel: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
 static uint32_t fast_stage_bytes(const int32_t *tmeta) {
     const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
@@ -979,9 +1027,10 @@ static uint32_t fast_stage_bytes(const int32_t *tmeta) {
 static cudaError_t ensure_write_smem(size_t smem3) {
     static size_t limit = 0;
     if (smem3 <= limit) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(decode_fast_write_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(decode_fast_write_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    cudaError_t e = cudaFuncSetAttribute(decode_fast_write_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e == cudaSuccess) limit = smem3;
     return e;
 }
@@ -991,43 +1040,46 @@ static cudaError_t ensure_write_smem(size_t smem3) {
 // bit_start.  lead = 1: tile 0 belongs to the previous shard (see F1); nwt and nsubf count it, nseg does not.
 static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
                             unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw,
-                            size_t n_out, int32_t *d_status, bool esc, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st) {
+                            size_t n_out, int32_t *d_status, int mode, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    if (mode_t2(mode)) DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
         const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
-        if (esc) decode_fast_sync_kernel<true><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead);
-        else decode_fast_sync_kernel<false><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead);
+#define DC_F1(M) decode_fast_sync_kernel<M><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead)
+        if (mode == 0) DC_F1(0); else if (mode == 1) DC_F1(1); else if (mode == 2) DC_F1(2); else DC_F1(3);
+#undef DC_F1
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(mode) ? 1 : 0);
     }
     return cuda_status(cudaGetLastError());
 }
 
 static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
                              unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out, size_t n_out,
-                             int32_t *d_status, bool esc, uint32_t stage_bytes, int lead, cudaStream_t st) {
+                             int32_t *d_status, int mode, uint32_t stage_bytes, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
-    const size_t smem3 = fast_tables_bytes(esc) + (size_t)kF_Warps * stage_bytes;
+    const size_t smem3 = fast_tables_bytes(mode) + (size_t)kF_Warps * stage_bytes;
     DC_CUDA_TRY(ensure_write_smem(smem3));
     LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
     const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-    if (esc) decode_fast_write_kernel<true><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead);
-    else decode_fast_write_kernel<false><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead);
+#define DC_F3(M) decode_fast_write_kernel<M><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead)
+    if (mode == 0) DC_F3(0); else if (mode == 1) DC_F3(1); else if (mode == 2) DC_F3(2); else DC_F3(3);
+#undef DC_F3
     return cuda_status(cudaGetLastError());
 }
 
 static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
                        unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out,
-                       size_t n_out, int32_t *d_status, bool esc, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
+                       size_t n_out, int32_t *d_status, int mode, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
                        cudaStream_t st) {
-    const int rc = launch_fast_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, n_out, d_status, esc, chain, last_chunk, 0, st);
+    const int rc = launch_fast_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, chain, last_chunk, 0, st);
     if (rc != DC_OK) return rc;
-    return launch_fast_write(d_bits, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, 0, st);
+    return launch_fast_write(d_bits, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, 0, st);
 }
 
 // test hook: 1 = always take the robust path, 2 = pretend the fast path's guess failed after running it
@@ -1088,13 +1140,13 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
 
-    const bool esc = tmeta[7] > DC_LUT_BITS;  // max_bits: codes longer than the LUT index need the escape path
+    const int mode = fast_mode(tmeta);
     const int force = decode_force_mode();
     if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
     const uint32_t stage_bytes = fast_stage_bytes(tmeta);
     {
-        const int rc = launch_fast(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, nullptr, 1, st);
+        const int rc = launch_fast(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, nullptr, 1, st);
         if (rc != DC_OK) return rc;
     }
     // did every segment start on a code boundary?  (blocking read of one flag)
@@ -1117,7 +1169,7 @@ struct ShardGeom {
     int lead;
     FastWorkspace fw;
     DecodeChain *chain;
-    bool esc;
+    int mode;
     uint32_t stage_bytes;
 };
 }  // namespace
@@ -1151,7 +1203,7 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
     DC_CUDA_TRY(cudaStreamSynchronize(st));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
-    g->esc = tmeta[7] > DC_LUT_BITS;
+    g->mode = fast_mode(tmeta);
     g->stage_bytes = fast_stage_bytes(tmeta);
     return DC_OK;
 }
@@ -1167,7 +1219,7 @@ extern "C" int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, un
     DecodeChain init = {0ull, has_halo ? 0u : first_code_bit, 0, 0u, 0u};
     DC_CUDA_TRY(cudaMemcpyAsync(g.chain, &init, sizeof init, cudaMemcpyHostToDevice, st));
     // (F2 never checks the symbol total here: last_chunk = 0; the caller checks the sum over all shards)
-    rc = launch_fast_sync(g.base, first_code_bit, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, 0, nullptr, g.esc, g.chain, 0, g.lead, st);
+    rc = launch_fast_sync(g.base, first_code_bit, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, 0, nullptr, g.mode, g.chain, 0, g.lead, st);
     if (rc != DC_OK) return rc;
     DC_CUDA_TRY(cudaMemcpyAsync(d_summary, g.chain, sizeof(DecodeChain), cudaMemcpyDeviceToDevice, st));
     return DC_OK;
@@ -1182,7 +1234,7 @@ extern "C" int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, u
     ShardGeom g;
     int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
     if (rc != DC_OK) return rc;
-    return launch_fast_write(g.base, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, d_out, n_out, d_status, g.esc, g.stage_bytes, g.lead, st);
+    return launch_fast_write(g.base, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, d_out, n_out, d_status, g.mode, g.stage_bytes, g.lead, st);
 }
 
 // ================================================================================================ pipelined host decompress
@@ -1258,7 +1310,7 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
-    const bool esc = tmeta[7] > DC_LUT_BITS;
+    const int mode = fast_mode(tmeta);
     const uint32_t stage_bytes = fast_stage_bytes(tmeta);
 
     cudaStream_t up = g_pipe.up, cp = g_pipe.cp, dn = g_pipe.dn;
@@ -1282,13 +1334,13 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
         const uint8_t *bits_k = d_bits + k * chunk_bytes;
         {
-            const int rc = launch_fast_sync(bits_k, 0, end_rel, nsubf, nwt, nseg, d_table, fw, n_out, d_status, esc, d_chain, last, 0, cp);
+            const int rc = launch_fast_sync(bits_k, 0, end_rel, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, d_chain, last, 0, cp);
             if (rc != DC_OK) return rc;
         }
         DC_CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_ring[k], d_chain, sizeof(DecodeChain), cudaMemcpyDeviceToHost, cp));
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f2[k], cp));
         {
-            const int rc = launch_fast_write(bits_k, end_rel, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, esc, stage_bytes, 0, cp);
+            const int rc = launch_fast_write(bits_k, end_rel, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, 0, cp);
             if (rc != DC_OK) return rc;
         }
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f3[k], cp));

@@ -36,6 +36,8 @@ extern "C" {
 #define DC_MAX_LEAVES 512       /* dc_host_huffman accepts max_leaf_value < DC_MAX_LEAVES */
 #define DC_LUT_BITS 12          /* decode look-up table index width */
 #define DC_LUT2_SUBTABLES 256   /* second-level tables of 16 entries (codes of 13..16 bits) */
+#define DC_TRIT_WINDOW 8        /* radix 3: trits a decode look-up sees (index = their base-3 value) */
+#define DC_LUT_ENTRIES 6564     /* entries of the multi-symbol tables: max(2^12, 3^8), rounded up to a multiple of 4 */
 
 enum dc_status {
     DC_OK = 0,
@@ -80,12 +82,14 @@ typedef struct dc_huff_table {
     uint32_t len_offset[32];
     uint16_t sorted[DC_NSLOTS + 1]; /* symbols in (length, value) order */
     uint16_t lut[1 << DC_LUT_BITS]; /* index = next 12 bits: nbits << 8 | symbol; 0 = escape (longer/unused) */
-    /* multi-symbol tables, same index: every code that lies completely inside the 12 bits.
+    /* multi-symbol tables, same index: every code that lies completely inside the 12 bits.  Radix 3 (packed_radix == 3):
+     * the index is the base-3 value of the next DC_TRIT_WINDOW = 8 trits (0 .. 6560) and the entries cover every code
+     * inside those 8 trits; bit counts are those of the 2-bit-per-trit stream.
      *   lut_count: total bits | count << 16 | first code's bits << 24            (0 = escape)
      *   lut_pair : symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | first code's bits << 24 (5 bits)
  *              | unused-slot flag << 29 | count(0..2) << 30                                     (0 = escape) */
-    uint32_t lut_count[1 << DC_LUT_BITS];
-    uint32_t lut_pair[1 << DC_LUT_BITS];
+    uint32_t lut_count[DC_LUT_ENTRIES];
+    uint32_t lut_pair[DC_LUT_ENTRIES];
     /* second level, for codes of 13..16 bits: a 12-bit window that is the prefix of such codes has the marker entry
      *   lut_count = 0xFF000000 | subtable,  lut_pair = 0x1F000000 | subtable
      * and lut2[subtable * 16 + next 4 bits] = code bits << 8 | symbol (0 = no code of <= 16 bits there).  Longer codes

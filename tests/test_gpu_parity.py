@@ -410,6 +410,11 @@ def test_radix3_trit_payload(dc, oracle):
             finally:
                 dc.lib().dc_debug_decode_mode(old)
             assert int(status.item()) == 0 and torch.equal(out, data)
+    # a 2-bit field of 3 in the kernels' stream is not a trit: reported, never decoded as something else
+    broken = t2.clone()
+    broken[nb // 2] = 0xFF
+    out, status = dc.huff_decode(broken, nbits, table, size)
+    assert int(status.item()) == dc.DC_ERR_CORRUPT
     # a payload byte outside 1..243 is reported
     bad = torch.tensor([0, 5, 244], dtype=torch.uint8, device="cuda")
     _, ust = dc.trit_unpack(bad, 15)

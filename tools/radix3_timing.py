@@ -21,3 +21,20 @@ for n_ary in (3,4):
         ntr = nb // 2
         pay = torch.empty((ntr + 4) // 5 + 16, dtype=torch.uint8, device=dev)
         print("   trit_pack ms", round(tm(lambda: dc.trit_pack(res.payload, ntr, out=pay)), 3), "trit_unpack ms", round(tm(lambda: dc.trit_unpack(pay, ntr)), 3))
+# per-kernel breakdown of the decode for every radix (n = 2 and 3 take the ESC instantiations on Zipf data)
+import ctypes as C
+L = dc.lib()
+for n_ary in (2, 3, 4, 16):
+    t=dc.huff_build(dc.histogram(data),n_ary); out=torch.empty(n+n//2,dtype=torch.uint8,device=dev)
+    res=dc.huff_encode(data,t,out=out); nb=res.bits(); dec=torch.empty(n,dtype=torch.uint8,device=dev)
+    dc.huff_decode(res.payload,nb,t,n,out=dec); torch.cuda.synchronize()
+    L.dc_profile_reset(); L.dc_profile_enable(1)
+    for _ in range(3):
+        dc.huff_encode(data,t,out=out); dc.huff_decode(res.payload,nb,t,n,out=dec)
+    torch.cuda.synchronize(); L.dc_profile_enable(0)
+    row=[]
+    for kid in range(40):
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+        if cnt.value: row.append(f"{L.dc_profile_kernel_name(kid).decode()}={ms.value/cnt.value:.3f}")
+    print("n", n_ary, "max_bits", t.download().max_bits, "bits/sym", round(nb/n,3), " ".join(row))
