@@ -290,11 +290,13 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
                                  : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
     }
     // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
-    {
+    const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead (block-uniform)
+    if (!need2) {
+        if (tid == 0) { tab->lut2_used = 0; tab->reserved1 = 0; }
+    } else {
         __syncthreads();
         unsigned char *s_flag = (unsigned char *)s_scnt;     // [4096] 1 = this window is the prefix of 13..16-bit codes
         unsigned short *s_sub = (unsigned short *)s_icount;  // [4096] its subtable
-        const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead
         // the code (13..16 bits) that a left-aligned 16-bit window starts with; 0 if none
         auto long_code = [&](unsigned int w16) -> unsigned int {
             for (int l = min_len; l <= max_len && l < 32; l++) {
@@ -315,14 +317,35 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             s_flag[e] = any ? 1 : 0;
         }
         __syncthreads();
-        if (tid == 0) {  // 4096 flags, a few microseconds: number the prefixes in index order
-            int nsub = 0;
-            for (int e = 0; e < (1 << DC_LUT_BITS); e++) {
-                s_sub[e] = 0xFFFF;
-                if (s_flag[e] && nsub < DC_LUT2_SUBTABLES) s_sub[e] = (unsigned short)nsub++;
+        {   // number the flagged prefixes in index order: four windows per thread, a block-wide exclusive scan
+            static_assert((1 << DC_LUT_BITS) == 4 * kTabThreads, "four LUT windows per thread");
+            const int lane = tid & 31, warp = tid >> 5;
+            int mine = 0;
+            for (int j = 0; j < 4; j++) mine += s_flag[4 * tid + j];
+            int incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += x;
             }
-            tab->lut2_used = nsub;
-            tab->reserved1 = 0;
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            int id = incl - mine, total = 0;
+            for (int w = 0; w < kTabThreads / 32; w++) {
+                if (w < warp) id += s_warp[w];
+                total += s_warp[w];
+            }
+            for (int j = 0; j < 4; j++) {
+                const int e = 4 * tid + j;
+                s_sub[e] = 0xFFFF;
+                if (s_flag[e]) {
+                    if (id < DC_LUT2_SUBTABLES) s_sub[e] = (unsigned short)id;
+                    id++;
+                }
+            }
+            if (tid == 0) {
+                tab->lut2_used = total < DC_LUT2_SUBTABLES ? total : DC_LUT2_SUBTABLES;
+                tab->reserved1 = 0;
+            }
         }
         __syncthreads();
         for (int i = tid; i < DC_LUT2_SUBTABLES * 16; i += kTabThreads) tab->lut2[i] = 0;

@@ -39,7 +39,7 @@ def report(name, alg_bytes, n, best, med, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size-mib", type=int, default=1024)
-    ap.add_argument("--radices", default="2,4,16")
+    ap.add_argument("--radices", default="2,3,4,16")
     ap.add_argument("--hist-variants", default="0,1,2,3,4,5")
     args = ap.parse_args()
     n = args.size_mib << 20
@@ -88,6 +88,14 @@ def main():
                 parts[L.dc_profile_kernel_name(kid).decode()] = [round(ms.value / cnt.value, 4), cnt.value]
         report(f"decode[n={n_ary}]", n + c, n, best, med, kernels_ms_avg_and_launches=parts)
         del dws
+        if n_ary == 3:  # the kernels' stream has 2 bits per trit; K7 converts to / from the 5-trits-per-byte payload
+            ntr = nbits // 2
+            pay = torch.empty((ntr + 4) // 5 + 16, dtype=torch.uint8, device=dev)
+            best, med = timeit(lambda: dc.trit_pack(payload, ntr, out=pay))
+            report("trit_pack[n=3]", c + (ntr + 4) // 5, n, best, med, payload_ratio=round((ntr + 4) // 5 / n, 4))
+            best, med = timeit(lambda: dc.trit_unpack(pay, ntr))
+            report("trit_unpack[n=3]", c + (ntr + 4) // 5, n, best, med)
+            del pay
 
     thr4, base4 = synth.zipf_nybble_spec()
     sym = data
@@ -119,7 +127,15 @@ def main():
     del back
     best, med = timeit(lambda: dc.nybble_text_decompress(comp), reps=3, warm=1)
     report("nybble_text_decompress", 2 * clen + n, n, best, med)
-    del text, comp
+    del comp
+    # the adaptive (move-to-front) mode on the same text: K8 positions + K6
+    buf, ln, stt2 = dc.nybble_adaptive_compress(text)
+    alen = int(ln.item())
+    assert int(stt2.item()) == 0
+    del buf
+    best, med = timeit(lambda: dc.nybble_adaptive_compress(text), reps=3, warm=1)
+    report("nybble_adaptive_compress", 2 * n + alen, n, best, med, compressed_ratio=round(alen / n, 4))
+    del text
     a = torch.empty(n, dtype=torch.uint8, device=dev)
     best, med = timeit(lambda: a.copy_(sym))
     report("torch copy_ (reference point)", 2 * n, n, best, med)
