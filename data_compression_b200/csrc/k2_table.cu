@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         // digit, no symbol, flagged -- so the decoders need no escape branch; with longer codes 0 = escape
         const bool total_lut = bpd != 0 && max_len * bpd <= DC_LUT_BITS;
         const unsigned int dead = (unsigned int)bpd;
-        tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : 0u);
+        tab->lut_count[e] = count ? (used | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : (DC_LUT_COUNT_MARK | DC_LUT_NO_SUBTABLE));
         tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
-                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
+                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : (DC_LUT_PAIR_MARK | DC_LUT_NO_SUBTABLE));
     }
     // radix 3: the same two tables indexed by the base-3 value of the next DC_TRIT_WINDOW trits (the kernels compute it from
     // the 2-bit fields), so a look-up sees 8 trits instead of the 6 a 12-bit index would hold; bit counts are T2 bits
@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         }
         const bool total_lut = max_len <= DC_TRIT_WINDOW;
         const unsigned int dead = 2u, ubits = 2u * used;
-        tab->lut_count[e] = count ? (ubits | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : 0u);
+        tab->lut_count[e] = count ? (ubits | (count << 16) | (first << 24)) : (total_lut ? (dead | (dead << 24)) : (DC_LUT_COUNT_MARK | DC_LUT_NO_SUBTABLE));
         tab->lut_pair[e] = count ? (sym0 | (sym1 << 8) | (used2 << 16) | (first << 24) | ((count < 2 ? count : 2u) << 30))
-                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : 0u);
+                                 : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : (DC_LUT_PAIR_MARK | DC_LUT_NO_SUBTABLE));
     }
     // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
     const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead (block-uniform)
@@ -348,14 +348,39 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             }
         }
         __syncthreads();
-        for (int i = tid; i < DC_LUT2_SUBTABLES * 16; i += kTabThreads) tab->lut2[i] = 0;
+        for (int i = tid; i < (DC_LUT2_SUBTABLES + 1) * 16; i += kTabThreads) tab->lut2[i] = 0;
         __syncthreads();
         for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
             const unsigned int id = s_sub[e];
             if (id == 0xFFFFu) continue;
             for (unsigned int sfx = 0; sfx < 16; sfx++) tab->lut2[id * 16 + sfx] = (uint16_t)long_code(((unsigned int)e << 4) | sfx);
-            tab->lut_count[e] = 0xFF000000u | id;
-            tab->lut_pair[e] = 0x1F000000u | id;
+            tab->lut_count[e] = DC_LUT_COUNT_MARK | id;
+            tab->lut_pair[e] = DC_LUT_PAIR_MARK | id;
+        }
+    }
+    // ---- 8. 14-bit count table for the decoder's synchronisation pass (tables whose longest code has 13 or 14 bits)
+    if (bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS && max_len * bpd <= DC_LUT14_BITS) {
+        // the code a left-aligned 14-bit window starts with, among those of at most `avail` bits: bits << 8 | 1, or 0
+        auto code_bits = [&](unsigned int w14, int avail) -> unsigned int {
+            for (int l = min_len; l <= max_len; l++) {
+                const int lb = l * bpd;
+                if (lb > avail) break;
+                const unsigned int v = w14 >> (DC_LUT14_BITS - lb);
+                if (s_lencount[l] && v >= s_first[l] && v - s_first[l] < s_lencount[l]) return (unsigned int)lb;
+            }
+            return 0u;
+        };
+        for (int e = tid; e < (1 << DC_LUT14_BITS); e += kTabThreads) {
+            unsigned int used = 0, count = 0, first = 0;
+            while (used < DC_LUT14_BITS) {
+                const unsigned int nb = code_bits(((unsigned int)e << used) & ((1u << DC_LUT14_BITS) - 1u), DC_LUT14_BITS - (int)used);
+                if (nb == 0) break;
+                if (count == 0) first = nb;
+                used += nb;
+                count++;
+            }
+            // every code fits the index, so a window without a code starts with an unused slot: one digit, no symbol
+            tab->lut14[e] = (uint16_t)(count ? (used | (count << 8) | (first << 12)) : ((unsigned int)bpd | ((unsigned int)bpd << 12)));
         }
     }
     if (tid == 0) {

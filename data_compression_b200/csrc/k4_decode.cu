@@ -366,9 +366,13 @@ constexpr int kF_SegTiles = 16;                    // 16 KB of bitstream per war
 //   1  ESC: codes of 13..16 bits through the second-level table, longer ones by canonical search
 //   2  T2 (radix 3, one 2-bit field per trit): the index is the base-3 value of the next 8 trits, every code fits
 //   3  T2 + ESC: codes of more than 8 trits by canonical search
+//   4  F1 only: tables whose longest code has 13 or 14 bits count through the 14-bit-indexed u16 table (no escapes; an
+//      escape test inside the look-up loop costs F1 a third of its speed, F3 nothing: it is bound by the LSU pipe)
 __host__ __device__ constexpr bool mode_esc(int m) { return (m & 1) != 0; }
 __host__ __device__ constexpr bool mode_t2(int m) { return (m & 2) != 0; }
-__host__ __device__ constexpr int mode_window(int m) { return mode_t2(m) ? 2 * DC_TRIT_WINDOW : DC_LUT_BITS; }  // bits a look-up sees
+__host__ __device__ constexpr int mode_window(int m) { return m == 4 ? DC_LUT14_BITS : mode_t2(m) ? 2 * DC_TRIT_WINDOW : DC_LUT_BITS; }  // bits a look-up sees
+__host__ __device__ constexpr int mode_lut_words(int m) { return m == 4 ? (1 << DC_LUT14_BITS) / 2 : mode_t2(m) ? DC_LUT_ENTRIES : (1 << DC_LUT_BITS); }
+__host__ __device__ constexpr int mode_count_shift(int m) { return m == 4 ? 8 : 16; }   // where a count entry keeps its number of codes
 constexpr int kTritLutEntries = 6561;  // 3^DC_TRIT_WINDOW
 
 struct FastHeader {  // the canonical arrays for the escape path
@@ -379,8 +383,8 @@ struct FastHeader {  // the canonical arrays for the escape path
 template <int MODE>
 struct FastTables {  // shared-memory copy: one multi-symbol LUT (+ the second level for MODE 1) + the header
     FastHeader h;
-    uint32_t lut[mode_t2(MODE) ? DC_LUT_ENTRIES : (1 << DC_LUT_BITS)];
-    uint16_t lut2[MODE == 1 ? DC_LUT2_SUBTABLES * 16 : 8];  // codes of 13..16 bits
+    uint32_t lut[mode_lut_words(MODE)];
+    uint16_t lut2[MODE == 1 ? (DC_LUT2_SUBTABLES + 1) * 16 : 8];  // codes of 13..16 bits; the last sub-table is empty
 };
 static size_t fast_tables_bytes(int mode) {
     const size_t b = mode == 0 ? sizeof(FastTables<0>) : mode == 1 ? sizeof(FastTables<1>) : mode == 2 ? sizeof(FastTables<2>) : sizeof(FastTables<3>);
@@ -389,10 +393,10 @@ static size_t fast_tables_bytes(int mode) {
 
 template <int MODE>
 __device__ __forceinline__ void load_fast_tables(FastTables<MODE> *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut) {
-    constexpr int kEntries = mode_t2(MODE) ? kTritLutEntries : (1 << DC_LUT_BITS);
-    for (int i = threadIdx.x; i < kEntries; i += blockDim.x) t->lut[i] = lut[i];
+    constexpr int kWords = MODE == 4 ? mode_lut_words(4) : mode_t2(MODE) ? kTritLutEntries : (1 << DC_LUT_BITS);
+    for (int i = threadIdx.x; i < kWords; i += blockDim.x) t->lut[i] = lut[i];
     if (MODE == 1)
-        for (int i = threadIdx.x; i < DC_LUT2_SUBTABLES * 16 / 2; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
+        for (int i = threadIdx.x; i < (DC_LUT2_SUBTABLES + 1) * 16 / 2; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
     for (int i = threadIdx.x; i < 32; i += blockDim.x) {
         t->h.first_code[i] = tab->first_code[i];
         t->h.len_count[i] = tab->len_count[i];
@@ -437,11 +441,11 @@ __device__ __noinline__ int decode_escape(const FastHeader *t, uint32_t w, int *
     return 0;
 }
 
-// a look-up that did not resolve (ESC tables): e is 0 (canonical search) or the marker of a second-level table indexed by
-// the 4 bits behind the window.  Returns the code's bits (0 = unused slot).
+// a look-up that did not resolve (ESC tables): e names a second-level table indexed by the 4 bits behind the window, or
+// none (DC_LUT_NO_SUBTABLE: canonical search).  Returns the code's bits (0 = unused slot).
 template <int MODE>
 __device__ __forceinline__ int escape_code(const FastTables<MODE> *t, uint32_t e, uint32_t x, int *sym) {
-    if (MODE == 1 && e) {
+    if (MODE == 1 && (e & 0xFFFFu) != DC_LUT_NO_SUBTABLE) {
         const uint32_t e2 = t->lut2[((e & 0xFFFFu) << 4) | ((x >> (28 - DC_LUT_BITS)) & 15u)];
         if (e2) {
             *sym = (int)(e2 & 0xFFu);
@@ -450,8 +454,8 @@ __device__ __forceinline__ int escape_code(const FastTables<MODE> *t, uint32_t e
     }
     return decode_escape(&t->h, x, sym);
 }
-__device__ __forceinline__ bool is_escape_count(uint32_t e) { return e == 0 || (e >> 24) == 0xFFu; }
-__device__ __forceinline__ bool is_escape_pair(uint32_t e) { return e == 0 || (e >> 24) == 0x1Fu; }
+__device__ __forceinline__ bool is_escape_count(uint32_t e) { return (int32_t)e < 0; }       // DC_LUT_COUNT_MARK | x
+__device__ __forceinline__ bool is_escape_pair(uint32_t e) { return e >= DC_LUT_PAIR_MARK; }  // count field == 3
 
 // LUT entry for the window in the top 12 bits of x: base + (x >> 20) * 4 as one shift and one multiply-add (written in
 // PTX so that it is not canonicalised back into shift, mask and add) in front of the LDS
@@ -460,6 +464,10 @@ __device__ __forceinline__ bool is_escape_pair(uint32_t e) { return e == 0 || (e
 template <int MODE>
 __device__ __forceinline__ uint32_t lds_lut(uint32_t lut, uint32_t x) {
     uint32_t v, idx;
+    if (MODE == 4) {  // u16 entries, 14-bit index
+        asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(v) : "r"(x >> (32 - DC_LUT14_BITS)), "r"(lut));
+        return v;
+    }
     if (mode_t2(MODE)) {
         const uint32_t s1 = x - ((x >> 2) & 0x33330000u);
         const uint32_t s2 = s1 - 7u * ((s1 >> 4) & 0x0F0F0000u);
@@ -512,6 +520,9 @@ __device__ __forceinline__ void sync_lookup_multi(const FastTables<MODE> *t, uin
         const int nb = escape_code(t, e, x, &sym);
         p += nb ? nb : t->h.bpd;
         csum += nb ? 0x10000u : 0u;
+    } else if (MODE == 4) {
+        p = add_byte(e, 0, p);
+        csum += e & 0x0FFFu;    // byte 1 accumulates the number of codes
     } else {
         p = add_byte(e, 0, p);  // bits of every code inside the window
         csum += e;              // byte 2 accumulates their number (byte 0 only carries into the unused byte 1)
@@ -526,6 +537,9 @@ __device__ __forceinline__ void sync_lookup_single(const FastTables<MODE> *t, ui
         const int nb = escape_code(t, e, x, &sym);
         p += nb ? nb : t->h.bpd;
         scnt += nb ? 1u : 0u;
+    } else if (MODE == 4) {
+        p += e >> 12;
+        scnt += (e & 0x0F00u) ? 1u : 0u;
     } else {
         p += e >> 24;                            // the first code only
         scnt += (e & 0x00FF0000u) ? 1u : 0u;     // an unused slot counts nothing
@@ -560,9 +574,9 @@ __device__ __forceinline__ void sync_walk(const FastTables<MODE> *t, uint32_t lu
                     while ((int)p <= stop1) sync_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, scnt);
                 }
             }
-            csum += scnt << 16;
+            csum += scnt << mode_count_shift(MODE);
         }
-        const uint32_t cw = csum >> 16;  // byte 2 (byte 3 stays empty: at most 44 symbols per word)
+        const uint32_t cw = csum >> mode_count_shift(MODE);  // the count byte (only its low byte is kept: at most 46 symbols per word)
         if (FIRST) {
             if (k < 4) { r.chk[0] = put_byte(r.chk[0], k & 3, p); r.wc[0] = put_byte(r.wc[0], k & 3, cw); }
             else       { r.chk[1] = put_byte(r.chk[1], k & 3, p); r.wc[1] = put_byte(r.wc[1], k & 3, cw); }
@@ -648,7 +662,7 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
     // lead = 1: tile 0 of d_bits is the last tile of the PREVIOUS shard of a longer stream; the first code of this
     // shard is unknown and segment 0 finds it like every other segment does, by synchronising over the tile in front
     __shared__ FastTables<MODE> s_t;
-    load_fast_tables(&s_t, tab, tab->lut_count);
+    load_fast_tables(&s_t, tab, MODE == 4 ? (const uint32_t *)tab->lut14 : tab->lut_count);
     __syncthreads();
     if (chain) bit_start = chain->next_start;  // a later chunk of a stream: its first code starts where the previous chunk's last one ended
     uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_t.lut);
@@ -1010,11 +1024,15 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 }
 
 
+constexpr int kSyncW14 = 0x10;
 // which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table)
 static int fast_mode(const int32_t *tmeta) {
     if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
-    return tmeta[7] > DC_LUT_BITS ? 1 : 0;                          // max_bits against the 12-bit index
+    if (tmeta[7] <= DC_LUT_BITS) return 0;                          // max_bits against the 12-bit index
+    return tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1;          // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
 }
+static int write_mode(int mode) { return mode & 3; }
+static int sync_mode(int mode) { return (mode & kSyncW14) ? 4 : (mode & 3); }
 
 // staging tile per warp of the write kernel: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
 static uint32_t fast_stage_bytes(const int32_t *tmeta) {
@@ -1043,17 +1061,18 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
                             size_t n_out, int32_t *d_status, int mode, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
-    if (mode_t2(mode)) DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));
+    if (mode_t2(write_mode(mode))) DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
         const unsigned int g1 = (unsigned int)(want < sms * 8 ? want : sms * 8);
 #define DC_F1(M) decode_fast_sync_kernel<M><<<g1, kF_Threads, 0, st>>>(d_bits, bit_start, end, d_table, fw, nsubf, nwt, nseg, chain, lead)
-        if (mode == 0) DC_F1(0); else if (mode == 1) DC_F1(1); else if (mode == 2) DC_F1(2); else DC_F1(3);
+        const int sm = sync_mode(mode);
+        if (sm == 0) DC_F1(0); else if (sm == 1) DC_F1(1); else if (sm == 2) DC_F1(2); else if (sm == 3) DC_F1(3); else DC_F1(4);
 #undef DC_F1
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(mode) ? 1 : 0);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(write_mode(mode)) ? 1 : 0);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1063,6 +1082,7 @@ static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsi
                              int32_t *d_status, int mode, uint32_t stage_bytes, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    mode = write_mode(mode);
     const size_t smem3 = fast_tables_bytes(mode) + (size_t)kF_Warps * stage_bytes;
     DC_CUDA_TRY(ensure_write_smem(smem3));
     LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);

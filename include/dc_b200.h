@@ -36,8 +36,14 @@ extern "C" {
 #define DC_MAX_LEAVES 512       /* dc_host_huffman accepts max_leaf_value < DC_MAX_LEAVES */
 #define DC_LUT_BITS 12          /* decode look-up table index width */
 #define DC_LUT2_SUBTABLES 256   /* second-level tables of 16 entries (codes of 13..16 bits) */
+#define DC_LUT14_BITS 14        /* index width of the count table for tables whose longest code has 13 or 14 bits */
 #define DC_TRIT_WINDOW 8        /* radix 3: trits a decode look-up sees (index = their base-3 value) */
 #define DC_LUT_ENTRIES 6564     /* entries of the multi-symbol tables: max(2^12, 3^8), rounded up to a multiple of 4 */
+/* entries of the multi-symbol tables that do not resolve in one look-up: one compare tells them apart ((int32)count entry
+ * < 0, pair entry >= 0xC0000000); the low 16 bits name a second-level table, DC_LUT_NO_SUBTABLE = none (canonical search) */
+#define DC_LUT_COUNT_MARK 0xFF000000u
+#define DC_LUT_PAIR_MARK 0xC0000000u
+#define DC_LUT_NO_SUBTABLE DC_LUT2_SUBTABLES   /* an extra, empty sub-table */
 
 enum dc_status {
     DC_OK = 0,
@@ -85,18 +91,22 @@ typedef struct dc_huff_table {
     /* multi-symbol tables, same index: every code that lies completely inside the 12 bits.  Radix 3 (packed_radix == 3):
      * the index is the base-3 value of the next DC_TRIT_WINDOW = 8 trits (0 .. 6560) and the entries cover every code
      * inside those 8 trits; bit counts are those of the 2-bit-per-trit stream.
-     *   lut_count: total bits | count << 16 | first code's bits << 24            (0 = escape)
+     *   lut_count: total bits | count << 16 | first code's bits << 24            (DC_LUT_COUNT_MARK | x = escape)
      *   lut_pair : symbol0 | symbol1 << 8 | bits of (up to) two codes << 16 | first code's bits << 24 (5 bits)
- *              | unused-slot flag << 29 | count(0..2) << 30                                     (0 = escape) */
+ *              | unused-slot flag << 29 | count(0..2) << 30                     (DC_LUT_PAIR_MARK | x = escape) */
     uint32_t lut_count[DC_LUT_ENTRIES];
     uint32_t lut_pair[DC_LUT_ENTRIES];
     /* second level, for codes of 13..16 bits: a 12-bit window that is the prefix of such codes has the marker entry
-     *   lut_count = 0xFF000000 | subtable,  lut_pair = 0x1F000000 | subtable
+     *   lut_count = DC_LUT_COUNT_MARK | subtable,  lut_pair = DC_LUT_PAIR_MARK | subtable
      * and lut2[subtable * 16 + next 4 bits] = code bits << 8 | symbol (0 = no code of <= 16 bits there).  Longer codes
-     * and unused slots keep the entry 0 = canonical search. */
-    uint16_t lut2[DC_LUT2_SUBTABLES * 16];
+     * and unused slots have the subtable DC_LUT_NO_SUBTABLE = canonical search. */
+    uint16_t lut2[(DC_LUT2_SUBTABLES + 1) * 16];
     int32_t lut2_used;        /* subtables in use */
     int32_t reserved1;
+    /* the decoder's synchronisation pass only counts codes; for tables whose longest code has 13 or 14 bits (binary
+     * codes of byte data, typically) it uses this 14-bit-indexed table instead, which needs no escape:
+     * total bits | count << 8 | first code's bits << 12 of every code inside the next 14 bits.  Filled only then. */
+    uint16_t lut14[1 << DC_LUT14_BITS];
 } dc_huff_table;
 
 /* ------------------------------------------------------------------------- library */

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_table_struct_layout(built):
     # offsets the kernels and the Python mirror must agree on
     T = built.HuffTableStruct
-    assert ctypes.sizeof(T) == 14304 + 2 * 6564 * 4 + 256 * 16 * 2 + 8
+    assert ctypes.sizeof(T) == 14304 + 2 * 6564 * 4 + 257 * 16 * 2 + 8 + 2 * (1 << 14)
     assert T.total_symbols.offset == 40 and T.lengths.offset == 56 and T.enc64.offset % 8 == 0
     assert built.lib().dc_version().startswith(b"dc_b200")
     assert built.lib().dc_status_string(-5) == b"corrupt bitstream"

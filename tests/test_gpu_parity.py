@@ -185,7 +185,7 @@ def test_wide_codes_up_to_30_bits(dc, oracle):
     assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
 
 
-@pytest.mark.parametrize("n_ary,depths", [(2, 14), (2, 15), (4, 7), (4, 8), (16, 4)])
+@pytest.mark.parametrize("n_ary,depths", [(2, 13), (2, 14), (2, 15), (4, 7), (4, 8), (16, 4)])
 def test_mid_codes_13_to_16_bits(dc, oracle, n_ary, depths):
     """Tables whose longest code is 13..16 bits: the 16-bit instantiation of the single-pass encoder and the escape
     path of the decoder (codes longer than the 12 LUT index bits).  Skewed data so the long codes are rare but present,

@@ -67,7 +67,7 @@ def main():
     for n_ary in [int(x) for x in args.radices.split(",") if x != ""]:
         table = dc.HuffTable(dev)
         best, med = timeit(lambda: dc.huff_build(hist, n_ary, table))
-        report(f"table[n={n_ary}]", 259 * 8, 0, best, med)
+        report(f"table[n={n_ary}]", 259 * 8, 0, best, med, max_bits=table.download().max_bits)
         res = dc.huff_encode(data, table, out=payload, workspace=ws)
         nbits = res.bits()
         c = (nbits + 7) // 8
