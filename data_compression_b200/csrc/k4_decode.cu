@@ -735,7 +735,8 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
 // ------------------------------------------------------------------------------------------ F2
 __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
                                                                 int32_t *__restrict__ d_status, DecodeChain *__restrict__ chain,
-                                                                int last_chunk, int check_input) {
+                                                                int last_chunk, int check_input,
+                                                                DecodeChain *__restrict__ host_chain) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
     __shared__ int s_bad;
@@ -784,6 +785,10 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
             chain->next_start = ws.seg_exit[nseg - 1];
             chain->mismatch |= s_bad;
             chain->first_assumed = ws.seg_assumed[0];
+            if (host_chain) {  // mapped host memory: the host learns the chunk's symbol count without a copy-engine transfer
+                *host_chain = *chain;
+                __threadfence_system();
+            }
         }
         if (!s_bad && last_chunk && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
     }
@@ -1058,7 +1063,8 @@ static cudaError_t ensure_write_smem(size_t smem3) {
 // bit_start.  lead = 1: tile 0 belongs to the previous shard (see F1); nwt and nsubf count it, nseg does not.
 static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
                             unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw,
-                            size_t n_out, int32_t *d_status, int mode, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st) {
+                            size_t n_out, int32_t *d_status, int mode, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st,
+                            DecodeChain *host_chain = nullptr) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     if (mode_t2(write_mode(mode))) DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));
@@ -1072,7 +1078,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
     }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(write_mode(mode)) ? 1 : 0);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(write_mode(mode)) ? 1 : 0, host_chain);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1271,7 +1277,7 @@ constexpr unsigned long long kPipeChunkTiles = 32768;  // 32 MiB of bitstream; a
 struct PipeState {
     cudaStream_t up = nullptr, cp = nullptr, dn = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_f2, ev_f3;
-    DecodeChain *h_ring = nullptr;
+    DecodeChain *h_ring = nullptr, *d_ring = nullptr;   // mapped pinned memory: F2 stores the chain state of chunk k into slot k
     size_t ring = 0;
     int ensure(size_t k) {
         if (!up) {
@@ -1289,7 +1295,8 @@ struct PipeState {
         if (ring < k) {
             if (h_ring) cudaFreeHost(h_ring);
             h_ring = nullptr; ring = 0;
-            DC_CUDA_TRY(cudaMallocHost((void **)&h_ring, k * sizeof(DecodeChain)));
+            DC_CUDA_TRY(cudaHostAlloc((void **)&h_ring, k * sizeof(DecodeChain), cudaHostAllocMapped));
+            DC_CUDA_TRY(cudaHostGetDevicePointer((void **)&d_ring, h_ring, 0));
             ring = k;
         }
         return DC_OK;
@@ -1354,10 +1361,12 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
         const uint8_t *bits_k = d_bits + k * chunk_bytes;
         {
-            const int rc = launch_fast_sync(bits_k, 0, end_rel, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, d_chain, last, 0, cp);
+            // F2 also stores the chain state into the mapped ring: a cudaMemcpyAsync of these 24 bytes would queue on the
+            // device-to-host copy engine behind the previous chunk's 44 MB of output and lock-step the pipeline with it
+            const int rc = launch_fast_sync(bits_k, 0, end_rel, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, d_chain, last, 0, cp,
+                                            g_pipe.d_ring + k);
             if (rc != DC_OK) return rc;
         }
-        DC_CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_ring[k], d_chain, sizeof(DecodeChain), cudaMemcpyDeviceToHost, cp));
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_f2[k], cp));
         {
             const int rc = launch_fast_write(bits_k, end_rel, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, 0, cp);

@@ -30,3 +30,15 @@ for name, fn in (("H2D", lambda: g.copy_(h_in, non_blocking=True)), ("D2H", lamb
     fn(); torch.cuda.synchronize()
     t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"{name} {n/dt/1e9:.1f} GB/s")
+# both directions at once (the decompress pipeline's floor: payload up while decoded bytes go down)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+gp = torch.empty(p.size, dtype=torch.uint8, device=dev)
+hp = h_pay[: p.size]
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    with torch.cuda.stream(s1):
+        gp.copy_(hp, non_blocking=True)
+    with torch.cuda.stream(s2):
+        h_out.copy_(g, non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"H2D {p.size/1e6:.0f} MB + D2H {n/1e6:.0f} MB concurrently: {1e3*dt:.2f} ms")
