@@ -1342,7 +1342,9 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
 
     cudaStream_t up = g_pipe.up, cp = g_pipe.cp, dn = g_pipe.dn;
     for (size_t k = 0; k < nchunk; k++) {
-        const size_t o = (size_t)(k * chunk_bytes), len = (size_t)min((unsigned long long)(nbytes - o), chunk_bytes);
+        // 64 bytes more than the chunk: its last code, and the look-ahead word of its last lane, reach into the next chunk
+        // (which uploads the same bytes again); so chunk k can be decoded as soon as upload k is in
+        const size_t o = (size_t)(k * chunk_bytes), len = (size_t)min((unsigned long long)(nbytes - o), chunk_bytes + 64);
         DC_CUDA_TRY(cudaMemcpyAsync(d_bits + o, h_payload + o, len, cudaMemcpyHostToDevice, up));
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_up[k], up));
     }
@@ -1357,7 +1359,7 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         const unsigned long long nsubf = (bits_here + kF_SubBits - 1) / kF_SubBits;
         const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
         const int last = k + 1 == nchunk;
-        DC_CUDA_TRY(cudaStreamWaitEvent(cp, g_pipe.ev_up[last ? k : k + 1], 0));
+        DC_CUDA_TRY(cudaStreamWaitEvent(cp, g_pipe.ev_up[k], 0));
         // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
         const uint8_t *bits_k = d_bits + k * chunk_bytes;
         {
