@@ -386,8 +386,9 @@ struct FastTables {  // shared-memory copy: one multi-symbol LUT (+ the second l
     uint32_t lut[mode_lut_words(MODE)];
     uint16_t lut2[MODE == 1 ? (DC_LUT2_SUBTABLES + 1) * 16 : 8];  // codes of 13..16 bits; the last sub-table is empty
 };
-static size_t fast_tables_bytes(int mode) {
-    const size_t b = mode == 0 ? sizeof(FastTables<0>) : mode == 1 ? sizeof(FastTables<1>) : mode == 2 ? sizeof(FastTables<2>) : sizeof(FastTables<3>);
+static size_t fast_tables_bytes(int mode, int lut2_tables) {
+    const size_t b = mode == 0 ? sizeof(FastTables<0>) : mode == 1 ? offsetof(FastTables<1>, lut2) + (size_t)lut2_tables * 32
+                   : mode == 2 ? sizeof(FastTables<2>) : sizeof(FastTables<3>);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -395,8 +396,10 @@ template <int MODE>
 __device__ __forceinline__ void load_fast_tables(FastTables<MODE> *t, const dc_huff_table *__restrict__ tab, const uint32_t *lut) {
     constexpr int kWords = MODE == 4 ? mode_lut_words(4) : mode_t2(MODE) ? kTritLutEntries : (1 << DC_LUT_BITS);
     for (int i = threadIdx.x; i < kWords; i += blockDim.x) t->lut[i] = lut[i];
-    if (MODE == 1)
-        for (int i = threadIdx.x; i < (DC_LUT2_SUBTABLES + 1) * 16 / 2; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
+    if (MODE == 1) {
+        const int words = min(tab->lut2_used, DC_LUT2_SUBTABLES) * 8;   // 16 u16 entries per table
+        for (int i = threadIdx.x; i < words; i += blockDim.x) ((uint32_t *)t->lut2)[i] = ((const uint32_t *)tab->lut2)[i];
+    }
     for (int i = threadIdx.x; i < 32; i += blockDim.x) {
         t->h.first_code[i] = tab->first_code[i];
         t->h.len_count[i] = tab->len_count[i];
@@ -873,10 +876,10 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
                                                                        unsigned long long nsub, unsigned long long ntiles,
                                                                        unsigned long long nseg, uint8_t *__restrict__ out,
                                                                        unsigned long long n_out, uint32_t stage_bytes,
-                                                                       int32_t *__restrict__ d_status, int lead) {
+                                                                       int32_t *__restrict__ d_status, int lead, uint32_t tables_bytes) {
     extern __shared__ __align__(16) uint8_t fast_smem[];
     FastTables<MODE> *s_t = (FastTables<MODE> *)fast_smem;
-    uint8_t *s_stage = fast_smem + ((sizeof(FastTables<MODE>) + 15) & ~(size_t)15);
+    uint8_t *s_stage = fast_smem + tables_bytes;  // MODE 1: only the second-level tables in use are resident
     if (*ws.mismatch) return;  // the robust path redoes the stream
     load_fast_tables(s_t, tab, tab->lut_pair);
     __syncthreads();
@@ -1034,9 +1037,11 @@ constexpr int kSyncW14 = 0x10;
 static int fast_mode(const int32_t *tmeta) {
     if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
     if (tmeta[7] <= DC_LUT_BITS) return 0;                          // max_bits against the 12-bit index
-    return tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1;          // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
+    const int sub = tmeta[10] < 0 ? 0 : (tmeta[10] > DC_LUT2_SUBTABLES ? DC_LUT2_SUBTABLES : tmeta[10]);
+    return (tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1) | (sub << 8);   // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
 }
 static int write_mode(int mode) { return mode & 3; }
+static int lut2_tables(int mode) { return mode >> 8; }   // second-level tables in use (F3 keeps only those in shared memory)
 static int sync_mode(int mode) { return (mode & kSyncW14) ? 4 : (mode & 3); }
 
 // staging tile per warp of the write kernel: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
@@ -1088,12 +1093,13 @@ static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsi
                              int32_t *d_status, int mode, uint32_t stage_bytes, int lead, cudaStream_t st) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    const uint32_t tables_bytes = (uint32_t)fast_tables_bytes(write_mode(mode), lut2_tables(mode));
     mode = write_mode(mode);
-    const size_t smem3 = fast_tables_bytes(mode) + (size_t)kF_Warps * stage_bytes;
+    const size_t smem3 = tables_bytes + (size_t)kF_Warps * stage_bytes;
     DC_CUDA_TRY(ensure_write_smem(smem3));
     LaunchScope ls(DC_K_DECODE_FAST_WRITE, st);
     const unsigned int g3 = (unsigned int)(want < sms * 4 ? want : sms * 4);
-#define DC_F3(M) decode_fast_write_kernel<M><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead)
+#define DC_F3(M) decode_fast_write_kernel<M><<<g3, kF_Threads, smem3, st>>>(d_bits, end, d_table, fw, nsubf, nwt, nseg, d_out, n_out, stage_bytes, d_status, lead, tables_bytes)
     if (mode == 0) DC_F3(0); else if (mode == 1) DC_F3(1); else if (mode == 2) DC_F3(2); else DC_F3(3);
 #undef DC_F3
     return cuda_status(cudaGetLastError());
@@ -1160,8 +1166,9 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     const unsigned long long sms = (unsigned long long)sm_count();
 
     // the table must be usable before any bit is interpreted
-    int32_t tmeta[10];
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, st));
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DC_CUDA_TRY(cudaStreamSynchronize(st));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
@@ -1224,8 +1231,9 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
     g->fw.seg_exit = (uint32_t *)(w + off[9]);
     g->fw.seg_off = (unsigned long long *)(w + off[10]);
     g->chain = (DecodeChain *)(w + 32);
-    int32_t tmeta[10];
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, st));
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DC_CUDA_TRY(cudaStreamSynchronize(st));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
@@ -1332,8 +1340,9 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
     DecodeChain *d_chain = (DecodeChain *)(w + 32);
 
     // the table (built on the legacy stream by the caller) must be usable before any bit is interpreted
-    int32_t tmeta[10];
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, sizeof tmeta, cudaMemcpyDeviceToHost, 0));
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
