@@ -20,7 +20,7 @@
 // Decompress.  The nibble parse is K6's, but which letter a hit nibble means depends on the context, i.e. on the byte
 // decoded just before, and on every list update before that: a serial chain through the output ("replicas
 // only").  K6 writes hit nibbles as 0x80 | position; mtf_resolve_kernel walks the output once and replaces them --
-// one lane does the chain, the warp moves the bytes.  About 20 MB/s: correct, and only parallel across strings.
+// one lane does the chain, the warp moves the bytes.  About 11 MB/s: correct, and only parallel across strings.
 #include "dc_common.cuh"
 
 namespace dc {

@@ -107,6 +107,11 @@ def test_decompress_host_pipelined(dc, oracle, n_ary):
     assert np.array_equal(lengths, ln)
     want, wbits = oracle.pack(data[: 1 << 20], el, ev, oracle.bits_per_digit(n_ary))
     assert np.array_equal(payload[: wbits // 8], want[: wbits // 8])
+    # the whole payload against the oracle's single stream
+    import os
+    full, fbits, _ = oracle.pack_mt(data, el, ev, oracle.bits_per_digit(n_ary), 0, threads=os.cpu_count() or 1,
+                                    out=np.empty(n + n // 4 + 64, dtype=np.uint8))
+    assert bits == fbits and np.array_equal(payload, full[: (fbits + 7) // 8])
     back = dc.hostapi.huff_decompress(payload, bits, lengths, n_ary, n)
     assert np.array_equal(back, data)
     with pytest.raises(dc.DcError) as e:
