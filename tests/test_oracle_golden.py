@@ -172,3 +172,20 @@ def test_unpack_flags_unused_slot(oracle):
     bits = np.array([0b11000000], dtype=np.uint8)
     out, status = oracle.unpack(bits, 0, 2, lengths, 2, 1, return_status=True)
     assert status == oracle.ORC_ERR_CORRUPT
+
+
+def test_nybble_compressors_round_trip_property(oracle):
+    """Both modes of the oracle's nybble compressor invert on arbitrary 7-bit strings, never emit a NUL, and never grow the
+    text by more than the type byte (the ' ' + raw fall-back, nybble_compression.c:1018-1037)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.binary(min_size=1, max_size=600).map(lambda b: bytes((x % 127) + 1 for x in b)))
+    def check(text):
+        for comp_fn, dec_fn in ((oracle.nybble_static_compress, oracle.nybble_static_decompress),
+                                (oracle.nybble_adaptive_compress, oracle.nybble_adaptive_decompress)):
+            comp = comp_fn(text)
+            assert 0 not in comp and len(comp) <= len(text) + 1
+            assert dec_fn(comp) == text
+
+    check()
