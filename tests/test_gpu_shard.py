@@ -72,7 +72,7 @@ def test_sharded_cuda_encode_equals_single_stream(n_ary, sizes):
     assert all(results.get(r) for r in range(world)), dict(results)
 
 
-def _stream_worker(rank, world, port, n_ary, n, results):
+def _stream_worker(rank, world, port, n_ary, n, results, s_exp=1.1):
     import sys
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -86,7 +86,7 @@ def _stream_worker(rank, world, port, n_ary, n, results):
         from data_compression_b200.shard import ShardedHuffman
         from oracle import pyoracle as O
         O.build()
-        thr, base = synth.zipf_bytes_spec()
+        thr, base = synth.zipf_thresholds(255, s_exp), 1
         stream = synth.host_stream(n, 1234 + n_ary, thr, base)
         # the bitstream comes from the ORACLE (BASELINE config 5: "reference-produced"), and is cut blindly into byte ranges
         lengths, el, ev, st = O.build_tables(O.histogram_u8(stream), n_ary)
@@ -105,10 +105,12 @@ def _stream_worker(rank, world, port, n_ary, n, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_ary,n,world", [(2, 700001, 2), (4, 300000, 2), (16, 123457, 2), (2, 5000, 2), (4, 2000000, 4)])
-def test_one_stream_cut_blindly_over_ranks(n_ary, n, world):
-    """Config 5: one oracle-produced bitstream, byte ranges per rank, first codes found by boundary synchronisation."""
+@pytest.mark.parametrize("n_ary,n,world,s_exp", [(2, 700001, 2, 1.1), (4, 300000, 2, 1.1), (16, 123457, 2, 1.1), (2, 5000, 2, 1.1),
+                                                 (4, 2000000, 4, 1.1), (4, 900001, 2, 1.5), (2, 900001, 2, 1.5)])
+def test_one_stream_cut_blindly_over_ranks(n_ary, n, world, s_exp):
+    """Config 5: one oracle-produced bitstream, byte ranges per rank, first codes found by boundary synchronisation.
+    Zipf(1.5) gives tables whose longest code exceeds the 12-bit index (the 14-bit count table / the escape forms)."""
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_stream_worker, args=(world, _free_port(), n_ary, n, results), nprocs=world, join=True)
+    mp.spawn(_stream_worker, args=(world, _free_port(), n_ary, n, results, s_exp), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world)), dict(results)
