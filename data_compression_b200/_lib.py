@@ -85,6 +85,8 @@ SYMBOLS = [
     ("dc_nybble_adaptive_workspace_bytes", _sz, [_sz]),
     ("dc_nybble_adaptive_compress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     ("dc_nybble_adaptive_decompress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    ("dc_nybble_text_compress_batch", _i, [_vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _vp]),
+    ("dc_nybble_text_decompress_batch", _i, [_vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _vp]),
     ("dc_synth_fill", _i, [_vp, _sz, _u64, _vp, _i, _i, _vp]),
     ("dc_host_histogram", _i, [C.c_char_p, _i, _ip]),
     ("dc_host_histogram_u8", _i, [_vp, _sz, _u64p]),

@@ -279,6 +279,39 @@ def nybble_adaptive_decompress(src: torch.Tensor):
     return _nybble_text("dc_nybble_adaptive_decompress", src, 2 * src.numel() + 2)
 
 
+def _nybble_text_batch(fn_name: str, strings, modify: bool, slot) -> list:
+    """Many strings through one launch (one thread per string).  `strings`: a sequence of bytes objects; returns a list of bytes."""
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lens = np.array([len(s) for s in strings], dtype=np.int64)
+    src_off = np.zeros(len(strings) + 1, dtype=np.int64)
+    np.cumsum(lens, out=src_off[1:])
+    dst_off = np.zeros(len(strings) + 1, dtype=np.int64)
+    np.cumsum(np.array([slot(int(n)) for n in lens], dtype=np.int64), out=dst_off[1:])
+    flat = np.frombuffer(b"".join(bytes(s) for s in strings), dtype=np.uint8)
+    d_src = torch.from_numpy(flat.copy() if flat.size else np.zeros(1, dtype=np.uint8)).to(dev)
+    d_dst = torch.zeros(max(int(dst_off[-1]), 1), dtype=torch.uint8, device=dev)
+    d_so, d_do = torch.from_numpy(src_off).to(dev), torch.from_numpy(dst_off).to(dev)
+    d_len = torch.zeros(max(len(strings), 1), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(getattr(lib(), fn_name)(d_src.data_ptr(), d_so.data_ptr(), len(strings), int(bool(modify)), d_dst.data_ptr(), d_do.data_ptr(),
+                                  d_len.data_ptr(), status.data_ptr(), _stream()), fn_name)
+    check(int(status.item()), fn_name)
+    out, out_len = d_dst.cpu().numpy(), d_len.cpu().numpy()
+    return [out[int(dst_off[i]): int(dst_off[i]) + int(out_len[i])].tobytes() for i in range(len(strings))]
+
+
+def nybble_text_compress_batch(strings, modify: bool = False) -> list:
+    """compress_bytestring(s, dst, modify) nybble_compression.c:887 for every s of `strings`, one GPU thread per string
+    (the "replicas" parallelism of the adaptive mode).  Returns the compressed strings."""
+    return _nybble_text_batch("dc_nybble_text_compress_batch", strings, modify, lambda n: n + 2)
+
+
+def nybble_text_decompress_batch(strings, modify: bool = False) -> list:
+    """decompress_bytestring(s, dst, modify) nybble_compression.c:734 for every s of `strings`."""
+    return _nybble_text_batch("dc_nybble_text_decompress_batch", strings, modify, lambda n: 2 * n + 2)
+
+
 def synth_fill(out: torch.Tensor, seed: int, thresholds: torch.Tensor, value_base: int) -> torch.Tensor:
     """Fill `out` (uint8, CUDA) with the counter-based synthetic stream (see synth.py)."""
     _need_cuda(out, "out")

@@ -215,6 +215,108 @@ __global__ void __launch_bounds__(32) mtf_resolve_kernel(uint8_t *__restrict__ b
     }
 }
 
+// ------------------------------------------------------------------------------------------ replicas: many strings per call
+// SURVEY 8e gives the adaptive compressor "replicas only" as its parallelism; the reference's own use is many short
+// strings (messages of a microcontroller program).  One thread per string walks it exactly as the reference does --
+// compress_bytestring :887-1038 / decompress_bytestring :734-817, either mode -- with the 16 lists in local memory.
+struct MtfLists {
+    unsigned long long l[kMtfCtx];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < kMtfCtx; c++) l[c] = kMtfInit;
+    }
+};
+
+// returns the compressed length; status: DC_ERR_SYMBOL for a byte outside 0x01..0x7F, DC_ERR_CAPACITY if cap < n + 2
+__device__ size_t text_compress_one(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ dst, size_t cap, bool modify, int *status) {
+    if (n == 0) { if (cap) dst[0] = 0; return 0; }
+    if (cap < n + 2) { *status = DC_ERR_CAPACITY; return 0; }
+    MtfLists t;
+    t.init();
+    size_t o = 0;
+    dst[o++] = 0xAF;
+    dst[o++] = src[0];
+    int off = 0;
+    bool bad = false;
+    for (size_t i = 1; i < n; i++) {
+        const uint32_t s = src[i], c = mtf_ctx(src[i - 1]);
+        bad |= s == 0 || s >= 0x80u;
+        const int at = mtf_find(t.l[c], s);
+        int used;
+        if (at == 8) {
+            if (off == 0) { dst[o] = (uint8_t)s; used = 2; }
+            else { dst[o] = src[i - 1]; dst[o + 1] = (uint8_t)s; used = 3; }   // the half-written byte becomes a literal (:855-857)
+        } else {
+            const uint32_t nyb = 8u | (uint32_t)at;
+            if (off == 0) dst[o] = (uint8_t)(nyb << 4);
+            else dst[o] |= (uint8_t)nyb;
+            used = 1;
+        }
+        if (modify) t.l[c] = mtf_touch(t.l[c], s, at);
+        off += used;
+        if (off > 1) { o++; off -= 2; }
+        if (off > 1) { o++; off -= 2; }
+    }
+    if (off != 0) dst[o++] = src[n - 1];                 // trailing half byte -> literal (:1000-1009)
+    if (bad) { *status = DC_ERR_SYMBOL; return 0; }
+    if (o >= n) {                                        // not shorter: ' ' + raw copy (:1018-1037)
+        dst[0] = ' ';
+        for (size_t i = 0; i < n; i++) dst[1 + i] = src[i];
+        o = n + 1;
+    }
+    if (o < cap) dst[o] = 0;
+    return o;
+}
+
+__device__ size_t text_decompress_one(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ dst, size_t cap, bool modify, int *status) {
+    size_t o = 0;
+    if (n == 0) { if (cap) dst[0] = 0; return 0; }
+    if (src[0] == 0xAFu) {
+        if (n < 2) { if (cap) dst[0] = 0; return 0; }
+        if (cap < 2 * n) { *status = DC_ERR_CAPACITY; return 0; }   // at most 2n - 3 bytes
+        MtfLists t;
+        t.init();
+        dst[o++] = src[1];
+        size_t p = 2;
+        int off = 0;
+        while (p < n) {
+            const uint32_t b = src[p], nb = p + 1 < n ? src[p + 1] : 0u;
+            const uint32_t nyb = off == 0 ? (b >> 4) & 15u : b & 15u, next = off == 0 ? b & 15u : (nb >> 4) & 15u;
+            const uint32_t c = mtf_ctx(dst[o - 1]);
+            uint32_t out;
+            int at;
+            if (nyb & 8u) { at = (int)(nyb & 7u); out = (uint32_t)(t.l[c] >> (8 * at)) & 0xFFu; off += 1; }
+            else { out = ((nyb & 7u) << 4) + next; at = mtf_find(t.l[c], out); off += 2; }
+            dst[o++] = (uint8_t)out;
+            if (modify) t.l[c] = mtf_touch(t.l[c], out, at);
+            if (off >= 2) { p++; off -= 2; }
+        }
+    } else {
+        size_t p = src[0] == ' ' ? 1 : 0;                 // LITERAL skips the type byte (:799-805), anything else copies (:806-812)
+        if (cap < n) { *status = DC_ERR_CAPACITY; return 0; }
+        while (p < n) dst[o++] = src[p++];
+    }
+    if (o < cap) dst[o] = 0;
+    return o;
+}
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(128) text_batch_kernel(const uint8_t *__restrict__ src, const unsigned long long *__restrict__ src_off,
+                                                         size_t count, int modify, uint8_t *__restrict__ dst,
+                                                         const unsigned long long *__restrict__ dst_off,
+                                                         unsigned long long *__restrict__ out_len, int32_t *__restrict__ d_status) {
+    const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= count) return;
+    const unsigned long long s0 = src_off[i], s1 = src_off[i + 1], d0 = dst_off[i], d1 = dst_off[i + 1];
+    int st = DC_OK;
+    size_t len = 0;
+    if (s1 < s0 || d1 < d0) st = DC_ERR_ARG;
+    else len = COMPRESS ? text_compress_one(src + s0, (size_t)(s1 - s0), dst + d0, (size_t)(d1 - d0), modify != 0, &st)
+                        : text_decompress_one(src + s0, (size_t)(s1 - s0), dst + d0, (size_t)(d1 - d0), modify != 0, &st);
+    out_len[i] = len;
+    if (st != DC_OK) set_status(d_status, st);
+}
+
 // ------------------------------------------------------------------------------------------ host side (internal)
 static size_t mtf_blocks(size_t n) { return (n + kMtfBlock - 1) / kMtfBlock; }
 static size_t mtf_chunks(size_t n) { return (mtf_blocks(n) + kMtfChunk - 1) / kMtfChunk; }
@@ -260,3 +362,29 @@ int mtf_resolve(uint8_t *d_buf, const unsigned long long *d_len, const int32_t *
 }
 
 }  // namespace dc
+
+using namespace dc;
+
+template <bool COMPRESS>
+static int text_batch(const uint8_t *d_src, const uint64_t *d_src_off, size_t count, int modify, uint8_t *d_dst, const uint64_t *d_dst_off,
+                      uint64_t *d_out_len, int32_t *d_status, void *stream) {
+    if (count && (!d_src_off || !d_dst_off || !d_out_len || !d_src || !d_dst)) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    if (count == 0) return DC_OK;
+    LaunchScope ls(DC_K_TEXT_BATCH, st);
+    text_batch_kernel<COMPRESS><<<(unsigned int)((count + 127) / 128), 128, 0, st>>>(d_src, (const unsigned long long *)d_src_off, count, modify, d_dst,
+                                                                                    (const unsigned long long *)d_dst_off,
+                                                                                    (unsigned long long *)d_out_len, d_status);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int dc_nybble_text_compress_batch(const uint8_t *d_src, const uint64_t *d_src_off, size_t count, int modify, uint8_t *d_dst,
+                                             const uint64_t *d_dst_off, uint64_t *d_out_len, int32_t *d_status, void *stream) {
+    return text_batch<true>(d_src, d_src_off, count, modify, d_dst, d_dst_off, d_out_len, d_status, stream);
+}
+
+extern "C" int dc_nybble_text_decompress_batch(const uint8_t *d_src, const uint64_t *d_src_off, size_t count, int modify, uint8_t *d_dst,
+                                               const uint64_t *d_dst_off, uint64_t *d_out_len, int32_t *d_status, void *stream) {
+    return text_batch<false>(d_src, d_src_off, count, modify, d_dst, d_dst_off, d_out_len, d_status, stream);
+}

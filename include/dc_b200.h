@@ -149,6 +149,7 @@ enum dc_kernel_id {
     DC_K_MTF_WALK,
     DC_K_MTF_SCAN,
     DC_K_MTF_RESOLVE,
+    DC_K_TEXT_BATCH,
     DC_K_SYNTH,
     DC_K_COUNT
 };
@@ -308,6 +309,18 @@ int dc_nybble_adaptive_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, 
                                 int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 int dc_nybble_adaptive_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,
                                   int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Many strings per call -- the parallelism SURVEY 8e gives the adaptive mode ("replicas only"), and the reference's own
+ * use (many short strings).  String i is d_src[d_src_off[i] .. d_src_off[i + 1]), its output slot
+ * d_dst[d_dst_off[i] .. d_dst_off[i + 1]) (compress: >= length + 2 bytes, decompress: >= 2 * length), and
+ * d_out_len[i] gets its output length; one thread walks one string as compress_bytestring() / decompress_bytestring()
+ * do (modify = 0: static table, 1: adaptive contexts).  *d_status: the first error of any string.
+ */
+int dc_nybble_text_compress_batch(const uint8_t *d_src, const uint64_t *d_src_off, size_t count, int modify, uint8_t *d_dst,
+                                  const uint64_t *d_dst_off, uint64_t *d_out_len, int32_t *d_status, void *stream);
+int dc_nybble_text_decompress_batch(const uint8_t *d_src, const uint64_t *d_src_off, size_t count, int modify, uint8_t *d_dst,
+                                    const uint64_t *d_dst_off, uint64_t *d_out_len, int32_t *d_status, void *stream);
 
 /* ------------------------------------------------------------------------- synthetic inputs (bench/tests) */
 

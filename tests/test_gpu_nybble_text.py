@@ -154,3 +154,31 @@ def test_adaptive_decoder_on_arbitrary_streams(dc, oracle):
             want = oracle.nybble_adaptive_decompress(comp)
             got, st, _, _ = _run(dc.nybble_adaptive_decompress, comp)
             assert st == 0 and got == want, (n, head)
+
+
+# ------------------------------------------------------------------------------------------ many strings per call (replicas)
+
+@pytest.mark.parametrize("modify", [False, True])
+def test_batch_matches_reference_and_oracle(dc, oracle, modify):
+    g = load_golden("nybble.json")["adaptive" if modify else "static"]
+    texts = [bytes.fromhex(c["text"]) for c in g]
+    comps = [bytes.fromhex(c["compressed"]) for c in g]
+    assert dc.nybble_text_compress_batch(texts, modify) == comps            # the unmodified reference's own outputs
+    assert dc.nybble_text_decompress_batch(comps, modify) == texts
+    rng = np.random.default_rng(17 + int(modify))
+    many = [b"", b"a", b"e", b"ab", b" e"]
+    for k in range(3000):
+        n = int(rng.integers(1, 200))
+        many.append(_english(rng, n) if k % 3 else rng.integers(1, 128, size=n, dtype=np.uint8).tobytes())
+    comp_fn = oracle.nybble_adaptive_compress if modify else oracle.nybble_static_compress
+    dec_fn = oracle.nybble_adaptive_decompress if modify else oracle.nybble_static_decompress
+    want = [comp_fn(t) for t in many]
+    got = dc.nybble_text_compress_batch(many, modify)
+    assert got == want
+    assert dc.nybble_text_decompress_batch(want, modify) == many
+    # arbitrary streams through the decoder (nibble-granular literals, unknown type bytes)
+    junk = [bytes([0xAF, 0x41]) + rng.integers(1, 256, size=int(rng.integers(0, 60)), dtype=np.uint8).tobytes() for _ in range(500)]
+    assert dc.nybble_text_decompress_batch(junk, modify) == [dec_fn(j) for j in junk]
+    with pytest.raises(dc.DcError) as e:
+        dc.nybble_text_compress_batch([b"ok", b"bad\x80byte"], modify)
+    assert e.value.status == dc.DC_ERR_SYMBOL
