@@ -350,6 +350,10 @@ extern "C" int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bi
     if (rc != DC_OK) return rc;
     if (trits) {
         if (total_bits & 1) return DC_ERR_ARG;
+        // large streams: chunked like the other radices, every chunk unpacked on the device before it is decoded
+        rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status, d_packed);
+        if (rc <= 0) return rc;
+        if (rc != 1) return DC_ERR_CUDA;
         if (pbytes) DC_CUDA_TRY(cudaMemcpyAsync(d_packed, payload, pbytes, cudaMemcpyHostToDevice, 0));
         rc = dc_trit_unpack(d_packed, ntrits, d_bits, d_status, nullptr);
         if (rc != DC_OK) return rc;
@@ -358,7 +362,7 @@ extern "C" int dc_host_huff_decompress(const uint8_t *payload, uint64_t total_bi
         if (st0 != DC_OK) return st0;
     } else {
         // large streams: chunked, with the upload, the decode and the download overlapping
-        rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status);
+        rc = host_decompress_pipelined(payload, total_bits, d_tab, d_bits, d_out, d_ws, ws_bytes, out, n_out, d_status, nullptr);
         if (rc <= 0) return rc;
         if (rc != 1 && nbytes) return DC_ERR_CUDA;
         // one-shot path.  (After a pipelined attempt that fell back the payload is on the device already; copying it

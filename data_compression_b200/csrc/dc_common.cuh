@@ -45,10 +45,14 @@ struct TableRaw {
 int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
                  TableRaw raw, cudaStream_t st);
 
-// pipelined form of dc_host_huff_decompress (k4_decode.cu): DC_OK / negative dc_status / +1 = use the one-shot path
+// pipelined form of dc_host_huff_decompress (k4_decode.cu): DC_OK / negative dc_status / +1 = use the one-shot path.
+// d_packed != nullptr: radix 3, h_payload is the 5-trits-per-byte payload (total_bits = 2 * trits) and every chunk is
+// unpacked into d_bits on the device before it is decoded
 int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
                               uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
-                              int32_t *d_status);
+                              int32_t *d_status, uint8_t *d_packed);
+// K7 unpack without the status reset (k7_trits.cu)
+int trit_unpack_launch(const uint8_t *d_payload, unsigned long long ntrits, uint8_t *d_t2, int32_t *d_status, cudaStream_t st);
 
 // K8 (k8_mtf.cu): the move-to-front contexts of the adaptive nybble compressor, used by K6
 size_t mtf_workspace_bytes(size_t n);

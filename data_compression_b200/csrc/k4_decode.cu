@@ -1314,7 +1314,8 @@ static PipeState g_pipe;
 
 int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
                               uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
-                              int32_t *d_status) {
+                              int32_t *d_status, uint8_t *d_packed) {
+    const bool trits = d_packed != nullptr;
     const size_t nbytes = (size_t)((total_bits + 7) / 8);
     static unsigned long long chunk_tiles = 0;
     if (chunk_tiles == 0) {  // DC_PIPE_CHUNK_MIB: tuning knob (a multiple of the 16 KB segment either way)
@@ -1322,7 +1323,11 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         const unsigned long long mib = e ? strtoull(e, nullptr, 10) : 0;
         chunk_tiles = mib >= 1 && mib <= 1024 ? mib * 1024 : kPipeChunkTiles;
     }
-    const unsigned long long chunk_bytes = chunk_tiles * (kF_TileVecs * 16ull);
+    unsigned long long chunk_bytes = chunk_tiles * (kF_TileVecs * 16ull);
+    // radix 3: a chunk of the 2-bit-per-trit stream has to be whole segments (16 KB) AND whole 16-byte groups of the
+    // payload (20 bytes of stream each): multiples of 81 920 bytes
+    if (trits) chunk_bytes = chunk_bytes / 81920 * 81920;
+    if (chunk_bytes == 0) return 1;
     const size_t nchunk = (size_t)((nbytes + chunk_bytes - 1) / chunk_bytes);
     if (nchunk < 3 || decode_force_mode() != 0) return 1;
     size_t off[12];
@@ -1354,7 +1359,13 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         // 64 bytes more than the chunk: its last code, and the look-ahead word of its last lane, reach into the next chunk
         // (which uploads the same bytes again); so chunk k can be decoded as soon as upload k is in
         const size_t o = (size_t)(k * chunk_bytes), len = (size_t)min((unsigned long long)(nbytes - o), chunk_bytes + 64);
-        DC_CUDA_TRY(cudaMemcpyAsync(d_bits + o, h_payload + o, len, cudaMemcpyHostToDevice, up));
+        if (trits) {  // 4 trits per stream byte, 5 per payload byte
+            const size_t po = o / 5 * 4, pbytes = (size_t)((total_bits / 2 + 4) / 5);
+            const size_t plen = min(pbytes - po, (size_t)(chunk_bytes / 5 * 4) + 64);
+            DC_CUDA_TRY(cudaMemcpyAsync(d_packed + po, h_payload + po, plen, cudaMemcpyHostToDevice, up));
+        } else {
+            DC_CUDA_TRY(cudaMemcpyAsync(d_bits + o, h_payload + o, len, cudaMemcpyHostToDevice, up));
+        }
         DC_CUDA_TRY(cudaEventRecord(g_pipe.ev_up[k], up));
     }
     DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), cp));
@@ -1369,6 +1380,12 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
         const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
         const int last = k + 1 == nchunk;
         DC_CUDA_TRY(cudaStreamWaitEvent(cp, g_pipe.ev_up[k], 0));
+        if (trits) {  // this chunk's trits, and 256 of the next chunk's (the 64 bytes of look-ahead), into the stream buffer
+            const unsigned long long t0 = k * chunk_bytes * 4ull, ntrits = total_bits / 2;
+            const unsigned long long cnt = min(ntrits - t0, chunk_bytes * 4ull + 256ull);
+            const int rc = trit_unpack_launch(d_packed + k * chunk_bytes / 5 * 4, cnt, d_bits + k * chunk_bytes, d_status, cp);
+            if (rc != DC_OK) return rc;
+        }
         // F1 and F2, the chain state for the host, then F3 (launch_fast's order, with the read-back in between)
         const uint8_t *bits_k = d_bits + k * chunk_bytes;
         {

@@ -158,12 +158,17 @@ extern "C" int dc_trit_pack(const uint8_t *d_t2, uint64_t ntrits, uint8_t *d_pay
     return cuda_status(cudaGetLastError());
 }
 
-extern "C" int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t *d_t2, int32_t *d_status, void *stream) {
-    if (ntrits && (!d_t2 || !d_payload || ((uintptr_t)d_t2 & 3))) return DC_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+// the launch alone: *d_status is only ever set (the pipelined host decompress shares one status word over all chunks)
+int dc::trit_unpack_launch(const uint8_t *d_payload, unsigned long long ntrits, uint8_t *d_t2, int32_t *d_status, cudaStream_t st) {
     if (ntrits == 0) return DC_OK;
     LaunchScope ls(DC_K_TRIT_UNPACK, st);
     trit_unpack_kernel<<<trit_grid(ntrits), kTritThreads, 0, st>>>(d_payload, ntrits, d_t2, d_status);
     return cuda_status(cudaGetLastError());
+}
+
+extern "C" int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t *d_t2, int32_t *d_status, void *stream) {
+    if (ntrits && (!d_t2 || !d_payload || ((uintptr_t)d_t2 & 3))) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    return trit_unpack_launch(d_payload, ntrits, d_t2, d_status, st);
 }

@@ -126,3 +126,28 @@ def test_nybble_host(dc, oracle):
         s = np.array(c["symbols"], dtype=np.uint8)
         assert dc.hostapi.nybble_pack(s).tolist() == c["packed"]
         assert dc.hostapi.nybble_unpack(np.array(c["packed"], dtype=np.uint8), s.size).tolist() == c["symbols"]
+
+
+def test_radix3_host_pipelined(dc, oracle):
+    """Radix 3 on host buffers at a size that takes the chunked decompress: every chunk of the 5-trits-per-byte payload is
+    unpacked on the device and decoded while the next one is uploaded; payload against the oracle, then the round trip."""
+    import torch
+    from data_compression_b200 import synth
+    thr, base = synth.zipf_bytes_spec()
+    n = 140 * (1 << 20) + 777
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(d, 4242, synth.device_thresholds(thr, "cuda"), base)
+    data = d.cpu().numpy()
+    del d
+    payload, bits, lengths = dc.hostapi.huff_compress(data, 3)
+    ln, el, ev, st = oracle.build_tables(oracle.histogram_u8(data), 3)
+    want, wtrits = oracle.pack_trits(data, el, ev)
+    assert st == 0 and np.array_equal(lengths, ln) and bits == 2 * wtrits and np.array_equal(payload, want)
+    assert bits // 8 > 3 * 32768000                       # more than three chunks of the 2-bit-per-trit stream
+    back = dc.hostapi.huff_decompress(payload, bits, lengths, 3, n)
+    assert np.array_equal(back, data)
+    broken = payload.copy()
+    broken[payload.size // 2] = 250                       # not a payload byte (1..243)
+    with pytest.raises(dc.DcError) as e:
+        dc.hostapi.huff_decompress(broken, bits, lengths, 3, n)
+    assert e.value.status == dc.DC_ERR_CORRUPT

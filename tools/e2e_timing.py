@@ -7,7 +7,7 @@ import data_compression_b200 as dc
 from data_compression_b200 import synth, hostapi
 
 n = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024) << 20
-n_ary = 4
+n_ary = int(os.environ.get("N_ARY", 4))
 dev = torch.device("cuda:0")
 thr, base = synth.zipf_bytes_spec()
 d = torch.empty(n, dtype=torch.uint8, device=dev)
