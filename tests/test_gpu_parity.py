@@ -219,6 +219,39 @@ def test_mid_codes_13_to_16_bits(dc, oracle, n_ary, depths):
         assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
 
 
+@pytest.mark.parametrize("depths", [9, 12, 15])
+def test_radix3_long_codes(dc, oracle, depths):
+    """Radix 3 with codes of more than 8 trits: the trit-indexed tables hold no entry for them and the decoder takes the
+    canonical search (the T2 + ESC instantiations); 15 trits = 30 bits is the reference's limit (lengths < 16 digits)."""
+    ln = np.zeros(259, dtype=np.int32)
+    sym = 1
+    for depth in range(1, depths):            # two symbols at each depth, three at the last: a complete ternary code
+        for _ in range(2):
+            ln[sym] = depth; sym += 1
+    for _ in range(3):
+        ln[sym] = depths; sym += 1
+    el, ev, st = oracle.convert_lengths_to_encode_table(ln, 3)
+    assert st == 0
+    table = dc.huff_table_from_lengths(_dev(ln), 3)
+    t = table.download()
+    assert t.status == 0 and t.packed_radix == 3 and t.max_bits == 2 * depths
+    rng = np.random.default_rng(depths)
+    used = np.flatnonzero(ln)
+    w = 0.5 ** (ln[used] * 0.8)
+    for size in (150001, 4096 * 8 * 2 + 5):
+        data = rng.choice(used, size=size, p=w / w.sum()).astype(np.uint8)
+        assert ln[data].max() == depths      # the longest codes do occur
+        res = dc.huff_encode(_dev(data), table, out=torch.empty(data.size * 4 + 64, dtype=torch.uint8, device="cuda"))
+        nbits = res.bits()
+        want, wtrits = oracle.pack_trits(data, el, ev)
+        assert nbits == 2 * wtrits
+        payload, pst = dc.trit_pack(res.payload, wtrits)
+        assert int(pst.item()) == 0 and np.array_equal(payload.cpu().numpy(), want)
+        t2, ust = dc.trit_unpack(payload, wtrits)
+        out, status = dc.huff_decode(t2, nbits, table, data.size)
+        assert int(ust.item()) == 0 and int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
+
+
 def test_degenerate_alphabets(dc, oracle):
     # one distinct symbol: 1-bit codes (binary), 128 symbols per 128-bit subsequence
     for n_ary in PACKABLE:
