@@ -531,9 +531,24 @@ __device__ __forceinline__ void sync_lookup_multi(const FastTables<MODE> *t, uin
         csum += e;              // byte 2 accumulates their number (byte 0 only carries into the unused byte 1)
     }
 }
+// radix 3: the index is computed from ALL eight 2-bit fields of the window, so bits behind the end of the stream (whatever
+// the caller's buffer holds there; a field of 3 carries into the trits in front of it) must not reach it.  Only the
+// one-code-at-a-time steps of a ragged last tile can look past the end; `end_rel` = bits from the start of the lane's
+// subsequence to the end of the STREAM (a code may well reach into the next subsequence).
 template <int MODE>
-__device__ __forceinline__ void sync_lookup_single(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt) {
-    const uint32_t x = __funnelshift_l(lo, hi, p);
+__device__ __forceinline__ uint32_t window_at(uint32_t hi, uint32_t lo, uint32_t p, uint32_t end_rel) {
+    uint32_t x = __funnelshift_l(lo, hi, p);
+    if (mode_t2(MODE) && end_rel != 0xFFFFFFFFu) {
+        const uint32_t valid = end_rel - p;
+        if (valid < 32u) x &= ~(0xFFFFFFFFu >> valid);
+    }
+    return x;
+}
+
+template <int MODE>
+__device__ __forceinline__ void sync_lookup_single(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &scnt,
+                                                   uint32_t end_rel = 0xFFFFFFFFu) {
+    const uint32_t x = window_at<MODE>(hi, lo, p, end_rel);
     const uint32_t e = lds_lut<MODE>(lut, x);
     if (mode_esc(MODE) && is_escape_count(e)) {
         int sym;
@@ -554,7 +569,7 @@ __device__ __forceinline__ void sync_lookup_single(const FastTables<MODE> *t, ui
 // FULL: lim == 256 for every lane of the warp (all tiles but the stream's last).
 template <int MODE, bool FIRST, bool FULL>
 __device__ __forceinline__ void sync_walk(const FastTables<MODE> *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t p, uint32_t lim,
-                                          bool merged, SyncRecord &r) {
+                                          bool merged, SyncRecord &r, uint32_t end_rel = 0xFFFFFFFFu) {
     constexpr int kWin = mode_window(MODE);
     const int multi_lim = (int)lim - kWin;  // every code inside the index window then starts before lim
 #pragma unroll
@@ -574,7 +589,7 @@ __device__ __forceinline__ void sync_walk(const FastTables<MODE> *t, uint32_t lu
 #pragma unroll
                 for (int j = 0; j < kF_SubWords; j++) {
                     const int stop1 = min(32 * (j + 1), (int)lim) - 1;
-                    while ((int)p <= stop1) sync_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, scnt);
+                    while ((int)p <= stop1) sync_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, scnt, end_rel);
                 }
             }
             csum += scnt << mode_count_shift(MODE);
@@ -706,7 +721,7 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
             SyncRecord r;
             r.chk[0] = r.chk[1] = r.wc[0] = r.wc[1] = r.exit = 0;
             if (full) sync_walk<MODE, true, true>(&s_t, lut, w, start, lim, false, r);
-            else if (active) sync_walk<MODE, true, false>(&s_t, lut, w, start, lim, false, r);
+            else if (active) sync_walk<MODE, true, false>(&s_t, lut, w, start, lim, false, r, cur.bits_left - sub_bit0);
             while (true) {
                 uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, r.exit, 1);
                 if (lane == 0) ns = start;
@@ -714,7 +729,7 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
                 if (!__any_sync(0xFFFFFFFFu, redo)) break;
                 start = ns;
                 if (full) sync_walk<MODE, false, true>(&s_t, lut, w, start, lim, !redo, r);
-                else sync_walk<MODE, false, false>(&s_t, lut, w, start, lim, !redo, r);
+                else sync_walk<MODE, false, false>(&s_t, lut, w, start, lim, !redo, r, active ? cur.bits_left - sub_bit0 : 0u);
             }
             carry = __shfl_sync(0xFFFFFFFFu, r.exit, 31);
             if (tt < (uint32_t)warm) {
@@ -827,8 +842,8 @@ __device__ __forceinline__ void write_lookup_multi(const FastTables<MODE> *t, ui
 }
 template <int MODE>
 __device__ __forceinline__ void write_lookup_single(const FastTables<MODE> *t, uint32_t lut, uint32_t hi, uint32_t lo, uint32_t &p, uint32_t &dst,
-                                                    uint32_t &flags) {
-    const uint32_t x = __funnelshift_l(lo, hi, p);
+                                                    uint32_t &flags, uint32_t end_rel = 0xFFFFFFFFu) {
+    const uint32_t x = window_at<MODE>(hi, lo, p, end_rel);
     const uint32_t e = lds_lut<MODE>(lut, x);
     if (mode_esc(MODE) && is_escape_pair(e)) {
         int sym = 0;
@@ -851,7 +866,7 @@ __device__ __forceinline__ void write_lookup_single(const FastTables<MODE> *t, u
 // decode bits [p, lim) of the lane's subsequence into shared memory at dst (a shared-space byte address)
 template <int MODE, bool FULL>
 __device__ __forceinline__ void write_walk(const FastTables<MODE> *t, uint32_t lut, const uint32_t (&w)[kF_SubWords + 1], uint32_t &p, uint32_t lim,
-                                           uint32_t &dst, uint32_t &flags) {
+                                           uint32_t &dst, uint32_t &flags, uint32_t end_rel = 0xFFFFFFFFu) {
     constexpr int kWin = mode_window(MODE);
     const int multi_lim = (int)lim - kWin;
 #pragma unroll
@@ -865,7 +880,7 @@ __device__ __forceinline__ void write_walk(const FastTables<MODE> *t, uint32_t l
 #pragma unroll
         for (int j = 0; j < kF_SubWords; j++) {
             const int stop1 = min(32 * (j + 1), (int)lim) - 1;
-            while ((int)p <= stop1) write_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, dst, flags);
+            while ((int)p <= stop1) write_lookup_single<MODE>(t, lut, w[j], w[j + 1], p, dst, flags, end_rel);
         }
     }
 }
@@ -928,7 +943,7 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
                 const uint32_t dst0 = stage_addr + a + (incl - my_cnt);
                 uint32_t p = start, dst = dst0, flags = 0;
                 if (full) write_walk<MODE, true>(s_t, lut, w, p, lim, dst, flags);
-                else write_walk<MODE, false>(s_t, lut, w, p, lim, dst, flags);
+                else write_walk<MODE, false>(s_t, lut, w, p, lim, dst, flags, cur.bits_left - sub_bit0);
                 if ((flags & kPairUnused) || dst - dst0 != my_cnt || p > cur.bits_left - sub_bit0) corrupt = true;
             }
             __syncwarp();

@@ -219,6 +219,31 @@ def test_mid_codes_13_to_16_bits(dc, oracle, n_ary, depths):
         assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
 
 
+def test_radix3_stream_end_on_a_byte_boundary_with_garbage_behind(dc, oracle):
+    """Radix 3 look-ups index by all eight 2-bit fields of their window: bytes behind the end of the stream (here 0xFF = fields
+    of 3) must not reach the index.  Found by tools/fuzz.py: streams that end on a byte boundary in a buffer with garbage."""
+    rng = np.random.default_rng(99)
+    for size in (7, 100, 4097, 70001):
+        alphabet = rng.choice(np.arange(1, 256), size=40, replace=False).astype(np.uint8)
+        data = rng.choice(alphabet, size=size).astype(np.uint8)
+        hist = oracle.histogram_u8(data)
+        ln, el, ev, st = oracle.build_tables(hist, 3)
+        trits = np.cumsum(ln[data])
+        keep = int(np.flatnonzero(trits % 4 == 0)[-1]) + 1      # a prefix whose stream ends on a byte boundary
+        data = data[:keep]
+        d = _dev(data)
+        table = dc.huff_table_from_lengths(_dev(ln.astype(np.int32)), 3)
+        res = dc.huff_encode(d, table, out=torch.empty(keep * 4 + 64, dtype=torch.uint8, device="cuda"))
+        nbits = res.bits()
+        assert nbits % 8 == 0 and nbits == 2 * int(trits[keep - 1])
+        nb = nbits // 8
+        for fill in (0xFF, 0xAA, 0x00):
+            buf = torch.full((nb + 4096,), fill, dtype=torch.uint8, device="cuda")
+            buf[:nb] = res.payload[:nb]
+            out, status = dc.huff_decode(buf, nbits, table, keep)
+            assert int(status.item()) == 0 and torch.equal(out, d), (size, fill)
+
+
 @pytest.mark.parametrize("depths", [9, 12, 15])
 def test_radix3_long_codes(dc, oracle, depths):
     """Radix 3 with codes of more than 8 trits: the trit-indexed tables hold no entry for them and the decoder takes the
