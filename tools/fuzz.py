@@ -51,6 +51,17 @@ while time.time() < t_end:
     if not ok:
         fails += 1
         print("MISMATCH", it, n_ary, nsym, skew, size, t.max_bits, flush=True)
+    # a shard's view: the same input at a non-zero bit phase (leading bits belong to the previous shard)
+    if n_ary != 3:
+        phase = int(rng.integers(1, 8))
+        res_p = dc.huff_encode(d, table, out=torch.empty(size * 4 + 64, dtype=torch.uint8, device="cuda"), bit_phase=phase)
+        want_p, wb = O.pack(data, el, ev, O.bits_per_digit(n_ary), phase)
+        okp = res_p.bits() == wb and np.array_equal(res_p.payload[: (wb + phase + 7) // 8].cpu().numpy(), want_p)
+        out_p, st_p = dc.huff_decode(res_p.payload, wb, table, size, bit_start=phase)
+        okp = okp and int(st_p.item()) == 0 and np.array_equal(out_p.cpu().numpy(), data)
+        if not okp:
+            fails += 1
+            print("PHASE MISMATCH", it, n_ary, nsym, skew, size, t.max_bits, phase, flush=True)
     # damage: flip a few bytes of the stream, decode must terminate with some status
     if nbits >= 64:
         broken = stream[: (nbits + 7) // 8 + 64].clone()
