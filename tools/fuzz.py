@@ -25,6 +25,13 @@ while time.time() < t_end:
     hist = dc.histogram(d)
     o_hist = O.histogram_u8(data)
     assert np.array_equal(hist.cpu().numpy().astype(np.uint64), o_hist)
+    # tables are exact for every radix (the payload only for 2, 3, 4, 16): one more radix per iteration, tables only
+    n_other = int(rng.integers(5, 40))
+    t_o = dc.huff_build(hist, n_other).download()
+    ln_o, el_o, ev_o, st_o = O.build_tables(o_hist, n_other)
+    if not (np.array_equal(np.array(t_o.lengths[:259]), ln_o) and ((st_o != 0) or np.array_equal(np.array(t_o.values[:259], dtype=np.uint32), ev_o))):
+        fails += 1
+        print("TABLE MISMATCH", it, n_other, nsym, skew, size, flush=True)
     table = dc.huff_build(hist, n_ary)
     t = table.download()
     ln, el, ev, st = O.build_tables(o_hist, n_ary)
