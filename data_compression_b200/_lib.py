@@ -79,6 +79,8 @@ SYMBOLS = [
     ("dc_nybble_unpack", _i, [_vp, _sz, _vp, _vp]),
     ("dc_trit_pack", _i, [_vp, _u64, _vp, _vp, _vp]),
     ("dc_trit_unpack", _i, [_vp, _u64, _vp, _vp, _vp]),
+    ("dc_base64url_pack", _i, [_vp, _u64, _vp, _vp]),
+    ("dc_base64url_unpack", _i, [_vp, _u64, _vp, _vp, _vp]),
     ("dc_nybble_text_workspace_bytes", _sz, [_sz]),
     ("dc_nybble_text_compress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     ("dc_nybble_text_decompress", _i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),

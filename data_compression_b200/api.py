@@ -243,6 +243,25 @@ def trit_unpack(payload: torch.Tensor, ntrits: int):
     return t2, status
 
 
+def base64url_pack(bits: torch.Tensor, nbits: int) -> torch.Tensor:
+    """The binary payload as base64url characters, 6 bits each through int2digit() (n_ary_huffman.c:371-426, :1646-1671):
+    ceil(nbits / 6) characters, RFC 4648 without padding."""
+    _need_cuda(bits, "bits")
+    nchars = (nbits + 5) // 6
+    out = torch.empty(max(nchars, 1) + 16, dtype=torch.uint8, device=bits.device)
+    check(lib().dc_base64url_pack(bits.data_ptr(), nbits, out.data_ptr(), _stream()), "dc_base64url_pack")
+    return out[:nchars]
+
+
+def base64url_unpack(chars: torch.Tensor, nbits: int):
+    """Inverse (digit2int() :428-455 accepts both alphabets for 62 / 63).  Returns (bytes[: ceil(nbits / 8)] + slack, status)."""
+    _need_cuda(chars, "chars")
+    out = torch.empty((nbits + 7) // 8 + 64, dtype=torch.uint8, device=chars.device)
+    status = torch.empty(1, dtype=torch.int32, device=chars.device)
+    check(lib().dc_base64url_unpack(chars.data_ptr(), nbits, out.data_ptr(), status.data_ptr(), _stream()), "dc_base64url_unpack")
+    return out, status
+
+
 def _nybble_text(fn_name: str, src: torch.Tensor, cap: int):
     _need_cuda(src, "src")
     n = src.numel()

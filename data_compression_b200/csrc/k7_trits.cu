@@ -1,4 +1,5 @@
-// k7_trits.cu -- K7: the 5-trits-per-byte payload of radix 3.
+// k7_trits.cu -- K7: the digit packings of SURVEY 8f row N4: the 5-trits-per-byte payload of radix 3, and (at the end of the
+// file) the base64url text form of the binary payload.
 //
 // The reference's default radix is 3 (n_ary_huffman.c:2529) and its author sketches the storage at :745-748: "grab 5
 // trits at a time, convert into a number 1..243, and store as an 8-bit octet (which never uses byte 0 or 244..255)".
@@ -138,6 +139,115 @@ __global__ void __launch_bounds__(kTritThreads) trit_unpack_kernel(const uint8_t
     if (bad) set_status(d_status, DC_ERR_CORRUPT);
 }
 
+// ---------------------------------------------------------------------------------------- base64url text form (n = 2)
+// The reference's unfinished packer emits the binary code as base64url characters, 6 bits each, through int2digit()
+// (n_ary_huffman.c:371-426, :1646-1671).  Layout: character k = int2digit(bits [6k, 6k + 6) of the payload, most significant
+// first, zero padded) -- RFC 4648 without '=' padding.  A thread turns 12 bytes into 16 characters and back.
+constexpr int kB64Threads = 256;
+
+__device__ __forceinline__ uint32_t b64_char(uint32_t v) {  // int2digit() :371-426
+    return v < 26 ? 'A' + v : v < 52 ? 'a' + (v - 26) : v < 62 ? '0' + (v - 52) : v == 62 ? '-' : '_';
+}
+
+__global__ void __launch_bounds__(kB64Threads) b64_pack_kernel(const uint8_t *__restrict__ bits, unsigned long long nbits,
+                                                               uint8_t *__restrict__ chars) {
+    __shared__ uint8_t s_lut[64];
+    if (threadIdx.x < 64) s_lut[threadIdx.x] = (uint8_t)b64_char(threadIdx.x);
+    __syncthreads();
+    const unsigned long long nbytes = (nbits + 7) / 8, nchars = (nbits + 5) / 6, groups = (nchars + 15) / 16;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * kB64Threads + threadIdx.x; g < groups;
+         g += (unsigned long long)gridDim.x * kB64Threads) {
+        const unsigned long long ib = g * 12, ob = g * 16;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (ib + 12 <= nbytes) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) w[k] = bswap32(__ldg((const uint32_t *)(bits + ib) + k));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) x = (x << 8) | (ib + 4 * k + b < nbytes ? (uint32_t)bits[ib + 4 * k + b] : 0u);
+                w[k] = x;
+            }
+        }
+        // bits behind the end of the stream are padding: zero (the last byte of the caller's buffer may hold anything there)
+        {
+            const unsigned long long first = ib * 8;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const long long keep = (long long)nbits - (long long)(first + 32 * k);
+                if (keep <= 0) w[k] = 0;
+                else if (keep < 32) w[k] &= ~(0xFFFFFFFFu >> keep);
+            }
+        }
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int bit = 6 * c, a = bit >> 5, sft = bit & 31;
+            const uint32_t v = __funnelshift_l(w[a + 1], w[a], sft) >> 26;
+            o[c >> 2] |= (uint32_t)s_lut[v] << (8 * (c & 3));
+        }
+        if (ob + 16 <= nchars) {
+            stg_stream((uint4 *)(chars + ob), make_uint4(o[0], o[1], o[2], o[3]));
+        } else {
+            for (int c = 0; c < 16; c++)
+                if (ob + c < nchars) chars[ob + c] = (uint8_t)(o[c >> 2] >> (8 * (c & 3)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kB64Threads) b64_unpack_kernel(const uint8_t *__restrict__ chars, unsigned long long nbits,
+                                                                 uint8_t *__restrict__ bits, int32_t *__restrict__ d_status) {
+    __shared__ uint8_t s_lut[256];   // digit2int() :428-455: both alphabets for 62 / 63; 0xFF = not a digit
+    for (int c = threadIdx.x; c < 256; c += kB64Threads) {
+        uint32_t v = 0xFF;
+        for (uint32_t i = 0; i < 64; i++)
+            if (b64_char(i) == (uint32_t)c) v = i;
+        if (c == '+') v = 62;
+        if (c == '/') v = 63;
+        s_lut[c] = (uint8_t)v;
+    }
+    __syncthreads();
+    const unsigned long long nbytes = (nbits + 7) / 8, nchars = (nbits + 5) / 6, groups = (nchars + 15) / 16;
+    bool bad = false;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * kB64Threads + threadIdx.x; g < groups;
+         g += (unsigned long long)gridDim.x * kB64Threads) {
+        const unsigned long long ib = g * 16, ob = g * 12;
+        uint32_t in[4];
+        if (ib + 16 <= nchars && ((uintptr_t)(chars + ib) & 15) == 0) {
+            const uint4 v = ldg_stream((const uint4 *)(chars + ib));
+            in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) x |= (ib + 4 * k + b < nchars ? (uint32_t)chars[ib + 4 * k + b] : (uint32_t)'A') << (8 * b);
+                in[k] = x;
+            }
+        }
+        uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const uint32_t v = s_lut[(in[c >> 2] >> (8 * (c & 3))) & 0xFFu];
+            bad |= v == 0xFFu;
+            const int bit = 6 * c, a = bit >> 5, sft = bit & 31;
+            const uint32_t x = v & 63u;
+            if (sft <= 26) w[a] |= x << (26 - sft);
+            else { w[a] |= x >> (sft - 26); w[a + 1] |= x << (58 - sft); }
+        }
+        if (ob + 12 <= nbytes) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) ((uint32_t *)(bits + ob))[k] = bswap32(w[k]);
+        } else {
+            for (int k = 0; k < 12; k++)
+                if (ob + k < nbytes) bits[ob + k] = (uint8_t)(w[k >> 2] >> (24 - 8 * (k & 3)));
+        }
+    }
+    if (bad) set_status(d_status, DC_ERR_CORRUPT);
+}
+
 }  // namespace dc
 
 using namespace dc;
@@ -171,4 +281,29 @@ extern "C" int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t
     cudaStream_t st = (cudaStream_t)stream;
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     return trit_unpack_launch(d_payload, ntrits, d_t2, d_status, st);
+}
+
+static int b64_grid(unsigned long long nbits) {
+    const unsigned long long groups = ((nbits + 5) / 6 + 15) / 16, want = (groups + kB64Threads - 1) / kB64Threads;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+extern "C" int dc_base64url_pack(const uint8_t *d_bits, uint64_t nbits, uint8_t *d_chars, void *stream) {
+    if (nbits && (!d_bits || !d_chars || ((uintptr_t)d_bits & 3) || ((uintptr_t)d_chars & 15))) return DC_ERR_ARG;
+    if (nbits == 0) return DC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    LaunchScope ls(DC_K_B64_PACK, st);
+    b64_pack_kernel<<<b64_grid(nbits), kB64Threads, 0, st>>>(d_bits, nbits, d_chars);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int dc_base64url_unpack(const uint8_t *d_chars, uint64_t nbits, uint8_t *d_bits, int32_t *d_status, void *stream) {
+    if (nbits && (!d_bits || !d_chars || ((uintptr_t)d_bits & 3))) return DC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    if (nbits == 0) return DC_OK;
+    LaunchScope ls(DC_K_B64_UNPACK, st);
+    b64_unpack_kernel<<<b64_grid(nbits), kB64Threads, 0, st>>>(d_chars, nbits, d_bits, d_status);
+    return cuda_status(cudaGetLastError());
 }

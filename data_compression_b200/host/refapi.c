@@ -92,3 +92,13 @@ void decompress_bytestring(const char *source, char *dest, bool modify) {
 void nybble_compress(const char *source, char *dest) { compress_bytestring(source, dest, true); }
 
 void nybble_decompress(const char *source, char *dest) { decompress_bytestring(source, dest, true); }
+
+int digit2int(char input_digit) {
+    static const char digits[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+    if (input_digit == '+') return 62;
+    if (input_digit == '/') return 63;
+    for (int i = 0; i < 64; i++)
+        if (digits[i] == input_digit) return i;
+    done("digit2int", DC_ERR_ARG);
+    return -1;
+}

@@ -49,6 +49,12 @@ int decode_items_with_codes(const int max_symbol_value, const int canonical_leng
 /* bits emitted by the last represent_items_with_codes() call (the reference's signature has no slot for it) */
 uint64_t represent_items_last_total_bits(void);
 
+/* n_ary_huffman.c:428-455, verbatim signature: the value 0..63 of a base64url digit ('+' and '/' are accepted for 62 and 63,
+ * :441-445); aborts on anything else, like the reference's assert.  A table look-up: host code.  The stream forms -- the
+ * binary payload as base64url text, 6 bits per character, as the unfinished packer intends (:1646-1671) -- are
+ * dc_base64url_pack / dc_base64url_unpack in dc_b200.h. */
+int digit2int(char input_digit);
+
 /* nybble_compression.c:1091-1114, verbatim signature: store one nibble into *dest, offset 0 = the HIGH nibble.
  * One nibble per call is no work for a GPU; it is here so that a caller of the reference links unchanged (it goes
  * through the same pack kernel as the stream form below, which is the one to use). */

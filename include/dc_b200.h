@@ -146,6 +146,8 @@ enum dc_kernel_id {
     DC_K_TEXT_EMIT,
     DC_K_TRIT_PACK,
     DC_K_TRIT_UNPACK,
+    DC_K_B64_PACK,
+    DC_K_B64_UNPACK,
     DC_K_MTF_WALK,
     DC_K_MTF_SCAN,
     DC_K_MTF_RESOLVE,
@@ -277,6 +279,16 @@ int dc_nybble_unpack(const uint8_t *d_packed, size_t n_sym, uint8_t *d_sym, void
  */
 int dc_trit_pack(const uint8_t *d_t2, uint64_t ntrits, uint8_t *d_payload, int32_t *d_status, void *stream);
 int dc_trit_unpack(const uint8_t *d_payload, uint64_t ntrits, uint8_t *d_t2, int32_t *d_status, void *stream);
+
+/*
+ * The base64url text form of a binary payload: the reference's unfinished packer emits 6 bits per character through
+ * int2digit() (n_ary_huffman.c:371-426, :1646-1671).  Character k = int2digit(bits [6k, 6k + 6), most significant first,
+ * zero padded) -- RFC 4648 without '=' padding; ceil(nbits / 6) characters.  dc_base64url_unpack accepts what digit2int()
+ * accepts (:428-455: '-' or '+' for 62, '_' or '/' for 63), writes ceil(nbits / 8) bytes and sets *d_status =
+ * DC_ERR_CORRUPT for any other character.  d_bits: 4-byte aligned; d_chars: 16-byte aligned for dc_base64url_pack.
+ */
+int dc_base64url_pack(const uint8_t *d_bits, uint64_t nbits, uint8_t *d_chars, void *stream);
+int dc_base64url_unpack(const uint8_t *d_chars, uint64_t nbits, uint8_t *d_bits, int32_t *d_status, void *stream);
 
 /* ------------------------------------------------------------------------- K6 static-table nybble compressor */
 

@@ -82,6 +82,11 @@ int orc_pack_trits(const uint8_t *in, size_t n, const int elen[], const unsigned
 int orc_unpack_trits(const uint8_t *packed, uint64_t total_trits, int max_symbol_value, const int lengths[],
                      uint8_t *out, size_t n_out_capacity, size_t *n_decoded);
 
+/* base64url text form of a binary payload: int2digit() n_ary_huffman.c:371-426 / digit2int() :428-455, 6 bits per character
+ * as the unfinished packer intends (:1646-1671).  pack returns the number of characters; unpack ORC_OK / ORC_ERR_CORRUPT. */
+size_t orc_base64url_pack(const uint8_t *bits, uint64_t nbits, uint8_t *chars);
+int orc_base64url_unpack(const uint8_t *chars, uint64_t nbits, uint8_t *bits);
+
 /* nybble_compression.c:1091-1114 (write_nybble, #else branches) and :767-773 (split): high nibble first. */
 void orc_nybble_pack(const uint8_t *sym, size_t n_sym, uint8_t *packed);
 void orc_nybble_unpack(const uint8_t *packed, size_t n_sym, uint8_t *sym);

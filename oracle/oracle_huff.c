@@ -532,3 +532,42 @@ int orc_unpack_trits(const uint8_t *packed, uint64_t total_trits, int max_symbol
     if (n_decoded) *n_decoded = o;
     return ORC_OK;
 }
+
+/* ---------------------------------------------------------------- base64url text form of a binary payload (row N4)
+ * int2digit() n_ary_huffman.c:371-426 (the base64url table) and digit2int() :428-455 (which also takes '+' and '/');
+ * the unfinished packer (:1646-1671) emits 6 bits per character.  Character k = bits [6k, 6k + 6), most significant
+ * first, zero padded. */
+static const char k_b64url[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+
+size_t orc_base64url_pack(const uint8_t *bits, uint64_t nbits, uint8_t *chars) {
+    const uint64_t nchars = (nbits + 5) / 6;
+    for (uint64_t k = 0; k < nchars; k++) {
+        unsigned v = 0;
+        for (int b = 0; b < 6; b++) {
+            const uint64_t i = 6 * k + (uint64_t)b;
+            const unsigned bit = i < nbits ? (bits[i >> 3] >> (7 - (i & 7))) & 1u : 0u;
+            v = (v << 1) | bit;
+        }
+        chars[k] = (uint8_t)k_b64url[v];
+    }
+    return (size_t)nchars;
+}
+
+int orc_base64url_unpack(const uint8_t *chars, uint64_t nbits, uint8_t *bits) {
+    const uint64_t nchars = (nbits + 5) / 6, nbytes = (nbits + 7) / 8;
+    memset(bits, 0, (size_t)nbytes);
+    for (uint64_t k = 0; k < nchars; k++) {
+        const char c = (char)chars[k];
+        int v = -1;
+        for (int i = 0; i < 64; i++)
+            if (k_b64url[i] == c) v = i;
+        if (c == '+') v = 62;
+        if (c == '/') v = 63;
+        if (v < 0) return ORC_ERR_CORRUPT;
+        for (int b = 0; b < 6; b++) {
+            const uint64_t i = 6 * k + (uint64_t)b;
+            if (i < 8 * nbytes && ((v >> (5 - b)) & 1)) bits[i >> 3] |= (uint8_t)(0x80u >> (i & 7));
+        }
+    }
+    return ORC_OK;
+}

@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
                   "orc_nybble_adaptive_compress", "orc_nybble_adaptive_decompress"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
             getattr(L, f).restype = C.c_size_t
+        L.orc_base64url_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_base64url_pack.restype = C.c_size_t
+        L.orc_base64url_unpack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_base64url_unpack.restype = C.c_int
         _lib = L
     return _lib
 
@@ -249,6 +253,22 @@ def nybble_static_decompress(src: bytes) -> bytes:
     out = np.zeros(s.size * 2 + 8, dtype=np.uint8)
     n = lib().orc_nybble_static_decompress(s.ctypes.data, s.size, out.ctypes.data)
     return out[:n].tobytes()
+
+
+def base64url_pack(bits, nbits: int) -> bytes:
+    b = _u8(bits)
+    out = np.zeros((nbits + 5) // 6 + 8, dtype=np.uint8)
+    n = lib().orc_base64url_pack(b.ctypes.data, nbits, out.ctypes.data)
+    return out[:n].tobytes()
+
+
+def base64url_unpack(chars, nbits: int) -> np.ndarray:
+    c = _u8(chars)
+    out = np.zeros((nbits + 7) // 8 + 8, dtype=np.uint8)
+    st = lib().orc_base64url_unpack(c.ctypes.data, nbits, out.ctypes.data)
+    if st != ORC_OK:
+        raise ValueError(f"orc_base64url_unpack status {st}")
+    return out[: (nbits + 7) // 8]
 
 
 def nybble_adaptive_compress(src: bytes) -> bytes:

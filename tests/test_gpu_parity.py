@@ -277,6 +277,43 @@ def test_radix3_long_codes(dc, oracle, depths):
         assert int(ust.item()) == 0 and int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), data)
 
 
+def test_base64url_text_form_of_the_binary_payload(dc, oracle):
+    """Row N4, second half: the reference's unfinished packer emits the binary code 6 bits per character through int2digit()
+    (n_ary_huffman.c:371-426, :1646-1671).  Against the oracle and, on whole bytes, against RFC 4648 itself."""
+    import base64
+    rng = np.random.default_rng(46)
+    for nbits in (1, 5, 6, 7, 8, 95, 96, 97, 4096 * 8, 1000003, (1 << 23) + 5):
+        nb = (nbits + 7) // 8
+        raw = rng.integers(0, 256, size=nb, dtype=np.uint8)
+        buf = torch.full((nb + 64,), 0xFF, dtype=torch.uint8, device="cuda")   # whatever lies behind the stream must not matter
+        buf[:nb] = _dev(raw)
+        chars = dc.base64url_pack(buf, nbits)
+        want = oracle.base64url_pack(raw, nbits)
+        assert bytes(chars.cpu().numpy()) == want, nbits
+        if nbits % 8 == 0:
+            assert want == base64.urlsafe_b64encode(raw.tobytes()).rstrip(b"=")
+        back, st = dc.base64url_unpack(chars.clone(), nbits)
+        assert int(st.item()) == 0 and np.array_equal(back[:nb].cpu().numpy(), oracle.base64url_unpack(want, nbits))
+    # digit2int() also takes the RFC 4648 standard alphabet (:441-445); anything else is reported
+    raw = rng.integers(0, 256, size=3000, dtype=np.uint8)
+    std = np.frombuffer(base64.b64encode(raw.tobytes()), dtype=np.uint8)
+    back, st = dc.base64url_unpack(_dev(std), 24000)
+    assert int(st.item()) == 0 and np.array_equal(back[:3000].cpu().numpy(), raw)
+    bad = std.copy(); bad[1234] = ord("!")
+    _, st = dc.base64url_unpack(_dev(bad), 24000)
+    assert int(st.item()) == dc.DC_ERR_CORRUPT
+    # the real thing: a binary Huffman payload as text and back, then decoded
+    data = _zipf(dc, 200001, seed=12)
+    table = dc.huff_build(dc.histogram(data), 2)
+    res = dc.huff_encode(data, table)
+    nbits = res.bits()
+    text = dc.base64url_pack(res.payload, nbits)
+    assert text.numel() == (nbits + 5) // 6
+    bits_back, st = dc.base64url_unpack(text.clone(), nbits)
+    out, status = dc.huff_decode(bits_back, nbits, table, data.numel())
+    assert int(st.item()) == 0 and int(status.item()) == 0 and torch.equal(out, data)
+
+
 def test_degenerate_alphabets(dc, oracle):
     # one distinct symbol: 1-bit codes (binary), 128 symbols per 128-bit subsequence
     for n_ary in PACKABLE:

@@ -14,7 +14,8 @@ HOST = os.path.join(ROOT, "data_compression_b200", "host")
 REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
 REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
              "decode_items_with_codes", "write_nybble", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
-             "decompress_bytestring", "dc_container_compress", "dc_container_decompress"]
+             "decompress_bytestring", "nybble_compress", "nybble_decompress", "digit2int", "dc_container_compress",
+             "dc_container_decompress"]
 
 
 @pytest.fixture(scope="module")
@@ -29,6 +30,21 @@ def test_refapi_exports_reference_names(built):
     assert not missing, missing
     assert os.access(os.path.join(HOST, "n_ary_huffman"), os.X_OK)
     assert os.access(os.path.join(HOST, "nybble_compression"), os.X_OK)
+
+
+def test_digit2int_is_the_base64url_table(built):
+    """digit2int() n_ary_huffman.c:428-455: the base64url alphabet, plus '+' and '/' (:441-445).  A host table look-up."""
+    import base64
+    L = ctypes.CDLL(REFAPI)
+    L.digit2int.argtypes = [ctypes.c_char]
+    L.digit2int.restype = ctypes.c_int
+    alphabet = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_"
+    assert [L.digit2int(bytes([c])) for c in alphabet] == list(range(64))
+    assert L.digit2int(b"+") == 62 and L.digit2int(b"/") == 63
+    # the same table as RFC 4648: every 6-bit value through Python's encoder
+    for v in range(64):
+        ch = base64.urlsafe_b64encode(bytes([v << 2]))[:1]
+        assert L.digit2int(ch) == v
 
 
 def test_cli_aborts_without_device(built):

@@ -189,3 +189,23 @@ def test_nybble_compressors_round_trip_property(oracle):
             assert dec_fn(comp) == text
 
     check()
+
+
+def test_base64url_text_form(oracle):
+    """int2digit() n_ary_huffman.c:371-426 is the RFC 4648 base64url alphabet and the unfinished packer emits 6 bits per
+    character (:1646-1671): on whole bytes the text form is Python's urlsafe base64 without padding."""
+    import base64
+    rng = np.random.default_rng(64)
+    for nbytes in (0, 1, 2, 3, 4, 11, 12, 13, 1000, 4099):
+        raw = rng.integers(0, 256, size=nbytes, dtype=np.uint8).tobytes()
+        text = oracle.base64url_pack(raw, 8 * nbytes)
+        assert text == base64.urlsafe_b64encode(raw).rstrip(b"=")
+        assert oracle.base64url_unpack(text, 8 * nbytes).tobytes() == raw
+        std = base64.b64encode(raw).rstrip(b"=")                       # digit2int() also takes '+' and '/' (:441-445)
+        assert oracle.base64url_unpack(std, 8 * nbytes).tobytes() == raw
+    # a bit count that is no multiple of 6 or 8: zero padding in the last character, bits behind the end ignored
+    raw = bytes([0b10110111, 0b01011111])
+    assert oracle.base64url_pack(raw, 11) == b"t0"                       # 101101 = 45 = 't' | 11010(0) = 52 = '0'
+    assert oracle.base64url_unpack(b"t0", 11).tobytes() == bytes([0b10110111, 0b01000000])
+    with pytest.raises(ValueError):
+        oracle.base64url_unpack(b"t!", 11)
