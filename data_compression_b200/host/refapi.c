@@ -102,3 +102,29 @@ int digit2int(char input_digit) {
     done("digit2int", DC_ERR_ARG);
     return -1;
 }
+
+int power(const int base, const int exp) {
+    if (exp < 0) done("power", DC_ERR_ARG);
+    int r = 1;
+    for (int b = base, e = exp; e > 0; e >>= 1, b *= b)
+        if (e & 1) r *= b;
+    return r;
+}
+
+int array_max(const int max_symbol_value, const int canonical_lengths[]) {
+    int m = 0;
+    for (int i = 0; i < max_symbol_value; i++) {
+        if (canonical_lengths[i] < 0) done("array_max", DC_ERR_ARG);
+        if (canonical_lengths[i] > m) m = canonical_lengths[i];
+    }
+    return m;
+}
+
+int array_min(const int max_symbol_value, const int canonical_lengths[]) {
+    int m = 300;
+    for (int i = 0; i < max_symbol_value; i++) {
+        if (canonical_lengths[i] < 0) done("array_min", DC_ERR_ARG);
+        if (canonical_lengths[i] != 0 && canonical_lengths[i] < m) m = canonical_lengths[i];
+    }
+    return m;
+}

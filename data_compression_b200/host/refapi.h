@@ -49,6 +49,14 @@ int decode_items_with_codes(const int max_symbol_value, const int canonical_leng
 /* bits emitted by the last represent_items_with_codes() call (the reference's signature has no slot for it) */
 uint64_t represent_items_last_total_bits(void);
 
+/* n_ary_huffman.c:1317-1327, :1330-1352, :1354-1379, verbatim signatures: integer power; the largest length and the smallest
+ * non-zero length over canonical_lengths[0 .. max_symbol_value) -- the last slot is NOT looked at, as written (300 if every
+ * length is zero).  Scalar helpers over 259 integers: host code (the device table keeps the same two numbers in
+ * dc_huff_table.max_len / .min_len).  A negative length aborts, like the reference's assert. */
+int power(const int base, const int exp);
+int array_max(const int max_symbol_value, const int canonical_lengths[]);
+int array_min(const int max_symbol_value, const int canonical_lengths[]);
+
 /* n_ary_huffman.c:428-455, verbatim signature: the value 0..63 of a base64url digit ('+' and '/' are accepted for 62 and 63,
  * :441-445); aborts on anything else, like the reference's assert.  A table look-up: host code.  The stream forms -- the
  * binary payload as base64url text, 6 bits per character, as the unfinished packer intends (:1646-1671) -- are

@@ -14,7 +14,7 @@ HOST = os.path.join(ROOT, "data_compression_b200", "host")
 REFAPI = os.path.join(ROOT, "data_compression_b200", "libdc_b200_refapi.so")
 REF_NAMES = ["histogram", "huffman", "convert_lengths_to_encode_table", "represent_items_with_codes",
              "decode_items_with_codes", "write_nybble", "nybble_pack_stream", "nybble_unpack_stream", "compress_bytestring",
-             "decompress_bytestring", "nybble_compress", "nybble_decompress", "digit2int", "dc_container_compress",
+             "decompress_bytestring", "nybble_compress", "nybble_decompress", "digit2int", "power", "array_max", "array_min", "dc_container_compress",
              "dc_container_decompress"]
 
 
@@ -45,6 +45,40 @@ def test_digit2int_is_the_base64url_table(built):
     for v in range(64):
         ch = base64.urlsafe_b64encode(bytes([v << 2]))[:1]
         assert L.digit2int(ch) == v
+
+
+def test_length_helpers_match_the_reference(built):
+    """power / array_max / array_min (n_ary_huffman.c:1317-1379) against the unmodified reference functions, incl. the
+    as-written quirk that the last slot is not looked at."""
+    import numpy as np
+    from oracle import pyoracle as O
+    L = ctypes.CDLL(REFAPI)
+    ip = ctypes.POINTER(ctypes.c_int)
+    for f in (L.array_max, L.array_min):
+        f.argtypes = [ctypes.c_int, ip]
+        f.restype = ctypes.c_int
+    L.power.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.power.restype = ctypes.c_int
+    R = O.ref_huff() if O.have_ref() else None
+    if R is not None:
+        for f in (R.array_max, R.array_min):
+            f.argtypes = [ctypes.c_int, ip]
+            f.restype = ctypes.c_int
+        R.power.argtypes = [ctypes.c_int, ctypes.c_int]
+        R.power.restype = ctypes.c_int
+    rng = np.random.default_rng(8)
+    for _ in range(200):
+        ln = rng.integers(0, 16, size=259).astype(np.int32) * (rng.random(259) < rng.random()).astype(np.int32)
+        p = ln.ctypes.data_as(ip)
+        body = ln[:258]
+        assert L.array_max(258, p) == int(body.max())                                  # slot 258 is not looked at (:1336, :1361)
+        assert L.array_min(258, p) == (int(body[body > 0].min()) if (body > 0).any() else 300)
+        if R is not None:
+            assert L.array_max(258, p) == R.array_max(258, p) and L.array_min(258, p) == R.array_min(258, p)
+    for b, e in ((2, 0), (2, 10), (3, 5), (4, 15), (16, 7), (10, 9), (7, 1)):
+        assert L.power(b, e) == b ** e
+        if R is not None:
+            assert L.power(b, e) == R.power(b, e)
 
 
 def test_cli_aborts_without_device(built):
