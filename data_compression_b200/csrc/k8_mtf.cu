@@ -133,8 +133,15 @@ __global__ void __launch_bounds__(256) mtf_reduce_kernel(const unsigned long lon
     if (t >= nchunks * kMtfCtx) return;
     const size_t chunk = t / kMtfCtx, c = t % kMtfCtx;
     const size_t b0 = chunk * kMtfChunk, b1 = min(nblocks, b0 + kMtfChunk);
-    unsigned long long acc = lists[b0 * kMtfCtx + c];
-    for (size_t b = b0 + 1; b < b1; b++) acc = mtf_compose(acc, lists[b * kMtfCtx + c]);
+    // eight loads in flight, then the eight compositions (the chain is serial, the loads are not)
+    unsigned long long acc = kMtfHoles;
+    for (size_t b = b0; b < b1; b += 8) {
+        unsigned long long e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = b + j < b1 ? lists[(b + j) * kMtfCtx + c] : kMtfHoles;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc = mtf_compose(acc, e[j]);
+    }
     chunks[t] = acc;
 }
 
@@ -173,10 +180,15 @@ __global__ void __launch_bounds__(256) mtf_apply_kernel(unsigned long long *__re
     const size_t chunk = t / kMtfCtx, c = t % kMtfCtx;
     const size_t b0 = chunk * kMtfChunk, b1 = min(nblocks, b0 + kMtfChunk);
     unsigned long long st = chunks[t];
-    for (size_t b = b0; b < b1; b++) {
-        const unsigned long long e = lists[b * kMtfCtx + c];
-        lists[b * kMtfCtx + c] = st;
-        st = mtf_compose(st, e);
+    for (size_t b = b0; b < b1; b += 8) {
+        unsigned long long e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = b + j < b1 ? lists[(b + j) * kMtfCtx + c] : kMtfHoles;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (b + j < b1) lists[(b + j) * kMtfCtx + c] = st;
+            st = mtf_compose(st, e[j]);
+        }
     }
 }
 
