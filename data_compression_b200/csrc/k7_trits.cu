@@ -42,14 +42,28 @@ __global__ void __launch_bounds__(kTritThreads) trit_pack_kernel(const uint8_t *
     const unsigned long long t2_bytes = (2 * ntrits + 7) / 8, out_bytes = (ntrits + 4) / 5;
     const unsigned long long nthreads_needed = (ntrits + kTritsPerThread - 1) / kTritsPerThread;
     bool bad = false;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * kTritThreads + threadIdx.x; t < nthreads_needed;
-         t += (unsigned long long)gridDim.x * kTritThreads) {
+    // the next group's five words are loaded while this one is converted (the kernel waits on memory otherwise)
+    const unsigned long long stride = (unsigned long long)gridDim.x * kTritThreads;
+    auto whole = [&](unsigned long long t) { return t < nthreads_needed && t * 20 + 20 <= t2_bytes; };
+    unsigned long long t = (unsigned long long)blockIdx.x * kTritThreads + threadIdx.x;
+    uint32_t nx[5] = {0, 0, 0, 0, 0};
+    bool nx_whole = whole(t);
+    if (nx_whole) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) nx[k] = __ldg((const uint32_t *)(t2 + t * 20) + k);
+    }
+    for (; t < nthreads_needed; t += stride) {
         const unsigned long long ib = t * 20, ob = t * 16;
         uint32_t w[6];
-        if (ib + 20 <= t2_bytes) {
+        const bool cur_whole = nx_whole;
 #pragma unroll
-            for (int k = 0; k < 5; k++) w[k] = bswap32(__ldg((const uint32_t *)(t2 + ib) + k));
-        } else {
+        for (int k = 0; k < 5; k++) w[k] = bswap32(nx[k]);
+        nx_whole = whole(t + stride);
+        if (nx_whole) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) nx[k] = __ldg((const uint32_t *)(t2 + (t + stride) * 20) + k);
+        }
+        if (!cur_whole) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 uint32_t x = 0;
@@ -101,14 +115,19 @@ __global__ void __launch_bounds__(kTritThreads) trit_unpack_kernel(const uint8_t
     const unsigned long long in_bytes = (ntrits + 4) / 5, t2_bytes = (2 * ntrits + 7) / 8;
     const unsigned long long nthreads_needed = (ntrits + kTritsPerThread - 1) / kTritsPerThread;
     bool bad = false;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * kTritThreads + threadIdx.x; t < nthreads_needed;
-         t += (unsigned long long)gridDim.x * kTritThreads) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * kTritThreads;
+    auto whole = [&](unsigned long long t) { return t < nthreads_needed && t * 16 + 16 <= in_bytes && ((uintptr_t)(packed + t * 16) & 15) == 0; };
+    unsigned long long t = (unsigned long long)blockIdx.x * kTritThreads + threadIdx.x;
+    uint4 nx = make_uint4(0, 0, 0, 0);
+    bool nx_whole = whole(t);
+    if (nx_whole) nx = ldg_stream((const uint4 *)(packed + t * 16));
+    for (; t < nthreads_needed; t += stride) {
         const unsigned long long ib = t * 16, ob = t * 20;
-        uint32_t in[4];
-        if (ib + 16 <= in_bytes && ((uintptr_t)(packed + ib) & 15) == 0) {
-            const uint4 v = ldg_stream((const uint4 *)(packed + ib));
-            in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
-        } else {
+        uint32_t in[4] = {nx.x, nx.y, nx.z, nx.w};
+        const bool cur_whole = nx_whole;
+        nx_whole = whole(t + stride);
+        if (nx_whole) nx = ldg_stream((const uint4 *)(packed + (t + stride) * 16));
+        if (!cur_whole) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 uint32_t x = 0;
