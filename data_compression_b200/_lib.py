@@ -40,7 +40,7 @@ class HuffTableStruct(C.Structure):
         ("first_code", C.c_uint32 * 32), ("len_count", C.c_uint32 * 32), ("len_offset", C.c_uint32 * 32),
         ("sorted", C.c_uint16 * (DC_NSLOTS + 1)), ("lut", C.c_uint16 * (1 << DC_LUT_BITS)),
         ("lut_count", C.c_uint32 * DC_LUT_ENTRIES), ("lut_pair", C.c_uint32 * DC_LUT_ENTRIES),
-        ("lut2", C.c_uint16 * (257 * 16)), ("lut2_used", C.c_int32), ("reserved1", C.c_int32), ("lut14", C.c_uint16 * (1 << 14)),
+        ("lut2", C.c_uint16 * (257 * 16)), ("lut2_used", C.c_int32), ("fsm_states", C.c_int32), ("lut14", C.c_uint16 * (1 << 14)),
     ]
 
 

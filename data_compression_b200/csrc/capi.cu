@@ -7,42 +7,52 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "dc_common.cuh"
 
 namespace dc {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
-// ---- per-kernel event timing (dc_profile_*)
+// ---- per-kernel event timing (dc_profile_*).  One mutex guards all of it: launches may come from several host threads.
 struct ProfPair { cudaEvent_t a, b; int id; };
-static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfPair> g_prof_pending;
 static std::vector<cudaEvent_t> g_prof_pool;
-static cudaEvent_t g_prof_open[DC_K_COUNT];
 static double g_prof_ms[DC_K_COUNT];
 static unsigned long long g_prof_n[DC_K_COUNT];
 
-static cudaEvent_t prof_event() {
+static cudaEvent_t prof_event() {   // caller holds g_prof_mu
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e = nullptr;
     cudaEventCreate(&e);
     return e;
 }
-void prof_begin(int id, cudaStream_t st) {
-    if (!g_prof_on || id < 0 || id >= DC_K_COUNT) return;
-    g_prof_open[id] = prof_event();
-    cudaEventRecord(g_prof_open[id], st);
+// the opening event travels in the LaunchScope that made it, so concurrent launches of one kernel group do not share state
+void *prof_begin(int id, cudaStream_t st) {
+    if (!g_prof_on.load(std::memory_order_relaxed) || id < 0 || id >= DC_K_COUNT) return nullptr;
+    cudaEvent_t e;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        e = prof_event();
+    }
+    cudaEventRecord(e, st);
+    return (void *)e;
 }
-void prof_end(int id, cudaStream_t st) {
-    if (!g_prof_on || id < 0 || id >= DC_K_COUNT || !g_prof_open[id]) return;
-    ProfPair p = {g_prof_open[id], prof_event(), id};
-    g_prof_open[id] = nullptr;
+void prof_end(int id, cudaStream_t st, void *open) {
+    if (!open) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfPair p = {(cudaEvent_t)open, prof_event(), id};
     cudaEventRecord(p.b, st);
     g_prof_pending.push_back(p);
 }
-static void prof_collect() {
+static void prof_collect() {   // caller holds g_prof_mu
     for (const ProfPair &p : g_prof_pending) {
         float ms = 0.f;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
@@ -55,15 +65,33 @@ static void prof_collect() {
     g_prof_pending.clear();
 }
 
+// per-device facts, looked up by the CURRENT device of the calling thread
+static std::mutex g_dev_mu;
+static int g_sm_count[64];
 int sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;  // B200
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_sm_count[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        g_sm_count[dev] = sms;
     }
-    return sms;
+    return g_sm_count[dev];
+}
+// opt-in dynamic shared memory of a kernel: the attribute is per device and only ever grows (it is a limit, not a request)
+static std::map<std::pair<int, const void *>, size_t> g_smem_limit;
+cudaError_t ensure_dynamic_smem(const void *func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    size_t &limit = g_smem_limit[std::make_pair(dev, func)];
+    if (bytes <= limit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) limit = bytes;
+    return e;
 }
 
 // grow-only device scratch for the host-pointer entry points (single-threaded use, like the reference)
@@ -115,20 +143,23 @@ extern "C" int dc_device_count(void) {
     return n;
 }
 
-extern "C" uint64_t dc_launch_count(void) { return g_launches; }
+extern "C" uint64_t dc_launch_count(void) { return g_launches.load(); }
 
 extern "C" int dc_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!on) prof_collect();
     g_prof_on = on != 0;
     return DC_OK;
 }
 extern "C" int dc_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_collect();
     for (int i = 0; i < DC_K_COUNT; i++) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
     return DC_OK;
 }
 extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
     if (id < 0 || id >= DC_K_COUNT) return DC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_collect();
     if (total_ms) *total_ms = g_prof_ms[id];
     if (launches) *launches = g_prof_n[id];
@@ -136,7 +167,7 @@ extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
 }
 extern "C" const char *dc_profile_kernel_name(int id) {
     static const char *names[DC_K_COUNT] = {"histogram", "table", "bits_for_hist", "encode_count", "encode_scan", "encode", "encode_mid", "encode_wide", "decode_sync", "decode_handoff",
-                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "b64_pack", "b64_unpack", "mtf_walk", "mtf_scan", "mtf_resolve", "text_batch", "synth"};
+                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "b64_pack", "b64_unpack", "mtf_walk", "mtf_scan", "mtf_resolve", "text_batch", "synth", "decode_fsm_build", "decode_fsm_sync", "decode_fsm_write", "encode_plan", "encode_fast"};
     return id >= 0 && id < DC_K_COUNT ? names[id] : "?";
 }
 

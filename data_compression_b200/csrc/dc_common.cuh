@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "dc_b200.h"
 
 namespace dc {
@@ -11,17 +13,18 @@ namespace dc {
 // every kernel launch in the library goes through LaunchScope: it feeds the launch counter (bench
 // "gpu_launches") and, when dc_profile_enable(1) was called, brackets the launch with CUDA events on the
 // launching stream so per-kernel durations can be read back (dc_profile_kernel).
-extern unsigned long long g_launches;
-void prof_begin(int kernel_id, cudaStream_t st);
-void prof_end(int kernel_id, cudaStream_t st);
+extern std::atomic<unsigned long long> g_launches;
+void *prof_begin(int kernel_id, cudaStream_t st);            // returns the opening event (nullptr when profiling is off)
+void prof_end(int kernel_id, cudaStream_t st, void *open);
 struct LaunchScope {
     int id;
     cudaStream_t st;
+    void *open;
     LaunchScope(int kernel_id, cudaStream_t stream) : id(kernel_id), st(stream) {
-        g_launches++;
-        prof_begin(id, st);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        open = prof_begin(id, st);
     }
-    ~LaunchScope() { prof_end(id, st); }
+    ~LaunchScope() { prof_end(id, st, open); }
 };
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? DC_OK : DC_ERR_CUDA; }
@@ -32,8 +35,10 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? DC_OK : DC_ERR
         if (_e != cudaSuccess) return DC_ERR_CUDA; \
     } while (0)
 
-// SM count of the current device (cached); the grids below are sized in multiples of it
+// SM count of the current device (cached per device); the grids below are sized in multiples of it
 int sm_count();
+// raise a kernel's opt-in dynamic shared memory limit on the current device if `bytes` needs it (per device, thread-safe)
+cudaError_t ensure_dynamic_smem(const void *func, size_t bytes);
 
 // K2 internals shared with the host-pointer entry points (generic alphabets, raw arrays)
 struct TableRaw {
@@ -60,6 +65,33 @@ size_t mtf_workspace_bytes(size_t n);
 int mtf_positions(const uint8_t *d_src, size_t n, uint8_t *d_pos, void *d_ws, cudaStream_t st);
 // d_buf[1..*d_len): bytes with bit 7 are 0x80 | position and are replaced by the letter they mean (only if *d_mode == 0)
 int mtf_resolve(uint8_t *d_buf, const unsigned long long *d_len, const int32_t *d_mode, cudaStream_t st);
+
+// ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
+constexpr int kFsmMaxStates = 256;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates (9 bits)
+// Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.
+__host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_t *count, int min_len, int max_len, int bpd,
+                                            uint32_t *ilo, uint32_t *ihi, uint32_t *base) {
+    if (!(bpd == 1 || bpd == 2 || bpd == 4)) return 0;
+    if (min_len < 1 || max_len < min_len || max_len >= 16) return 0;
+    if (min_len * bpd < 2) return 0;   // a 1-bit code: up to 8 symbols per byte
+    if (count[max_len] == 0) return 0;
+    const unsigned long long last = (unsigned long long)first[max_len] + count[max_len] - 1;
+    if (last >> (bpd * max_len)) return 0;   // over-subscribed lengths: values do not fit their digits
+    unsigned total = 0;
+    for (int d = 0; d < max_len; d++) {
+        const unsigned long long lo = d < min_len ? 0ull : (unsigned long long)first[d] + count[d];
+        const unsigned long long hi = last >> (bpd * (max_len - d));
+        if (hi < lo) return 0;
+        if (d >= min_len && d + 1 <= max_len && (unsigned long long)first[d + 1] != (lo << bpd)) return 0;   // not the canonical chain
+        ilo[d] = (uint32_t)lo;
+        ihi[d] = (uint32_t)hi;
+        base[d] = total;
+        total += (unsigned)(hi - lo + 1);
+        if (total > (unsigned)kFsmMaxStates) return 0;
+    }
+    if (min_len <= max_len && first[min_len] != 0) return 0;
+    return (int)total;
+}
 
 // ---------------------------------------------------------------- device helpers
 

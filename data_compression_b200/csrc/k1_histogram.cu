@@ -198,8 +198,7 @@ int launch_histogram(const uint8_t *d_in, size_t n, unsigned long long *d_hist, 
             if (R == 2) hist_warp_atomic_kernel<2><<<grid, 256, smem, st>>>(d_in, n, d_hist);
             else if (R == 4) hist_warp_atomic_kernel<4><<<grid, 256, smem, st>>>(d_in, n, d_hist);
             else {
-                static bool attr = false;
-                if (!attr) { cudaFuncSetAttribute(hist_warp_atomic_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+                DC_CUDA_TRY(ensure_dynamic_smem((const void *)hist_warp_atomic_kernel<8>, smem));
                 hist_warp_atomic_kernel<8><<<grid, 256, smem, st>>>(d_in, n, d_hist);
             }
             break;

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
     const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead (block-uniform)
     if (!need2) {
-        if (tid == 0) { tab->lut2_used = 0; tab->reserved1 = 0; }
+        if (tid == 0) tab->lut2_used = 0;
     } else {
         __syncthreads();
         unsigned char *s_flag = (unsigned char *)s_scnt;     // [4096] 1 = this window is the prefix of 13..16-bit codes
@@ -344,7 +344,6 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
             }
             if (tid == 0) {
                 tab->lut2_used = total < DC_LUT2_SUBTABLES ? total : DC_LUT2_SUBTABLES;
-                tab->reserved1 = 0;
             }
         }
         __syncthreads();
@@ -396,6 +395,10 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         tab->packed_radix = t2 ? 3 : 0;
         tab->total_symbols = s_totsym;
         tab->total_bits = s_totbits;
+        // the byte-stepped decoder (k4_fsm.cuh) applies if the code tree has at most 256 internal nodes, no 1-bit code
+        uint32_t cnt[32], ilo[32], ihi[32], base[32];
+        for (int d = 0; d < 32; d++) cnt[d] = (d >= min_len && d <= max_len) ? s_lencount[d] : 0u;
+        tab->fsm_states = (status == DC_OK && !t2 && max_len < 16) ? fsm_geometry(s_first, cnt, min_len, max_len, bpd, ilo, ihi, base) : 0;
     }
 }
 

@@ -759,12 +759,8 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
         sp.bleft = ws.bleft;
         sp.bright = ws.bright;
         const size_t smem12 = (size_t)kEncWarps * sp_stage_words(kSpTightBits) * 4, smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
-        static bool attr = false;
-        if (!attr) {
-            DC_CUDA_TRY(cudaFuncSetAttribute(encode_single_kernel<kSpTightBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12));
-            DC_CUDA_TRY(cudaFuncSetAttribute(encode_single_kernel<kNarrowBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            attr = true;
-        }
+        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kSpTightBits>, smem12));
+        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kNarrowBits>, smem16));
         {   // the instantiation that does not match the table returns before it takes a ticket
             LaunchScope ls(DC_K_ENCODE, st);
             encode_single_kernel<kSpTightBits><<<nruns, kEncThreads, smem12, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,

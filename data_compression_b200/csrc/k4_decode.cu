@@ -625,7 +625,9 @@ struct FastWorkspace {
     uint32_t *seg_cnt, *seg_assumed, *seg_exit;      // [nseg]
     unsigned long long *seg_off;                     // [nseg]
     int32_t *mismatch;                               // F2: some segment started on a wrong guess
+    void *fsm;                                       // byte-stepped decoder: header + F1 table + F3 table (k4_fsm.cuh)
     __host__ __device__ int32_t *bad_input() const { return mismatch + 2; }  // F1 (T2 streams): a 2-bit field of 3; zeroed per launch
+    __host__ __device__ uint32_t *start_slot() const { return (uint32_t *)(mismatch + 3); }  // FSM F1 -> F3: the first segment's start token
 };
 
 // A warp's view of its segment: 32-bit positions relative to the segment start, tiles streamed through
@@ -669,6 +671,10 @@ struct SegCursor {
         w[8] = lane == 31 ? wrap : right;
     }
 };
+
+}  // namespace dc
+#include "k4_fsm.cuh"
+namespace dc {
 
 // ------------------------------------------------------------------------------------------ F1
 template <int MODE>
@@ -991,7 +997,8 @@ static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbi
     o[8] = take(nseg * 4);        // fast: seg_assumed
     o[9] = take(nseg * 4);        // fast: seg_exit
     o[10] = take(nseg * 8);       // fast: seg_off
-    if (off) for (int i = 0; i < 11; i++) off[i] = o[i];
+    o[11] = take(kFsmWorkspaceBytes);  // byte-stepped decoder: its tables (built per call from the code table)
+    if (off) for (int i = 0; i < 12; i++) off[i] = o[i];
     if (nsub_out) *nsub_out = nsub;
     if (ntiles_out) *ntiles_out = ntiles;
     return p;
@@ -1035,11 +1042,7 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
         decode_scan_kernel<<<1, 1024, 0, st>>>(ws, ntiles, n_out, d_status);
     }
     const size_t smem4 = ((sizeof(DecTables) + 15) & ~(size_t)15) + (kTileWords + kHaloWords) * 4 + kDecStageBytes;
-    static bool attr = false;
-    if (!attr) {
-        DC_CUDA_TRY(cudaFuncSetAttribute(decode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        attr = true;
-    }
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)decode_write_kernel, smem4));
     const int grid4 = (int)(ntiles < (unsigned long long)sms * 4 ? ntiles : (unsigned long long)sms * 4);
     LaunchScope ls(DC_K_DECODE_WRITE, st);
     decode_write_kernel<<<grid4, kDecThreads, smem4, st>>>(d_bits, end, d_table, ws, nsub, ntiles, d_out, n_out, d_status);
@@ -1048,16 +1051,34 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 
 
 constexpr int kSyncW14 = 0x10;
-// which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table)
+constexpr int kModeFsm = 0x20;   // the byte-stepped kernels of k4_fsm.cuh; bits 20..28: states, bits 29..31: min(shortest code's bits, 8) - 1
+static int decode_force_mode();
+// which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table, lut2_used, fsm_states)
 static int fast_mode(const int32_t *tmeta) {
     if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
-    if (tmeta[7] <= DC_LUT_BITS) return 0;                          // max_bits against the 12-bit index
-    const int sub = tmeta[10] < 0 ? 0 : (tmeta[10] > DC_LUT2_SUBTABLES ? DC_LUT2_SUBTABLES : tmeta[10]);
-    return (tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1) | (sub << 8);   // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
+    int mode;
+    if (tmeta[7] <= DC_LUT_BITS) {
+        mode = 0;                          // max_bits against the 12-bit index
+    } else {
+        const int sub = tmeta[10] < 0 ? 0 : (tmeta[10] > DC_LUT2_SUBTABLES ? DC_LUT2_SUBTABLES : tmeta[10]);
+        mode = (tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1) | (sub << 8);   // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
+    }
+    if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxStates && decode_force_mode() != 3) {
+        const int min_bits = tmeta[5] * tmeta[1];
+        mode |= kModeFsm | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
+    }
+    return mode;
 }
 static int write_mode(int mode) { return mode & 3; }
-static int lut2_tables(int mode) { return mode >> 8; }   // second-level tables in use (F3 keeps only those in shared memory)
+static int lut2_tables(int mode) { return (mode >> 8) & 0x1FF; }   // second-level tables in use (F3 keeps only those in shared memory)
 static int sync_mode(int mode) { return (mode & kSyncW14) ? 4 : (mode & 3); }
+static int fsm_states(int mode) { return (mode >> 20) & 0x1FF; }
+static int fsm_min_bits(int mode) { return (int)(((unsigned)mode >> 29) & 7u) + 1; }
+// a stream whose first code does not start on a digit boundary of the byte grid keeps the window kernels
+static int mode_for_start(int mode, int bpd, unsigned long long start) {
+    if ((mode & kModeFsm) && !(start & kFsmToken) && bpd > 0 && start % (unsigned)bpd != 0) mode &= ~kModeFsm;
+    return mode;
+}
 
 // staging tile per warp of the write kernel: a lane decodes at most 256 / min_bits symbols, plus the code that crosses its end
 static uint32_t fast_stage_bytes(const int32_t *tmeta) {
@@ -1068,14 +1089,78 @@ static uint32_t fast_stage_bytes(const int32_t *tmeta) {
 // the write kernel's dynamic shared memory limit only ever grows (the attribute is a limit, not a request: setting it
 // lower for one table would make the next launch for a table with shorter codes fail)
 static cudaError_t ensure_write_smem(size_t smem3) {
-    static size_t limit = 0;
-    if (smem3 <= limit) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(decode_fast_write_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_fast_write_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-    if (e == cudaSuccess) limit = smem3;
+    cudaError_t e = ensure_dynamic_smem((const void *)decode_fast_write_kernel<0>, smem3);
+    if (e == cudaSuccess) e = ensure_dynamic_smem((const void *)decode_fast_write_kernel<1>, smem3);
+    if (e == cudaSuccess) e = ensure_dynamic_smem((const void *)decode_fast_write_kernel<2>, smem3);
+    if (e == cudaSuccess) e = ensure_dynamic_smem((const void *)decode_fast_write_kernel<3>, smem3);
     return e;
+}
+
+// ---- the byte-stepped kernels (k4_fsm.cuh)
+static uint32_t fsm_stage_bytes(int mode) {   // half a tile always fits: 16 lanes x the most symbols a lane can hold
+    const uint32_t per_lane = (uint32_t)(kF_SubBits / fsm_min_bits(mode)) + 2u;
+    return (16u * per_lane + 48u + 15u) & ~15u;
+}
+static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsigned long long end, unsigned long long nsubf,
+                           unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, int mode,
+                           DecodeChain *chain, int lead, cudaStream_t st) {
+    const int nstates = fsm_states(mode);
+    const FsmTables t = fsm_tables_at(fw.fsm);
+    {
+        LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
+        fsm_build_kernel<<<nstates + 1, 256, 0, st>>>(d_table, t);
+    }
+    const size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
+    const int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
+    const int per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)fsm_sync_kernel, smem));
+    const unsigned long long want = (nseg + (threads / 32) - 1) / (threads / 32), cap = (unsigned long long)sm_count() * per_sm;
+    FsmSyncArgs a;
+    a.d_bits = d_bits;
+    a.end = end;
+    a.nsub = nsubf;
+    a.ntiles = nwt;
+    a.nseg = nseg;
+    a.start_token = (uint32_t)start;
+    a.lead = lead;
+    a.chain = chain;
+    LaunchScope ls(DC_K_DECODE_FSM_SYNC, st);
+    fsm_sync_kernel<<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
+    return cuda_status(cudaGetLastError());
+}
+static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
+                            unsigned long long nseg, FastWorkspace fw, uint8_t *d_out, size_t n_out, int32_t *d_status, int mode,
+                            int lead, cudaStream_t st) {
+    const int rows = fsm_states(mode) + 1;   // + DEAD
+    const FsmTables t = fsm_tables_at(fw.fsm);
+    const uint32_t stage = fsm_stage_bytes(mode);
+    const size_t budget = 227 * 1024 - 1024;
+    int warps = 24;
+    size_t hot = rows;
+    if (kFsmHeaderBytes + hot * kFsmWriteRowBytes + (size_t)warps * stage > budget)
+        hot = (budget - kFsmHeaderBytes - (size_t)warps * stage) / kFsmWriteRowBytes;
+    const bool split = hot < (size_t)rows;
+    const size_t smem = kFsmHeaderBytes + hot * kFsmWriteRowBytes + (size_t)warps * stage;
+    const int per_sm = smem <= 56 * 1024 ? 2 : 1;   // (2 x 768 threads: the register file allows no more)
+    DC_CUDA_TRY(ensure_dynamic_smem(split ? (const void *)fsm_write_kernel<true> : (const void *)fsm_write_kernel<false>, smem));
+    const unsigned long long want = (nseg + warps - 1) / warps, cap = (unsigned long long)sm_count() * per_sm;
+    FsmWriteArgs a;
+    a.d_bits = d_bits;
+    a.end = end;
+    a.nsub = nsubf;
+    a.ntiles = nwt;
+    a.nseg = nseg;
+    a.out = d_out;
+    a.n_out = n_out;
+    a.lead = lead;
+    a.stage_bytes = stage;
+    a.hot_rows = (uint32_t)hot;
+    a.d_status = d_status;
+    LaunchScope ls(DC_K_DECODE_FSM_WRITE, st);
+    const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+    if (split) fsm_write_kernel<true><<<grid, warps * 32, smem, st>>>(a, t, fw);
+    else fsm_write_kernel<false><<<grid, warps * 32, smem, st>>>(a, t, fw);
+    return cuda_status(cudaGetLastError());
 }
 
 // F1 + F2, then F3, over `nwt` warp tiles of the bitstream at d_bits (`end` = end of the STREAM in bits from d_bits; a chunk
@@ -1087,6 +1172,10 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
                             DecodeChain *host_chain = nullptr) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
+    if (mode & kModeFsm) {
+        const int rc = launch_fsm_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, mode, chain, lead, st);
+        if (rc != DC_OK) return rc;
+    } else {
     if (mode_t2(write_mode(mode))) DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));
     {
         LaunchScope ls(DC_K_DECODE_FAST_SYNC, st);
@@ -1096,9 +1185,10 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
         if (sm == 0) DC_F1(0); else if (sm == 1) DC_F1(1); else if (sm == 2) DC_F1(2); else if (sm == 3) DC_F1(3); else DC_F1(4);
 #undef DC_F1
     }
+    }
     {
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, mode_t2(write_mode(mode)) ? 1 : 0, host_chain);
+        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1106,6 +1196,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
 static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
                              unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out, size_t n_out,
                              int32_t *d_status, int mode, uint32_t stage_bytes, int lead, cudaStream_t st) {
+    if (mode & kModeFsm) return launch_fsm_write(d_bits, end, nsubf, nwt, nseg, fw, d_out, n_out, d_status, mode, lead, st);
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     const uint32_t tables_bytes = (uint32_t)fast_tables_bytes(write_mode(mode), lut2_tables(mode));
@@ -1175,20 +1266,21 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     fw.seg_assumed = (uint32_t *)(w + off[8]);
     fw.seg_exit = (uint32_t *)(w + off[9]);
     fw.seg_off = (unsigned long long *)(w + off[10]);
+    fw.fsm = w + off[11];
     const unsigned long long end = bit_start + nbits;
     const unsigned long long nsubf = (end + kF_SubBits - 1) / kF_SubBits;
     const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
     const unsigned long long sms = (unsigned long long)sm_count();
 
     // the table must be usable before any bit is interpreted
-    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
     DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DC_CUDA_TRY(cudaStreamSynchronize(st));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
 
-    const int mode = fast_mode(tmeta);
+    const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], bit_start);
     const int force = decode_force_mode();
     if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
@@ -1217,7 +1309,7 @@ struct ShardGeom {
     int lead;
     FastWorkspace fw;
     DecodeChain *chain;
-    int mode;
+    int mode, bpd;
     uint32_t stage_bytes;
 };
 }  // namespace
@@ -1245,14 +1337,17 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
     g->fw.seg_assumed = (uint32_t *)(w + off[8]);
     g->fw.seg_exit = (uint32_t *)(w + off[9]);
     g->fw.seg_off = (unsigned long long *)(w + off[10]);
+    g->fw.fsm = w + off[11];
+
     g->chain = (DecodeChain *)(w + 32);
-    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
     DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DC_CUDA_TRY(cudaStreamSynchronize(st));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     g->mode = fast_mode(tmeta);
+    g->bpd = tmeta[1];
     g->stage_bytes = fast_stage_bytes(tmeta);
     return DC_OK;
 }
@@ -1260,11 +1355,16 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
 extern "C" int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, unsigned first_code_bit, uint64_t shard_bits,
                                          uint64_t stream_bits_left, const dc_huff_table *d_table, dc_shard_summary *d_summary,
                                          void *d_workspace, size_t workspace_bytes, void *stream) {
-    if (!d_summary || (!has_halo && first_code_bit >= (unsigned)kSubBits)) return DC_ERR_ARG;
+    if (!d_summary || (!has_halo && !(first_code_bit & kFsmToken) && first_code_bit >= (unsigned)kSubBits)) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     ShardGeom g;
     int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
     if (rc != DC_OK) return rc;
+    if (!has_halo) {
+        if ((first_code_bit & kFsmToken) && !(g.mode & kModeFsm)) return DC_ERR_ARG;   // a state token, but the table has no state machine
+        g.mode = mode_for_start(g.mode, g.bpd, first_code_bit);
+    }
+    DC_CUDA_TRY(cudaMemcpyAsync(g.fw.mismatch + 1, &g.mode, sizeof(int), cudaMemcpyHostToDevice, st));   // the write phase takes the same kernels
     DecodeChain init = {0ull, has_halo ? 0u : first_code_bit, 0, 0u, 0u};
     DC_CUDA_TRY(cudaMemcpyAsync(g.chain, &init, sizeof init, cudaMemcpyHostToDevice, st));
     // (F2 never checks the symbol total here: last_chunk = 0; the caller checks the sum over all shards)
@@ -1283,6 +1383,8 @@ extern "C" int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, u
     ShardGeom g;
     int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
     if (rc != DC_OK) return rc;
+    DC_CUDA_TRY(cudaMemcpyAsync(&g.mode, g.fw.mismatch + 1, sizeof(int), cudaMemcpyDeviceToHost, st));   // what the sync phase decided
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
     return launch_fast_write(g.base, g.end, g.nsubf, g.nwt, g.nseg, d_table, g.fw, d_out, n_out, d_status, g.mode, g.stage_bytes, g.lead, st);
 }
 
@@ -1357,12 +1459,13 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
     fw.seg_assumed = (uint32_t *)(w + off[8]);
     fw.seg_exit = (uint32_t *)(w + off[9]);
     fw.seg_off = (unsigned long long *)(w + off[10]);
+    fw.fsm = w + off[11];
     DecodeChain *d_chain = (DecodeChain *)(w + 32);
 
     // the table (built on the legacy stream by the caller) must be usable before any bit is interpreted
-    int32_t tmeta[12];   // the table's first ten words, then lut2_used
+    int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
     DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
     DC_CUDA_TRY(cudaStreamSynchronize(0));
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;

@@ -1,0 +1,586 @@
+// k4_fsm.cuh -- K4, byte-stepped decoder: the code as a finite-state machine that eats one BYTE per table look-up.
+// (Included by k4_decode.cu, which owns the workspace, the scan kernel F2 and the entry points.)
+//
+// Why.  The window decoders in k4_decode.cu spend ~8 instructions per look-up (funnel shift, index, address, LDS, position
+// update, count update, compare, branch), most of them on the half-rate integer ALU pipe, and every 32-bit word of a
+// lane's subsequence is its own data-dependent loop, so a warp runs the slowest lane's trip count (ncu, round 1: 555 M +
+// 604 M warp instructions per GiB, ALU pipe 55-60 %, a third of the lane slots idle).  A prefix code read from a byte
+// boundary is fully described by WHERE INSIDE A CODE the boundary falls -- one of the internal nodes of the code tree,
+// at most 256 of them for byte alphabets.  So the tables here are indexed by (state, next byte):
+//   F1  u16  number of codes that END in this byte | next state << 8
+//   F3  u64  up to four decoded symbols | PRMT selector 0x3210 + 0x1111 * count | next state << 16
+// and a walk is 32 fixed, fully unrolled steps per 256-bit subsequence: no positions, no windows, no look-ahead word,
+// no loop condition, no divergence, codes of any length at the same speed.  F1: PRMT (index = state, byte) + IMAD +
+// LDS + IADD per byte.  F3: the symbols of a step are appended to a 4-byte sliding window with one PRMT whose selector
+// comes from the table, completed 32-bit words go to the staging tile with a predicated STS (so the shared-memory
+// stores are words, not bytes), and the fill state advances with one IMAD: 4 ALU + 3 FMA + 2 LSU slots per byte.
+//
+// States.  Canonical n-ary code (n = 2, 4, 16; a digit is bpd bits): at depth d (digits) the values
+// [first[d], first[d] + count[d]) are leaves, [ilo[d], ihi[d]] = [first[d] + count[d], last >> bpd (max_len - d)] are
+// internal nodes, everything above is an unused slot (the reference's dummy leaves).  State id = base[d] + (v -
+// ilo[d]): breadth first, the root is 0.  Streams whose codes start on digit boundaries relative to the BYTE grid only
+// ever stop on such nodes at byte boundaries (bit_start % bpd == 0; anything else takes the window kernels).
+// An unused slot sends F1 back to the root (legal on speculative paths, as in the window kernels) and F3, which only
+// walks true paths, into an absorbing DEAD state that is reported as DC_ERR_CORRUPT.
+//
+// Eligibility (fsm_geometry): bpd in {1, 2, 4}, shortest code >= 2 bits (at most 4 symbols per byte, 128 per
+// subsequence), <= 256 internal nodes, lengths < 16 digits.  Everything else (radix 3, 1-bit codes) keeps the window
+// kernels.  The first tile of a stream that does not start on a byte boundary and the ragged last tile are walked digit
+// by digit by a generic routine (two tiles per call).
+#pragma once
+
+namespace dc {
+
+constexpr int kFsmMaxDepth = 32;
+constexpr uint32_t kFsmToken = 0x80000000u;   // start / exit tokens of the FSM path: kFsmToken | state (else: a bit offset)
+
+struct FsmHeader {
+    int32_t nstates, bpd, n_ary, min_len, max_len, reserved[3];
+    uint32_t first[kFsmMaxDepth], count[kFsmMaxDepth], off[kFsmMaxDepth];
+    uint32_t ilo[kFsmMaxDepth], ihi[kFsmMaxDepth], base[kFsmMaxDepth];
+    uint16_t sorted[DC_NSLOTS + 1];
+};
+constexpr size_t kFsmHeaderBytes = (sizeof(FsmHeader) + 255) & ~(size_t)255;
+constexpr size_t kFsmSyncRowBytes = 256 * sizeof(uint16_t);            // F1: one state
+constexpr size_t kFsmWriteRowBytes = 256 * sizeof(unsigned long long); // F3: one state
+constexpr size_t kFsmSyncTableBytes = kFsmMaxStates * kFsmSyncRowBytes;
+constexpr size_t kFsmWriteTableBytes = (kFsmMaxStates + 1) * kFsmWriteRowBytes;
+constexpr size_t kFsmWorkspaceBytes = kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes;
+
+struct FsmTables {   // where the three pieces live in the decode workspace
+    FsmHeader *hdr;
+    uint16_t *sync;
+    unsigned long long *write;
+};
+static inline FsmTables fsm_tables_at(void *p) {
+    char *c = (char *)p;
+    FsmTables t;
+    t.hdr = (FsmHeader *)c;
+    t.sync = (uint16_t *)(c + kFsmHeaderBytes);
+    t.write = (unsigned long long *)(c + kFsmHeaderBytes + kFsmSyncTableBytes);
+    return t;
+}
+
+// one digit x from node (d, v): a symbol (>= 0), nothing (-1, inside a code) or an unused slot (-2); (d, v) = next node
+__device__ __forceinline__ int fsm_digit(const FsmHeader *h, int &d, uint32_t &v, uint32_t x) {
+    d++;
+    v = (v << h->bpd) | x;
+    if (d >= h->min_len) {
+        const uint32_t c = h->count[d], f = h->first[d];
+        if (c && v >= f && v - f < c) {
+            const int sym = (int)(h->sorted[h->off[d] + (v - f)] & 0xFFu);
+            d = 0;
+            v = 0;
+            return sym;
+        }
+    }
+    if (d < h->max_len && v >= h->ilo[d] && v <= h->ihi[d]) return -1;
+    d = 0;
+    v = 0;
+    return -2;
+}
+__device__ __forceinline__ uint32_t fsm_state_id(const FsmHeader *h, int d, uint32_t v) { return h->base[d] + (v - h->ilo[d]); }
+__device__ __forceinline__ void fsm_state_node(const FsmHeader *h, uint32_t id, int &d, uint32_t &v) {
+    int dd = 0;
+    while (dd + 1 < h->max_len && h->base[dd + 1] <= id) dd++;
+    d = dd;
+    v = h->ilo[dd] + (id - h->base[dd]);
+}
+
+// ------------------------------------------------------------------------------------------ table build
+// grid = nstates + 1 CTAs of 256 threads: CTA s fills row s of both tables (thread = byte value); row nstates is DEAD.
+__global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t) {
+    __shared__ FsmHeader h;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kFsmMaxDepth; i += 256) {
+        h.first[i] = tab->first_code[i];
+        h.count[i] = tab->len_count[i];
+        h.off[i] = tab->len_offset[i];
+        h.ilo[i] = h.ihi[i] = h.base[i] = 0;
+    }
+    for (int i = tid; i <= DC_NSLOTS; i += 256) h.sorted[i] = tab->sorted[i];
+    __syncthreads();
+    if (tid == 0) {
+        h.bpd = tab->bits_per_digit;
+        h.n_ary = tab->n_ary;
+        h.min_len = tab->min_len;
+        h.max_len = tab->max_len;
+        // lengths outside [min_len, max_len] have no codes (K2 scans skip the last slot, as the reference does)
+        for (int d = 0; d < kFsmMaxDepth; d++)
+            if (d < h.min_len || d > h.max_len) h.count[d] = 0;
+        h.nstates = (tab->status == DC_OK && tab->packed_radix == 0)
+                        ? fsm_geometry(h.first, h.count, h.min_len, h.max_len, h.bpd, h.ilo, h.ihi, h.base) : 0;
+        h.reserved[0] = h.reserved[1] = h.reserved[2] = 0;
+    }
+    __syncthreads();
+    const int ns = h.nstates;
+    if (blockIdx.x == 0) {
+        uint32_t *dst = (uint32_t *)t.hdr;
+        const uint32_t *src = (const uint32_t *)&h;
+        for (int i = tid; i < (int)(sizeof(FsmHeader) / 4); i += 256) dst[i] = src[i];
+    }
+    const int s = blockIdx.x;
+    if (ns == 0 || s > ns) return;
+    if (s == ns) {  // DEAD: absorbs everything, emits nothing
+        t.write[(size_t)s * 256 + tid] = (unsigned long long)(0x3210u | ((uint32_t)ns << 16)) << 32;
+        return;
+    }
+    int d0;
+    uint32_t v0;
+    fsm_state_node(&h, (uint32_t)s, d0, v0);
+    const int bpd = h.bpd, steps = 8 / bpd;
+    const uint32_t mask = (1u << bpd) - 1u;
+    {   // F1: an unused slot sends the walk back to the root
+        int d = d0;
+        uint32_t v = v0, cnt = 0;
+        for (int k = 0; k < steps; k++) {
+            const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
+            cnt += r >= 0;
+        }
+        t.sync[(size_t)s * 256 + tid] = (uint16_t)(cnt | (fsm_state_id(&h, d, v) << 8));
+    }
+    {   // F3: an unused slot is the end of the true path
+        int d = d0;
+        uint32_t v = v0, cnt = 0, syms = 0, next = 0;
+        bool dead = false;
+        for (int k = 0; k < steps && !dead; k++) {
+            const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
+            if (r >= 0) { syms |= (uint32_t)r << (8 * cnt); cnt++; }
+            dead = r == -2;
+        }
+        next = dead ? (uint32_t)ns : fsm_state_id(&h, d, v);
+        const uint32_t meta = (0x3210u + 0x1111u * cnt) | (next << 16);
+        t.write[(size_t)s * 256 + tid] = (unsigned long long)syms | ((unsigned long long)meta << 32);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16_at(uint32_t base, uint32_t idx) {
+    uint32_t v;
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(v) : "r"(idx), "r"(base));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64_at(uint32_t base, uint32_t idx) {
+    uint2 v;
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %2, 8, %3;\n\tld.shared.v2.u32 {%0, %1}, [a];\n\t}" : "=r"(v.x), "=r"(v.y) : "r"(idx), "r"(base));
+    return v;
+}
+
+// bit i (0 = first bit of the stream buffer, MSB first within a byte) .. as `bpd` bits; the caller keeps i + bpd <= limit
+__device__ __forceinline__ uint32_t stream_digit(const uint8_t *__restrict__ bits, unsigned long long i, int bpd) {
+    const uint32_t b = __ldg(bits + (i >> 3));
+    return (b >> (8 - bpd - (int)(i & 7))) & ((1u << bpd) - 1u);
+}
+
+// generic walk of bits [p, lim) of the stream from node (d, v); symbols go to `sink(sym)`.  Returns the symbol count;
+// `dead` is set when an unused slot was met.  (The slow tiles: the first one of a stream that starts inside a byte, and
+// the last one.)
+template <typename Sink>
+__device__ __forceinline__ uint32_t fsm_walk_digits(const FsmHeader *h, const uint8_t *__restrict__ bits, unsigned long long p,
+                                                    unsigned long long lim, int &d, uint32_t &v, bool &dead, Sink sink) {
+    uint32_t cnt = 0;
+    const int bpd = h->bpd;
+    while (p + bpd <= lim) {
+        const int r = fsm_digit(h, d, v, stream_digit(bits, p, bpd));
+        if (r >= 0) { sink((uint32_t)r, cnt); cnt++; }
+        if (r == -2) dead = true;
+        p += bpd;
+    }
+    return cnt;
+}
+
+// a warp's view of its segment: one 32-byte load per lane, one tile ahead (little-endian words as loaded: byte 0 of a
+// word is the first byte of the stream, which is the order the byte steps want)
+struct FsmCursor {
+    const uint4 *src;
+    unsigned long long vec_left;   // 16-byte vectors of the stream from the segment's first tile on
+    uint4 n0, n1;
+    uint32_t fetched;
+    int lane;
+    __device__ __forceinline__ void init(const uint8_t *d_bits, unsigned long long first_tile, unsigned long long nvec, int lane_) {
+        lane = lane_;
+        const unsigned long long vec0 = first_tile * kF_TileVecs;
+        src = (const uint4 *)d_bits + vec0 + 2 * lane;
+        vec_left = nvec > vec0 ? nvec - vec0 : 0;
+        fetched = 0;
+        fetch();
+    }
+    __device__ __forceinline__ void fetch() {
+        n0 = make_uint4(0, 0, 0, 0);
+        n1 = make_uint4(0, 0, 0, 0);
+        const unsigned long long i = (unsigned long long)fetched * kF_TileVecs + 2 * lane;
+        if (i + 1 < vec_left) ldg_256(src, n0, n1);
+        else if (i < vec_left) n0 = ldg_stream(src);
+        src += kF_TileVecs;
+        fetched++;
+    }
+    // the lane's eight words of the current tile; prefetches the next one only if the warp will walk it
+    __device__ __forceinline__ void take(uint32_t (&w)[8], bool more) {
+        w[0] = n0.x; w[1] = n0.y; w[2] = n0.z; w[3] = n0.w;
+        w[4] = n1.x; w[5] = n1.y; w[6] = n1.z; w[7] = n1.w;
+        if (more) fetch();
+    }
+};
+
+// ------------------------------------------------------------------------------------------ F1 (FSM)
+
+// replace byte k of `word` by byte `src_byte` of `from`
+template <int K, int SRC>
+__device__ __forceinline__ uint32_t put_byte_from(uint32_t word, uint32_t from) {
+    constexpr uint32_t sel = (0x3210u & ~(0xFu << (4 * K))) | ((uint32_t)(4 + SRC) << (4 * K));
+    return prmt(word, from, sel);
+}
+
+// Walk the lane's 32 bytes from state `st`.  Record: chk byte k = state after word k, wc byte k = codes that ended in word k.
+// FIRST: whole subsequence.  !FIRST: re-walk until the state at a word end equals the recorded one (same path from there on).
+template <bool FIRST>
+__device__ __forceinline__ void fsm_sync_walk(uint32_t tab, const uint32_t (&w)[8], uint32_t st, bool merged, uint32_t (&chk)[2],
+                                              uint32_t (&wc)[2]) {
+    uint32_t e = st << 8;   // the previous entry: state in byte 1
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (!FIRST && !__any_sync(0xFFFFFFFFu, !merged)) return;
+        if (FIRST || !merged) {
+            uint32_t cs;
+            e = lds_u16_at(tab, prmt(w[k], e, 0x7750u));
+            cs = e;
+            e = lds_u16_at(tab, prmt(w[k], e, 0x7751u));
+            cs += e;
+            e = lds_u16_at(tab, prmt(w[k], e, 0x7752u));
+            cs += e;
+            e = lds_u16_at(tab, prmt(w[k], e, 0x7753u));
+            cs += e;
+            const int h = k >> 2;
+            const uint32_t old = chk[h];
+            uint32_t neu, nwc;
+            switch (k & 3) {
+                case 0: neu = put_byte_from<0, 1>(old, e); nwc = put_byte_from<0, 0>(wc[h], cs); break;
+                case 1: neu = put_byte_from<1, 1>(old, e); nwc = put_byte_from<1, 0>(wc[h], cs); break;
+                case 2: neu = put_byte_from<2, 1>(old, e); nwc = put_byte_from<2, 0>(wc[h], cs); break;
+                default: neu = put_byte_from<3, 1>(old, e); nwc = put_byte_from<3, 0>(wc[h], cs); break;
+            }
+            chk[h] = neu;
+            wc[h] = nwc;
+            if (!FIRST && k < 7 && neu == old) merged = true;
+        }
+    }
+}
+
+struct FsmSyncArgs {
+    const uint8_t *d_bits;
+    unsigned long long end;        // bits of the stream from d_bits on
+    unsigned long long nsub, ntiles, nseg;
+    uint32_t start_token;          // first segment (lead == 0): kFsmToken | state, or a bit offset (< 256) of the first code
+    int lead;
+    const DecodeChain *chain;
+};
+
+// slow tile: every lane walks its part digit by digit.  start: kFsmToken | state for a lane that begins at bit 0 of its
+// subsequence, else the bit offset (lane 0 only) of the first code.
+__device__ __forceinline__ void fsm_slow_sync_lane(const FsmHeader *h, const uint8_t *__restrict__ d_bits, unsigned long long sub_bit0,
+                                                   uint32_t lim, uint32_t start, uint32_t &cnt, uint32_t &exit_state) {
+    int d = 0;
+    uint32_t v = 0;
+    unsigned long long p = sub_bit0;
+    if (start & kFsmToken) fsm_state_node(h, start & 0x1FFu, d, v);
+    else p += start;
+    bool dead = false;
+    cnt = fsm_walk_digits(h, d_bits, p, sub_bit0 + lim, d, v, dead, [](uint32_t, uint32_t) {});
+    exit_state = fsm_state_id(h, d, v);
+}
+
+__global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTables t, FastWorkspace ws) {
+    extern __shared__ __align__(16) uint8_t fsm_smem[];
+    FsmHeader *s_h = (FsmHeader *)fsm_smem;
+    uint16_t *s_tab = (uint16_t *)(fsm_smem + kFsmHeaderBytes);
+    {
+        const uint32_t *src = (const uint32_t *)t.hdr;
+        uint32_t *dst = (uint32_t *)s_h;
+        for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        const int words = s_h->nstates * 128;
+        const uint4 *s4 = (const uint4 *)t.sync;
+        uint4 *d4 = (uint4 *)s_tab;
+        for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d4[i] = s4[i];
+        __syncthreads();
+    }
+    uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+    asm volatile("" : "+r"(tab));
+    uint32_t start_token = a.start_token;
+    if (a.chain) start_token = a.chain->next_start;
+    if (start_token == 0) start_token = kFsmToken;   // bit 0 of the first byte = the root at a byte boundary
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ws.start_slot() = start_token;   // F3 walks the first lane the same way
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
+    const unsigned long long tile_bits = 32ull * kF_SubBits;
+    for (unsigned long long seg = (unsigned long long)blockIdx.x * warps + warp; seg < a.nseg; seg += (unsigned long long)gridDim.x * warps) {
+        const bool exact = seg == 0 && a.lead == 0;
+        const int warm = exact ? 0 : 1;
+        const unsigned long long tile0 = (unsigned long long)a.lead + seg * kF_SegTiles - warm;
+        FsmCursor cur;
+        cur.init(a.d_bits, tile0, nvec, lane);
+        const uint32_t ntile = (uint32_t)min((unsigned long long)(kF_SegTiles + warm), a.ntiles - tile0);
+        uint16_t *info = ws.sub_info + tile0 * 32 + lane;
+        const unsigned long long sub_left = a.nsub - tile0 * 32;
+        uint32_t carry = exact ? start_token : kFsmToken;   // token of the state in front of lane 0
+        uint32_t assumed = carry, total = 0;
+        for (uint32_t tt = 0; tt < ntile; tt++, info += 32) {
+            uint32_t w[8];
+            cur.take(w, tt + 1 < ntile);
+            const unsigned long long tbit0 = (tile0 + tt) * tile_bits;
+            const bool full = tbit0 + tile_bits <= a.end && (carry & kFsmToken);   // warp-uniform
+            uint32_t start, cnt, exit_state;
+            if (full) {
+                start = lane == 0 ? (carry & 0xFFu) : 0u;
+                uint32_t chk[2] = {0, 0}, wc[2] = {0, 0};
+                fsm_sync_walk<true>(tab, w, start, false, chk, wc);
+                while (true) {
+                    uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, chk[1] >> 24, 1);
+                    if (lane == 0) ns = start;
+                    const bool redo = ns != start;
+                    if (!__any_sync(0xFFFFFFFFu, redo)) break;
+                    start = ns;
+                    fsm_sync_walk<false>(tab, w, start, !redo, chk, wc);
+                }
+                exit_state = chk[1] >> 24;
+                cnt = __dp4a(wc[0], 0x01010101u, __dp4a(wc[1], 0x01010101u, 0u));
+            } else {
+                const unsigned long long sub_bit0 = tbit0 + (unsigned long long)lane * kF_SubBits;
+                const bool active = sub_bit0 < a.end;
+                const uint32_t lim = active ? (uint32_t)min((unsigned long long)kF_SubBits, a.end - sub_bit0) : 0u;
+                uint32_t st = lane == 0 ? carry : kFsmToken;
+                cnt = 0;
+                exit_state = st & 0x1FFu;
+                if (active) fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state);
+                while (true) {
+                    uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, exit_state, 1) | kFsmToken;
+                    if (lane == 0) ns = st;
+                    const bool redo = active && ns != st;
+                    if (!__any_sync(0xFFFFFFFFu, redo)) break;
+                    if (redo) {
+                        st = ns;
+                        fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state);
+                    }
+                }
+                // lanes behind the end pass the last active lane's exit on
+                const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
+                const int last = act ? 31 - __clz(act) : 0;
+                const uint32_t ex = __shfl_sync(0xFFFFFFFFu, exit_state, last);
+                if (!active) exit_state = ex;
+                start = st & kFsmToken ? (st & 0xFFu) : 0u;   // (a bit-offset start: F3 gets the offset from its own arguments)
+            }
+            carry = __shfl_sync(0xFFFFFFFFu, exit_state, 31) | kFsmToken;
+            if (tt < (uint32_t)warm) {
+                assumed = carry;
+            } else {
+                if ((unsigned long long)tt * 32 + lane < sub_left) *info = (uint16_t)(start | (cnt << 8));
+                total += cnt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        if (lane == 0) {
+            ws.seg_cnt[seg] = total;
+            ws.seg_assumed[seg] = assumed;
+            ws.seg_exit[seg] = carry;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ F3 (FSM)
+
+struct FsmWriteArgs {
+    const uint8_t *d_bits;
+    unsigned long long end, nsub, ntiles, nseg;
+    uint8_t *out;
+    unsigned long long n_out;
+    int lead;
+    uint32_t stage_bytes;      // per warp
+    uint32_t hot_rows;         // rows of the F3 table resident in shared memory (all of them unless SPLIT)
+    int32_t *d_status;
+};
+
+__device__ __forceinline__ uint2 ldg_u64_at(const unsigned long long *base, uint32_t idx) {
+    uint2 v;
+    asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(base + idx));
+    return v;
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+
+// One byte step of the write walk.  acc = the lane's last four symbols (newest in the top byte), G = 8 x pending bytes in its
+// low 5 bits (bit 5 toggles when a word completes), wptr = shared address of the word being filled.
+template <bool SPLIT, int J>
+__device__ __forceinline__ void fsm_write_step(uint32_t tab, const unsigned long long *__restrict__ gtab, uint32_t hot_limit, uint32_t w,
+                                               uint32_t &meta, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
+    const uint32_t idx = prmt(w, meta, 0xF760u | (uint32_t)J);   // byte J | state << 8 (9 bits); byte 3 = sign of a byte that is 0 or 1
+    uint2 e;
+    if (SPLIT) {
+        if (idx < hot_limit) e = lds_u64_at(tab, idx);
+        else e = ldg_u64_at(gtab, idx);
+    } else {
+        e = lds_u64_at(tab, idx);
+    }
+    const uint32_t sw = __funnelshift_l(acc, e.x, G);   // the pending bytes, then this step's symbols
+    acc = prmt(acc, e.x, e.y);                          // slide the window by `count` bytes
+    // G += 8 * count (one IMAD on the whole meta word: its low nibble is the count, everything else lands above bit 6);
+    // bit 5 of G toggles exactly when a word has been completed: store it and advance (one LOP3 into a predicate)
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .u32 g2, x;\n\t"
+        "mad.lo.u32 g2, %3, 8, %1;\n\t"
+        "xor.b32 x, g2, %1;\n\t"
+        "and.b32 x, x, 32;\n\t"
+        "setp.ne.u32 q, x, 0;\n\t"
+        "@q st.shared.u32 [%0], %2;\n\t"
+        "@q add.u32 %0, %0, 4;\n\t"
+        "mov.u32 %1, g2;\n\t}"
+        : "+r"(wptr), "+r"(G)
+        : "r"(sw), "r"(e.y)
+        : "memory");
+    meta = e.y;
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void fsm_write_walk(uint32_t tab, const unsigned long long *__restrict__ gtab, uint32_t hot_limit,
+                                               const uint32_t (&w)[8], uint32_t &meta, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        fsm_write_step<SPLIT, 0>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
+        fsm_write_step<SPLIT, 1>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
+        fsm_write_step<SPLIT, 2>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
+        fsm_write_step<SPLIT, 3>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTables t, FastWorkspace ws) {
+    extern __shared__ __align__(16) uint8_t fsm_smem[];
+    FsmHeader *s_h = (FsmHeader *)fsm_smem;
+    unsigned long long *s_tab = (unsigned long long *)(fsm_smem + kFsmHeaderBytes);
+    if (*ws.mismatch) return;  // the robust path redoes the stream
+    {
+        const uint32_t *src = (const uint32_t *)t.hdr;
+        uint32_t *dst = (uint32_t *)s_h;
+        for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
+        const uint4 *s4 = (const uint4 *)t.write;
+        uint4 *d4 = (uint4 *)s_tab;
+        const int vecs = (int)a.hot_rows * 128;   // 2 KB per row
+        for (int i = threadIdx.x; i < vecs; i += blockDim.x) d4[i] = s4[i];
+        __syncthreads();
+    }
+    uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+    asm volatile("" : "+r"(tab));
+    const uint32_t hot_limit = a.hot_rows * 256u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    uint8_t *stage = fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * kFsmWriteRowBytes + (size_t)warp * a.stage_bytes;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+    const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
+    const unsigned long long tile_bits = 32ull * kF_SubBits;
+    const uint32_t dead_state = (uint32_t)s_h->nstates;
+    const uint32_t start_token = *ws.start_slot();   // written by F1 (a bit offset only for a stream that starts inside a byte)
+    bool corrupt = false;
+    for (unsigned long long seg = (unsigned long long)blockIdx.x * warps + warp; seg < a.nseg; seg += (unsigned long long)gridDim.x * warps) {
+        const unsigned long long tile0 = (unsigned long long)a.lead + seg * kF_SegTiles;
+        FsmCursor cur;
+        cur.init(a.d_bits, tile0, nvec, lane);
+        const uint32_t ntile = (uint32_t)min((unsigned long long)kF_SegTiles, a.ntiles - tile0);
+        const uint16_t *info = ws.sub_info + tile0 * 32 + lane;
+        const unsigned long long sub_left = a.nsub - tile0 * 32;
+        unsigned long long ob = ws.seg_off[seg];
+        uint32_t next_info = lane < sub_left ? *info : 0u;
+        for (uint32_t tt = 0; tt < ntile; tt++) {
+            uint32_t w[8];
+            cur.take(w, tt + 1 < ntile);
+            const uint32_t my_info = next_info;
+            info += 32;
+            next_info = (tt + 1 < ntile && (unsigned long long)(tt + 1) * 32 + lane < sub_left) ? *info : 0u;
+            const uint32_t my_cnt = my_info >> 8;
+            uint32_t incl = my_cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += x;
+            }
+            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t excl = incl - my_cnt;
+            const unsigned long long tbit0 = (tile0 + tt) * tile_bits;
+            const bool first_lane_offset = seg == 0 && a.lead == 0 && tt == 0 && !(start_token & kFsmToken);
+            const bool full = tbit0 + tile_bits <= a.end && (unsigned long long)(tt + 1) * 32 <= sub_left && !first_lane_offset;   // warp-uniform
+            if (!full) {
+                // slow tile: digit by digit, bytes straight to the output
+                const unsigned long long sub_bit0 = tbit0 + (unsigned long long)lane * kF_SubBits;
+                if (sub_bit0 < a.end && (unsigned long long)tt * 32 + lane < sub_left) {
+                    const uint32_t lim = (uint32_t)min((unsigned long long)kF_SubBits, a.end - sub_bit0);
+                    int d = 0;
+                    uint32_t v = 0;
+                    unsigned long long p = sub_bit0;
+                    if (first_lane_offset && lane == 0) p += start_token;
+                    else fsm_state_node(s_h, my_info & 0xFFu, d, v);
+                    bool dead = false;
+                    uint8_t *dst = a.out + ob + excl;
+                    const unsigned long long room = a.n_out > ob + excl ? a.n_out - (ob + excl) : 0ull;
+                    const uint32_t c = fsm_walk_digits(s_h, a.d_bits, p, sub_bit0 + lim, d, v, dead, [&](uint32_t sym, uint32_t i) {
+                        if (i < room && i < my_cnt) dst[i] = (uint8_t)sym;
+                    });
+                    // a code that is cut off by the end of the STREAM (not by the end of the lane's subsequence)
+                    const bool cut = sub_bit0 + lim == a.end && (d != 0 || ((a.end - p) % (unsigned)s_h->bpd) != 0);
+                    if (dead || c != my_cnt || cut) corrupt = true;
+                }
+                ob += tile_total;
+                continue;
+            }
+            // fast tile, in one pass or (more symbols than the staging tile holds) lanes 0..15, then 16..31
+            const uint32_t half_total = __shfl_sync(0xFFFFFFFFu, incl, 15);
+            const uint32_t a0 = (uint32_t)(((uintptr_t)a.out + ob) & 15);
+            const bool one_pass = a0 + tile_total + 8 <= a.stage_bytes;
+            const int npass = one_pass ? 1 : 2;
+            for (int pass = 0; pass < npass; pass++) {
+                const bool mine = one_pass || (lane >> 4) == pass;
+                const uint32_t pass_excl0 = (!one_pass && pass == 1) ? half_total : 0u;
+                const uint32_t pass_total = one_pass ? tile_total : (pass == 0 ? half_total : tile_total - half_total);
+                const unsigned long long pob = ob + pass_excl0;
+                const uint32_t al = (uint32_t)(((uintptr_t)a.out + pob) & 15);
+                const uint32_t pos0 = al + (excl - pass_excl0);
+                __syncwarp();  // the previous copy-out has read the staging tile
+                if (lane == 0) *(uint32_t *)(stage + ((al + pass_total) & ~3u)) = 0u;   // the one boundary word nobody's first store initialises
+                __syncwarp();
+                uint32_t wptr0 = stage_addr + (pos0 & ~3u), wptr = wptr0, G = 8u * (pos0 & 3u), acc = 0u;
+                uint32_t meta = (my_info & 0xFFu) << 16;
+                if (mine && my_cnt) fsm_write_walk<SPLIT>(tab, t.write, hot_limit, w, meta, acc, G, wptr);
+                __syncwarp();
+                if (mine && my_cnt) {
+                    const uint32_t pend = (G >> 3) & 3u;
+                    if (pend) atomicOr((uint32_t *)(stage + (wptr - stage_addr)), __funnelshift_l(acc, 0u, G));
+                    const uint32_t written = (wptr - wptr0) + pend - (pos0 & 3u);
+                    if (written != my_cnt || (meta >> 16) == dead_state) corrupt = true;
+                }
+                __syncwarp();
+                // copy-out: staging byte i <-> out[pob - al + i]; 16-byte words are aligned on both sides
+                const uint32_t span = al + pass_total;
+                if (pob + pass_total <= a.n_out) {
+                    const uint32_t jfull = span >> 4;
+                    const uint32_t head = al ? 1u : 0u;
+                    for (uint32_t j = head + lane; j < jfull; j += 32)
+                        stg_stream((uint4 *)(a.out + (pob - al)) + j, *(const uint4 *)(stage + j * 16));
+                    const uint32_t k = lane < 16 ? (uint32_t)lane : jfull * 16 + (lane - 16);
+                    const bool edge = lane < 16 ? (al != 0 || jfull == 0) : (jfull != 0);
+                    if (edge && k >= al && k < span) a.out[pob - al + k] = stage[k];
+                } else {  // more symbols than the caller expects (corrupt stream): clamp every byte
+                    for (uint32_t k = al + lane; k < span; k += 32)
+                        if (pob - al + k < a.n_out) a.out[pob - al + k] = stage[k];
+                }
+            }
+            ob += tile_total;
+        }
+    }
+    if (corrupt) set_status(a.d_status, DC_ERR_CORRUPT);
+}
+
+}  // namespace dc

@@ -102,7 +102,7 @@ typedef struct dc_huff_table {
      * and unused slots have the subtable DC_LUT_NO_SUBTABLE = canonical search. */
     uint16_t lut2[(DC_LUT2_SUBTABLES + 1) * 16];
     int32_t lut2_used;        /* subtables in use */
-    int32_t reserved1;
+    int32_t fsm_states;       /* internal nodes of the code tree if the byte-stepped decoder applies (k4_fsm.cuh), else 0 */
     /* the decoder's synchronisation pass only counts codes; for tables whose longest code has 13 or 14 bits (binary
      * codes of byte data, typically) it uses this 14-bit-indexed table instead, which needs no escape:
      * total bits | count << 8 | first code's bits << 12 of every code inside the next 14 bits.  Filled only then. */
@@ -153,6 +153,11 @@ enum dc_kernel_id {
     DC_K_MTF_RESOLVE,
     DC_K_TEXT_BATCH,
     DC_K_SYNTH,
+    DC_K_DECODE_FSM_BUILD,
+    DC_K_DECODE_FSM_SYNC,
+    DC_K_DECODE_FSM_WRITE,
+    DC_K_ENCODE_PLAN,
+    DC_K_ENCODE_FAST,
     DC_K_COUNT
 };
 /* on != 0: bracket every kernel launch with CUDA events on its launching stream */

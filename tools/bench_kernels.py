@@ -81,7 +81,7 @@ def main():
         assert int(st.item()) == 0 and torch.equal(out, data)
         parts = {}
         import ctypes as C
-        for kid in range(32):
+        for kid in range(64):
             ms, cnt = C.c_double(0), C.c_uint64(0)
             L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
             if cnt.value:

@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_hostapi.py tests/test_gpu_shard.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -15
+python tools/bench_kernels.py --size-mib 1024 --radices 2,4,16 --hist-variants 0 2>&1 | grep -i "decode\|encode" | cut -c1-600
