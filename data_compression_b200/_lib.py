@@ -71,6 +71,8 @@ SYMBOLS = [
     ("dc_huff_bits_for_hist", _i, [_vp, _vp, _vp, _vp]),
     ("dc_huff_encode_workspace_bytes", _sz, [_sz]),
     ("dc_huff_encode", _i, [_vp, _sz, _vp, _vp, _sz, _u, _vp, _vp, _vp, _sz, _vp]),
+    ("dc_histogram_u8_runs", _i, [_vp, _sz, _vp, _vp, _sz, _vp]),
+    ("dc_huff_encode_planned", _i, [_vp, _sz, _vp, _vp, _sz, _u, _vp, _vp, _vp, _sz, _vp]),
     ("dc_huff_decode_workspace_bytes", _sz, [_u64, _u64]),
     ("dc_huff_decode", _i, [_vp, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_huff_decode_shard_sync", _i, [_vp, _i, _u, _u64, _u64, _vp, _vp, _vp, _sz, _vp]),

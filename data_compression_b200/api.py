@@ -62,6 +62,22 @@ def histogram(data: torch.Tensor, out: torch.Tensor | None = None, variant: int 
     return out
 
 
+def encode_workspace(n: int, device) -> torch.Tensor:
+    """A workspace for huff_encode / histogram_runs on n input bytes."""
+    return torch.empty(max(lib().dc_huff_encode_workspace_bytes(n), 16), dtype=torch.uint8, device=device)
+
+
+def histogram_runs(data: torch.Tensor, workspace: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """histogram() that also leaves one small histogram per 32 KB run in the encode workspace, so that
+    huff_encode(..., workspace=workspace, planned=True) knows every run's bit offset without a second data pass."""
+    _need_cuda(data, "data")
+    if out is None:
+        out = torch.empty(DC_NSLOTS, dtype=torch.int64, device=data.device)
+    check(lib().dc_histogram_u8_runs(data.data_ptr(), data.numel(), out.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                     _stream()), "dc_histogram_u8_runs")
+    return out
+
+
 def huff_build(hist: torch.Tensor, n_ary: int, table: HuffTable | None = None) -> HuffTable:
     """hist (259 x int64, CUDA) -> code table.  Replaces huffman() :1161 + convert_lengths_to_encode_table() :1382."""
     _need_cuda(hist, "hist")
@@ -104,7 +120,7 @@ class EncodeResult:
 
 
 def huff_encode(data: torch.Tensor, table: HuffTable, out: torch.Tensor | None = None, bit_phase: int = 0,
-                workspace: torch.Tensor | None = None) -> EncodeResult:
+                workspace: torch.Tensor | None = None, planned: bool = False) -> EncodeResult:
     """Encode `data` (uint8, CUDA) with `table`.  Replaces represent_items_with_codes() :1621.
 
     Returns the payload buffer (capacity-sized; the first ceil((bit_phase+bits)/8) bytes are valid) together
@@ -118,9 +134,10 @@ def huff_encode(data: torch.Tensor, table: HuffTable, out: torch.Tensor | None =
         workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=data.device)
     total_bits = torch.empty(1, dtype=torch.int64, device=data.device)
     status = torch.empty(1, dtype=torch.int32, device=data.device)
-    check(lib().dc_huff_encode(data.data_ptr(), n, table.ptr, out.data_ptr(), out.numel(), bit_phase,
-                               total_bits.data_ptr(), status.data_ptr(), workspace.data_ptr(), workspace.numel(),
-                               _stream()), "dc_huff_encode")
+    fn = lib().dc_huff_encode_planned if planned else lib().dc_huff_encode   # planned: `workspace` comes from histogram_runs(data, ...)
+    check(fn(data.data_ptr(), n, table.ptr, out.data_ptr(), out.numel(), bit_phase,
+             total_bits.data_ptr(), status.data_ptr(), workspace.data_ptr(), workspace.numel(),
+             _stream()), "dc_huff_encode")
     return EncodeResult(out, total_bits, status)
 
 
@@ -186,9 +203,10 @@ class ShardDecoder:
 
 def huff_compress(data: torch.Tensor, n_ary: int):
     """histogram -> table -> encode on one GPU.  Returns (payload tensor, total_bits int, HuffTable)."""
-    hist = histogram(data)
+    ws = encode_workspace(data.numel(), data.device)
+    hist = histogram_runs(data, ws) if data.data_ptr() % 16 == 0 else histogram(data)
     table = huff_build(hist, n_ary)
-    res = huff_encode(data, table)
+    res = huff_encode(data, table, workspace=ws, planned=data.data_ptr() % 16 == 0)
     nbits = res.bits()
     return res.payload[: (nbits + 7) // 8], nbits, table
 

@@ -59,6 +59,9 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
 // K7 unpack without the status reset (k7_trits.cu)
 int trit_unpack_launch(const uint8_t *d_payload, unsigned long long ntrits, uint8_t *d_t2, int32_t *d_status, cudaStream_t st);
 
+// K1 with one 256 x u16 histogram per 32 KB run (k1_histogram.cu), for the planned encoder
+int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st);
+
 // K8 (k8_mtf.cu): the move-to-front contexts of the adaptive nybble compressor, used by K6
 size_t mtf_workspace_bytes(size_t n);
 // d_pos[i] = position of d_src[i] in its context's list just before it is touched (8 = absent; d_pos[0] = 8)

@@ -174,6 +174,60 @@ __global__ void __launch_bounds__(kLpThreads) hist_lane_private_kernel(const uin
         if (total[b]) atomicAdd(&hist[b], total[b]);
 }
 
+// ------------------------------------------------------------------------------------------ histogram + run histograms
+// The encoder wants the bit offset of every 32 KB run before it starts (k3_encode.cu, "planned single pass"); that is
+// sum(count[s] * length[s]) over the runs in front -- known as soon as the code lengths are, if the histogram pass keeps
+// one small histogram per run.  Same counting as variant A<1>; a CTA walks whole runs, and after each run its 256
+// threads fold the eight warp tables into 256 u16 counts (512 bytes per 32 KB of input: 1.6 % extra traffic).
+constexpr int kHistRunBytes = 32768;   // == kRunBytes of k3_encode.cu
+__global__ void __launch_bounds__(256) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n, unsigned long long *__restrict__ hist,
+                                                         uint16_t *__restrict__ run_hist, unsigned int nruns) {
+    constexpr int kWarps = 8;
+    __shared__ uint32_t smem[kWarps * 256];
+    for (int i = threadIdx.x; i < kWarps * 256; i += 256) smem[i] = 0;
+    __syncthreads();
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t *wh = smem + warp * 256;
+    unsigned long long total = 0;
+#define DC_COUNT_WORD(w)                      \
+    atomicAdd(&wh[(w) & 0xFFu], 1u);          \
+    atomicAdd(&wh[((w) >> 8) & 0xFFu], 1u);   \
+    atomicAdd(&wh[((w) >> 16) & 0xFFu], 1u);  \
+    atomicAdd(&wh[(w) >> 24], 1u);
+    for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        const size_t base = (size_t)run * kHistRunBytes;
+        const uint4 *vin = (const uint4 *)(in + base);
+        if (base + kHistRunBytes <= n) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = ldg_stream(vin + tid + u * 256);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                DC_COUNT_WORD(v[u].x) DC_COUNT_WORD(v[u].y) DC_COUNT_WORD(v[u].z) DC_COUNT_WORD(v[u].w)
+            }
+        } else {  // the ragged last run
+            const size_t len = n - base, nvec = len / 16;
+            for (size_t i = tid; i < nvec; i += 256) {
+                const uint4 v = ldg_stream(vin + i);
+                DC_COUNT_WORD(v.x) DC_COUNT_WORD(v.y) DC_COUNT_WORD(v.z) DC_COUNT_WORD(v.w)
+            }
+            for (size_t i = nvec * 16 + tid; i < len; i += 256) atomicAdd(&wh[in[base + i]], 1u);
+        }
+        __syncthreads();
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) {
+            c += smem[w * 256 + tid];
+            smem[w * 256 + tid] = 0;
+        }
+        run_hist[(size_t)run * 256 + tid] = (uint16_t)c;   // <= 32768
+        total += c;
+        __syncthreads();
+    }
+#undef DC_COUNT_WORD
+    if (total) atomicAdd(&hist[tid], total);
+}
+
 int hist_variant() {
     static int v = -1;
     if (v < 0) {
@@ -224,6 +278,19 @@ extern "C" int dc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hist, 
     if (!d_hist || (!d_in && n)) return DC_ERR_ARG;
     return dc::launch_histogram(d_in, n, (unsigned long long *)d_hist, dc::hist_variant(), (cudaStream_t)stream);
 }
+
+namespace dc {
+int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st) {
+    DC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, DC_NSLOTS * sizeof(unsigned long long), st));
+    if (n == 0) return DC_OK;
+    const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
+    if (nruns > 0x0FFFFFF0ull) return DC_ERR_ARG;
+    LaunchScope ls(DC_K_HISTOGRAM, st);
+    const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 8);
+    hist_runs_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
+    return cuda_status(cudaGetLastError());
+}
+}  // namespace dc
 
 // bench/test hook: run a specific counter layout (see the table at the top of this file)
 extern "C" int dc_histogram_u8_variant(const uint8_t *d_in, size_t n, uint64_t *d_hist, int variant, void *stream) {

@@ -43,6 +43,7 @@ constexpr int kChunkSubs = 8;
 constexpr int kChunkBytes = kSubTile * kChunkSubs;      // 4 KB per warp
 constexpr int kRunBytes = kChunkBytes * kEncWarps;      // 32 KB per CTA
 constexpr int kNarrowBits = 16;                         // code pairs fit 32 bits
+constexpr int kPlannedMaxBits = 12;                     // the planned single pass (encode_fast_kernel) takes tables up to this
 
 template <bool WIDE>
 struct EncCfg {
@@ -110,7 +111,6 @@ __global__ void __launch_bounds__(kEncThreads) encode_count_kernel(const uint8_t
     __shared__ uint32_t s_len[256];
     __shared__ uint32_t s_chunk[kEncWarps];
     if (!table_usable(tab, d_status)) return;
-    if (tab->max_bits <= kNarrowBits) return;  // narrow tables take the single-pass kernel
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_len[tid] = (uint32_t)(tab->enc64[tid] >> 32);
     __syncthreads();
@@ -170,7 +170,6 @@ __global__ void __launch_bounds__(kScanThreads) encode_scan_kernel(const dc_huff
     __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ok = tab->status == DC_OK && tab->bits_per_digit != 0;
-    if (tab->max_bits <= kNarrowBits) return;  // narrow tables take the single-pass kernel
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (unsigned int base = 0; base < nruns; base += kScanThreads * kScanItems) {
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
     __shared__ entry_t s_enc[256];
 
     if (tab->status != DC_OK || tab->bits_per_digit == 0) return;  // reported by the count kernel
-    if ((tab->max_bits > kNarrowBits) != WIDE) return;            // the other instantiation handles this table
+    if (WIDE && tab->max_bits <= kNarrowBits) return;             // the single-pass kernels handle this table
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // bytes [0, stream_bytes) of `out` are written, nothing else; refuse the whole stream if they do not fit
@@ -536,7 +535,7 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
     constexpr int kSpStageWords = sp_stage_words(MAXBITS);
     {   // this instantiation's tables: (12, 16] or [1, 12]; wide tables take the three-launch path
         const int mb = tab->max_bits;
-        if (mb > MAXBITS || (MAXBITS > kSpTightBits && mb <= kSpTightBits)) return;
+        if (mb > MAXBITS || mb <= kPlannedMaxBits) return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -702,20 +701,401 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
     }  // next ticket
 }
 
-static size_t enc_ws_layout(size_t n, size_t off[8]) {
+
+// ================================================================================================ planned single pass
+// Tables whose longest code has at most 12 bits.  The bit offset of every 32 KB run is known BEFORE the launch (E1 + E2
+// from the input, or the run histograms K1 left behind: dc_histogram_u8_runs + encode_plan_kernel), so a run needs
+// nothing from any other CTA: no tickets, no descriptors, no spinning.  What is left is one barrier among the 16 warps
+// of a run (2 KB chunks) to add up their bit counts.
+//
+// The inner loop is built around the two pipes that bound the first version (ncu, round 1: integer ALU pipe 63 %, one
+// LDS per symbol at 2.7 wavefronts):
+//   * lane-private table: row b (256 bytes) holds byte b's entry once per lane, lane L at +4L, so a look-up never has a
+//     bank conflict and its address is ONE instruction: PRMT(input word, 4 * lane) = byte << 8 | 4 * lane.
+//   * entry = code LEFT-aligned | 1 << 7 | length.  A pair is combined with one shift whose amount is the first
+//     entry's low 5 bits, taken straight from the entry, and one LOP3: V = (e0 | e1 >> l0) & ~0xFF (<= 24 bits).
+//     The running position P += e0 + e1 is exact in its low 7 bits (they never see the code bits above), which is all
+//     the shifts (P mod 32) and the word-completion test (bit 5 toggles) need; the markers count the symbols that
+//     had a code in bits 7..10 of the same sums.
+//   * emit: cur |= V >> P; next = V << (32 - P) (funnel shift of V:0); when bit 5 of P toggles the word is complete:
+//     predicated STS, cur = next, wi += 4.
+constexpr int kFwWarps = 16;                                 // warps (= chunks) per run
+constexpr int kFwGroups = 2;                                 // runs in flight per CTA (they share the table)
+constexpr int kFwThreads = kFwWarps * kFwGroups * 32;        // 1024
+constexpr int kFwChunkBytes = kRunBytes / kFwWarps;          // 2 KB
+constexpr int kFwChunkSubs = kFwChunkBytes / kSubTile;       // 4
+constexpr int kFwMaxBits = kPlannedMaxBits;
+constexpr int kFwStageWords = kSpZeroPrefix + kFwChunkBytes * kFwMaxBits / 32 + 12;   // per warp
+constexpr int kFwTableBytes = 256 * 256;
+// The table sits at the ABSOLUTE shared-memory address 0x20000, so that the address of a look-up is one PRMT and nothing
+// else: byte 0 = 4 * lane, byte 1 = the input byte, byte 2 = 0x02 (from the lane constant).  The staging buffers lie in
+// front of it; the kernel computes the padding from its own window base (1 KB of system-reserved memory on sm_100).
+constexpr uint32_t kFwTableAddr = 0x20000u;
+constexpr size_t kFwStageBytes = (size_t)kFwWarps * kFwGroups * kFwStageWords * 4;   // 100 352
+constexpr size_t kFwXchgBytes = (size_t)kFwGroups * 2 * kFwWarps * 8 * 4;            // per group: 2 copies x 16 warps x 8 words
+constexpr size_t kFwSmemBytes = kFwTableAddr + kFwTableBytes - 1024;                  // dynamic bytes when the window starts at 1 KB
+
+__device__ __forceinline__ uint32_t fw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// the entry of byte K of w for this lane (lanec = 0x20000 | 4 * lane): one PRMT builds the whole shared-memory address
+template <int K>
+__device__ __forceinline__ uint32_t fw_entry(uint32_t w, uint32_t lanec) {
+    uint32_t e;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(fw_prmt(w, lanec, 0x7604u | ((uint32_t)K << 4))));
+    return e;
+}
+
+struct FwWorkspace {
+    const unsigned long long *run_off;   // [nruns + 1] exclusive bit offsets, last = total
+    uint32_t *bstate;
+    uint4 *bleft, *bright;
+};
+
+// one sub-tile (32 lanes x 16 symbols) appended to the warp's staging buffer at bit position `bitpos`
+template <bool FULL>
+__device__ __forceinline__ void fw_subtile(uint32_t *stage, const uint32_t (&w)[4], int valid, int lane, uint32_t lanec,
+                                           uint32_t &bitpos, uint32_t &bad) {
+    uint32_t V[8], S[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t e0 = fw_entry<0>(w[q], lanec), e1 = fw_entry<1>(w[q], lanec);
+        uint32_t e2 = fw_entry<2>(w[q], lanec), e3 = fw_entry<3>(w[q], lanec);
+        if (!FULL) {   // positions behind the end of the input: no bits, but counted as "has a code"
+            if (4 * q + 0 >= valid) e0 = 0x80u;
+            if (4 * q + 1 >= valid) e1 = 0x80u;
+            if (4 * q + 2 >= valid) e2 = 0x80u;
+            if (4 * q + 3 >= valid) e3 = 0x80u;
+        }
+        V[2 * q] = (e0 | __funnelshift_r(e1, 0u, e0)) & 0xFFFFFF00u;        // e1 >> (e0 & 31)
+        V[2 * q + 1] = (e2 | __funnelshift_r(e3, 0u, e2)) & 0xFFFFFF00u;
+        S[2 * q] = e0 + e1;
+        S[2 * q + 1] = e2 + e3;
+    }
+    const uint32_t sa = S[0] + S[1] + S[2] + S[3], sb = S[4] + S[5] + S[6] + S[7];
+    bad |= ~(sa & sb);                         // bit 10 stays clear only if all 8 + 8 symbols had a code
+    const uint32_t my_bits = (sa & 127u) + (sb & 127u);
+    uint32_t incl = my_bits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += x;
+    }
+    const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const bool fast = __all_sync(0xFFFFFFFFu, my_bits >= 32u);
+    const uint32_t pos = bitpos + incl - my_bits;
+    if (fast) {
+        // plain stores: a lane writes every word it completes.  The leading `lead` bits of its first word are its left
+        // neighbour's trailing bits (lane 0: the previous sub-tile's, already in the buffer)
+        const uint32_t lead = pos & 31u;
+        uint32_t wi = (uint32_t)__cvta_generic_to_shared(stage + (pos >> 5));
+        const uint32_t first_wi = wi;
+        uint32_t left_tail = 0;
+        if (lane == 0 && lead != 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(left_tail) : "r"(first_wi) : "memory");
+        uint32_t cur = 0, P = pos;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t.reg .u32 h, nx, p2, x;\n\t"
+                "shf.r.wrap.b32 h, %4, 0, %2;\n\t"        // V >> (P & 31)
+                "or.b32 %1, %1, h;\n\t"
+                "shf.r.wrap.b32 nx, 0, %4, %2;\n\t"       // V << (32 - (P & 31)), 0 when P & 31 == 0
+                "add.u32 p2, %2, %3;\n\t"
+                "xor.b32 x, p2, %2;\n\t"
+                "and.b32 x, x, 32;\n\t"
+                "setp.ne.u32 q, x, 0;\n\t"
+                "@q st.shared.u32 [%0], %1;\n\t"
+                "@q mov.u32 %1, nx;\n\t"
+                "@q add.u32 %0, %0, 4;\n\t"
+                "mov.u32 %2, p2;\n\t}"
+                : "+r"(wi), "+r"(cur), "+r"(P)
+                : "r"(S[k]), "r"(V[k])
+                : "memory");
+        }
+        const uint32_t lt = __shfl_up_sync(0xFFFFFFFFu, cur, 1);   // cur = the trailing partial word, left-aligned
+        if (lane != 0) left_tail = lt;
+        if (lead != 0) {
+            uint32_t t;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(first_wi) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(first_wi), "r"(t | left_tail) : "memory");
+        }
+        if (lane == 31) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wi), "r"(cur) : "memory");
+    } else {
+        // very short codes or a ragged tile: shared-memory OR on zeroed words (emit_bits)
+        const uint32_t z0 = (bitpos >> 5) + 1, z1 = ((bitpos + tile_bits) >> 5) + 1;
+        for (uint32_t i = z0 + lane; i <= z1; i += 32) stage[i] = 0;
+        __syncwarp();
+        uint32_t wi = pos >> 5, nb = pos & 31, hi = 0, lo = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t len = S[k] & 127u;
+            emit_bits(stage, hi, lo, nb, wi, len ? V[k] >> (32u - len) : 0u, len);
+        }
+        stage_or_if(stage + wi, lo << ((32u - nb) & 31u), nb != 0u);
+    }
+    __syncwarp();
+    bitpos += tile_bits;
+}
+
+__device__ __forceinline__ void fw_group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kFwWarps * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                    const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
+                                                                    size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
+                                                                    int32_t *__restrict__ d_status, uint32_t smem_bytes) {
+    extern __shared__ __align__(16) uint8_t fw_smem[];   // [exchange | staging buffers | padding | table at 0x20000]
+    if (!table_usable(tab, d_status)) return;
+    if (tab->max_bits > kFwMaxBits) return;   // the look-back single pass (13 .. 16 bits) or the 64-bit-entry kernel takes this table
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = warp / kFwWarps, gw = warp % kFwWarps;
+    const size_t stream_bytes = (size_t)(((unsigned long long)phase + ws.run_off[nruns] + 7) >> 3);
+    if (stream_bytes > out_cap) {
+        if (blockIdx.x == 0 && tid == 0) set_status(d_status, DC_ERR_CAPACITY);
+        return;
+    }
+    const uint32_t window = (uint32_t)__cvta_generic_to_shared(fw_smem);
+    if (window + kFwXchgBytes + kFwStageBytes > kFwTableAddr || kFwTableAddr + kFwTableBytes > window + smem_bytes) {
+        if (blockIdx.x == 0 && tid == 0) set_status(d_status, DC_ERR_CUDA);   // the window does not start where sm_100 puts it
+        return;
+    }
+    uint32_t *s_tab = (uint32_t *)(fw_smem + (kFwTableAddr - window));
+    for (int i = tid; i < 256 * 32; i += kFwThreads) {
+        const int b = i >> 5;
+        const uint32_t e = tab->enc[b], l = e & 63u;
+        s_tab[b * 64 + (i & 31)] = l ? (((e >> 6) << (32u - l)) | 0x80u | l) : 0u;
+    }
+    __syncthreads();
+    // what a warp shows its run: its bit count and the first 128 bits of its chunk (the left neighbour completes the 16-byte
+    // word the two share).  Two copies, used alternately, so that ONE barrier per run is enough: a warp that is already
+    // staging the next run writes the other copy.
+    uint32_t *xchg_base = (uint32_t *)fw_smem + group * (2 * kFwWarps * 8);
+    uint32_t *stage = (uint32_t *)(fw_smem + kFwXchgBytes) + warp * kFwStageWords;
+    const uint32_t lanec = kFwTableAddr | (4u * lane);
+    const size_t nchunks = (n + kFwChunkBytes - 1) / kFwChunkBytes;
+    const unsigned int stride = gridDim.x * kFwGroups;
+    uint32_t bad = 0, parity = 0;
+    uint4 v[kFwChunkSubs];
+    unsigned int run = blockIdx.x * kFwGroups + group;
+    auto full_chunk = [&](unsigned int r) { return r < nruns && ((size_t)r * kFwWarps + gw + 1) * kFwChunkBytes <= n; };
+    auto load_chunk = [&](unsigned int r) {
+        const uint4 *src = (const uint4 *)(in + ((size_t)r * kFwWarps + gw) * kFwChunkBytes) + lane;
+#pragma unroll
+        for (int t = 0; t < kFwChunkSubs; t++) v[t] = ldg_stream(src + t * 32);
+    };
+    if (full_chunk(run)) load_chunk(run);
+    for (; run < nruns; run += stride, parity ^= 1u) {
+        const size_t chunk = (size_t)run * kFwWarps + gw;
+        const bool have_chunk = chunk < nchunks;
+        const size_t chunk_base = chunk * kFwChunkBytes;
+        const size_t chunk_len = have_chunk ? min((size_t)kFwChunkBytes, n - chunk_base) : 0;
+        const bool last_chunk = chunk == nchunks - 1;
+        const unsigned long long run_excl = ws.run_off[run];   // (needed behind the barrier: in flight until then)
+
+        // ---- 1. encode the chunk into the staging buffer (chunk-local bit offsets behind a zero prefix)
+        __syncwarp();
+        if (lane <= kSpZeroPrefix) stage[lane] = 0;
+        uint32_t bitpos = 32u * kSpZeroPrefix;
+        __syncwarp();
+        if (chunk_len == (size_t)kFwChunkBytes) {
+#pragma unroll
+            for (int t = 0; t < kFwChunkSubs; t++) {
+                const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+                fw_subtile<true>(stage, w, kEncPerThread, lane, lanec, bitpos, bad);
+            }
+        } else {  // the ragged last chunk of the stream (or no chunk at all)
+            const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
+#pragma unroll 1
+            for (int t = 0; t < nsub; t++) {
+                const size_t base = chunk_base + (size_t)t * kSubTile + (size_t)lane * kEncPerThread;
+                const int valid = base < n ? (int)min((size_t)kEncPerThread, n - base) : 0;
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
+                fw_subtile<false>(stage, w, valid, lane, lanec, bitpos, bad);
+            }
+        }
+        // the next run's input is on its way while this one waits for its neighbours and is copied out
+        if (full_chunk(run + stride)) load_chunk(run + stride);
+        if (lane < 8) stage[(bitpos >> 5) + 1 + lane] = 0;  // the copy-out reads up to 5 words past the last bit
+        const uint32_t chunk_bits = bitpos - 32u * kSpZeroPrefix;
+        __syncwarp();
+        uint32_t *xchg = xchg_base + parity * (kFwWarps * 8);
+        if (lane < 5) xchg[gw * 8 + lane] = lane == 0 ? chunk_bits : stage[kSpZeroPrefix - 1 + lane];
+        fw_group_barrier(group);
+
+        // ---- 2. the chunk's place in the stream: the run's planned offset + the chunks in front of it
+        unsigned long long excl = run_excl;
+        {
+            uint32_t mine = lane < gw ? xchg[lane * 8] : 0u;   // kFwWarps <= 32
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            excl += __shfl_sync(0xFFFFFFFFu, mine, 0);
+        }
+
+        // ---- 3. copy-out at the global alignment
+        if (have_chunk) {
+            const unsigned long long g = (unsigned long long)phase + excl, gend = g + chunk_bits;
+            const size_t stream_bytes_here = (size_t)((gend + 7) >> 3);
+            const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this chunk
+            const uint32_t r = (uint32_t)(g & 127), t = (uint32_t)(gend & 127);
+            const bool shared_first = chunk != 0 && r != 0;           // first word also holds the previous chunk's bits
+            if (!(v1 == v0 && !last_chunk)) {   // (< 128 bits from 2048 symbols: symbols without codes, reported below)
+                const uint32_t nvec = (uint32_t)(v1 - v0);
+                const uint32_t sbit0 = 32u * kSpZeroPrefix - r;            // staging bit of the first bit of 16-byte word v0
+                const uint32_t sbit1 = nvec * 128u + sbit0;                // ... of 16-byte word v1
+                SpWorkspace sp;
+                sp.ticket = nullptr;
+                sp.desc = nullptr;
+                sp.bstate = ws.bstate;
+                sp.bleft = ws.bleft;
+                sp.bright = ws.bright;
+                // 3a. the 16-byte words shared with the neighbouring chunks: inside the run the LEFT chunk owns the word (it
+                // takes the right chunk's leading bits from what that warp published); across runs both sides deposit their
+                // half and the second arrival stores the word
+                if (shared_first && gw == 0 && lane == 8) {
+                    const uint4 m = make_uint4(stage_word(stage, sbit0), stage_word(stage, sbit0 + 32), stage_word(stage, sbit0 + 64),
+                                               stage_word(stage, sbit0 + 96));
+                    const uint32_t ends = (last_chunk && v1 == v0) ? (uint32_t)(stream_bytes_here - v0 * 16) : 0u;
+                    sp_boundary_merge(sp, run, false, m, ends, out, v0, out_cap);   // boundary `run`: between run - 1 and run
+                }
+                if (t != 0 && !(shared_first && v1 == v0)) {
+                    if (last_chunk) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
+                        const uint32_t rem_bytes = (t + 7) >> 3;
+                        if (lane < (int)rem_bytes) out[v1 * 16 + lane] = (uint8_t)(stage_word(stage, sbit1 + 8u * lane) >> 24);
+                    } else if (gw == kFwWarps - 1) {
+                        if (lane == 16) {
+                            const uint4 m = make_uint4(stage_word(stage, sbit1), stage_word(stage, sbit1 + 32), stage_word(stage, sbit1 + 64),
+                                                       stage_word(stage, sbit1 + 96));
+                            sp_boundary_merge(sp, run + 1, true, m, 0u, out, v1, out_cap);
+                        }
+                    } else if (lane < 16) {
+                        // own trailing t bits | the right chunk's first 128 - t bits: bits [128 - t, 256 - t) of (128 zero bits, its
+                        // first 128 bits), i.e. its published words shifted right by t
+                        const uint32_t *rw = xchg + (gw + 1) * 8;   // [bits, w0, w1, w2, w3]
+                        const uint32_t q = (128u - t) + 32u * (lane >> 2), a = q >> 5, sft = q & 31u;   // window word a, a + 1 of (0,0,0,0,w0..w3)
+                        const uint32_t hi = a >= 4 ? rw[a - 3] : 0u, lo = a + 1 >= 4 ? (a + 1 < 8 ? rw[a - 2] : 0u) : 0u;
+                        const uint32_t word = stage_word(stage, sbit1 + 32u * (lane >> 2)) | __funnelshift_l(lo, hi, sft);
+                        const unsigned long long rend = gend + rw[0];
+                        size_t limit = out_cap;
+                        if (chunk + 1 == nchunks - 1) limit = min(limit, (size_t)((rend + 7) >> 3));
+                        const size_t byte = (size_t)v1 * 16 + lane;
+                        if (byte < limit) out[byte] = (uint8_t)(word >> (24 - 8 * (lane & 3)));
+                    }
+                }
+                // 3b. the words that are this chunk's alone
+                uint4 *dst = (uint4 *)out + v0;
+                const uint32_t sh = sbit0 & 31;
+                const uint32_t *sw = stage + (sbit0 >> 5);
+                for (uint32_t j = (shared_first ? 1u : 0u) + lane; j < nvec; j += 32) {
+                    const uint32_t *p = sw + 4 * j;
+                    const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4];
+                    uint4 o;
+                    o.x = bswap32(__funnelshift_l(a1, a0, sh));
+                    o.y = bswap32(__funnelshift_l(a2, a1, sh));
+                    o.z = bswap32(__funnelshift_l(a3, a2, sh));
+                    o.w = bswap32(__funnelshift_l(a4, a3, sh));
+                    stg_stream(dst + j, o);
+                }
+            }
+        }
+    }
+    if (((bad >> 10) & 1u) != 0u) set_status(d_status, DC_ERR_SYMBOL);
+}
+
+// ------------------------------------------------------------------------------------------ plan (run offsets from run histograms)
+// bits of run r = sum over symbols of run_hist[r][s] * bits(s): one warp per run (a lane takes 8 of the 256 u16 counts with one
+// 16-byte load); the CTA that finishes last scans the run totals into exclusive offsets (E2's arithmetic) -- one launch.
+constexpr int kPlanThreads = 1024;
+__global__ void __launch_bounds__(kPlanThreads) encode_plan_kernel(const uint16_t *__restrict__ run_hist, const dc_huff_table *__restrict__ tab,
+                                                                   EncWorkspace ws, unsigned int nruns, unsigned int *__restrict__ done,
+                                                                   unsigned long long *__restrict__ d_total_bits, int32_t *__restrict__ d_status) {
+    __shared__ uint32_t s_len[256];
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ok = table_usable(tab, d_status);
+    if (tid < 256) s_len[tid] = ok ? (uint32_t)(tab->enc64[tid] >> 32) : 0u;
+    __syncthreads();
+    bool missing = false;
+    for (unsigned int run = blockIdx.x * (kPlanThreads / 32) + warp; run < nruns; run += gridDim.x * (kPlanThreads / 32)) {
+        const uint4 v = *((const uint4 *)(run_hist + (size_t)run * 256) + lane);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t c = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu, l = s_len[8 * lane + k];
+            missing |= c != 0 && l == 0;
+            sum += c * l;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if (lane == 0) ws.run_bits[run] = sum;
+    }
+    if (missing && ok) set_status(d_status, DC_ERR_SYMBOL);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of run_bits by the last CTA (every other CTA's totals are visible: fence + counter)
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    constexpr int kItems = 8;
+    for (unsigned int base = 0; base < nruns; base += kPlanThreads * kItems) {
+        const unsigned int first = base + tid * kItems;
+        uint32_t item[kItems];
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int k = 0; k < kItems; k++) {
+            item[k] = first + k < nruns ? __ldcg(ws.run_bits + first + k) : 0u;
+            mine += item[k];
+        }
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry;
+        for (int w = 0; w < warp; w++) off += s_warp[w];
+        off += incl - mine;
+#pragma unroll
+        for (int k = 0; k < kItems; k++) {
+            if (first + k < nruns) ws.run_off[first + k] = off;
+            off += item[k];
+        }
+        __syncthreads();
+        if (tid == kPlanThreads - 1) s_carry = off;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ws.run_off[nruns] = s_carry;
+        if (d_total_bits) *d_total_bits = s_carry;
+    }
+}
+
+static size_t enc_ws_layout(size_t n, size_t off[10]) {
     const size_t nruns = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
     size_t p = 64;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o[8];
-    o[0] = take(nruns * 4);              // run_bits                  (wide path)
-    o[1] = take(nruns * kEncWarps * 4);  // chunk_rel                 (wide path)
-    o[2] = take((nruns + 1) * 8);        // run_off                   (wide path)
-    o[3] = take((nchunks + 1) * 4 + 64); // bstate, then the ticket   (zeroed together)
-    o[6] = o[3] + (nchunks + 1) * 4;     // ticket (4-byte aligned, inside the bstate block)
-    o[7] = take(nchunks * 8);            // desc                      (single pass; zeroed)
+    size_t o[10];
+    o[0] = take(nruns * 4);              // run_bits
+    o[1] = take(nruns * kEncWarps * 4);  // chunk_rel                 (64-bit-entry path)
+    o[2] = take((nruns + 1) * 8);        // run_off
+    o[3] = take((nchunks + 1) * 4 + 64); // bstate, then the ticket and the plan's counter (zeroed together)
+    o[6] = o[3] + (nchunks + 1) * 4;     // ticket (4-byte aligned, inside the bstate block); the plan's counter follows it
+    o[7] = take(nchunks * 8);            // desc                      (look-back single pass; zeroed)
     o[4] = take((nchunks + 1) * 16);     // bleft
     o[5] = take((nchunks + 1) * 16);     // bright
-    if (off) for (int i = 0; i < 8; i++) off[i] = o[i];
+    o[8] = take(nruns * 512);            // run histograms (dc_histogram_u8_runs -> dc_huff_encode_planned)
+    o[9] = 0;
+    if (off) for (int i = 0; i < 10; i++) off[i] = o[i];
     return p;
 }
 
@@ -723,18 +1103,22 @@ static size_t enc_ws_layout(size_t n, size_t off[8]) {
 
 using namespace dc;
 
+static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                              unsigned bit_phase, EncWorkspace ws, char *w, const size_t *off, unsigned int nruns,
+                              unsigned long long *d_total_bits, int32_t *d_status, cudaStream_t st, bool planned);
+
 extern "C" size_t dc_huff_encode_workspace_bytes(size_t n) { return enc_ws_layout(n, nullptr); }
 
-extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out,
-                              size_t out_capacity, unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status,
-                              void *d_workspace, size_t workspace_bytes, void *stream) {
+static int encode_entry(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                        unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                        void *stream, bool planned) {
     if (!d_table || (n && (!d_in || !d_out || !d_workspace)) || bit_phase > 7) return DC_ERR_ARG;
     if ((((uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_workspace) & 15) != 0) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     if (d_total_bits) DC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, sizeof(uint64_t), st));
     if (n == 0) return DC_OK;
-    size_t off[8];
+    size_t off[10];
     const size_t need = enc_ws_layout(n, off);
     if (workspace_bytes < need) return DC_ERR_CAPACITY;
     const size_t nruns64 = (n + kRunBytes - 1) / kRunBytes, nchunks = (n + kChunkBytes - 1) / kChunkBytes;
@@ -751,29 +1135,17 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
     // bstate + ticket and (contiguous, see enc_ws_layout) the look-back descriptors are zeroed in one memset
     DC_CUDA_TRY(cudaMemsetAsync(w + off[3], 0, (off[7] - off[3]) + nchunks * 8, st));
     const unsigned int sms = (unsigned int)sm_count();
-    {
-        SpWorkspace sp;
-        sp.ticket = (unsigned int *)(w + off[6]);
-        sp.desc = (unsigned long long *)(w + off[7]);
-        sp.bstate = ws.bstate;
-        sp.bleft = ws.bleft;
-        sp.bright = ws.bright;
-        const size_t smem12 = (size_t)kEncWarps * sp_stage_words(kSpTightBits) * 4, smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
-        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kSpTightBits>, smem12));
-        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kNarrowBits>, smem16));
-        {   // the instantiation that does not match the table returns before it takes a ticket
-            LaunchScope ls(DC_K_ENCODE, st);
-            encode_single_kernel<kSpTightBits><<<nruns, kEncThreads, smem12, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
-                                                                                  nruns, (unsigned long long *)d_total_bits, d_status);
-        }
+    if (planned) {
+        // the bit offset of every run from the run histograms K1 left in this workspace (dc_histogram_u8_runs)
         {
-            LaunchScope ls(DC_K_ENCODE_MID, st);
-            encode_single_kernel<kNarrowBits><<<min(nruns, sms * 3u), kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
-                                                                                 nruns, (unsigned long long *)d_total_bits, d_status);
+            LaunchScope ls(DC_K_ENCODE_PLAN, st);
+            const unsigned int want = (nruns + kPlanThreads / 32 - 1) / (kPlanThreads / 32);
+            encode_plan_kernel<<<min(want, sms), kPlanThreads, 0, st>>>((const uint16_t *)(w + off[8]), d_table, ws, nruns,
+                                                                        (unsigned int *)(w + off[6]) + 1, (unsigned long long *)d_total_bits, d_status);
         }
+        return launch_encode_body(d_in, n, d_table, d_out, out_capacity, bit_phase, ws, w, off, nruns, (unsigned long long *)d_total_bits, d_status, st, true);
     }
-    // tables with codes longer than 16 bits: count + scan + 64-bit-entry encode; for all others these three
-    // launches return at once
+    // the bit offset of every run, from the input: E1 (bits per run) + E2 (exclusive scan, total)
     {
         LaunchScope ls(DC_K_ENCODE_COUNT, st);
         encode_count_kernel<<<min(nruns, sms * 8u), kEncThreads, 0, st>>>(d_in, n, d_table, ws, nruns, d_status);
@@ -782,9 +1154,61 @@ extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table
         LaunchScope ls(DC_K_ENCODE_SCAN, st);
         encode_scan_kernel<<<1, kScanThreads, 0, st>>>(d_table, ws, nruns, (unsigned long long *)d_total_bits);
     }
-    {
-        // tables with codes longer than 16 bits take the 64-bit-entry instantiation; for all others this
-        // launch is a few hundred CTAs that return at once
+    return launch_encode_body(d_in, n, d_table, d_out, out_capacity, bit_phase, ws, w, off, nruns, (unsigned long long *)d_total_bits, d_status, st, false);
+}
+
+extern "C" int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                              unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
+                              void *stream) {
+    return encode_entry(d_in, n, d_table, d_out, out_capacity, bit_phase, d_total_bits, d_status, d_workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int dc_huff_encode_planned(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                                      unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace,
+                                      size_t workspace_bytes, void *stream) {
+    return encode_entry(d_in, n, d_table, d_out, out_capacity, bit_phase, d_total_bits, d_status, d_workspace, workspace_bytes, stream, true);
+}
+
+extern "C" int dc_histogram_u8_runs(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *d_encode_workspace, size_t workspace_bytes,
+                                    void *stream) {
+    if (!d_hist || (n && (!d_in || !d_encode_workspace))) return DC_ERR_ARG;
+    if ((((uintptr_t)d_in | (uintptr_t)d_encode_workspace) & 15) != 0) return DC_ERR_ARG;
+    size_t off[10];
+    if (workspace_bytes < enc_ws_layout(n, off)) return DC_ERR_CAPACITY;
+    return launch_histogram_runs(d_in, n, (unsigned long long *)d_hist, (uint16_t *)((char *)d_encode_workspace + off[8]), (cudaStream_t)stream);
+}
+
+// the kernels behind the planned run offsets (ws.run_off): exactly one of them does the work, the others return at once
+static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                              unsigned bit_phase, EncWorkspace ws, char *w, const size_t *off, unsigned int nruns,
+                              unsigned long long *d_total_bits, int32_t *d_status, cudaStream_t st, bool planned) {
+    (void)planned;
+    const unsigned int sms = (unsigned int)sm_count();
+    {   // codes up to 12 bits
+        FwWorkspace fw;
+        fw.run_off = ws.run_off;
+        fw.bstate = ws.bstate;
+        fw.bleft = ws.bleft;
+        fw.bright = ws.bright;
+        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel, kFwSmemBytes));
+        LaunchScope ls(DC_K_ENCODE_FAST, st);
+        encode_fast_kernel<<<min((nruns + kFwGroups - 1) / kFwGroups, sms), kFwThreads, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity,
+                                                                                                           bit_phase, fw, nruns, d_status, (uint32_t)kFwSmemBytes);
+    }
+    {   // 13 .. 16 bits: the look-back single pass
+        SpWorkspace sp;
+        sp.ticket = (unsigned int *)(w + off[6]);
+        sp.desc = (unsigned long long *)(w + off[7]);
+        sp.bstate = ws.bstate;
+        sp.bleft = ws.bleft;
+        sp.bright = ws.bright;
+        const size_t smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
+        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kNarrowBits>, smem16));
+        LaunchScope ls(DC_K_ENCODE_MID, st);
+        encode_single_kernel<kNarrowBits><<<min(nruns, sms * 3u), kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
+                                                                                             nruns, d_total_bits, d_status);
+    }
+    {   // longer codes: 64-bit entries
         LaunchScope ls(DC_K_ENCODE_WIDE, st);
         encode_run_kernel<true><<<min(nruns, sms * 4u), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
                                                                              ws, nruns, d_status);

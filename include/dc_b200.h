@@ -213,6 +213,21 @@ int dc_huff_encode(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, 
                    size_t out_capacity, unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status,
                    void *d_workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * The same encode with the run offsets PLANNED from the histogram pass instead of counted from the input a second
+ * time.  dc_histogram_u8_runs() is dc_histogram_u8() that also leaves one 256 x u16 histogram per 32 KB run of the
+ * input in the encode workspace (1.6 % of n); dc_huff_encode_planned() then derives the bit offset of every run from
+ * those and the code lengths (sum count * length: no data pass) and encodes in one read of the input.  Call order:
+ *   dc_histogram_u8_runs(d_in, n, d_hist, ws, ws_bytes, s);  [all-reduce d_hist;]  dc_huff_build(...);
+ *   dc_huff_encode_planned(d_in, n, table, ..., ws, ws_bytes, s);     -- same d_in, n and workspace
+ * Arguments, results and status codes are those of dc_huff_encode(); d_in must be 16-byte aligned for both calls.
+ */
+int dc_histogram_u8_runs(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *d_encode_workspace, size_t workspace_bytes,
+                         void *stream);
+int dc_huff_encode_planned(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out,
+                           size_t out_capacity, unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status,
+                           void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------- K4 decode */
 
 size_t dc_huff_decode_workspace_bytes(uint64_t bit_start, uint64_t nbits);

@@ -71,8 +71,36 @@ def main():
         res = dc.huff_encode(data, table, out=payload, workspace=ws)
         nbits = res.bits()
         c = (nbits + 7) // 8
+        import ctypes as C
+        L.dc_profile_reset(); L.dc_profile_enable(1)
         best, med = timeit(lambda: dc.huff_encode(data, table, out=payload, workspace=ws))
-        report(f"encode[n={n_ary}]", n + c, n, best, med, compressed_ratio=round(c / n, 4))
+        L.dc_profile_enable(0)
+        parts = {}
+        for kid in range(64):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                parts[L.dc_profile_kernel_name(kid).decode()] = [round(ms.value / cnt.value, 4), cnt.value]
+        report(f"encode[n={n_ary}]", n + c, n, best, med, compressed_ratio=round(c / n, 4), kernels_ms_avg_and_launches=parts)
+        # the planned path: histogram with run histograms -> table -> plan + encode
+        hist2 = torch.empty(259, dtype=torch.int64, device=dev)
+        best, med = timeit(lambda: dc.histogram_runs(data, ws, out=hist2))
+        report(f"histogram_runs", n, n, best, med)
+        assert torch.equal(hist2, hist)
+        ref_payload = payload[:c].clone()
+        payload.zero_()
+        L.dc_profile_reset(); L.dc_profile_enable(1)
+        best, med = timeit(lambda: dc.huff_encode(data, table, out=payload, workspace=ws, planned=True))
+        L.dc_profile_enable(0)
+        parts = {}
+        for kid in range(64):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            L.dc_profile_kernel(kid, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                parts[L.dc_profile_kernel_name(kid).decode()] = [round(ms.value / cnt.value, 4), cnt.value]
+        assert torch.equal(payload[:c], ref_payload), "planned encode differs"
+        report(f"encode_planned[n={n_ary}]", n + c, n, best, med, kernels_ms_avg_and_launches=parts)
+        del ref_payload
         dws = torch.empty(L.dc_huff_decode_workspace_bytes(0, nbits), dtype=torch.uint8, device=dev)
         st = torch.empty(1, dtype=torch.int32, device=dev)
         L.dc_profile_reset(); L.dc_profile_enable(1)

@@ -33,9 +33,10 @@ def main():
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     packed = torch.empty(n // 2, dtype=torch.uint8, device=dev)
     for _ in range(args.rounds):
-        hist = dc.histogram(data)
+        ws = dc.encode_workspace(n, dev)
+        hist = dc.histogram_runs(data, ws)
         table = dc.huff_build(hist, args.n_ary)
-        res = dc.huff_encode(data, table, out=payload)
+        res = dc.huff_encode(data, table, out=payload, workspace=ws, planned=True)
         nbits = res.bits()
         back, st = dc.huff_decode(payload, nbits, table, n, out=out)
         assert int(st.item()) == 0
