@@ -70,7 +70,7 @@ int mtf_positions(const uint8_t *d_src, size_t n, uint8_t *d_pos, void *d_ws, cu
 int mtf_resolve(uint8_t *d_buf, const unsigned long long *d_len, const int32_t *d_mode, cudaStream_t st);
 
 // ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
-constexpr int kFsmMaxStates = 256;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates (9 bits)
+constexpr int kFsmMaxStates = 255;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
 // Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.
 __host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_t *count, int min_len, int max_len, int bpd,
                                             uint32_t *ilo, uint32_t *ihi, uint32_t *base) {

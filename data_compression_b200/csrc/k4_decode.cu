@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_carry = chain ? chain->base : 0ull; s_bad = 0; }
     __syncthreads();
-    constexpr int kItems = 4;
+    constexpr int kItems = 16;   // 16 K segments (256 MiB of bitstream) per trip: the trips are serial, three barriers each
     for (unsigned long long base = 0; base < nseg; base += 1024 * kItems) {
         const unsigned long long first = base + (unsigned long long)tid * kItems;
         uint32_t item[kItems];
@@ -1053,6 +1053,12 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 constexpr int kSyncW14 = 0x10;
 constexpr int kModeFsm = 0x20;   // the byte-stepped kernels of k4_fsm.cuh; bits 20..28: states, bits 29..31: min(shortest code's bits, 8) - 1
 static int decode_force_mode();
+static bool fsm_rows_fit(const int32_t *tmeta) {
+    const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
+    const size_t per_lane = (size_t)(kF_SubBits / (min_bits < 8 ? min_bits : 8)) + 2, half = 16 * per_lane + 48, whole = 32 * per_lane + 48;
+    const size_t want = half > 2176 ? half : 2176, stage = ((want < whole ? want : whole) + 15) & ~(size_t)15;
+    return kFsmHeaderBytes + (size_t)(tmeta[11] + 1) * (kFsmWriteRowBytes + kFsmWriteXRowBytes) + 24 * stage + 256 <= 227 * 1024 - 1024;
+}
 // which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table, lut2_used, fsm_states)
 static int fast_mode(const int32_t *tmeta) {
     if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
@@ -1063,7 +1069,9 @@ static int fast_mode(const int32_t *tmeta) {
         const int sub = tmeta[10] < 0 ? 0 : (tmeta[10] > DC_LUT2_SUBTABLES ? DC_LUT2_SUBTABLES : tmeta[10]);
         mode = (tmeta[7] <= DC_LUT14_BITS ? (1 | kSyncW14) : 1) | (sub << 8);   // 13 or 14 bits: F1 counts through the 14-bit table (K2 fills it exactly then)
     }
-    if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxStates && decode_force_mode() != 3) {
+    // (a table whose write-pass rows do not all fit shared memory keeps the window kernels: a row read from global memory
+    // sits in the walk's dependent chain, and with 32 lanes some lane needs one in most steps -- measured 2.5x slower)
+    if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxStates && fsm_rows_fit(tmeta) && decode_force_mode() != 3) {
         const int min_bits = tmeta[5] * tmeta[1];
         mode |= kModeFsm | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
     }
@@ -1097,9 +1105,14 @@ static cudaError_t ensure_write_smem(size_t smem3) {
 }
 
 // ---- the byte-stepped kernels (k4_fsm.cuh)
-static uint32_t fsm_stage_bytes(int mode) {   // half a tile always fits: 16 lanes x the most symbols a lane can hold
+static uint32_t fsm_stage_bytes(int mode) {
+    // half a tile always fits (16 lanes x the most symbols a lane can hold): a tile with more symbols than the staging tile
+    // holds is walked in two halves.  That must stay the exception -- a half walk costs a whole one -- so the tile is never
+    // smaller than 2176 bytes (a typical 1 KB tile decodes to 1300 .. 1500 symbols) unless a whole worst-case tile is
     const uint32_t per_lane = (uint32_t)(kF_SubBits / fsm_min_bits(mode)) + 2u;
-    return (16u * per_lane + 48u + 15u) & ~15u;
+    const uint32_t half = 16u * per_lane + 48u, whole = 32u * per_lane + 48u;
+    const uint32_t want = half > 2176u ? half : 2176u;
+    return ((want < whole ? want : whole) + 15u) & ~15u;
 }
 static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsigned long long end, unsigned long long nsubf,
                            unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, int mode,
@@ -1134,13 +1147,13 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
     const int rows = fsm_states(mode) + 1;   // + DEAD
     const FsmTables t = fsm_tables_at(fw.fsm);
     const uint32_t stage = fsm_stage_bytes(mode);
-    const size_t budget = 227 * 1024 - 1024;
+    const size_t budget = 227 * 1024 - 1024, row = kFsmWriteRowBytes + kFsmWriteXRowBytes;
     int warps = 24;
     size_t hot = rows;
-    if (kFsmHeaderBytes + hot * kFsmWriteRowBytes + (size_t)warps * stage > budget)
-        hot = (budget - kFsmHeaderBytes - (size_t)warps * stage) / kFsmWriteRowBytes;
+    if (kFsmHeaderBytes + hot * row + (size_t)warps * stage + 256 > budget)
+        hot = (budget - kFsmHeaderBytes - (size_t)warps * stage - 256) / row;
     const bool split = hot < (size_t)rows;
-    const size_t smem = kFsmHeaderBytes + hot * kFsmWriteRowBytes + (size_t)warps * stage;
+    const size_t smem = kFsmHeaderBytes + hot * row + (size_t)warps * stage + 256;
     const int per_sm = smem <= 56 * 1024 ? 2 : 1;   // (2 x 768 threads: the register file allows no more)
     DC_CUDA_TRY(ensure_dynamic_smem(split ? (const void *)fsm_write_kernel<true> : (const void *)fsm_write_kernel<false>, smem));
     const unsigned long long want = (nseg + warps - 1) / warps, cap = (unsigned long long)sm_count() * per_sm;

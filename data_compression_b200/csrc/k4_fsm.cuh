@@ -8,7 +8,9 @@
 // boundary is fully described by WHERE INSIDE A CODE the boundary falls -- one of the internal nodes of the code tree,
 // at most 256 of them for byte alphabets.  So the tables here are indexed by (state, next byte):
 //   F1  u16  number of codes that END in this byte | next state << 8
-//   F3  u64  up to four decoded symbols | PRMT selector 0x3210 + 0x1111 * count | next state << 16
+//   F3  u32  symbol 0 | symbol 1 << 8 | next state << 16 | count << 24   (+ u16: symbols 2 and 3, read only by the
+//            few lanes whose byte completes more than two codes: a random 8-byte gather costs 5.9 shared-memory
+//            wavefronts, a 4-byte one 3.1, and the walks are bound by exactly those bank-conflict replays)
 // and a walk is 32 fixed, fully unrolled steps per 256-bit subsequence: no positions, no windows, no look-ahead word,
 // no loop condition, no divergence, codes of any length at the same speed.  F1: PRMT (index = state, byte) + IMAD +
 // LDS + IADD per byte.  F3: the symbols of a step are appended to a 4-byte sliding window with one PRMT whose selector
@@ -42,22 +44,26 @@ struct FsmHeader {
 };
 constexpr size_t kFsmHeaderBytes = (sizeof(FsmHeader) + 255) & ~(size_t)255;
 constexpr size_t kFsmSyncRowBytes = 256 * sizeof(uint16_t);            // F1: one state
-constexpr size_t kFsmWriteRowBytes = 256 * sizeof(unsigned long long); // F3: one state
+constexpr size_t kFsmWriteRowBytes = 256 * sizeof(uint32_t);           // F3: one state, symbols 0 and 1
+constexpr size_t kFsmWriteXRowBytes = 256 * sizeof(uint16_t);          // F3: one state, symbols 2 and 3
 constexpr size_t kFsmSyncTableBytes = kFsmMaxStates * kFsmSyncRowBytes;
 constexpr size_t kFsmWriteTableBytes = (kFsmMaxStates + 1) * kFsmWriteRowBytes;
-constexpr size_t kFsmWorkspaceBytes = kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes;
+constexpr size_t kFsmWriteXTableBytes = (kFsmMaxStates + 1) * kFsmWriteXRowBytes;
+constexpr size_t kFsmWorkspaceBytes = kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes + kFsmWriteXTableBytes;
 
 struct FsmTables {   // where the three pieces live in the decode workspace
     FsmHeader *hdr;
     uint16_t *sync;
-    unsigned long long *write;
+    uint32_t *write;
+    uint16_t *writex;
 };
 static inline FsmTables fsm_tables_at(void *p) {
     char *c = (char *)p;
     FsmTables t;
     t.hdr = (FsmHeader *)c;
     t.sync = (uint16_t *)(c + kFsmHeaderBytes);
-    t.write = (unsigned long long *)(c + kFsmHeaderBytes + kFsmSyncTableBytes);
+    t.write = (uint32_t *)(c + kFsmHeaderBytes + kFsmSyncTableBytes);
+    t.writex = (uint16_t *)(c + kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes);
     return t;
 }
 
@@ -122,7 +128,8 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
     const int s = blockIdx.x;
     if (ns == 0 || s > ns) return;
     if (s == ns) {  // DEAD: absorbs everything, emits nothing
-        t.write[(size_t)s * 256 + tid] = (unsigned long long)(0x3210u | ((uint32_t)ns << 16)) << 32;
+        t.write[(size_t)s * 256 + tid] = (uint32_t)ns << 16;
+        t.writex[(size_t)s * 256 + tid] = 0;
         return;
     }
     int d0;
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
             dead = r == -2;
         }
         next = dead ? (uint32_t)ns : fsm_state_id(&h, d, v);
-        const uint32_t meta = (0x3210u + 0x1111u * cnt) | (next << 16);
-        t.write[(size_t)s * 256 + tid] = (unsigned long long)syms | ((unsigned long long)meta << 32);
+        t.write[(size_t)s * 256 + tid] = (syms & 0xFFFFu) | (next << 16) | (cnt << 24);
+        t.writex[(size_t)s * 256 + tid] = (uint16_t)(syms >> 16);
     }
 }
 
@@ -166,9 +173,9 @@ __device__ __forceinline__ uint32_t lds_u16_at(uint32_t base, uint32_t idx) {
     asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(v) : "r"(idx), "r"(base));
     return v;
 }
-__device__ __forceinline__ uint2 lds_u64_at(uint32_t base, uint32_t idx) {
-    uint2 v;
-    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %2, 8, %3;\n\tld.shared.v2.u32 {%0, %1}, [a];\n\t}" : "=r"(v.x), "=r"(v.y) : "r"(idx), "r"(base));
+__device__ __forceinline__ uint32_t lds_u32_at(uint32_t base, uint32_t idx) {
+    uint32_t v;
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" : "=r"(v) : "r"(idx), "r"(base));
     return v;
 }
 
@@ -406,32 +413,38 @@ struct FsmWriteArgs {
     int32_t *d_status;
 };
 
-__device__ __forceinline__ uint2 ldg_u64_at(const unsigned long long *base, uint32_t idx) {
-    uint2 v;
-    asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(base + idx));
-    return v;
-}
 __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool p) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
 
+struct FsmWriteTabs {
+    uint32_t tab, xtab;            // shared-memory addresses of the resident rows
+    const uint32_t *gtab;          // the whole tables in global memory (SPLIT: rows behind hot_limit are read from here)
+    const uint16_t *gxtab;
+    uint32_t hot_limit;            // hot rows * 256
+};
+
 // One byte step of the write walk.  acc = the lane's last four symbols (newest in the top byte), G = 8 x pending bytes in its
-// low 5 bits (bit 5 toggles when a word completes), wptr = shared address of the word being filled.
+// low 5 bits (bit 5 toggles when a word completes), wptr = shared address of the word being filled, e = the previous entry.
 template <bool SPLIT, int J>
-__device__ __forceinline__ void fsm_write_step(uint32_t tab, const unsigned long long *__restrict__ gtab, uint32_t hot_limit, uint32_t w,
-                                               uint32_t &meta, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
-    const uint32_t idx = prmt(w, meta, 0xF760u | (uint32_t)J);   // byte J | state << 8 (9 bits); byte 3 = sign of a byte that is 0 or 1
-    uint2 e;
-    if (SPLIT) {
-        if (idx < hot_limit) e = lds_u64_at(tab, idx);
-        else e = ldg_u64_at(gtab, idx);
-    } else {
-        e = lds_u64_at(tab, idx);
+__device__ __forceinline__ void fsm_write_step(const FsmWriteTabs &T, uint32_t w, uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
+    const uint32_t idx = prmt(w, e, 0xFF60u | (uint32_t)J);   // byte J | state << 8; bytes 2, 3 = sign of the count byte = 0
+    const bool hot = !SPLIT || idx < T.hot_limit;
+    if (hot) e = lds_u32_at(T.tab, idx);
+    else e = __ldg(T.gtab + idx);
+    const uint32_t c = e >> 24;
+    uint32_t syms = e;   // symbols 0 and 1 (the state and the count above them are never taken: a window slides by c bytes)
+    if (c >= 3u) {
+        uint32_t x;
+        if (hot) asm volatile("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(x) : "r"(idx), "r"(T.xtab));
+        else x = __ldg(T.gxtab + idx);
+        syms = prmt(e, x, 0x5410u);
     }
-    const uint32_t sw = __funnelshift_l(acc, e.x, G);   // the pending bytes, then this step's symbols
-    acc = prmt(acc, e.x, e.y);                          // slide the window by `count` bytes
-    // G += 8 * count (one IMAD on the whole meta word: its low nibble is the count, everything else lands above bit 6);
-    // bit 5 of G toggles exactly when a word has been completed: store it and advance (one LOP3 into a predicate)
+    const uint32_t sw = __funnelshift_l(acc, syms, G);   // the pending bytes, then this step's symbols
+    uint32_t sel;
+    asm("mad.lo.u32 %0, %1, 0x1111, 0x3210;" : "=r"(sel) : "r"(c));
+    acc = prmt(acc, syms, sel);                           // slide the window by c bytes
+    // G += 8 c; bit 5 of G toggles exactly when a word has been completed: store it and advance
     asm volatile(
         "{\n\t.reg .pred q;\n\t.reg .u32 g2, x;\n\t"
         "mad.lo.u32 g2, %3, 8, %1;\n\t"
@@ -442,20 +455,18 @@ __device__ __forceinline__ void fsm_write_step(uint32_t tab, const unsigned long
         "@q add.u32 %0, %0, 4;\n\t"
         "mov.u32 %1, g2;\n\t}"
         : "+r"(wptr), "+r"(G)
-        : "r"(sw), "r"(e.y)
+        : "r"(sw), "r"(c)
         : "memory");
-    meta = e.y;
 }
 
 template <bool SPLIT>
-__device__ __forceinline__ void fsm_write_walk(uint32_t tab, const unsigned long long *__restrict__ gtab, uint32_t hot_limit,
-                                               const uint32_t (&w)[8], uint32_t &meta, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
+__device__ __forceinline__ void fsm_write_walk(const FsmWriteTabs &T, const uint32_t (&w)[8], uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        fsm_write_step<SPLIT, 0>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
-        fsm_write_step<SPLIT, 1>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
-        fsm_write_step<SPLIT, 2>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
-        fsm_write_step<SPLIT, 3>(tab, gtab, hot_limit, w[k], meta, acc, G, wptr);
+        fsm_write_step<SPLIT, 0>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<SPLIT, 1>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<SPLIT, 2>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<SPLIT, 3>(T, w[k], e, acc, G, wptr);
     }
 }
 
@@ -463,23 +474,28 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTables t, FastWorkspace ws) {
     extern __shared__ __align__(16) uint8_t fsm_smem[];
     FsmHeader *s_h = (FsmHeader *)fsm_smem;
-    unsigned long long *s_tab = (unsigned long long *)(fsm_smem + kFsmHeaderBytes);
+    uint32_t *s_tab = (uint32_t *)(fsm_smem + kFsmHeaderBytes);
+    uint16_t *s_xtab = (uint16_t *)(fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * kFsmWriteRowBytes);
     if (*ws.mismatch) return;  // the robust path redoes the stream
     {
         const uint32_t *src = (const uint32_t *)t.hdr;
         uint32_t *dst = (uint32_t *)s_h;
         for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
-        const uint4 *s4 = (const uint4 *)t.write;
-        uint4 *d4 = (uint4 *)s_tab;
-        const int vecs = (int)a.hot_rows * 128;   // 2 KB per row
-        for (int i = threadIdx.x; i < vecs; i += blockDim.x) d4[i] = s4[i];
+        const uint4 *s4 = (const uint4 *)t.write, *x4 = (const uint4 *)t.writex;
+        uint4 *d4 = (uint4 *)s_tab, *dx4 = (uint4 *)s_xtab;
+        for (int i = threadIdx.x; i < (int)a.hot_rows * 64; i += blockDim.x) d4[i] = s4[i];    // 1 KB per row
+        for (int i = threadIdx.x; i < (int)a.hot_rows * 32; i += blockDim.x) dx4[i] = x4[i];   // 512 bytes per row
         __syncthreads();
     }
-    uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_tab);
-    asm volatile("" : "+r"(tab));
-    const uint32_t hot_limit = a.hot_rows * 256u;
+    FsmWriteTabs T;
+    T.tab = (uint32_t)__cvta_generic_to_shared(s_tab);
+    T.xtab = (uint32_t)__cvta_generic_to_shared(s_xtab);
+    asm volatile("" : "+r"(T.tab), "+r"(T.xtab));
+    T.gtab = t.write;
+    T.gxtab = t.writex;
+    T.hot_limit = a.hot_rows * 256u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    uint8_t *stage = fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * kFsmWriteRowBytes + (size_t)warp * a.stage_bytes;
+    uint8_t *stage = fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * (kFsmWriteRowBytes + kFsmWriteXRowBytes) + (size_t)warp * a.stage_bytes;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
     const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
     const unsigned long long tile_bits = 32ull * kF_SubBits;
@@ -553,13 +569,13 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
                 __syncwarp();
                 uint32_t wptr0 = stage_addr + (pos0 & ~3u), wptr = wptr0, G = 8u * (pos0 & 3u), acc = 0u;
                 uint32_t meta = (my_info & 0xFFu) << 16;
-                if (mine && my_cnt) fsm_write_walk<SPLIT>(tab, t.write, hot_limit, w, meta, acc, G, wptr);
+                if (mine && my_cnt) fsm_write_walk<SPLIT>(T, w, meta, acc, G, wptr);
                 __syncwarp();
                 if (mine && my_cnt) {
                     const uint32_t pend = (G >> 3) & 3u;
                     if (pend) atomicOr((uint32_t *)(stage + (wptr - stage_addr)), __funnelshift_l(acc, 0u, G));
                     const uint32_t written = (wptr - wptr0) + pend - (pos0 & 3u);
-                    if (written != my_cnt || (meta >> 16) == dead_state) corrupt = true;
+                    if (written != my_cnt || ((meta >> 16) & 0xFFu) == dead_state) corrupt = true;
                 }
                 __syncwarp();
                 // copy-out: staging byte i <-> out[pob - al + i]; 16-byte words are aligned on both sides
