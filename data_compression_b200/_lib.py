@@ -77,6 +77,21 @@ SYMBOLS = [
     ("dc_huff_decode", _i, [_vp, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_huff_decode_shard_sync", _i, [_vp, _i, _u, _u64, _u64, _vp, _vp, _vp, _sz, _vp]),
     ("dc_huff_decode_shard_write", _i, [_vp, _i, _u64, _u64, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
+    ("dc_shard_unique_id", _i, [_vp]),
+    ("dc_shard_comm_create", _i, [_vp, _i, _i, C.POINTER(C.c_void_p)]),
+    ("dc_shard_comm_from_nccl", _i, [_vp, _i, _i, C.POINTER(C.c_void_p)]),
+    ("dc_shard_comm_destroy", _i, [_vp]),
+    ("dc_shard_comm_rank", _i, [_vp]),
+    ("dc_shard_comm_world", _i, [_vp]),
+    ("dc_shard_huff_encode_workspace_bytes", _sz, [_sz, _i]),
+    ("dc_shard_huff_encode", _i, [_vp, _vp, _sz, _i, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    ("dc_shard_huff_encode_info", _i, [_vp, _sz, _i, _u64p, _u64p, _u64p, _vp]),
+    ("dc_shard_huff_gather", _i, [_vp, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
+    ("dc_shard_huff_decode_workspace_bytes", _sz, [_sz, _i]),
+    ("dc_shard_huff_decode_stream", _i, [_vp, _vp, _sz, _u64, _vp, _vp, _sz, _u64p, _u64p, _u64p, _vp, _vp, _sz, _vp]),
+    ("dc_shard_nybble_range", _i, [_u64, _i, _i, _u64p, _u64p]),
+    ("dc_shard_nybble_pack", _i, [_u64, _i, _i, _vp, _vp, _vp, _vp]),
+    ("dc_shard_nybble_unpack", _i, [_u64, _i, _i, _vp, _vp, _vp]),
     ("dc_nybble_pack", _i, [_vp, _sz, _vp, _vp, _vp]),
     ("dc_nybble_unpack", _i, [_vp, _sz, _vp, _vp]),
     ("dc_trit_pack", _i, [_vp, _u64, _vp, _vp, _vp]),

@@ -133,6 +133,7 @@ extern "C" const char *dc_status_string(int s) {
         case DC_ERR_CORRUPT: return "corrupt bitstream";
         case DC_ERR_SYMBOL: return "symbol without a code / nibble symbol >= 16";
         case DC_ERR_RADIX: return "payload packing needs n in {2,4,16}";
+        case DC_ERR_NCCL: return "NCCL unavailable (libnccl.so.2 / $DC_NCCL_LIB) or a collective failed";
         default: return "unknown status";
     }
 }
@@ -264,9 +265,10 @@ extern "C" int dc_host_convert_lengths_to_encode_table(int max_symbol_value, con
 static int encode_from_table(const uint8_t *h_in, size_t n, dc_huff_table *d_tab, uint8_t *h_out, size_t out_capacity,
                              uint64_t *total_bits, size_t *bytes_written, uint8_t *d_in, uint8_t *d_out, size_t d_cap,
                              void *d_ws, size_t ws_bytes, uint64_t *d_bits, int32_t *d_status, bool input_resident, bool trits,
-                             uint8_t *d_packed) {
+                             uint8_t *d_packed, bool planned = false) {
     if (!input_resident && n) DC_CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n, cudaMemcpyHostToDevice, 0));
-    int rc = dc_huff_encode(d_in, n, d_tab, d_out, d_cap, 0, d_bits, d_status, d_ws, ws_bytes, nullptr);
+    int rc = planned ? dc_huff_encode_planned(d_in, n, d_tab, d_out, d_cap, 0, d_bits, d_status, d_ws, ws_bytes, nullptr)
+                     : dc_huff_encode(d_in, n, d_tab, d_out, d_cap, 0, d_bits, d_status, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
     uint64_t bits = 0;
     int32_t st = 0;
@@ -346,13 +348,15 @@ extern "C" long long dc_host_huff_compress(const uint8_t *in, size_t n, int comp
     uint64_t *d_bits = (uint64_t *)g_arena.take(8);
     int32_t *d_status = (int32_t *)g_arena.take(4);
     if (n) DC_CUDA_TRY(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, 0));
-    rc = dc_histogram_u8(d_in, n, d_hist, nullptr);
+    // the histogram pass leaves one small histogram per 32 KB run in the workspace: the encoder then knows every run's bit
+    // offset without reading the input a second time
+    rc = dc_histogram_u8_runs(d_in, n, d_hist, d_ws, ws_bytes, nullptr);
     if (rc != DC_OK) return rc;
     rc = dc_huff_build(d_hist, compressed_symbols, d_tab, nullptr);
     if (rc != DC_OK) return rc;
     size_t written = 0;
     rc = encode_from_table(in, n, d_tab, out, out_capacity, total_bits, &written, d_in, d_out, d_cap, d_ws, ws_bytes, d_bits,
-                           d_status, true, trits, d_packed);
+                           d_status, true, trits, d_packed, true);
     if (rc != DC_OK) return rc;
     DC_CUDA_TRY(cudaMemcpy(lengths_out, (const char *)d_tab + offsetof(dc_huff_table, lengths), DC_NSLOTS * 4,
                            cudaMemcpyDeviceToHost));

@@ -62,6 +62,10 @@ int trit_unpack_launch(const uint8_t *d_payload, unsigned long long ntrits, uint
 // K1 with one 256 x u16 histogram per 32 KB run (k1_histogram.cu), for the planned encoder
 int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st);
 
+int encode_planned_device_phase(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                                const uint32_t *d_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace,
+                                size_t workspace_bytes, cudaStream_t st);
+
 // K8 (k8_mtf.cu): the move-to-front contexts of the adaptive nybble compressor, used by K6
 size_t mtf_workspace_bytes(size_t n);
 // d_pos[i] = position of d_src[i] in its context's list just before it is touched (8 = absent; d_pos[0] = 8)

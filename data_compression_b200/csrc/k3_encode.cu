@@ -57,6 +57,7 @@ struct EncWorkspace {
     unsigned long long *run_off;   // [nruns+1]    E2 (exclusive; last = total)
     uint32_t *bstate;              // [nchunks+1]  arrivals at the boundary word between chunk b-1 and chunk b
     uint4 *bleft, *bright;         // [nchunks+1]  the two halves of that word (big-endian word domain)
+    const uint32_t *d_phase;       // != nullptr: the bit phase is read from device memory (a shard learns it from a collective)
 };
 
 // bits [bit, bit+32) of a big-endian word array
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
     __shared__ entry_t s_enc[256];
 
     if (tab->status != DC_OK || tab->bits_per_digit == 0) return;  // reported by the count kernel
+    if (ws.d_phase) phase = *ws.d_phase & 7u;
     if (WIDE && tab->max_bits <= kNarrowBits) return;             // the single-pass kernels handle this table
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -422,6 +424,7 @@ struct SpWorkspace {
     unsigned long long *desc;      // [nruns]      status << 62 | bits of the run
     uint32_t *bstate;              // [nchunks+1]  arrivals at the boundary word between chunk b-1 and chunk b
     uint4 *bleft, *bright;         // [nchunks+1]
+    const uint32_t *d_phase;
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
@@ -532,6 +535,7 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
     __shared__ uint32_t s_bits[kEncWarps];
     __shared__ unsigned long long s_run_excl;
     if (!table_usable(tab, d_status)) return;
+    if (ws.d_phase) phase = *ws.d_phase & 7u;
     constexpr int kSpStageWords = sp_stage_words(MAXBITS);
     {   // this instantiation's tables: (12, 16] or [1, 12]; wide tables take the three-launch path
         const int mb = tab->max_bits;
@@ -752,6 +756,7 @@ struct FwWorkspace {
     const unsigned long long *run_off;   // [nruns + 1] exclusive bit offsets, last = total
     uint32_t *bstate;
     uint4 *bleft, *bright;
+    const uint32_t *d_phase;
 };
 
 // one sub-tile (32 lanes x 16 symbols) appended to the warp's staging buffer at bit position `bitpos`
@@ -850,6 +855,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
     extern __shared__ __align__(16) uint8_t fw_smem[];   // [exchange | staging buffers | padding | table at 0x20000]
     if (!table_usable(tab, d_status)) return;
     if (tab->max_bits > kFwMaxBits) return;   // the look-back single pass (13 .. 16 bits) or the 64-bit-entry kernel takes this table
+    if (ws.d_phase) phase = *ws.d_phase & 7u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = warp / kFwWarps, gw = warp % kFwWarps;
     const size_t stream_bytes = (size_t)(((unsigned long long)phase + ws.run_off[nruns] + 7) >> 3);
     if (stream_bytes > out_cap) {
@@ -948,6 +954,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
                 SpWorkspace sp;
                 sp.ticket = nullptr;
                 sp.desc = nullptr;
+                sp.d_phase = nullptr;
                 sp.bstate = ws.bstate;
                 sp.bleft = ws.bleft;
                 sp.bright = ws.bright;
@@ -1044,7 +1051,7 @@ __global__ void __launch_bounds__(kPlanThreads) encode_plan_kernel(const uint16_
     // exclusive scan of run_bits by the last CTA (every other CTA's totals are visible: fence + counter)
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    constexpr int kItems = 8;
+    constexpr int kItems = 32;   // 32 K runs (1 GiB of input) per trip
     for (unsigned int base = 0; base < nruns; base += kPlanThreads * kItems) {
         const unsigned int first = base + tid * kItems;
         uint32_t item[kItems];
@@ -1111,7 +1118,7 @@ extern "C" size_t dc_huff_encode_workspace_bytes(size_t n) { return enc_ws_layou
 
 static int encode_entry(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
                         unsigned bit_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace, size_t workspace_bytes,
-                        void *stream, bool planned) {
+                        void *stream, bool planned, const uint32_t *d_phase = nullptr) {
     if (!d_table || (n && (!d_in || !d_out || !d_workspace)) || bit_phase > 7) return DC_ERR_ARG;
     if ((((uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)d_workspace) & 15) != 0) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1132,6 +1139,7 @@ static int encode_entry(const uint8_t *d_in, size_t n, const dc_huff_table *d_ta
     ws.bstate = (uint32_t *)(w + off[3]);
     ws.bleft = (uint4 *)(w + off[4]);
     ws.bright = (uint4 *)(w + off[5]);
+    ws.d_phase = d_phase;
     // bstate + ticket and (contiguous, see enc_ws_layout) the look-back descriptors are zeroed in one memset
     DC_CUDA_TRY(cudaMemsetAsync(w + off[3], 0, (off[7] - off[3]) + nchunks * 8, st));
     const unsigned int sms = (unsigned int)sm_count();
@@ -1169,6 +1177,15 @@ extern "C" int dc_huff_encode_planned(const uint8_t *d_in, size_t n, const dc_hu
     return encode_entry(d_in, n, d_table, d_out, out_capacity, bit_phase, d_total_bits, d_status, d_workspace, workspace_bytes, stream, true);
 }
 
+namespace dc {
+// dc_huff_encode_planned with the bit phase in device memory (shard_nccl.cu: the phase comes out of a collective)
+int encode_planned_device_phase(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
+                                const uint32_t *d_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace,
+                                size_t workspace_bytes, cudaStream_t st) {
+    return encode_entry(d_in, n, d_table, d_out, out_capacity, 0, d_total_bits, d_status, d_workspace, workspace_bytes, (void *)st, true, d_phase);
+}
+}  // namespace dc
+
 extern "C" int dc_histogram_u8_runs(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *d_encode_workspace, size_t workspace_bytes,
                                     void *stream) {
     if (!d_hist || (n && (!d_in || !d_encode_workspace))) return DC_ERR_ARG;
@@ -1190,6 +1207,7 @@ static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table
         fw.bstate = ws.bstate;
         fw.bleft = ws.bleft;
         fw.bright = ws.bright;
+        fw.d_phase = ws.d_phase;
         DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel, kFwSmemBytes));
         LaunchScope ls(DC_K_ENCODE_FAST, st);
         encode_fast_kernel<<<min((nruns + kFwGroups - 1) / kFwGroups, sms), kFwThreads, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity,
@@ -1202,6 +1220,7 @@ static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table
         sp.bstate = ws.bstate;
         sp.bleft = ws.bleft;
         sp.bright = ws.bright;
+        sp.d_phase = ws.d_phase;
         const size_t smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
         DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kNarrowBits>, smem16));
         LaunchScope ls(DC_K_ENCODE_MID, st);

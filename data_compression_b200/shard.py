@@ -253,3 +253,115 @@ class ShardedHuffman:
             if sz:
                 out[o: o + sz] |= p[:sz]
         return out
+
+
+class NcclShards:
+    """The C-ABI shard layer (dc_shard_* in include/dc_b200.h, csrc/shard_nccl.cu): NCCL collectives issued by the
+    library itself on a communicator of its own.  torch.distributed is only used once, to hand rank 0's NCCL id to
+    the other ranks; a single process (world 1) needs no process group at all."""
+
+    def __init__(self, device=None, group=None):
+        import ctypes as C
+
+        from ._lib import check, lib
+        self.C, self.L, self.check = C, lib(), check
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(self.L.dc_shard_unique_id(buf), "dc_shard_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world > 1:
+            t = ident.to(self.device) if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu()
+        raw = (C.c_ubyte * 128)(*[int(x) for x in ident])
+        comm = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.L.dc_shard_comm_create(raw, self.rank, self.world, C.byref(comm)), "dc_shard_comm_create")
+        self.comm = comm
+
+    def close(self):
+        if self.comm:
+            self.L.dc_shard_comm_destroy(self.comm)
+            self.comm = None
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    # ---- encode (BASELINE config 4)
+    def encode_buffers(self, n_local: int):
+        dev = self.device
+        from .api import HuffTable
+        return {"out": torch.empty(n_local + n_local // 4 + 4096, dtype=torch.uint8, device=dev),
+                "ws": torch.empty(max(self.L.dc_shard_huff_encode_workspace_bytes(n_local, self.world), 16), dtype=torch.uint8, device=dev),
+                "bits": torch.empty(1, dtype=torch.int64, device=dev), "status": torch.empty(1, dtype=torch.int32, device=dev),
+                "table": HuffTable(dev)}
+
+    def encode(self, local: torch.Tensor, n_ary: int, buf=None):
+        """Stream-ordered, non-blocking: returns the buffers (out, ws, bits, status, table) the call filled."""
+        buf = buf or self.encode_buffers(local.numel())
+        self.check(self.L.dc_shard_huff_encode(self.comm, local.data_ptr(), local.numel(), n_ary, buf["table"].ptr, buf["out"].data_ptr(),
+                                               buf["out"].numel(), buf["bits"].data_ptr(), buf["status"].data_ptr(), buf["ws"].data_ptr(),
+                                               buf["ws"].numel(), self._stream()), "dc_shard_huff_encode")
+        return buf
+
+    def encode_info(self, buf, n_local: int):
+        """Blocking: (bit offset of this shard, its bits, bits of the whole stream)."""
+        C = self.C
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.check(self.L.dc_shard_huff_encode_info(buf["ws"].data_ptr(), n_local, self.world, C.byref(a), C.byref(b), C.byref(c),
+                                                    self._stream()), "dc_shard_huff_encode_info")
+        self.check(int(buf["status"].item()), "dc_shard_huff_encode")
+        return a.value, b.value, c.value
+
+    def gather(self, buf, n_local: int, total_bits: int, root: int = 0, out=None):
+        """Blocking: the whole stream in one buffer on `root` (None elsewhere)."""
+        nbytes = (total_bits + 7) // 8
+        if self.rank == root and out is None:
+            out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        self.check(self.L.dc_shard_huff_gather(self.comm, root, buf["out"].data_ptr(), buf["ws"].data_ptr(), n_local,
+                                               out.data_ptr() if out is not None else None, out.numel() if out is not None else 0,
+                                               self._stream()), "dc_shard_huff_gather")
+        return out[:nbytes] if self.rank == root else None
+
+    # ---- decode of one blindly cut stream (BASELINE config 5)
+    def decode_buffers(self, part_bytes: int, out_capacity: int):
+        dev = self.device
+        return {"buf": torch.zeros(1024 + part_bytes + 1024, dtype=torch.uint8, device=dev),
+                "out": torch.empty(max(out_capacity, 16), dtype=torch.uint8, device=dev),
+                "ws": torch.empty(max(self.L.dc_shard_huff_decode_workspace_bytes(part_bytes, self.world), 16), dtype=torch.uint8, device=dev),
+                "status": torch.empty(1, dtype=torch.int32, device=dev)}
+
+    def decode_stream(self, buf, part_bytes: int, total_bits: int, table):
+        """buf["buf"][1024 : 1024 + mine] holds this rank's bytes.  Blocking.  Returns (symbols tensor, offset, total)."""
+        C = self.C
+        n, off, tot = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.check(self.L.dc_shard_huff_decode_stream(self.comm, buf["buf"].data_ptr(), part_bytes, total_bits, table.ptr, buf["out"].data_ptr(),
+                                                      buf["out"].numel(), C.byref(n), C.byref(off), C.byref(tot), buf["status"].data_ptr(),
+                                                      buf["ws"].data_ptr(), buf["ws"].numel(), self._stream()), "dc_shard_huff_decode_stream")
+        return buf["out"][: n.value], off.value, tot.value
+
+    # ---- nybble shards (no exchange)
+    def nybble_range(self, n_total: int):
+        C = self.C
+        lo, hi = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.L.dc_shard_nybble_range(n_total, self.rank, self.world, C.byref(lo), C.byref(hi)), "dc_shard_nybble_range")
+        return lo.value, hi.value
+
+    def nybble_pack(self, n_total: int, sym_local: torch.Tensor):
+        lo, hi = self.nybble_range(n_total)
+        packed = torch.empty(max((hi - lo + 1) // 2, 1), dtype=torch.uint8, device=sym_local.device)
+        status = torch.zeros(1, dtype=torch.int32, device=sym_local.device)
+        self.check(self.L.dc_shard_nybble_pack(n_total, self.rank, self.world, sym_local.data_ptr(), packed.data_ptr(), status.data_ptr(),
+                                               self._stream()), "dc_shard_nybble_pack")
+        return packed[: (hi - lo + 1) // 2], status
+
+    def nybble_unpack(self, n_total: int, packed_local: torch.Tensor):
+        lo, hi = self.nybble_range(n_total)
+        sym = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=packed_local.device)
+        self.check(self.L.dc_shard_nybble_unpack(n_total, self.rank, self.world, packed_local.data_ptr(), sym.data_ptr(), self._stream()),
+                   "dc_shard_nybble_unpack")
+        return sym[: hi - lo]

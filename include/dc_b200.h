@@ -53,7 +53,8 @@ enum dc_status {
     DC_ERR_CAPACITY = -4,      /* output buffer too small */
     DC_ERR_CORRUPT = -5,       /* bitstream hits an unused code slot / ends inside a code */
     DC_ERR_SYMBOL = -6,        /* input symbol has no code (length 0), or nibble symbol >= 16 (:1093) */
-    DC_ERR_RADIX = -7          /* payload packing is defined for n in {2,4,16} only */
+    DC_ERR_RADIX = -7,         /* payload packing is defined for n in {2,4,16} only */
+    DC_ERR_NCCL = -8           /* NCCL could not be loaded (libnccl.so.2 / $DC_NCCL_LIB) or a collective failed */
 };
 
 /*
@@ -255,15 +256,18 @@ int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, co
  * Geometry, the same for both calls:
  *   d_bits            first byte of the shard, 16-byte aligned, at a multiple of 1024 bytes of the stream
  *   has_halo          != 0: the 1024 bytes in front of d_bits are readable and hold the previous shard's tail
- *   first_code_bit    has_halo == 0 only: exact bit offset (< 128) of the first code that starts in the shard
+ *   first_code_bit    has_halo == 0 only: exact bit offset (< 128) of the first code that starts in the shard, or the
+ *                     previous shard's `exit` as reported
  *   shard_bits        bits of the stream that belong to this shard (a multiple of 8192 for all but the last shard)
  *   stream_bits_left  bits from d_bits to the end of the stream (>= shard_bits; up to 8 bytes past the shard are read)
  */
 typedef struct dc_shard_summary {
     uint64_t symbols;        /* codes that START in the shard */
-    uint32_t exit;           /* bits by which the shard's last code reaches into the next shard */
+    uint32_t exit;           /* where the shard's last code ends: bits it reaches into the next shard, or (byte-stepped decoder)
+                              * 0x80000000 | the code-tree state at the shard's end.  Opaque: compare with the next shard's
+                              * assumed_start, feed back as first_code_bit */
     int32_t resync;          /* != 0: some 16 KB segment inside the shard did not self-synchronise; decode the stream whole */
-    uint32_t assumed_start;  /* bit offset of the first code the shard assumed (== first_code_bit without a halo) */
+    uint32_t assumed_start;  /* what the shard assumed in front of its first byte (same encoding as exit; == first_code_bit without a halo) */
     uint32_t reserved;
 } dc_shard_summary;
 
@@ -275,6 +279,67 @@ int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, unsigned firs
 int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, uint64_t shard_bits, uint64_t stream_bits_left,
                                const dc_huff_table *d_table, uint8_t *d_out, size_t n_out, int32_t *d_status,
                                void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- shards over several GPUs (NCCL)
+ *
+ * One process per GPU; every call below is made by all ranks of a communicator with the current device set to the
+ * rank's GPU (SURVEY 8b last cell, 8e; BASELINE configs 4 and 5).  NCCL is bound at run time (dlopen of libnccl.so.2,
+ * or the library named by $DC_NCCL_LIB); without it these return DC_ERR_NCCL.  The data path has no bulk collective:
+ * the ranks exchange histograms (2 KB), shard edge bytes, 1 KB halos and 24-byte summaries.
+ */
+typedef struct dc_shard_comm dc_shard_comm;
+/* rank 0 makes an id (128 bytes = ncclUniqueId), hands it to the other ranks by any means, everybody creates */
+int dc_shard_unique_id(void *id128);
+int dc_shard_comm_create(const void *id128, int rank, int world, dc_shard_comm **out);
+/* or: wrap a communicator the caller already has (an ncclComm_t passed as void *); it is not destroyed with the wrapper */
+int dc_shard_comm_from_nccl(void *nccl_comm, int rank, int world, dc_shard_comm **out);
+int dc_shard_comm_destroy(dc_shard_comm *comm);
+int dc_shard_comm_rank(const dc_shard_comm *comm);
+int dc_shard_comm_world(const dc_shard_comm *comm);
+
+/*
+ * Encode one logical stream whose bytes are spread over the ranks in rank order (BASELINE config 4).  Stream-ordered,
+ * never blocks: local histogram -> ONE all-gather of the local histograms -> global table (d_table, identical on every
+ * rank) and every rank's bit total -> encode at bit phase O_r mod 8 (O_r = bits of the ranks in front) -> the bytes that
+ * neighbouring shards share are OR-merged.  d_out then holds stream bytes [O_r / 8, ceil((O_r + bits_r) / 8)); the
+ * concatenation over the ranks IS the single-stream payload of dc_huff_encode on the concatenated input.
+ *   d_total_bits  this rank's code bits (1 x u64, may be NULL);  d_status as dc_huff_encode
+ * dc_shard_huff_encode_info (blocking) reads O_r, bits_r and the stream's bit total back from the workspace;
+ * dc_shard_huff_gather (blocking) places all shards in one buffer on `root`.
+ */
+size_t dc_shard_huff_encode_workspace_bytes(size_t n_local, int world);
+int dc_shard_huff_encode(dc_shard_comm *comm, const uint8_t *d_in, size_t n_local, int n_ary, dc_huff_table *d_table,
+                         uint8_t *d_out, size_t out_capacity, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace,
+                         size_t workspace_bytes, void *stream);
+int dc_shard_huff_encode_info(const void *d_workspace, size_t n_local, int world, uint64_t *bit_offset, uint64_t *bits,
+                              uint64_t *total_bits, void *stream);
+int dc_shard_huff_gather(dc_shard_comm *comm, int root, const uint8_t *d_shard, const void *d_workspace, size_t n_local,
+                         uint8_t *d_stream, size_t stream_capacity, void *stream);
+
+/*
+ * Decode ONE stream of total_bits bits that is cut blindly into byte ranges (BASELINE config 5): rank r holds stream bytes
+ * [r * part_bytes, ...), part_bytes a multiple of 1024 and the same on every rank (the last ranks may hold less or
+ * nothing).  d_buf = [1024 bytes headroom | the rank's bytes | >= 1024 bytes tailroom], 16-byte aligned; the halos are
+ * exchanged here.  No side information about code boundaries: every rank synchronises over its left neighbour's tail,
+ * the summaries are all-gathered, a rank whose assumption was wrong starts over from its neighbour's real exit.  Blocking.
+ * On return d_out holds *n_symbols symbols that belong at *symbol_offset of the decoded output (*total_symbols in all).
+ */
+size_t dc_shard_huff_decode_workspace_bytes(size_t part_bytes, int world);
+int dc_shard_huff_decode_stream(dc_shard_comm *comm, uint8_t *d_buf, size_t part_bytes, uint64_t total_bits,
+                                const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity, uint64_t *n_symbols,
+                                uint64_t *symbol_offset, uint64_t *total_symbols, int32_t *d_status, void *d_workspace,
+                                size_t workspace_bytes, void *stream);
+
+/*
+ * Nybble pack / unpack over shards (write_nybble nybble_compression.c:1091-1114, split :767-773): no
+ * exchange at all -- shard starts are kept on even symbol indices so that no packed byte is shared.
+ * dc_shard_nybble_range gives the symbols [lo, hi) of n_total that `rank` takes; the pack / unpack calls work on the
+ * shard's own symbols (d_sym -> symbol lo) and packed bytes (d_packed -> byte lo / 2).
+ */
+int dc_shard_nybble_range(uint64_t n_total, int rank, int world, uint64_t *lo, uint64_t *hi);
+int dc_shard_nybble_pack(uint64_t n_total, int rank, int world, const uint8_t *d_sym, uint8_t *d_packed, int32_t *d_status,
+                         void *stream);
+int dc_shard_nybble_unpack(uint64_t n_total, int rank, int world, const uint8_t *d_packed, uint8_t *d_sym, void *stream);
 
 /* ------------------------------------------------------------------------- K5 nybble */
 
