@@ -291,14 +291,45 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
     uint32_t *stage = s_stage[warp];
     const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
 
+    __shared__ uint32_t s_cb[kEncWarps];
     for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
         const size_t chunk = (size_t)run * kEncWarps + warp;
+        // bit offsets of the run's chunks: a count of this warp's chunk first (the run's own offset is planned, the chunks'
+        // are not; the second read of the chunk comes out of L2)
+        uint32_t my_cb = 0;
+        if (chunk < nchunks) {
+            const size_t cbase = chunk * kChunkBytes, cend = min(n, cbase + (size_t)kChunkBytes);
+            for (size_t i = cbase + (size_t)lane * 16; i < cend; i += 512) {
+                if (i + 16 <= cend) {
+                    const uint4 v = ldg_stream((const uint4 *)(in + i));
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const entry_t e = s_enc[(wv[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+                        my_cb += WIDE ? (uint32_t)((unsigned long long)e >> 32) : ((uint32_t)e & 63u);
+                    }
+                } else {
+                    for (size_t j = i; j < cend; j++) {
+                        const entry_t e = s_enc[in[j]];
+                        my_cb += WIDE ? (uint32_t)((unsigned long long)e >> 32) : ((uint32_t)e & 63u);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_cb += __shfl_xor_sync(0xFFFFFFFFu, my_cb, o);
+        }
+        __syncthreads();   // the previous run's s_cb has been read
+        if (lane == 0) s_cb[warp] = my_cb;
+        __syncthreads();
+        uint32_t chunk_rel = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kEncWarps; w2++) chunk_rel += w2 < warp ? s_cb[w2] : 0u;
         if (chunk >= nchunks) continue;
         const size_t chunk_base = chunk * kChunkBytes;
         const size_t chunk_len = min((size_t)kChunkBytes, n - chunk_base);
         const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
         const int nfull = (int)(chunk_len / kSubTile);  // sub-tiles in which every lane has 16 symbols
-        unsigned long long g = (unsigned long long)phase + ws.run_off[run] + ws.chunk_rel[chunk];  // next bit to write
+        unsigned long long g = (unsigned long long)phase + ws.run_off[run] + chunk_rel;  // next bit to write
         const bool last_chunk = chunk == nchunks - 1;
         uint32_t carried = 0;  // lanes 0..3: the last 128 bits of the previous sub-tile of this chunk
         const uint8_t *src = in + chunk_base + (size_t)lane * kEncPerThread;  // this lane's 16 symbols of sub-tile 0
