@@ -382,6 +382,7 @@ def run_ours(args) -> None:
         b16 = S.encode_buffers(n)
         t_enc16 = timed(lambda: S.encode(data, 16, b16), reps=5, warm=2)
         off16, bits16, total16 = S.encode_info(b16, n)
+        S.gather(b16, n, total16, root=0)   # (the first exchange between two ranks sets up the NCCL peer connection)
         barrier()
         t0 = time.perf_counter()
         stream16 = S.gather(b16, n, total16, root=0)

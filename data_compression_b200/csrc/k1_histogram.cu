@@ -3,12 +3,12 @@
 // Replaces histogram() (n_ary_huffman.c:461-493): h[b]++ for every input byte, after zeroing h[0..258]
 // (:474-476).  Counts are 64-bit (the reference's int overflows at 2^31).
 //
-// The kernel is bound by the shared-memory update rate, not by HBM, so three counter layouts are kept
-// and selected at run time (DC_HIST_VARIANT, default chosen from measurements in profiles/):
-//   A<R>  per-warp u32 histograms, R lane-interleaved copies, shared-memory atomics
-//   B     per-LANE byte counters (lane == bank, so updates never conflict), plain load/add/store,
-//         folded into registers every 240 bytes per lane
-//   C     same layout as B, updated with one shared-memory atomic add of 1 << 8*(b&3)
+// The kernel is bound by the shared-memory atomic rate, not by HBM.  Two counter layouts:
+//   lane-private  [256 symbols][32 lanes] u32 per CTA: lane L only touches bank L, an atomic never has a bank conflict
+//                 (hist_runs_kernel: the default for 16-byte aligned input; also keeps one histogram per 32 KB run for the
+//                 planned encoder).  0.25 ms per GiB on Zipf and on uniform bytes.
+//   per-warp      256 u32 per warp, 2.3 wavefronts per atomic (hist_warp_atomic_kernel: round 1's winner among six layouts,
+//                 profiles/r1_v1_kernel_timings_1GiB.jsonl; kept for unaligned input).  0.32 / 0.42 ms per GiB.
 #include <stdlib.h>
 
 #include "dc_common.cuh"
@@ -69,163 +69,95 @@ __global__ void __launch_bounds__(256) hist_warp_atomic_kernel(const uint8_t *__
     }
 }
 
-// ------------------------------------------------------------------------------------------ variants B, C
-
-constexpr int kLpWarps = 4;                 // warps per CTA
-constexpr int kLpThreads = kLpWarps * 32;
-constexpr int kLpVecPerPeriod = 15;         // 15 x 16 B = 240 bytes per lane between folds (< 256)
-
-// fold the warp's 32 lane-private byte-counter columns into per-lane u32 registers and clear them.
-// lane L owns rows L and L+32 (bins 4L..4L+3 and 128+4L..128+4L+3); reads are rotated so that every
-// lane hits a different bank.
-__device__ __forceinline__ void fold_counters(uint32_t *wc, int lane, uint32_t acc[8]) {
-    __syncwarp();
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        uint32_t *row = wc + (lane + 32 * half) * 32;
-        uint32_t even = 0, odd = 0;  // 2 x 16-bit fields each; 32 copies x 255 < 65536
-#pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-            const int c = (lane + k) & 31;
-            const uint32_t w = row[c];
-            row[c] = 0;
-            even += w & 0x00FF00FFu;
-            odd += (w >> 8) & 0x00FF00FFu;
-        }
-        acc[half * 4 + 0] += even & 0xFFFFu;
-        acc[half * 4 + 1] += odd & 0xFFFFu;
-        acc[half * 4 + 2] += even >> 16;
-        acc[half * 4 + 3] += odd >> 16;
-    }
-    __syncwarp();
-}
-
-template <bool ATOMIC>
-__device__ __forceinline__ void count_word(uint32_t *col, uint8_t *colb, uint32_t w) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t b = (w >> (8 * k)) & 0xFFu;
-        if (ATOMIC) {
-            atomicAdd(col + (b >> 2) * 32, 1u << ((b & 3u) * 8));
-        } else {
-            uint8_t *p = colb + (b >> 2) * 128 + (b & 3u);
-            *p = (uint8_t)(*p + 1);
-        }
-    }
-}
-
-template <bool ATOMIC>
-__global__ void __launch_bounds__(kLpThreads) hist_lane_private_kernel(const uint8_t *__restrict__ in, size_t n,
-                                                                       unsigned long long *__restrict__ hist) {
-    __shared__ uint32_t cnt[kLpWarps][64 * 32];
-    __shared__ unsigned long long total[256];
-    for (int i = threadIdx.x; i < kLpWarps * 64 * 32; i += kLpThreads) (&cnt[0][0])[i] = 0;
-    for (int i = threadIdx.x; i < 256; i += kLpThreads) total[i] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wc = cnt[warp];
-    uint32_t *col = wc + lane;                 // word (row, lane): bank == lane
-    uint8_t *colb = (uint8_t *)(wc + lane);
-    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-    const size_t head = min((size_t)((16 - ((uintptr_t)in & 15)) & 15), n);
-    const size_t nvec = (n - head) / 16;
-    const uint4 *vin = (const uint4 *)(in + head);
-    if (blockIdx.x == 0 && warp == 0) {
-        for (size_t i = lane; i < head; i += 32) atomicAdd(&total[in[i]], 1ull);
-        for (size_t i = head + nvec * 16 + lane; i < n; i += 32) atomicAdd(&total[in[i]], 1ull);
-    }
-
-    // a period = kLpVecPerPeriod vectors per lane = 480 consecutive vectors per warp
-    constexpr size_t kPeriodVec = (size_t)kLpVecPerPeriod * 32;
-    const size_t nperiods = (nvec + kPeriodVec - 1) / kPeriodVec;
-    const size_t gwarp = (size_t)blockIdx.x * kLpWarps + warp, nwarps = (size_t)gridDim.x * kLpWarps;
-    for (size_t p = gwarp; p < nperiods; p += nwarps) {
-        const size_t base = p * kPeriodVec + lane;
-#pragma unroll
-        for (int g = 0; g < kLpVecPerPeriod; g += 5) {
-            uint4 v[5];
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const size_t idx = base + (size_t)(g + j) * 32;
-                v[j] = idx < nvec ? ldg_stream(vin + idx) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const size_t idx = base + (size_t)(g + j) * 32;
-                if (idx < nvec) {
-                    count_word<ATOMIC>(col, colb, v[j].x);
-                    count_word<ATOMIC>(col, colb, v[j].y);
-                    count_word<ATOMIC>(col, colb, v[j].z);
-                    count_word<ATOMIC>(col, colb, v[j].w);
-                }
-            }
-        }
-        fold_counters(wc, lane, acc);
-    }
-    // per-lane registers -> CTA totals -> one global atomic per bin per CTA
-#pragma unroll
-    for (int half = 0; half < 2; half++)
-#pragma unroll
-        for (int f = 0; f < 4; f++)
-            if (acc[half * 4 + f]) atomicAdd(&total[(lane + 32 * half) * 4 + f], (unsigned long long)acc[half * 4 + f]);
-    __syncthreads();
-    for (int b = threadIdx.x; b < 256; b += kLpThreads)
-        if (total[b]) atomicAdd(&hist[b], total[b]);
-}
-
 // ------------------------------------------------------------------------------------------ histogram + run histograms
 // The encoder wants the bit offset of every 32 KB run before it starts (k3_encode.cu, "planned single pass"); that is
 // sum(count[s] * length[s]) over the runs in front -- known as soon as the code lengths are, if the histogram pass keeps
 // one small histogram per run.  Same counting as variant A<1>; a CTA walks whole runs, and after each run its 256
 // threads fold the eight warp tables into 256 u16 counts (512 bytes per 32 KB of input: 1.6 % extra traffic).
 constexpr int kHistRunBytes = 32768;   // == kRunBytes of k3_encode.cu
-__global__ void __launch_bounds__(256) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n, unsigned long long *__restrict__ hist,
-                                                         uint16_t *__restrict__ run_hist, unsigned int nruns) {
-    constexpr int kWarps = 8;
-    __shared__ uint32_t smem[kWarps * 256];
-    for (int i = threadIdx.x; i < kWarps * 256; i += 256) smem[i] = 0;
+// Counters: [256 symbols][32 lanes] u32 per CTA -- lane L of every warp only ever touches column L, i.e. bank L, so a
+// shared-memory atomic never has a bank conflict (ncu, round 1: 2.3 wavefronts per ATOMS with per-warp 256-entry tables;
+// the kernel is bound by exactly those).  The counters are never cleared: after each run, warp w reads its 16 rows (one
+// conflict-free load + one REDUX per row) and the run's histogram is the difference to the totals it read the time before.
+constexpr int kHistRunThreads = 512;
+// RUNS: two counter tables used alternately, so that the snapshot of run r (table r & 1) overlaps the counting of run r + 1
+// (the other table) and one barrier per run is enough: it tells a warp that every count of the run has landed, and -- one
+// run later -- that every warp has finished reading the table the next run is about to count into.
+template <bool RUNS>
+__global__ void __launch_bounds__(kHistRunThreads, RUNS ? 3 : 4) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                                unsigned long long *__restrict__ hist,
+                                                                                uint16_t *__restrict__ run_hist, unsigned int nruns) {
+    extern __shared__ uint32_t s_cnt[];   // [RUNS ? 2 : 1][256 * 32]
+    for (int i = threadIdx.x; i < (RUNS ? 2 : 1) * 256 * 32; i += kHistRunThreads) s_cnt[i] = 0;
     __syncthreads();
-    const int tid = threadIdx.x, warp = tid >> 5;
-    uint32_t *wh = smem + warp * 256;
-    unsigned long long total = 0;
-#define DC_COUNT_WORD(w)                      \
-    atomicAdd(&wh[(w) & 0xFFu], 1u);          \
-    atomicAdd(&wh[((w) >> 8) & 0xFFu], 1u);   \
-    atomicAdd(&wh[((w) >> 16) & 0xFFu], 1u);  \
-    atomicAdd(&wh[(w) >> 24], 1u);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t col0 = (uint32_t)__cvta_generic_to_shared(s_cnt) + 4u * lane;
+    uint32_t seen_this = 0, seen_other = 0;   // lane r < 16: the total of row 16 * warp + r at the previous snapshot of the table
+                                              // this run counts into / of the other table
+    unsigned long long total = 0;   // ... and over all runs of this CTA
+#define DC_COUNT_BYTE(w, k)                                                                                          \
+    asm volatile("{\n\t.reg .u32 b, a;\n\tprmt.b32 b, %0, 0, 0x444" #k ";\n\tmad.lo.u32 a, b, 128, %1;\n\t"       \
+                 "red.shared.add.u32 [a], 1;\n\t}" ::"r"(w), "r"(col) : "memory");
+#define DC_COUNT_WORD(w) DC_COUNT_BYTE(w, 0) DC_COUNT_BYTE(w, 1) DC_COUNT_BYTE(w, 2) DC_COUNT_BYTE(w, 3)
+    auto snapshot = [&](unsigned int run, int which, uint32_t &seen) {   // the histogram of `run`, counted into table `which`
+        uint32_t mine = 0;
+        const uint32_t *tab = s_cnt + which * (256 * 32);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, tab[(warp * 16 + r) * 32 + lane]);
+            if (lane == r) mine = t;
+        }
+        if (lane < 16) {
+            const uint32_t d = mine - seen;
+            if (run_hist) run_hist[(size_t)run * 256 + warp * 16 + lane] = (uint16_t)d;   // <= 32768
+            total += d;
+            seen = mine;
+        }
+    };
+    unsigned int prev = 0xFFFFFFFFu;
+    int which = 0;
     for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
         const size_t base = (size_t)run * kHistRunBytes;
         const uint4 *vin = (const uint4 *)(in + base);
-        if (base + kHistRunBytes <= n) {
-            uint4 v[8];
+        const uint32_t col = col0 + (RUNS ? (uint32_t)which * (256u * 32u * 4u) : 0u);
+        const bool whole = base + kHistRunBytes <= n;
+        uint4 v[4];
+        if (whole) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = ldg_stream(vin + tid + u * 256);
+            for (int u = 0; u < 4; u++) v[u] = ldg_stream(vin + tid + u * kHistRunThreads);
+        }
+        if (RUNS && prev != 0xFFFFFFFFu) snapshot(prev, which ^ 1, seen_other);   // (while this run's loads are in flight)
+        if (whole) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 4; u++) {
                 DC_COUNT_WORD(v[u].x) DC_COUNT_WORD(v[u].y) DC_COUNT_WORD(v[u].z) DC_COUNT_WORD(v[u].w)
             }
         } else {  // the ragged last run
             const size_t len = n - base, nvec = len / 16;
-            for (size_t i = tid; i < nvec; i += 256) {
-                const uint4 v = ldg_stream(vin + i);
-                DC_COUNT_WORD(v.x) DC_COUNT_WORD(v.y) DC_COUNT_WORD(v.z) DC_COUNT_WORD(v.w)
+            for (size_t i = tid; i < nvec; i += kHistRunThreads) {
+                const uint4 x = ldg_stream(vin + i);
+                DC_COUNT_WORD(x.x) DC_COUNT_WORD(x.y) DC_COUNT_WORD(x.z) DC_COUNT_WORD(x.w)
             }
-            for (size_t i = nvec * 16 + tid; i < len; i += 256) atomicAdd(&wh[in[base + i]], 1u);
+            for (size_t i = nvec * 16 + tid; i < len; i += kHistRunThreads) {
+                const uint32_t w = in[base + i];
+                DC_COUNT_BYTE(w, 0)
+            }
         }
-        __syncthreads();
-        uint32_t c = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            c += smem[w * 256 + tid];
-            smem[w * 256 + tid] = 0;
-        }
-        run_hist[(size_t)run * 256 + tid] = (uint16_t)c;   // <= 32768
-        total += c;
-        __syncthreads();
+        if (!RUNS) continue;   // plain histogram: one snapshot at the end
+        __syncthreads();       // every count of this run has landed; every warp is done with the other table's snapshot
+        prev = run;
+        which ^= 1;
+        { const uint32_t t = seen_this; seen_this = seen_other; seen_other = t; }
     }
 #undef DC_COUNT_WORD
-    if (total) atomicAdd(&hist[tid], total);
+#undef DC_COUNT_BYTE
+    if (RUNS) {
+        if (prev != 0xFFFFFFFFu) snapshot(prev, which ^ 1, seen_other);
+    } else {
+        __syncthreads();
+        snapshot(0, 0, seen_this);
+    }
+    if (lane < 16 && total) atomicAdd(&hist[warp * 16 + lane], total);
 }
 
 int hist_variant() {
@@ -237,37 +169,21 @@ int hist_variant() {
     return v;
 }
 
+// variant 0: lane-private counters when the input is 16-byte aligned, else per-warp tables; variant 1: per-warp tables
 int launch_histogram(const uint8_t *d_in, size_t n, unsigned long long *d_hist, int variant, cudaStream_t st) {
     DC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, DC_NSLOTS * sizeof(unsigned long long), st));
     if (n == 0) return DC_OK;
     const int sms = sm_count();
-    const size_t nvec = n / 16 + 1;
     LaunchScope ls(DC_K_HISTOGRAM, st);
-    switch (variant) {
-        case 1: case 2: case 3: {
-            const int R = variant == 1 ? 2 : variant == 2 ? 4 : 8;
-            const size_t smem = (size_t)8 * 256 * R * 4;
-            const int per_sm = R == 8 ? 3 : 8;
-            const int grid = (int)min((size_t)sms * per_sm, (nvec + 255) / 256);
-            if (R == 2) hist_warp_atomic_kernel<2><<<grid, 256, smem, st>>>(d_in, n, d_hist);
-            else if (R == 4) hist_warp_atomic_kernel<4><<<grid, 256, smem, st>>>(d_in, n, d_hist);
-            else {
-                DC_CUDA_TRY(ensure_dynamic_smem((const void *)hist_warp_atomic_kernel<8>, smem));
-                hist_warp_atomic_kernel<8><<<grid, 256, smem, st>>>(d_in, n, d_hist);
-            }
-            break;
-        }
-        case 4: case 5: {
-            const size_t nper = (nvec + kLpVecPerPeriod * 32 - 1) / (kLpVecPerPeriod * 32);
-            const int grid = (int)min((size_t)sms * 6, (nper + kLpWarps - 1) / kLpWarps);
-            if (variant == 4) hist_lane_private_kernel<false><<<grid, kLpThreads, 0, st>>>(d_in, n, d_hist);
-            else hist_lane_private_kernel<true><<<grid, kLpThreads, 0, st>>>(d_in, n, d_hist);
-            break;
-        }
-        default: {
-            const int grid = (int)min((size_t)sms * 8, (nvec + 255) / 256);
-            hist_warp_atomic_kernel<1><<<grid, 256, 8 * 256 * 4, st>>>(d_in, n, d_hist);
-        }
+    if (variant == 0 && ((uintptr_t)d_in & 15) == 0 && n < ((size_t)1 << 46)) {
+        const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
+        // (a CTA's u32 counters hold its share of the input: at most 2^32 bytes per column needs n / grid < 2^32)
+        const unsigned int grid = (unsigned int)min(nruns, (size_t)sms * 4);
+        hist_runs_kernel<false><<<grid, kHistRunThreads, 256 * 32 * 4, st>>>(d_in, n, d_hist, nullptr, (unsigned int)nruns);
+    } else {
+        const size_t nvec = n / 16 + 1;
+        const int grid = (int)min((size_t)sms * 8, (nvec + 255) / 256);
+        hist_warp_atomic_kernel<1><<<grid, 256, 8 * 256 * 4, st>>>(d_in, n, d_hist);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -286,8 +202,9 @@ int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_h
     const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
     if (nruns > 0x0FFFFFF0ull) return DC_ERR_ARG;
     LaunchScope ls(DC_K_HISTOGRAM, st);
-    const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 8);
-    hist_runs_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
+    const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 3);
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)hist_runs_kernel<true>, 2 * 256 * 32 * 4));
+    hist_runs_kernel<true><<<grid, kHistRunThreads, 2 * 256 * 32 * 4, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
     return cuda_status(cudaGetLastError());
 }
 }  // namespace dc

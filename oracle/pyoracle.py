@@ -314,6 +314,9 @@ def ref_huff() -> C.CDLL:
         L.ref_convert_lengths_to_encode_table.argtypes = [C.c_int, i32p, C.c_int, i32p, u32p]
         L.ref_convert_lengths_to_encode_table.restype = None
         L.ref_run_tests.restype = None
+        if hasattr(L, "ref_compress_block"):
+            L.ref_compress_block.argtypes = [C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+            L.ref_compress_block.restype = None
         L.ref_silence_begin.restype = None
         L.ref_silence_end.restype = None
         _ref_huff = L
@@ -340,6 +343,15 @@ def ref_histogram(text: bytes, max_symbol_value: int = MAX_SYMBOL_VALUE) -> np.n
     h = np.full(max_symbol_value + 1, 0xBEEF, dtype=np.int32)
     ref_huff().ref_histogram(text, max_symbol_value, _p(h, C.c_int))
     return h
+
+
+def ref_compress_block(text: bytes, lengths, n: int, bufsize: int = 65000, fill: int = 0xFF) -> bytes:
+    """Unmodified static compress() (n_ary_huffman.c:1688): the whole output buffer, pre-filled with `fill`."""
+    ln = np.ascontiguousarray(lengths, dtype=np.int32).copy()
+    src = C.create_string_buffer(text, bufsize + 1)
+    dst = C.create_string_buffer(bytes([fill]) * (bufsize + 1), bufsize + 1)
+    ref_huff().ref_compress_block(MAX_SYMBOL_VALUE, _p(ln, C.c_int), n, bufsize, len(text), src, dst)
+    return dst.raw
 
 
 def ref_huffman(freqs, n: int, max_leaf_value: int | None = None) -> np.ndarray:

@@ -61,3 +61,14 @@ void ref_run_tests(void) {
     run_tests();
     ref_silence_end();
 }
+
+/* the reference's own block writer, static compress() (n_ary_huffman.c:1688-1815), on a buffer the caller pre-fills so that
+ * what it wrote can be told from what it left alone.  With -DNDEBUG the Huffman branch (compressed_symbols > 2) runs through
+ * its stubs and the function always ends in the raw pass-through block "<len>:\n\n<text>," (:1801-1814) written over the start
+ * of the buffer; behind a short text the table block it had formatted before (:1705-1747) is still there. */
+void ref_compress_block(int max_symbol_value, int *canonical_lengths, int compressed_symbols, int bufsize, int original_length,
+                        char *original_text, char *compressed_text) {
+    ref_silence_begin();
+    compress(max_symbol_value, canonical_lengths, compressed_symbols, bufsize, original_length, original_text, compressed_text);
+    ref_silence_end();
+}

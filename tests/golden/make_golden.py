@@ -132,5 +132,28 @@ def main():
     print("golden vectors written to", HERE)
 
 
+def container_golden():
+    """The reference's own block writer, static compress() (n_ary_huffman.c:1688-1815): what it leaves in its output buffer.
+    Under -DNDEBUG it always ends in the raw pass-through block "<len>:\\n\\n<text>," (no line feed behind the comma); with
+    compressed_symbols > 2 the table block "265:\\nX258:<259 digits>," it formatted first is still in the buffer behind a
+    short text (its first bytes are overwritten by the raw block)."""
+    rng = np.random.default_rng(11)
+    cases = []
+    texts = [b"A", b"hello world, hello netstrings" * 3,
+             bytes(rng.choice(np.frombuffer(b" etaoinsrhldcu.,\nTHE", dtype=np.uint8), size=3000).tolist())]
+    for n in (2, 3, 4):
+        for t in texts:
+            h = O.ref_histogram(t)
+            lengths = O.ref_huffman(h, n)
+            buf = O.ref_compress_block(t, lengths, n)
+            end = len(buf)
+            while end > 0 and buf[end - 1] == 0xFF:
+                end -= 1
+            cases.append({"n": n, "text": t.hex(), "lengths": lengths.tolist(), "buffer": buf[:min(end, len(t) + 400)].hex()})
+    with open(os.path.join(HERE, "container.json"), "w") as f:
+        json.dump({"source": "unmodified static compress() via oracle/ref_harness_huff.c, buffer pre-filled with 0xFF", "cases": cases}, f)
+
+
 if __name__ == "__main__":
     main()
+    container_golden()

@@ -34,7 +34,7 @@ def test_synth_matches_host_twin(dc):
             assert np.array_equal(d.cpu().numpy(), synth.host_stream(n, 12345, thr, base))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_histogram_variants_match_oracle(dc, oracle, variant):
     rng = np.random.default_rng(variant)
     zipf = _zipf(dc, (1 << 22) + 5).cpu().numpy()

@@ -155,12 +155,43 @@ def test_container_blocks(built, radix):
     n = L.dc_container_compress(radix, lengths.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), text, len(text), out, cap)
     blob = out.raw[:n]
     if radix == 10:     # no payload packing for this radix: the raw block, like the reference
-        assert blob == b"%d:\n\n" % (len(text) + 2) + text + b",\n"
+        assert blob == b"%d:\n\n" % (len(text) + 2) + text + b","
     else:
         digits = "".join("0123456789ABCDEF"[int(x)] for x in lengths)
-        assert blob.startswith(b"265:\nX258:" + digits.encode() + b",\n")   # the reference's table block (:1727-1747)
+        assert blob.startswith(b"265:\nX258:" + digits.encode() + b",")   # the reference's table block (:1727-1747)
         assert n < len(text)
     back = ctypes.create_string_buffer(len(text) + 2)
     m = L.dc_container_decompress(radix, blob, n, back, len(text) + 2)
     assert m == len(text) and back.raw[:m] == text
     assert L.dc_container_decompress(radix, blob[:-3], n - 3, back, len(text) + 2) == ctypes.c_size_t(-1).value   # truncated
+    both = blob + b"\n"   # the reader also takes the line feed the reference's reader asserts behind a block (:2049)
+    assert L.dc_container_decompress(radix, both, len(both), back, len(text) + 2) == len(text)
+
+
+@pytest.mark.gpu
+def test_container_table_block_equals_the_reference_writer(built):
+    """The table block 'X' byte for byte as the unmodified compress() formats it (n_ary_huffman.c:1705-1747): golden buffer
+    from tests/golden/container.json -- behind a one-byte text the block is still in the reference's buffer from offset 7."""
+    import json
+    import numpy as np
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "container.json")))["cases"]
+    L = ctypes.CDLL(REFAPI)
+    L.dc_container_compress.restype = ctypes.c_size_t
+    L.dc_container_compress.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t,
+                                        ctypes.c_char_p, ctypes.c_size_t]
+    seen = 0
+    for case in gold:
+        text, n = bytes.fromhex(case["text"]), case["n"]
+        if len(text) != 1 or n < 3:
+            continue
+        buf = bytes.fromhex(case["buffer"])
+        lengths = np.array(case["lengths"], dtype=np.int32)
+        ref_block = b"265:\nX2" + buf[7: 7 + 3 + 259 + 1]          # "58:" + one digit per length + ","
+        assert ref_block.endswith(b",") and len(ref_block) == 270
+        long_text = text * 20000                                     # same alphabet, long enough to be worth coding
+        cap = len(long_text) + len(long_text) // 4 + 4096
+        out = ctypes.create_string_buffer(cap + 1)
+        m = L.dc_container_compress(n, lengths.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), long_text, len(long_text), out, cap)
+        assert m != ctypes.c_size_t(-1).value and out.raw[:270] == ref_block, (n, out.raw[:40])
+        seen += 1
+    assert seen >= 2

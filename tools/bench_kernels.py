@@ -40,7 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size-mib", type=int, default=1024)
     ap.add_argument("--radices", default="2,3,4,16")
-    ap.add_argument("--hist-variants", default="0,1,2,3,4,5")
+    ap.add_argument("--hist-variants", default="0,1")
     args = ap.parse_args()
     n = args.size_mib << 20
     dev = torch.device("cuda:0")
