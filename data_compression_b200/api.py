@@ -34,6 +34,7 @@ class HuffTable:
 
     def __init__(self, device=None):
         self.buf = torch.empty(TABLE_BYTES, dtype=torch.uint8, device=device or torch.cuda.current_device())
+        self.n_ary = None   # set by huff_build / huff_table_from_lengths (sizes the default payload buffer)
 
     @property
     def ptr(self) -> int:
@@ -85,6 +86,7 @@ def huff_build(hist: torch.Tensor, n_ary: int, table: HuffTable | None = None) -
         raise ValueError("hist must be 259 x int64")
     table = table or HuffTable(hist.device)
     check(lib().dc_huff_build(hist.data_ptr(), n_ary, table.ptr, _stream()), "dc_huff_build")
+    table.n_ary = n_ary
     return table
 
 
@@ -94,6 +96,7 @@ def huff_table_from_lengths(lengths: torch.Tensor, n_ary: int, table: HuffTable 
         raise ValueError("lengths must be 259 x int32")
     table = table or HuffTable(lengths.device)
     check(lib().dc_huff_table_from_lengths(lengths.data_ptr(), n_ary, table.ptr, _stream()), "dc_huff_table_from_lengths")
+    table.n_ary = n_ary
     return table
 
 
@@ -128,7 +131,10 @@ def huff_encode(data: torch.Tensor, table: HuffTable, out: torch.Tensor | None =
     _need_cuda(data, "data")
     n = data.numel()
     if out is None:
-        out = torch.empty(n + n // 4 + 64, dtype=torch.uint8, device=data.device)
+        # a Huffman code of byte data never exceeds 8 bits per symbol by more than the skew allows: n + n / 4 covers every
+        # power-of-two radix; radix 3 runs on 2 bits per trit (uniform bytes: 5.08 trits = 10.2 bits per symbol)
+        cap = n + n // 2 + 64 if table.n_ary == 3 else n + n // 4 + 64
+        out = torch.empty(cap, dtype=torch.uint8, device=data.device)
     need = lib().dc_huff_encode_workspace_bytes(n)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=data.device)
@@ -169,8 +175,11 @@ class ShardDecoder:
 
     def __init__(self, buf: torch.Tensor, shard_bytes: int, shard_bits: int, stream_bits_left: int, table: HuffTable):
         _need_cuda(buf, "buf")
-        if buf.data_ptr() % 16 or buf.numel() < SHARD_ALIGN + shard_bytes + 16:
-            raise ValueError("buf: 16-byte aligned, 1024-byte halo + shard + 16 bytes")
+        final = stream_bits_left <= shard_bits
+        tail = 16 if final else SHARD_ALIGN   # the kernels load whole 1 KB tiles one ahead: a non-final shard needs the next one's head
+        if buf.data_ptr() % 16 or buf.numel() < SHARD_ALIGN + (shard_bytes + 15) // 16 * 16 + tail:
+            raise ValueError("buf: 16-byte aligned; 1024-byte halo + shard (rounded up to 16 bytes) + 1024 bytes behind a "
+                             "non-final shard (16 behind the last one)")
         self.buf, self.table = buf, table
         self.shard_bits, self.left = shard_bits, stream_bits_left
         self.ptr = buf.data_ptr() + SHARD_ALIGN

@@ -175,7 +175,7 @@ int launch_histogram(const uint8_t *d_in, size_t n, unsigned long long *d_hist, 
     if (n == 0) return DC_OK;
     const int sms = sm_count();
     LaunchScope ls(DC_K_HISTOGRAM, st);
-    if (variant == 0 && ((uintptr_t)d_in & 15) == 0 && n < ((size_t)1 << 46)) {
+    if (variant == 0 && ((uintptr_t)d_in & 15) == 0 && n < ((size_t)1 << 40)) {
         const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
         // (a CTA's u32 counters hold its share of the input: at most 2^32 bytes per column needs n / grid < 2^32)
         const unsigned int grid = (unsigned int)min(nruns, (size_t)sms * 4);

@@ -1442,9 +1442,9 @@ struct PipeState {
 };
 static PipeState g_pipe;
 
-int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
-                              uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
-                              int32_t *d_status, uint8_t *d_packed) {
+static int host_decompress_pipelined_body(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
+                                          uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
+                                          int32_t *d_status, uint8_t *d_packed) {
     const bool trits = d_packed != nullptr;
     const size_t nbytes = (size_t)((total_bits + 7) / 8);
     static unsigned long long chunk_tiles = 0;
@@ -1550,6 +1550,23 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
     int32_t stt = 0;
     DC_CUDA_TRY(cudaMemcpy(&stt, d_status, sizeof stt, cudaMemcpyDeviceToHost));
     return stt;
+}
+
+// Every exit of the body -- the error exits too -- passes through here: the three non-blocking streams may still have
+// uploads and kernels queued against arena memory that the next dc_host_* call reuses or frees on the legacy stream, which
+// does not order against them.
+int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, const dc_huff_table *d_table, uint8_t *d_bits,
+                              uint8_t *d_out, void *d_workspace, size_t workspace_bytes, uint8_t *h_out, size_t n_out,
+                              int32_t *d_status, uint8_t *d_packed) {
+    const int rc = host_decompress_pipelined_body(h_payload, total_bits, d_table, d_bits, d_out, d_workspace, workspace_bytes, h_out, n_out,
+                                                  d_status, d_packed);
+    if (g_pipe.up) {
+        cudaStreamSynchronize(g_pipe.up);
+        cudaStreamSynchronize(g_pipe.cp);
+        cudaStreamSynchronize(g_pipe.dn);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 }  // namespace dc

@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(kTritThreads) trit_pack_kernel(const uint8_t *
     bool bad = false;
     // the next group's five words are loaded while this one is converted (the kernel waits on memory otherwise)
     const unsigned long long stride = (unsigned long long)gridDim.x * kTritThreads;
-    auto whole = [&](unsigned long long t) { return t < nthreads_needed && t * 20 + 20 <= t2_bytes; };
+    // (a group that holds the last trit takes the byte-wise path even if its 20 bytes exist: the bits behind the last trit are
+    // padding -- whatever the caller's last byte holds there must not become a trit)
+    auto whole = [&](unsigned long long t) { return t < nthreads_needed && (t + 1) * kTritsPerThread <= ntrits; };
     unsigned long long t = (unsigned long long)blockIdx.x * kTritThreads + threadIdx.x;
     uint32_t nx[5] = {0, 0, 0, 0, 0};
     bool nx_whole = whole(t);

@@ -236,7 +236,8 @@ size_t dc_huff_decode_workspace_bytes(uint64_t bit_start, uint64_t nbits);
 /*
  * Replaces the absent Huffman block decoder (decompress() case 'X'/'Z', :2081-2089).
  * Self-synchronising parallel decode of `nbits` code bits that start `bit_start` (< 128) bits into
- * d_bits (16-byte aligned; at least ceil((bit_start+nbits)/8) readable bytes).  Exactly n_out symbols
+ * d_bits (16-byte aligned; readable up to ceil((bit_start+nbits)/8) rounded up to a multiple of 16 bytes: the kernels load
+ * 16-byte vectors).  Exactly n_out symbols
  * are expected.  May block on the stream internally while neighbouring tiles resynchronise.
  *   d_status     1 x i32: DC_OK / DC_ERR_CORRUPT / DC_ERR_CAPACITY; may be NULL
  */
@@ -259,7 +260,9 @@ int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, co
  *   first_code_bit    has_halo == 0 only: exact bit offset (< 128) of the first code that starts in the shard, or the
  *                     previous shard's `exit` as reported
  *   shard_bits        bits of the stream that belong to this shard (a multiple of 8192 for all but the last shard)
- *   stream_bits_left  bits from d_bits to the end of the stream (>= shard_bits; up to 8 bytes past the shard are read)
+ *   stream_bits_left  bits from d_bits to the end of the stream (>= shard_bits).  Readable memory: the kernels load 16-byte
+ *                     vectors and fetch one 1 KB tile ahead, so the shard's bytes rounded up to 16 must be readable, and behind
+ *                     a NON-final shard another 1024 bytes (the next shard's head)
  */
 typedef struct dc_shard_summary {
     uint64_t symbols;        /* codes that START in the shard */
@@ -399,7 +402,9 @@ int dc_nybble_text_decompress(const uint8_t *d_src, size_t n, uint8_t *d_dst, si
  * contexts (byte_to_context :517, update_context :665-687) instead of the static table.  Same arguments, limits and
  * status codes as the two functions above; the workspace is larger (dc_nybble_adaptive_workspace_bytes).
  * Compress is a parallel scan (the contexts are known from the input).  Decompress resolves the hit nibbles with one
- * serial walk over the output on the device -- the chain the format imposes; it is parallel only across strings.
+ * serial walk over the output on the device -- the chain the format imposes; it is parallel only across strings: ONE
+ * string decompresses at about 11 MB/s (a CPU core is faster).  The supported fast path for the adaptive mode is the batch
+ * form below (dc_nybble_text_decompress_batch: one thread per string, 40 GB/s over many short strings).
  */
 size_t dc_nybble_adaptive_workspace_bytes(size_t n);
 int dc_nybble_adaptive_compress(const uint8_t *d_src, size_t n, uint8_t *d_dst, size_t dst_capacity, uint64_t *d_out_len,

@@ -106,3 +106,39 @@ def test_adaptive_nybble_compressor_quarter_gib_equals_oracle(dc, oracle):
     comp = oracle.nybble_adaptive_compress(small)
     back, bl, st = dc.nybble_adaptive_decompress(torch.from_numpy(np.frombuffer(comp, dtype=np.uint8).copy()).cuda())
     assert int(st.item()) == 0 and np.array_equal(_host_of(back[: int(bl.item())]), small)
+
+
+@pytest.mark.parametrize("n_ary,gib", [(4, 4), (16, 4), (2, 4)])
+def test_four_gib_per_gpu_more_than_2_to_the_32_bits(dc, oracle, n_ary, gib):
+    """BASELINE configs[3] / [4] put 4 GiB on a GPU at G = 2: more than 2^32 bits of payload, more than 2^32 bytes of input.
+    Planned encode == the oracle's payload (compared on the device, the oracle packs block-parallel on the host cores);
+    decode of the ORACLE's stream == the input."""
+    from data_compression_b200 import synth
+    threads = os.cpu_count() or 1
+    n = gib << 30
+    thr, base = synth.zipf_bytes_spec()
+    data = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(data, synth.SEED_BASE + 3, synth.device_thresholds(thr, "cuda"), base)
+    host = _host_of(data)
+    ws = dc.encode_workspace(n, "cuda")
+    hist = dc.histogram_runs(data, ws)
+    o_hist = oracle.histogram_u8(host, threads=threads)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), o_hist)
+    table = dc.huff_build(hist, n_ary)
+    ln, el, ev, st = oracle.build_tables(o_hist, n_ary)
+    assert st == 0
+    res = dc.huff_encode(data, table, workspace=ws, planned=True)
+    nbits = res.bits()
+    assert nbits > 1 << 32
+    want, wbits, _ = oracle.pack_mt(host, el, ev, oracle.bits_per_digit(n_ary), 0, threads=threads,
+                                    out=np.empty(n + n // 4 + 64, dtype=np.uint8))
+    del host
+    assert nbits == wbits
+    nbytes = (nbits + 7) // 8
+    d_want = torch.from_numpy(want[: nbytes + 64]).cuda()
+    del want
+    assert torch.equal(res.payload[:nbytes], d_want[:nbytes])
+    del res, ws
+    torch.cuda.empty_cache()
+    out = dc.huff_decompress(d_want, wbits, table, n)
+    assert torch.equal(out, data)

@@ -107,3 +107,23 @@ def test_planned_errors(dc):
     nb = (res.bits() + 7) // 8
     _, res2, small = _planned(dc, ok, table, cap=nb - 1)
     assert int(res2.status.item()) == dc.DC_ERR_CAPACITY
+
+
+def test_radix3_default_payload_buffer_holds_uniform_bytes(dc):
+    """near-uniform bytes need 10.2 bits per symbol on the 2-bit-per-trit stream; the default buffer must hold them."""
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    data = torch.randint(0, 256, (300000,), dtype=torch.uint8, device="cuda", generator=g)
+    payload, nbits, table = dc.huff_compress(data, 3)
+    assert nbits > 8 * data.numel()
+    back, st = dc.huff_decode(payload, nbits, table, data.numel())
+    assert int(st.item()) == 0 and torch.equal(back, data)
+
+
+def test_trit_pack_ignores_bits_behind_the_last_trit(dc):
+    """79 trits fill 20 bytes of the 2-bit stream except the last field; whatever it holds is padding."""
+    t2 = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    t2[:20] = 0b01100001          # trits 1, 2, 0, 1 ...
+    a, sa = dc.trit_pack(t2.clone(), 79)
+    t2[19] |= 0b11                # a field of 3 behind the last trit
+    b, sb = dc.trit_pack(t2, 79)
+    assert int(sa.item()) == 0 and int(sb.item()) == 0 and torch.equal(a, b)
