@@ -80,31 +80,28 @@ constexpr int kHistRunBytes = 32768;   // == kRunBytes of k3_encode.cu
 // the kernel is bound by exactly those).  The counters are never cleared: after each run, warp w reads its 16 rows (one
 // conflict-free load + one REDUX per row) and the run's histogram is the difference to the totals it read the time before.
 constexpr int kHistRunThreads = 512;
-// RUNS: two counter tables used alternately, so that the snapshot of run r (table r & 1) overlaps the counting of run r + 1
-// (the other table) and one barrier per run is enough: it tells a warp that every count of the run has landed, and -- one
-// run later -- that every warp has finished reading the table the next run is about to count into.
+// (Two tables used alternately -- the snapshot of run r overlapping the counting of run r + 1, one barrier per run -- were
+// measured and dropped: 64 KB per CTA allow three CTAs per SM instead of four, 0.29 ms against 0.25.)
 template <bool RUNS>
-__global__ void __launch_bounds__(kHistRunThreads, RUNS ? 3 : 4) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n,
-                                                                                unsigned long long *__restrict__ hist,
-                                                                                uint16_t *__restrict__ run_hist, unsigned int nruns) {
-    extern __shared__ uint32_t s_cnt[];   // [RUNS ? 2 : 1][256 * 32]
-    for (int i = threadIdx.x; i < (RUNS ? 2 : 1) * 256 * 32; i += kHistRunThreads) s_cnt[i] = 0;
+__global__ void __launch_bounds__(kHistRunThreads, 4) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                                        unsigned long long *__restrict__ hist,
+                                                                        uint16_t *__restrict__ run_hist, unsigned int nruns) {
+    __shared__ uint32_t s_cnt[256 * 32];
+    for (int i = threadIdx.x; i < 256 * 32; i += kHistRunThreads) s_cnt[i] = 0;
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t col0 = (uint32_t)__cvta_generic_to_shared(s_cnt) + 4u * lane;
-    uint32_t seen_this = 0, seen_other = 0;   // lane r < 16: the total of row 16 * warp + r at the previous snapshot of the table
-                                              // this run counts into / of the other table
+    const uint32_t col = (uint32_t)__cvta_generic_to_shared(s_cnt) + 4u * lane;
+    uint32_t seen = 0;              // lane r < 16: the total of row 16 * warp + r at the previous snapshot
     unsigned long long total = 0;   // ... and over all runs of this CTA
 #define DC_COUNT_BYTE(w, k)                                                                                          \
     asm volatile("{\n\t.reg .u32 b, a;\n\tprmt.b32 b, %0, 0, 0x444" #k ";\n\tmad.lo.u32 a, b, 128, %1;\n\t"       \
                  "red.shared.add.u32 [a], 1;\n\t}" ::"r"(w), "r"(col) : "memory");
 #define DC_COUNT_WORD(w) DC_COUNT_BYTE(w, 0) DC_COUNT_BYTE(w, 1) DC_COUNT_BYTE(w, 2) DC_COUNT_BYTE(w, 3)
-    auto snapshot = [&](unsigned int run, int which, uint32_t &seen) {   // the histogram of `run`, counted into table `which`
+    auto snapshot = [&](unsigned int run) {   // the histogram of `run`: the totals now minus the totals at the snapshot before
         uint32_t mine = 0;
-        const uint32_t *tab = s_cnt + which * (256 * 32);
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, tab[(warp * 16 + r) * 32 + lane]);
+            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, s_cnt[(warp * 16 + r) * 32 + lane]);
             if (lane == r) mine = t;
         }
         if (lane < 16) {
@@ -114,20 +111,13 @@ __global__ void __launch_bounds__(kHistRunThreads, RUNS ? 3 : 4) hist_runs_kerne
             seen = mine;
         }
     };
-    unsigned int prev = 0xFFFFFFFFu;
-    int which = 0;
     for (unsigned int run = blockIdx.x; run < nruns; run += gridDim.x) {
         const size_t base = (size_t)run * kHistRunBytes;
         const uint4 *vin = (const uint4 *)(in + base);
-        const uint32_t col = col0 + (RUNS ? (uint32_t)which * (256u * 32u * 4u) : 0u);
-        const bool whole = base + kHistRunBytes <= n;
-        uint4 v[4];
-        if (whole) {
+        if (base + kHistRunBytes <= n) {
+            uint4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = ldg_stream(vin + tid + u * kHistRunThreads);
-        }
-        if (RUNS && prev != 0xFFFFFFFFu) snapshot(prev, which ^ 1, seen_other);   // (while this run's loads are in flight)
-        if (whole) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 DC_COUNT_WORD(v[u].x) DC_COUNT_WORD(v[u].y) DC_COUNT_WORD(v[u].z) DC_COUNT_WORD(v[u].w)
@@ -144,18 +134,15 @@ __global__ void __launch_bounds__(kHistRunThreads, RUNS ? 3 : 4) hist_runs_kerne
             }
         }
         if (!RUNS) continue;   // plain histogram: one snapshot at the end
-        __syncthreads();       // every count of this run has landed; every warp is done with the other table's snapshot
-        prev = run;
-        which ^= 1;
-        { const uint32_t t = seen_this; seen_this = seen_other; seen_other = t; }
+        __syncthreads();       // every count of this run has landed
+        snapshot(run);
+        __syncthreads();       // the snapshot is taken: the next run may count
     }
 #undef DC_COUNT_WORD
 #undef DC_COUNT_BYTE
-    if (RUNS) {
-        if (prev != 0xFFFFFFFFu) snapshot(prev, which ^ 1, seen_other);
-    } else {
+    if (!RUNS) {
         __syncthreads();
-        snapshot(0, 0, seen_this);
+        snapshot(0);
     }
     if (lane < 16 && total) atomicAdd(&hist[warp * 16 + lane], total);
 }
@@ -179,7 +166,7 @@ int launch_histogram(const uint8_t *d_in, size_t n, unsigned long long *d_hist, 
         const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
         // (a CTA's u32 counters hold its share of the input: at most 2^32 bytes per column needs n / grid < 2^32)
         const unsigned int grid = (unsigned int)min(nruns, (size_t)sms * 4);
-        hist_runs_kernel<false><<<grid, kHistRunThreads, 256 * 32 * 4, st>>>(d_in, n, d_hist, nullptr, (unsigned int)nruns);
+        hist_runs_kernel<false><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, nullptr, (unsigned int)nruns);
     } else {
         const size_t nvec = n / 16 + 1;
         const int grid = (int)min((size_t)sms * 8, (nvec + 255) / 256);
@@ -202,9 +189,8 @@ int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_h
     const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
     if (nruns > 0x0FFFFFF0ull) return DC_ERR_ARG;
     LaunchScope ls(DC_K_HISTOGRAM, st);
-    const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 3);
-    DC_CUDA_TRY(ensure_dynamic_smem((const void *)hist_runs_kernel<true>, 2 * 256 * 32 * 4));
-    hist_runs_kernel<true><<<grid, kHistRunThreads, 2 * 256 * 32 * 4, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
+    const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 4);
+    hist_runs_kernel<true><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
     return cuda_status(cudaGetLastError());
 }
 }  // namespace dc

@@ -31,6 +31,7 @@
 //           byte is written exactly once, in any scheduling order, with no pre-zeroed output.
 //   HBM traffic = 2N (count + encode reads) + C (write).
 // Both paths share the sub-tile steps A-C (lookup_items, emit_bits*, the shuffle scan).
+#include "chain_scan.cuh"
 #include "dc_common.cuh"
 
 namespace dc {
@@ -1047,18 +1048,19 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
 // 16-byte load); the CTA that finishes last scans the run totals into exclusive offsets (E2's arithmetic) -- one launch.
 constexpr int kPlanThreads = 1024;
 __global__ void __launch_bounds__(kPlanThreads) encode_plan_kernel(const uint16_t *__restrict__ run_hist, const dc_huff_table *__restrict__ tab,
-                                                                   EncWorkspace ws, unsigned int nruns, unsigned int *__restrict__ done,
+                                                                   EncWorkspace ws, unsigned int nruns, ChainSlots slots,
                                                                    unsigned long long *__restrict__ d_total_bits, int32_t *__restrict__ d_status) {
+    // CTA b takes the contiguous runs [lo, hi): a warp per run for the bit counts, a scan inside the CTA, CTA totals from CTA
+    // to CTA (chain_scan.cuh)
     __shared__ uint32_t s_len[256];
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
-    __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ok = table_usable(tab, d_status);
     if (tid < 256) s_len[tid] = ok ? (uint32_t)(tab->enc64[tid] >> 32) : 0u;
     __syncthreads();
+    const unsigned int per = (nruns + gridDim.x - 1) / gridDim.x, lo = min(nruns, per * blockIdx.x), hi = min(nruns, lo + per);
+    uint32_t *s_run = ws.run_bits + lo;   // bits of this CTA's runs (global, L2-resident: written and read inside the CTA)
     bool missing = false;
-    for (unsigned int run = blockIdx.x * (kPlanThreads / 32) + warp; run < nruns; run += gridDim.x * (kPlanThreads / 32)) {
+    for (unsigned int run = lo + warp; run < hi; run += kPlanThreads / 32) {
         const uint4 v = *((const uint4 *)(run_hist + (size_t)run * 256) + lane);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t sum = 0;
@@ -1070,51 +1072,26 @@ __global__ void __launch_bounds__(kPlanThreads) encode_plan_kernel(const uint16_
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-        if (lane == 0) ws.run_bits[run] = sum;
+        if (lane == 0) s_run[run - lo] = sum;
     }
     if (missing && ok) set_status(d_status, DC_ERR_SYMBOL);
-    __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // exclusive scan of run_bits by the last CTA (every other CTA's totals are visible: fence + counter)
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    constexpr int kItems = 32;   // 32 K runs (1 GiB of input) per trip
-    for (unsigned int base = 0; base < nruns; base += kPlanThreads * kItems) {
-        const unsigned int first = base + tid * kItems;
-        uint32_t item[kItems];
-        unsigned long long mine = 0;
-#pragma unroll
-        for (int k = 0; k < kItems; k++) {
-            item[k] = first + k < nruns ? __ldcg(ws.run_bits + first + k) : 0u;
-            mine += item[k];
-        }
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned long long off = s_carry;
-        for (int w = 0; w < warp; w++) off += s_warp[w];
-        off += incl - mine;
-#pragma unroll
-        for (int k = 0; k < kItems; k++) {
-            if (first + k < nruns) ws.run_off[first + k] = off;
-            off += item[k];
-        }
-        __syncthreads();
-        if (tid == kPlanThreads - 1) s_carry = off;
-        __syncthreads();
+    unsigned long long mine = 0;
+    for (unsigned int i = tid; i < hi - lo; i += kPlanThreads) mine += s_run[i];
+    unsigned long long cta_total;
+    block_exclusive(mine, &cta_total);
+    unsigned long long carry = chain_exclusive(slots, cta_total);
+    for (unsigned int base = 0; base < hi - lo; base += kPlanThreads) {
+        const unsigned int i = base + tid;
+        const unsigned long long c = i < hi - lo ? s_run[i] : 0ull;
+        unsigned long long trip_total;
+        const unsigned long long off = block_exclusive(c, &trip_total);
+        if (i < hi - lo) ws.run_off[lo + i] = carry + off;
+        carry += trip_total;
     }
-    if (tid == 0) {
-        ws.run_off[nruns] = s_carry;
-        if (d_total_bits) *d_total_bits = s_carry;
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        ws.run_off[nruns] = carry;
+        if (d_total_bits) *d_total_bits = carry;
     }
 }
 
@@ -1132,7 +1109,7 @@ static size_t enc_ws_layout(size_t n, size_t off[10]) {
     o[4] = take((nchunks + 1) * 16);     // bleft
     o[5] = take((nchunks + 1) * 16);     // bright
     o[8] = take(nruns * 512);            // run histograms (dc_histogram_u8_runs -> dc_huff_encode_planned)
-    o[9] = 0;
+    o[9] = take(kChainSlotsBytes);       // the plan kernel's CTA totals and flags (chain_scan.cuh)
     if (off) for (int i = 0; i < 10; i++) off[i] = o[i];
     return p;
 }
@@ -1177,10 +1154,14 @@ static int encode_entry(const uint8_t *d_in, size_t n, const dc_huff_table *d_ta
     if (planned) {
         // the bit offset of every run from the run histograms K1 left in this workspace (dc_histogram_u8_runs)
         {
+            ChainSlots slots;
+            slots.vals = (unsigned long long *)(w + off[9]);
+            slots.flags = (unsigned int *)(slots.vals + 256);
+            DC_CUDA_TRY(cudaMemsetAsync(slots.flags, 0, 256 * sizeof(unsigned int), st));
+            const unsigned int grid = min(min(sms, 256u), (nruns + 63) / 64);
             LaunchScope ls(DC_K_ENCODE_PLAN, st);
-            const unsigned int want = (nruns + kPlanThreads / 32 - 1) / (kPlanThreads / 32);
-            encode_plan_kernel<<<min(want, sms), kPlanThreads, 0, st>>>((const uint16_t *)(w + off[8]), d_table, ws, nruns,
-                                                                        (unsigned int *)(w + off[6]) + 1, (unsigned long long *)d_total_bits, d_status);
+            encode_plan_kernel<<<grid, kPlanThreads, 0, st>>>((const uint16_t *)(w + off[8]), d_table, ws, nruns, slots,
+                                                                                   (unsigned long long *)d_total_bits, d_status);
         }
         return launch_encode_body(d_in, n, d_table, d_out, out_capacity, bit_phase, ws, w, off, nruns, (unsigned long long *)d_total_bits, d_status, st, true);
     }

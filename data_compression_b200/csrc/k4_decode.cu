@@ -30,6 +30,7 @@
 
 #include <vector>
 
+#include "chain_scan.cuh"
 #include "dc_common.cuh"
 
 namespace dc {
@@ -626,6 +627,7 @@ struct FastWorkspace {
     unsigned long long *seg_off;                     // [nseg]
     int32_t *mismatch;                               // F2: some segment started on a wrong guess
     void *fsm;                                       // byte-stepped decoder: header + F1 table + F3 table (k4_fsm.cuh)
+    void *chain_slots;                               // F2: CTA totals and flags (chain_scan.cuh)
     __host__ __device__ int32_t *bad_input() const { return mismatch + 2; }  // F1 (T2 streams): a 2-bit field of 3; zeroed per launch
     __host__ __device__ uint32_t *start_slot() const { return (uint32_t *)(mismatch + 3); }  // FSM F1 -> F3: the first segment's start token
 };
@@ -760,52 +762,37 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
 __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
                                                                 int32_t *__restrict__ d_status, DecodeChain *__restrict__ chain,
                                                                 int last_chunk, int check_input,
-                                                                DecodeChain *__restrict__ host_chain) {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
-    __shared__ int s_bad;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = chain ? chain->base : 0ull; s_bad = 0; }
-    __syncthreads();
-    constexpr int kItems = 16;   // 16 K segments (256 MiB of bitstream) per trip: the trips are serial, three barriers each
-    for (unsigned long long base = 0; base < nseg; base += 1024 * kItems) {
-        const unsigned long long first = base + (unsigned long long)tid * kItems;
-        uint32_t item[kItems];
-        unsigned long long mine = 0;
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < kItems; k++) {
-            const unsigned long long i = first + k;
-            item[k] = i < nseg ? ws.seg_cnt[i] : 0u;
-            mine += item[k];
-            if (i < nseg && i > 0) bad |= ws.seg_assumed[i] != ws.seg_exit[i - 1];
-        }
-        if (bad) s_bad = 1;
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += x;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned long long off = s_carry;
-        for (int w = 0; w < warp; w++) off += s_warp[w];
-        off += incl - mine;
-#pragma unroll
-        for (int k = 0; k < kItems; k++) {
-            if (first + k < nseg) ws.seg_off[first + k] = off;
-            off += item[k];
-        }
-        __syncthreads();
-        if (tid == 1023) s_carry = off;
-        __syncthreads();
+                                                                DecodeChain *__restrict__ host_chain, ChainSlots slots) {
+    // CTA b takes the contiguous segments [lo, hi); totals travel from CTA to CTA (chain_scan.cuh).  A CTA's value carries its
+    // "some segment started on a wrong guess" flag above bit 56 (a symbol total stays far below).
+    const int tid = threadIdx.x;
+    const unsigned long long per = (nseg + gridDim.x - 1) / gridDim.x, lo = min(nseg, per * blockIdx.x), hi = min(nseg, lo + per);
+    unsigned long long mine = 0;
+    bool bad = false;
+    for (unsigned long long i = lo + tid; i < hi; i += 1024) {
+        mine += ws.seg_cnt[i];
+        if (i > 0) bad |= ws.seg_assumed[i] != ws.seg_exit[i - 1];
     }
-    if (tid == 0) {
+    const int any_bad = __syncthreads_or(bad);
+    unsigned long long cta_total;
+    block_exclusive(mine, &cta_total);
+    const unsigned long long before = chain_exclusive(slots, cta_total + ((unsigned long long)(any_bad ? 1 : 0) << 56));
+    const unsigned long long start = (chain ? chain->base : 0ull) + (before & ((1ull << 56) - 1));
+    unsigned long long carry = start;
+    for (unsigned long long base = lo; base < hi; base += 1024) {
+        const unsigned long long i = base + tid;
+        const unsigned long long c = i < hi ? ws.seg_cnt[i] : 0ull;
+        unsigned long long trip_total;
+        const unsigned long long off = block_exclusive(c, &trip_total);
+        if (i < hi) ws.seg_off[i] = carry + off;
+        carry += trip_total;
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {   // the last CTA has seen every total and every flag
+        int s_bad = ((before >> 56) != 0 || any_bad) ? 1 : 0;
         if (check_input && *ws.bad_input()) s_bad = 1;
         *ws.mismatch = s_bad;
         if (chain) {
-            chain->base = s_carry;
+            chain->base = carry;
             chain->next_start = ws.seg_exit[nseg - 1];
             chain->mismatch |= s_bad;
             chain->first_assumed = ws.seg_assumed[0];
@@ -814,7 +801,7 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
                 __threadfence_system();
             }
         }
-        if (!s_bad && last_chunk && s_carry != n_out) set_status(d_status, s_carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
+        if (!s_bad && last_chunk && carry != n_out) set_status(d_status, carry > n_out ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
     }
 }
 
@@ -997,7 +984,7 @@ static size_t dec_ws_layout(unsigned long long bit_start, unsigned long long nbi
     o[8] = take(nseg * 4);        // fast: seg_assumed
     o[9] = take(nseg * 4);        // fast: seg_exit
     o[10] = take(nseg * 8);       // fast: seg_off
-    o[11] = take(kFsmWorkspaceBytes);  // byte-stepped decoder: its tables (built per call from the code table)
+    o[11] = take(kFsmWorkspaceBytes + kChainSlotsBytes);  // byte-stepped decoder: its tables (built per call from the code table); F2's chain slots
     if (off) for (int i = 0; i < 12; i++) off[i] = o[i];
     if (nsub_out) *nsub_out = nsub;
     if (ntiles_out) *ntiles_out = ntiles;
@@ -1200,8 +1187,13 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
     }
     }
     {
+        ChainSlots slots;
+        slots.vals = (unsigned long long *)fw.chain_slots;
+        slots.flags = (unsigned int *)(slots.vals + 256);
+        DC_CUDA_TRY(cudaMemsetAsync(slots.flags, 0, 256 * sizeof(unsigned int), st));
+        const unsigned int g2 = (unsigned int)min((unsigned long long)min(sm_count(), 256), (nseg + 255) / 256);
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain);
+        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1280,6 +1272,7 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     fw.seg_exit = (uint32_t *)(w + off[9]);
     fw.seg_off = (unsigned long long *)(w + off[10]);
     fw.fsm = w + off[11];
+    fw.chain_slots = w + off[11] + kFsmWorkspaceBytes;
     const unsigned long long end = bit_start + nbits;
     const unsigned long long nsubf = (end + kF_SubBits - 1) / kF_SubBits;
     const unsigned long long nwt = (nsubf + 31) / 32, nseg = (nwt + kF_SegTiles - 1) / kF_SegTiles;
@@ -1351,6 +1344,7 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
     g->fw.seg_exit = (uint32_t *)(w + off[9]);
     g->fw.seg_off = (unsigned long long *)(w + off[10]);
     g->fw.fsm = w + off[11];
+    g->fw.chain_slots = w + off[11] + kFsmWorkspaceBytes;
 
     g->chain = (DecodeChain *)(w + 32);
     int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
@@ -1473,6 +1467,7 @@ static int host_decompress_pipelined_body(const uint8_t *h_payload, uint64_t tot
     fw.seg_exit = (uint32_t *)(w + off[9]);
     fw.seg_off = (unsigned long long *)(w + off[10]);
     fw.fsm = w + off[11];
+    fw.chain_slots = w + off[11] + kFsmWorkspaceBytes;
     DecodeChain *d_chain = (DecodeChain *)(w + 32);
 
     // the table (built on the legacy stream by the caller) must be usable before any bit is interpreted

@@ -144,18 +144,35 @@ static int stream_grid(size_t items_per_thread_total) {
 
 using namespace dc;
 
+// Unaligned buffers.  Symbols 2i, 2i + 1 live in packed byte i, so peeling an even head of h symbols moves the symbol pointer
+// by h and the packed pointer by h / 2: both become 16-byte aligned iff sym == 2 * packed (mod 16) -- which is what a shard
+// of an aligned stream looks like (symbol offset lo, byte offset lo / 2).  Then only the head and the tail go through the
+// byte kernels; any other combination of misalignments has no common vector grid and takes the byte kernel as a whole.
+static size_t nybble_head(const uint8_t *sym, const uint8_t *packed, size_t n_sym, bool *vector_ok) {
+    const uintptr_t s = (uintptr_t)sym, p = (uintptr_t)packed;
+    *vector_ok = ((s - 2 * p) & 15) == 0;
+    if (!*vector_ok) return 0;
+    const size_t h = (size_t)((32 - ((2 * p) & 31)) & 31);
+    return h < n_sym ? h : n_sym;
+}
+
 extern "C" int dc_nybble_pack(const uint8_t *d_sym, size_t n_sym, uint8_t *d_packed, int32_t *d_status, void *stream) {
     if ((!d_sym || !d_packed) && n_sym) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
     if (n_sym == 0) return DC_OK;
-    const bool aligned = (((uintptr_t)d_sym | (uintptr_t)d_packed) & 15) == 0;
-    const size_t nvec = aligned ? n_sym / 32 : 0;
+    bool vector_ok;
+    const size_t head = nybble_head(d_sym, d_packed, n_sym, &vector_ok);
+    const size_t nvec = vector_ok ? (n_sym - head) / 32 : 0;
+    if (head) {
+        LaunchScope ls(DC_K_NYBBLE_TAIL, st);
+        nybble_pack_bytes_kernel<<<1, kNybThreads, 0, st>>>(d_sym, 0, head, d_packed, d_status);
+    }
     if (nvec) {
         LaunchScope ls(DC_K_NYBBLE_PACK, st);
-        nybble_pack_kernel<<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_sym, nvec, (uint4 *)d_packed, d_status);
+        nybble_pack_kernel<<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)(d_sym + head), nvec, (uint4 *)(d_packed + head / 2), d_status);
     }
-    const size_t done = nvec * 32;
+    const size_t done = head + nvec * 32;
     if (done < n_sym) {
         const size_t bytes = (n_sym - done + 1) / 2;
         LaunchScope ls(DC_K_NYBBLE_TAIL, st);
@@ -168,14 +185,21 @@ extern "C" int dc_nybble_unpack(const uint8_t *d_packed, size_t n_sym, uint8_t *
     if ((!d_sym || !d_packed) && n_sym) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_sym == 0) return DC_OK;
-    const bool aligned = (((uintptr_t)d_sym | (uintptr_t)d_packed) & 15) == 0;
-    const size_t nvec = aligned ? n_sym / 32 : 0;
+    bool vector_ok;
+    const size_t head = nybble_head(d_sym, d_packed, n_sym, &vector_ok);
+    const size_t nvec = vector_ok ? (n_sym - head) / 32 : 0;
+    if (head) {
+        LaunchScope ls(DC_K_NYBBLE_TAIL, st);
+        nybble_unpack_bytes_kernel<<<1, kNybThreads, 0, st>>>(d_packed, 0, head, d_sym);
+    }
     if (nvec) {
         LaunchScope ls(DC_K_NYBBLE_UNPACK, st);
-        if (((uintptr_t)d_sym & 31) == 0) nybble_unpack_kernel<true><<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_packed, nvec, (uint4 *)d_sym);
-        else nybble_unpack_kernel<false><<<stream_grid(nvec), kNybThreads, 0, st>>>((const uint4 *)d_packed, nvec, (uint4 *)d_sym);
+        const uint4 *pv = (const uint4 *)(d_packed + head / 2);
+        uint4 *sv = (uint4 *)(d_sym + head);
+        if (((uintptr_t)sv & 31) == 0) nybble_unpack_kernel<true><<<stream_grid(nvec), kNybThreads, 0, st>>>(pv, nvec, sv);
+        else nybble_unpack_kernel<false><<<stream_grid(nvec), kNybThreads, 0, st>>>(pv, nvec, sv);
     }
-    const size_t done = nvec * 32;
+    const size_t done = head + nvec * 32;
     if (done < n_sym) {
         LaunchScope ls(DC_K_NYBBLE_TAIL, st);
         nybble_unpack_bytes_kernel<<<stream_grid(n_sym - done), kNybThreads, 0, st>>>(d_packed, done, n_sym, d_sym);

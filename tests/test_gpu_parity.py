@@ -426,6 +426,22 @@ def test_nybble_pack_unpack(dc, oracle):
     packed, status = dc.nybble_pack(v)
     assert np.array_equal(packed.cpu().numpy(), oracle.nybble_pack(v.cpu().numpy()))
     assert torch.equal(dc.nybble_unpack(packed, v.numel()), v)
+    # a shard of an aligned stream (symbols from an even offset, bytes from half of it): the head is peeled, the bulk stays vector
+    big = torch.empty(200000, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(big, 11, synth.device_thresholds(thr, "cuda"), base)
+    whole = oracle.nybble_pack(big.cpu().numpy())
+    for lo in (2, 6, 18, 30, 32, 34, 4094):
+        for n in (1, 5, 29, 31, 32, 33, 100001):
+            outbuf = torch.full((100100,), 0xEE, dtype=torch.uint8, device="cuda")
+            dst = outbuf[lo // 2: lo // 2 + (n + 1) // 2]
+            packed, status = dc.nybble_pack(big[lo: lo + n], out=dst)
+            assert int(status.item()) == 0
+            want = oracle.nybble_pack(big[lo: lo + n].cpu().numpy())
+            assert np.array_equal(dst.cpu().numpy(), want), (lo, n)
+            assert (outbuf[: lo // 2] == 0xEE).all() and (outbuf[lo // 2 + (n + 1) // 2:] == 0xEE).all(), (lo, n)
+            back = torch.full((200100,), 0xEE, dtype=torch.uint8, device="cuda")
+            dc.nybble_unpack(dst, n, out=back[lo: lo + n])
+            assert torch.equal(back[lo: lo + n], big[lo: lo + n]) and (back[:lo] == 0xEE).all() and (back[lo + n:] == 0xEE).all(), (lo, n)
     # a symbol >= 16 is reported (assert at nybble_compression.c:1093), its low nibble is packed
     bad = _dev(np.array([1, 2, 0x13, 4] * 16, dtype=np.uint8))
     packed, status = dc.nybble_pack(bad)
