@@ -437,19 +437,8 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
 }
 
 
-// ================================================================================================ single pass
-// Narrow tables (every code <= 16 bits): ONE launch, one read of the input.  A CTA takes a ticket for a
-// 32 KB run; each of its 8 warps encodes one 4 KB chunk into its own shared-memory staging buffer at
-// chunk-local bit offsets, so the chunk's bit count is known when the staging is complete.  Warp 0 publishes
-// the run's bit count in a descriptor and obtains the run's bit offset by decoupled look-back over the
-// descriptors of earlier runs (tickets make every predecessor a running or finished CTA, so the wait is
-// deadlock-free; looking back over runs, not chunks, keeps the walk to the resolved frontier short).  Every
-// warp then copies its staging buffer out, funnel-shifted to the global bit alignment, with 16-byte
-// streaming stores.  The 16-byte word shared by two chunks is merged by the second arrival.
+// ================================================================================================ shared pieces of the single-pass kernels
 constexpr int kSpZeroPrefix = 4;                                            // words of zeros in front of the data
-constexpr int kSpTightBits = 12;                                          // tables up to this run 4 CTAs per SM
-__host__ __device__ constexpr int sp_stage_words(int max_bits) { return kSpZeroPrefix + kChunkBytes * max_bits / 32 + 12; }  // per warp
-constexpr unsigned long long kDescAggregate = 1ull << 62, kDescInclusive = 2ull << 62, kDescValue = (1ull << 62) - 1;
 
 struct SpWorkspace {
     unsigned int *ticket;          // [1]          next run to hand out
@@ -458,16 +447,6 @@ struct SpWorkspace {
     uint4 *bleft, *bright;         // [nchunks+1]
     const uint32_t *d_phase;
 };
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 
 // The 16-byte word shared by the last chunk of one run and the first chunk of the next: both sides deposit
 // their half (big-endian word domain) and bump a counter; the second arrival stores the word.  `ends` != 0
@@ -498,246 +477,6 @@ __device__ __forceinline__ void sp_boundary_merge(const SpWorkspace &ws, unsigne
     }
 }
 
-// one sub-tile (32 lanes x 16 symbols) appended to the warp's staging buffer at bit position `bitpos`
-template <bool FULL>
-__device__ __forceinline__ void sp_subtile(uint32_t *stage, const uint32_t *s_enc, const uint32_t (&w)[4], int valid, int lane,
-                                           uint32_t &bitpos, uint32_t &flags) {
-    constexpr int kItems = kEncPerThread / 2;
-    uint32_t item_val[kItems], item_len[kItems];
-    uint32_t my_bits = 0;
-#pragma unroll
-    for (int k = 0; k < kEncPerThread; k += 2) {
-        uint32_t e0 = s_enc[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-        uint32_t e1 = s_enc[(w[k >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu];
-        if (!FULL && k >= valid) e0 = 1u << 31;       // not a symbol: no bits, not "missing"
-        if (!FULL && k + 1 >= valid) e1 = 1u << 31;
-        flags &= e0 & e1;                             // bit 31 survives only if every entry has a code
-        e0 &= 0x7FFFFFFFu;
-        e1 &= 0x7FFFFFFFu;
-        const uint32_t l1 = e1 & 63u;
-        item_val[k / 2] = ((e0 >> 6) << l1) | (e1 >> 6);
-        item_len[k / 2] = (e0 & 63u) + l1;
-        my_bits += (e0 & 63u) + l1;
-    }
-    uint32_t incl = my_bits;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += x;
-    }
-    const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const bool fast = __all_sync(0xFFFFFFFFu, my_bits >= 32u);
-    const uint32_t pos = bitpos + incl - my_bits;
-    uint32_t wi = pos >> 5, nb = pos & 31, hi = 0, lo = 0;
-    if (fast) {
-        // plain stores: a lane writes every word it completes.  The leading `lead` bits of its first word are
-        // its left neighbour's trailing bits (lane 0: the previous sub-tile's, already in the buffer)
-        const uint32_t first_wi = wi, lead = nb;
-        uint32_t left_tail = (lane == 0 && lead != 0) ? stage[first_wi] : 0u;
-#pragma unroll
-        for (int k = 0; k < kItems; k++) emit_bits_owned(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
-        const uint32_t my_tail = nb ? lo << (32u - nb) : 0u;
-        const uint32_t lt = __shfl_up_sync(0xFFFFFFFFu, my_tail, 1);
-        if (lane != 0) left_tail = lt;
-        if (lead != 0) stage[first_wi] |= left_tail;
-        if (lane == 31) stage[wi] = my_tail;
-    } else {
-        // word bitpos >> 5 holds the previous sub-tile's trailing bits (or zeros); clear everything behind it
-        const uint32_t z0 = (bitpos >> 5) + 1, z1 = ((bitpos + tile_bits) >> 5) + 1;
-        for (uint32_t i = z0 + lane; i <= z1; i += 32) stage[i] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < kItems; k++) emit_bits(stage, hi, lo, nb, wi, item_val[k], item_len[k]);
-        stage_or_if(stage + wi, lo << ((32u - nb) & 31u), nb != 0u);
-    }
-    __syncwarp();
-    bitpos += tile_bits;
-}
-
-template <int MAXBITS>
-__global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) encode_single_kernel(const uint8_t *__restrict__ in, size_t n,
-                                                                       const dc_huff_table *__restrict__ tab,
-                                                                       uint8_t *__restrict__ out, size_t out_cap, unsigned phase,
-                                                                       SpWorkspace ws, unsigned int nruns,
-                                                                       unsigned long long *__restrict__ d_total_bits,
-                                                                       int32_t *__restrict__ d_status) {
-    extern __shared__ __align__(16) uint32_t sp_smem[];
-    __shared__ uint32_t s_enc[256];
-    __shared__ unsigned int s_run;
-    __shared__ uint32_t s_bits[kEncWarps];
-    __shared__ unsigned long long s_run_excl;
-    if (!table_usable(tab, d_status)) return;
-    if (ws.d_phase) phase = *ws.d_phase & 7u;
-    constexpr int kSpStageWords = sp_stage_words(MAXBITS);
-    {   // this instantiation's tables: (12, 16] or [1, 12]; wide tables take the three-launch path
-        const int mb = tab->max_bits;
-        if (mb > MAXBITS || mb <= kPlannedMaxBits) return;
-    }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const uint32_t e = tab->enc[tid];
-        s_enc[tid] = e ? (e | (1u << 31)) : 0u;  // bit 31 = "has a code"
-    }
-    uint32_t *stage = sp_smem + warp * kSpStageWords;
-    const size_t nchunks = (n + kChunkBytes - 1) / kChunkBytes;
-    // one ticket = one run.  The 12-bit instantiation (the hot one) is launched with one CTA per run -- measured
-    // faster than a persistent loop, whose extra barrier keeps a CTA's warps in lockstep across runs; the 16-bit one
-    // loops over tickets so that it costs next to nothing when the table is not its own.
-    constexpr bool kPersistent = MAXBITS > kSpTightBits;
-    while (true) {
-    __syncthreads();  // the previous run's s_run / s_bits / s_run_excl have been read by every warp
-    if (tid == 0) s_run = atomicAdd(ws.ticket, 1u);
-    __syncthreads();
-    const unsigned int run = s_run;
-    if (run >= nruns) return;
-    const size_t chunk = (size_t)run * kEncWarps + warp;
-    const bool have_chunk = chunk < nchunks;  // the last run may be short of chunks; its idle warps still join the barriers
-    const size_t chunk_base = chunk * kChunkBytes;
-    const size_t chunk_len = have_chunk ? min((size_t)kChunkBytes, n - chunk_base) : 0;
-    const bool last_chunk = chunk == nchunks - 1;
-
-    // ---- 1. encode the chunk into the staging buffer (chunk-local bit offsets behind a zero prefix)
-    if (lane <= kSpZeroPrefix) stage[lane] = 0;
-    uint32_t bitpos = 32u * kSpZeroPrefix, flags = 0xFFFFFFFFu;
-    if (chunk_len == (size_t)kChunkBytes) {
-        uint4 v[kChunkSubs];
-        const uint4 *src = (const uint4 *)(in + chunk_base) + lane;
-#pragma unroll
-        for (int t = 0; t < kChunkSubs; t++) v[t] = ldg_stream(src + t * 32);
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < kChunkSubs; t++) {
-            const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
-            sp_subtile<true>(stage, s_enc, w, kEncPerThread, lane, bitpos, flags);
-        }
-    } else {  // the ragged last chunk of the stream (or no chunk at all)
-        __syncwarp();
-        const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
-#pragma unroll 1
-        for (int t = 0; t < nsub; t++) {
-            const size_t base = chunk_base + (size_t)t * kSubTile + (size_t)lane * kEncPerThread;
-            const int valid = base < n ? (int)min((size_t)kEncPerThread, n - base) : 0;
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
-            sp_subtile<false>(stage, s_enc, w, valid, lane, bitpos, flags);
-        }
-    }
-    if (lane < 8) stage[(bitpos >> 5) + 1 + lane] = 0;  // the copy-out reads up to 5 words past the last bit
-    const uint32_t chunk_bits = bitpos - 32u * kSpZeroPrefix;
-    if ((flags >> 31) == 0u) set_status(d_status, DC_ERR_SYMBOL);
-
-    // ---- 2. bit offset of the run by decoupled look-back over RUN descriptors (warp 0), of the chunk by a sum in the CTA
-    if (lane == 0) s_bits[warp] = chunk_bits;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t run_bits = 0;
-#pragma unroll
-        for (int w = 0; w < kEncWarps; w++) run_bits += s_bits[w];
-        unsigned long long excl = 0;
-        if (run > 0) {
-            if (lane == 0) st_relaxed_u64(ws.desc + run, kDescAggregate | run_bits);
-            long long base = (long long)run - 1;
-            while (true) {
-                const long long idx = base - lane;
-                unsigned long long d;
-                while (true) {
-                    d = idx >= 0 ? ld_relaxed_u64(ws.desc + idx) : kDescInclusive;
-                    if (!__any_sync(0xFFFFFFFFu, (d >> 62) == 0)) break;
-                    __nanosleep(200);  // back off: hundreds of CTAs poll the same few lines that their predecessors must write
-                }
-                const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 32;  // nearest predecessor with an inclusive prefix
-                unsigned long long part = lane <= stop ? (d & kDescValue) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-                excl += part;
-                if (incl_mask) break;
-                base -= 32;
-            }
-        }
-        if (lane == 0) {
-            st_relaxed_u64(ws.desc + run, kDescInclusive | (excl + run_bits));
-            s_run_excl = excl;
-        }
-    }
-    __syncthreads();
-    if (!have_chunk) { if (kPersistent) continue; return; }
-    unsigned long long excl = s_run_excl;
-#pragma unroll
-    for (int w = 0; w < kEncWarps; w++) excl += w < warp ? s_bits[w] : 0u;
-
-    // ---- 3. copy-out at the global alignment
-    const unsigned long long g = (unsigned long long)phase + excl, gend = g + chunk_bits;
-    const size_t stream_bytes_here = (size_t)((gend + 7) >> 3);
-    if (last_chunk && lane == 0 && d_total_bits) *d_total_bits = excl + chunk_bits;
-    if (stream_bytes_here > out_cap) {
-        if (lane == 0) set_status(d_status, DC_ERR_CAPACITY);
-        if (kPersistent) continue;
-        return;
-    }
-    const unsigned long long v0 = g >> 7, v1 = gend >> 7;  // 16-byte words [v0, v1) end inside this chunk
-    const uint32_t r = (uint32_t)(g & 127), t = (uint32_t)(gend & 127);
-    const bool shared_first = chunk != 0 && r != 0;           // first word also holds the previous chunk's bits
-    if (v1 == v0 && !last_chunk) { if (kPersistent) continue; return; }                   // < 128 bits from 4096 symbols: symbols without codes (reported)
-    const uint32_t nvec = (uint32_t)(v1 - v0);
-    const uint32_t sbit0 = 32u * kSpZeroPrefix - r;            // staging bit of the first bit of 16-byte word v0
-    const uint32_t sbit1 = nvec * 128u + sbit0;                // ... of 16-byte word v1
-
-    // 3a. the two 16-byte words this chunk shares with its neighbours.  Inside the CTA the LEFT chunk owns the
-    // shared word: it reads the right chunk's leading bits straight from that warp's staging buffer (complete
-    // since the barrier).  Across CTAs both sides deposit their half and the second arrival stores the word.
-    // These go first, so that their fences do not wait for the bulk stores below.
-    if (shared_first && warp == 0 && lane == 8) {
-        const uint4 m = make_uint4(stage_word(stage, sbit0), stage_word(stage, sbit0 + 32), stage_word(stage, sbit0 + 64),
-                                   stage_word(stage, sbit0 + 96));
-        // if the stream ends inside this word (a tiny last chunk), say how many of its bytes exist
-        const uint32_t ends = (last_chunk && v1 == v0) ? (uint32_t)(stream_bytes_here - v0 * 16) : 0u;
-        sp_boundary_merge(ws, (unsigned int)chunk, false, m, ends, out, v0, out_cap);
-    }
-    if (t != 0 && !(shared_first && v1 == v0)) {
-        if (last_chunk) {  // trailing partial 16-byte word of the stream, byte by byte (zero padded)
-            const uint32_t rem_bytes = (t + 7) >> 3;
-            if (lane < (int)rem_bytes) out[v1 * 16 + lane] = (uint8_t)(stage_word(stage, sbit1 + 8u * lane) >> 24);
-        } else if (warp == kEncWarps - 1) {
-            if (lane == 16) {
-                const uint4 m = make_uint4(stage_word(stage, sbit1), stage_word(stage, sbit1 + 32), stage_word(stage, sbit1 + 64),
-                                           stage_word(stage, sbit1 + 96));
-                sp_boundary_merge(ws, (unsigned int)chunk + 1, true, m, 0u, out, v1, out_cap);
-            }
-        } else if (lane < 16) {
-            // own trailing t bits | the right chunk's first 128 - t bits (its staging starts with 128 zero bits)
-            const uint32_t *right = stage + kSpStageWords;
-            const uint32_t rbit = 32u * kSpZeroPrefix - t;
-            const uint32_t word = stage_word(stage, sbit1 + 32u * (lane >> 2)) | stage_word(right, rbit + 32u * (lane >> 2));
-            // the right chunk may be the last of the stream and end inside this word
-            const unsigned long long rend = gend + s_bits[warp + 1];
-            size_t limit = out_cap;
-            if (chunk + 1 == nchunks - 1) limit = min(limit, (size_t)((rend + 7) >> 3));
-            const size_t byte = (size_t)v1 * 16 + lane;
-            if (byte < limit) out[byte] = (uint8_t)(word >> (24 - 8 * (lane & 3)));
-        }
-    }
-    // 3b. the words that are this chunk's alone
-    {
-        uint4 *dst = (uint4 *)out + v0;
-        const uint32_t sh = sbit0 & 31;
-        const uint32_t *sw = stage + (sbit0 >> 5);
-        for (uint32_t j = (shared_first ? 1u : 0u) + lane; j < nvec; j += 32) {
-            const uint32_t *p = sw + 4 * j;
-            const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4];
-            uint4 o;
-            o.x = bswap32(__funnelshift_l(a1, a0, sh));
-            o.y = bswap32(__funnelshift_l(a2, a1, sh));
-            o.z = bswap32(__funnelshift_l(a3, a2, sh));
-            o.w = bswap32(__funnelshift_l(a4, a3, sh));
-            stg_stream(dst + j, o);
-        }
-    }
-    if (!kPersistent) return;
-    }  // next ticket
-}
-
-
 // ================================================================================================ planned single pass
 // Tables whose longest code has at most 12 bits.  The bit offset of every 32 KB run is known BEFORE the launch (E1 + E2
 // from the input, or the run histograms K1 left behind: dc_histogram_u8_runs + encode_plan_kernel), so a run needs
@@ -755,20 +494,26 @@ __global__ void __launch_bounds__(kEncThreads, MAXBITS <= kSpTightBits ? 4 : 3) 
 //     had a code in bits 7..10 of the same sums.
 //   * emit: cur |= V >> P; next = V << (32 - P) (funnel shift of V:0); when bit 5 of P toggles the word is complete:
 //     predicated STS, cur = next, wi += 4.
-constexpr int kFwWarps = 16;                                 // warps (= chunks) per run
-constexpr int kFwGroups = 2;                                 // runs in flight per CTA (they share the table)
-constexpr int kFwThreads = kFwWarps * kFwGroups * 32;        // 1024
-constexpr int kFwChunkBytes = kRunBytes / kFwWarps;          // 2 KB
-constexpr int kFwChunkSubs = kFwChunkBytes / kSubTile;       // 4
-constexpr int kFwMaxBits = kPlannedMaxBits;
-constexpr int kFwStageWords = kSpZeroPrefix + kFwChunkBytes * kFwMaxBits / 32 + 12;   // per warp
+// Two instantiations.  PAIR: codes up to 12 bits, two symbols per emit step, 16 warps of 2 KB per run and two runs in flight
+// per CTA.  Single symbols: codes of 13 .. 16 bits (a pair no longer fits the 24 bits above the marker), 32 warps of 1 KB
+// per run -- the staging buffer of a chunk must hold 16 bits per symbol and all of them must lie in front of the table.
+template <int MAXBITS>
+struct FwCfg {
+    static constexpr bool kPair = MAXBITS <= kPlannedMaxBits;
+    static constexpr int kWarps = kPair ? 16 : 32;                 // warps (= chunks) per run
+    static constexpr int kGroups = 32 / kWarps;                    // runs in flight per CTA (they share the table)
+    static constexpr int kThreads = 1024;
+    static constexpr int kChunkBytes = kRunBytes / kWarps;         // 2 KB / 1 KB
+    static constexpr int kChunkSubs = kChunkBytes / kSubTile;      // 4 / 2
+    static constexpr int kStageWords = kSpZeroPrefix + kChunkBytes * MAXBITS / 32 + 12;   // per warp
+    static constexpr size_t kStageBytes = (size_t)32 * kStageWords * 4;
+    static constexpr size_t kXchgBytes = (size_t)kGroups * 2 * kWarps * 8 * 4;            // per group: 2 copies x warps x 8 words
+};
 constexpr int kFwTableBytes = 256 * 256;
 // The table sits at the ABSOLUTE shared-memory address 0x20000, so that the address of a look-up is one PRMT and nothing
 // else: byte 0 = 4 * lane, byte 1 = the input byte, byte 2 = 0x02 (from the lane constant).  The staging buffers lie in
 // front of it; the kernel computes the padding from its own window base (1 KB of system-reserved memory on sm_100).
 constexpr uint32_t kFwTableAddr = 0x20000u;
-constexpr size_t kFwStageBytes = (size_t)kFwWarps * kFwGroups * kFwStageWords * 4;   // 100 352
-constexpr size_t kFwXchgBytes = (size_t)kFwGroups * 2 * kFwWarps * 8 * 4;            // per group: 2 copies x 16 warps x 8 words
 constexpr size_t kFwSmemBytes = kFwTableAddr + kFwTableBytes - 1024;                  // dynamic bytes when the window starts at 1 KB
 
 __device__ __forceinline__ uint32_t fw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -876,17 +621,107 @@ __device__ __forceinline__ void fw_subtile(uint32_t *stage, const uint32_t (&w)[
     bitpos += tile_bits;
 }
 
-__device__ __forceinline__ void fw_group_barrier(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kFwWarps * 32) : "memory");
+// the same for tables with codes of 13 .. 16 bits: entry = code left-aligned | 1 << 9 | length, one symbol per emit step.
+// The low 9 bits of the sum of the 16 entries are the lane's bit count (<= 256), bits 9..13 count the symbols that had a code.
+template <bool FULL>
+__device__ __forceinline__ void fw_subtile_single(uint32_t *stage, const uint32_t (&w)[4], int valid, int lane, uint32_t lanec,
+                                                  uint32_t &bitpos, uint32_t &bad) {
+    uint32_t E[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        E[4 * q + 0] = fw_entry<0>(w[q], lanec);
+        E[4 * q + 1] = fw_entry<1>(w[q], lanec);
+        E[4 * q + 2] = fw_entry<2>(w[q], lanec);
+        E[4 * q + 3] = fw_entry<3>(w[q], lanec);
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (!FULL && k >= valid) E[k] = 0x200u;   // behind the end of the input: no bits, counted as "has a code"
+        sum += E[k];
+    }
+    bad |= ~sum >> 3;                             // bit 13 of the sum (16 symbols with a code) lands on bit 10 of `bad`
+    const uint32_t my_bits = sum & 511u;
+    uint32_t incl = my_bits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += x;
+    }
+    const uint32_t tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const bool fast = __all_sync(0xFFFFFFFFu, my_bits >= 32u);
+    const uint32_t pos = bitpos + incl - my_bits;
+    if (fast) {
+        const uint32_t lead = pos & 31u;
+        uint32_t wi = (uint32_t)__cvta_generic_to_shared(stage + (pos >> 5));
+        const uint32_t first_wi = wi;
+        uint32_t left_tail = 0;
+        if (lane == 0 && lead != 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(left_tail) : "r"(first_wi) : "memory");
+        uint32_t cur = 0, P = pos;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t.reg .u32 v, h, nx, p2, x;\n\t"
+                "and.b32 v, %3, 0xFFFF0000;\n\t"
+                "shf.r.wrap.b32 h, v, 0, %2;\n\t"
+                "or.b32 %1, %1, h;\n\t"
+                "shf.r.wrap.b32 nx, 0, v, %2;\n\t"
+                "add.u32 p2, %2, %3;\n\t"
+                "xor.b32 x, p2, %2;\n\t"
+                "and.b32 x, x, 32;\n\t"
+                "setp.ne.u32 q, x, 0;\n\t"
+                "@q st.shared.u32 [%0], %1;\n\t"
+                "@q mov.u32 %1, nx;\n\t"
+                "@q add.u32 %0, %0, 4;\n\t"
+                "mov.u32 %2, p2;\n\t}"
+                : "+r"(wi), "+r"(cur), "+r"(P)
+                : "r"(E[k])
+                : "memory");
+        }
+        const uint32_t lt = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
+        if (lane != 0) left_tail = lt;
+        if (lead != 0) {
+            uint32_t t;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(first_wi) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(first_wi), "r"(t | left_tail) : "memory");
+        }
+        if (lane == 31) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wi), "r"(cur) : "memory");
+    } else {
+        const uint32_t z0 = (bitpos >> 5) + 1, z1 = ((bitpos + tile_bits) >> 5) + 1;
+        for (uint32_t i = z0 + lane; i <= z1; i += 32) stage[i] = 0;
+        __syncwarp();
+        uint32_t wi = pos >> 5, nb = pos & 31, hi = 0, lo = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t len = E[k] & 31u;
+            emit_bits(stage, hi, lo, nb, wi, len ? E[k] >> (32u - len) : 0u, len);
+        }
+        stage_or_if(stage + wi, lo << ((32u - nb) & 31u), nb != 0u);
+    }
+    __syncwarp();
+    bitpos += tile_bits;
 }
 
-__global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_t *__restrict__ in, size_t n,
+template <int THREADS>
+__device__ __forceinline__ void fw_group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(THREADS) : "memory");
+}
+
+template <int MAXBITS>
+__global__ void __launch_bounds__(1024, 1) encode_fast_kernel(const uint8_t *__restrict__ in, size_t n,
                                                                     const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
                                                                     size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
                                                                     int32_t *__restrict__ d_status, uint32_t smem_bytes) {
+    typedef FwCfg<MAXBITS> Cfg;
+    constexpr int kFwWarps = Cfg::kWarps, kFwGroups = Cfg::kGroups, kFwThreads = Cfg::kThreads, kFwChunkBytes = Cfg::kChunkBytes;
+    constexpr int kFwChunkSubs = Cfg::kChunkSubs, kFwStageWords = Cfg::kStageWords;
+    constexpr size_t kFwStageBytes = Cfg::kStageBytes, kFwXchgBytes = Cfg::kXchgBytes;
     extern __shared__ __align__(16) uint8_t fw_smem[];   // [exchange | staging buffers | padding | table at 0x20000]
     if (!table_usable(tab, d_status)) return;
-    if (tab->max_bits > kFwMaxBits) return;   // the look-back single pass (13 .. 16 bits) or the 64-bit-entry kernel takes this table
+    {   // this instantiation's tables: [1, 12] (pairs) or (12, 16] (single symbols); longer codes take the 64-bit-entry kernel
+        const int mb = tab->max_bits;
+        if (mb > MAXBITS || (!Cfg::kPair && mb <= kPlannedMaxBits)) return;
+    }
     if (ws.d_phase) phase = *ws.d_phase & 7u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = warp / kFwWarps, gw = warp % kFwWarps;
     const size_t stream_bytes = (size_t)(((unsigned long long)phase + ws.run_off[nruns] + 7) >> 3);
@@ -903,7 +738,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
     for (int i = tid; i < 256 * 32; i += kFwThreads) {
         const int b = i >> 5;
         const uint32_t e = tab->enc[b], l = e & 63u;
-        s_tab[b * 64 + (i & 31)] = l ? (((e >> 6) << (32u - l)) | 0x80u | l) : 0u;
+        s_tab[b * 64 + (i & 31)] = l ? (((e >> 6) << (32u - l)) | (Cfg::kPair ? 0x80u : 0x200u) | l) : 0u;
     }
     __syncthreads();
     // what a warp shows its run: its bit count and the first 128 bits of its chunk (the left neighbour completes the 16-byte
@@ -941,7 +776,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
 #pragma unroll
             for (int t = 0; t < kFwChunkSubs; t++) {
                 const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
-                fw_subtile<true>(stage, w, kEncPerThread, lane, lanec, bitpos, bad);
+                if (Cfg::kPair) fw_subtile<true>(stage, w, kEncPerThread, lane, lanec, bitpos, bad);
+                else fw_subtile_single<true>(stage, w, kEncPerThread, lane, lanec, bitpos, bad);
             }
         } else {  // the ragged last chunk of the stream (or no chunk at all)
             const int nsub = (int)((chunk_len + kSubTile - 1) / kSubTile);
@@ -951,7 +787,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
                 const int valid = base < n ? (int)min((size_t)kEncPerThread, n - base) : 0;
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (int k = 0; k < valid; k++) w[k >> 2] |= (uint32_t)in[base + k] << (8 * (k & 3));
-                fw_subtile<false>(stage, w, valid, lane, lanec, bitpos, bad);
+                if (Cfg::kPair) fw_subtile<false>(stage, w, valid, lane, lanec, bitpos, bad);
+                else fw_subtile_single<false>(stage, w, valid, lane, lanec, bitpos, bad);
             }
         }
         // the next run's input is on its way while this one waits for its neighbours and is copied out
@@ -961,14 +798,14 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
         __syncwarp();
         uint32_t *xchg = xchg_base + parity * (kFwWarps * 8);
         if (lane < 5) xchg[gw * 8 + lane] = lane == 0 ? chunk_bits : stage[kSpZeroPrefix - 1 + lane];
-        fw_group_barrier(group);
+        fw_group_barrier<kFwWarps * 32>(group);
 
         // ---- 2. the chunk's place in the stream: the run's planned offset + the chunks in front of it
         unsigned long long excl = run_excl;
         {
             uint32_t mine = lane < gw ? xchg[lane * 8] : 0u;   // kFwWarps <= 32
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
             excl += __shfl_sync(0xFFFFFFFFu, mine, 0);
         }
 
@@ -1023,13 +860,20 @@ __global__ void __launch_bounds__(kFwThreads, 1) encode_fast_kernel(const uint8_
                         if (byte < limit) out[byte] = (uint8_t)(word >> (24 - 8 * (lane & 3)));
                     }
                 }
-                // 3b. the words that are this chunk's alone
+                // 3b. the words that are this chunk's alone.  Output vector j needs staging words s0 + 4 j .. s0 + 4 j + 4 with
+                // s0 = sbit0 / 32 = 4 q + d: two ALIGNED 16-byte loads (vectors q + j and q + j + 1: consecutive lanes read
+                // consecutive vectors, no bank conflict) and a warp-uniform choice of the five words by d -- five scalar
+                // loads at a stride of four words would be 4-way conflicts each
                 uint4 *dst = (uint4 *)out + v0;
-                const uint32_t sh = sbit0 & 31;
-                const uint32_t *sw = stage + (sbit0 >> 5);
+                const uint32_t sh = sbit0 & 31, s0 = sbit0 >> 5, d = s0 & 3u;
+                const uint4 *sv = (const uint4 *)stage + (s0 >> 2);
                 for (uint32_t j = (shared_first ? 1u : 0u) + lane; j < nvec; j += 32) {
-                    const uint32_t *p = sw + 4 * j;
-                    const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4];
+                    const uint4 A = sv[j], B = sv[j + 1];
+                    uint32_t a0, a1, a2, a3, a4;
+                    if (d == 0) { a0 = A.x; a1 = A.y; a2 = A.z; a3 = A.w; a4 = B.x; }
+                    else if (d == 1) { a0 = A.y; a1 = A.z; a2 = A.w; a3 = B.x; a4 = B.y; }
+                    else if (d == 2) { a0 = A.z; a1 = A.w; a2 = B.x; a3 = B.y; a4 = B.z; }
+                    else { a0 = A.w; a1 = B.x; a2 = B.y; a3 = B.z; a4 = B.w; }
                     uint4 o;
                     o.x = bswap32(__funnelshift_l(a1, a0, sh));
                     o.y = bswap32(__funnelshift_l(a2, a1, sh));
@@ -1105,7 +949,7 @@ static size_t enc_ws_layout(size_t n, size_t off[10]) {
     o[2] = take((nruns + 1) * 8);        // run_off
     o[3] = take((nchunks + 1) * 4 + 64); // bstate, then the ticket and the plan's counter (zeroed together)
     o[6] = o[3] + (nchunks + 1) * 4;     // ticket (4-byte aligned, inside the bstate block); the plan's counter follows it
-    o[7] = take(nchunks * 8);            // desc                      (look-back single pass; zeroed)
+    o[7] = take(64);                     // (unused)
     o[4] = take((nchunks + 1) * 16);     // bleft
     o[5] = take((nchunks + 1) * 16);     // bright
     o[8] = take(nruns * 512);            // run histograms (dc_histogram_u8_runs -> dc_huff_encode_planned)
@@ -1148,8 +992,8 @@ static int encode_entry(const uint8_t *d_in, size_t n, const dc_huff_table *d_ta
     ws.bleft = (uint4 *)(w + off[4]);
     ws.bright = (uint4 *)(w + off[5]);
     ws.d_phase = d_phase;
-    // bstate + ticket and (contiguous, see enc_ws_layout) the look-back descriptors are zeroed in one memset
-    DC_CUDA_TRY(cudaMemsetAsync(w + off[3], 0, (off[7] - off[3]) + nchunks * 8, st));
+    // the arrival counters of the 16-byte words that two runs share
+    DC_CUDA_TRY(cudaMemsetAsync(w + off[3], 0, (nchunks + 1) * 4 + 64, st));
     const unsigned int sms = (unsigned int)sm_count();
     if (planned) {
         // the bit offset of every run from the run histograms K1 left in this workspace (dc_histogram_u8_runs)
@@ -1211,33 +1055,25 @@ extern "C" int dc_histogram_u8_runs(const uint8_t *d_in, size_t n, uint64_t *d_h
 static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
                               unsigned bit_phase, EncWorkspace ws, char *w, const size_t *off, unsigned int nruns,
                               unsigned long long *d_total_bits, int32_t *d_status, cudaStream_t st, bool planned) {
-    (void)planned;
+    (void)planned; (void)w; (void)off; (void)d_total_bits;
     const unsigned int sms = (unsigned int)sm_count();
-    {   // codes up to 12 bits
-        FwWorkspace fw;
-        fw.run_off = ws.run_off;
-        fw.bstate = ws.bstate;
-        fw.bleft = ws.bleft;
-        fw.bright = ws.bright;
-        fw.d_phase = ws.d_phase;
-        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel, kFwSmemBytes));
+    FwWorkspace fw;
+    fw.run_off = ws.run_off;
+    fw.bstate = ws.bstate;
+    fw.bleft = ws.bleft;
+    fw.bright = ws.bright;
+    fw.d_phase = ws.d_phase;
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel<kPlannedMaxBits>, kFwSmemBytes));
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel<kNarrowBits>, kFwSmemBytes));
+    {   // codes up to 12 bits: two symbols per emit step
         LaunchScope ls(DC_K_ENCODE_FAST, st);
-        encode_fast_kernel<<<min((nruns + kFwGroups - 1) / kFwGroups, sms), kFwThreads, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity,
-                                                                                                           bit_phase, fw, nruns, d_status, (uint32_t)kFwSmemBytes);
+        encode_fast_kernel<kPlannedMaxBits><<<min((nruns + 1) / 2, sms), 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw,
+                                                                                                  nruns, d_status, (uint32_t)kFwSmemBytes);
     }
-    {   // 13 .. 16 bits: the look-back single pass
-        SpWorkspace sp;
-        sp.ticket = (unsigned int *)(w + off[6]);
-        sp.desc = (unsigned long long *)(w + off[7]);
-        sp.bstate = ws.bstate;
-        sp.bleft = ws.bleft;
-        sp.bright = ws.bright;
-        sp.d_phase = ws.d_phase;
-        const size_t smem16 = (size_t)kEncWarps * sp_stage_words(kNarrowBits) * 4;
-        DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_single_kernel<kNarrowBits>, smem16));
+    {   // 13 .. 16 bits: one symbol per emit step
         LaunchScope ls(DC_K_ENCODE_MID, st);
-        encode_single_kernel<kNarrowBits><<<min(nruns, sms * 3u), kEncThreads, smem16, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, sp,
-                                                                                             nruns, d_total_bits, d_status);
+        encode_fast_kernel<kNarrowBits><<<min(nruns, sms), 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw, nruns,
+                                                                                    d_status, (uint32_t)kFwSmemBytes);
     }
     {   // longer codes: 64-bit entries
         LaunchScope ls(DC_K_ENCODE_WIDE, st);
