@@ -28,6 +28,7 @@
 // advance by one digit and produce no symbol -- and are reported as DC_ERR_CORRUPT on the true path.
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "chain_scan.cuh"
@@ -1040,6 +1041,7 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 constexpr int kSyncW14 = 0x10;
 constexpr int kModeFsm = 0x20;   // the byte-stepped kernels of k4_fsm.cuh; bits 20..28: states, bits 29..31: min(shortest code's bits, 8) - 1
 static int decode_force_mode();
+static bool decode_tma();
 static bool fsm_rows_fit(const int32_t *tmeta) {
     const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
     const size_t per_lane = (size_t)(kF_SubBits / (min_bits < 8 ? min_bits : 8)) + 2, half = 16 * per_lane + 48, whole = 32 * per_lane + 48;
@@ -1110,10 +1112,16 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
         LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
         fsm_build_kernel<<<nstates + 1, 256, 0, st>>>(d_table, t);
     }
-    const size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
-    const int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
-    const int per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
-    DC_CUDA_TRY(ensure_dynamic_smem((const void *)fsm_sync_kernel, smem));
+    size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
+    int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
+    int per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
+
+    // north_star (4): the tile staged by the bulk-copy engine instead of a 32-byte load per lane (DC_DECODE_TMA=1; measured
+    // in DESIGN.md -- the default is whichever is faster)
+    const bool tma = decode_tma();
+    const uint32_t table_bytes = (uint32_t)(((size_t)nstates * kFsmSyncRowBytes + 127) & ~(size_t)127);
+    if (tma) smem = kFsmHeaderBytes + table_bytes + (size_t)(threads / 32) * (1024 + 8);
+    DC_CUDA_TRY(ensure_dynamic_smem(tma ? (const void *)fsm_sync_kernel<true> : (const void *)fsm_sync_kernel<false>, smem));
     const unsigned long long want = (nseg + (threads / 32) - 1) / (threads / 32), cap = (unsigned long long)sm_count() * per_sm;
     FsmSyncArgs a;
     a.d_bits = d_bits;
@@ -1125,7 +1133,9 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     a.lead = lead;
     a.chain = chain;
     LaunchScope ls(DC_K_DECODE_FSM_SYNC, st);
-    fsm_sync_kernel<<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
+    a.tma_table_bytes = table_bytes;
+    if (tma) fsm_sync_kernel<true><<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
+    else fsm_sync_kernel<false><<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
     return cuda_status(cudaGetLastError());
 }
 static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
@@ -1233,6 +1243,10 @@ static int decode_force_mode() {
         g_decode_force = e ? atoi(e) : 0;
     }
     return g_decode_force;
+}
+static bool decode_tma() {
+    static const bool on = [] { const char *e = getenv("DC_DECODE_TMA"); return e && atoi(e) != 0; }();
+    return on;
 }
 // test hook (not in the public header): 0 = normal, 1 = robust path only, 2 = fast path, then the robust path anyway
 extern "C" int dc_debug_decode_mode(int mode) {

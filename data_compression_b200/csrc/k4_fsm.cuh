@@ -235,6 +235,63 @@ struct FsmCursor {
     }
 };
 
+
+// The same view with the tile staged in shared memory by the bulk-copy engine (TMA, cp.async.bulk + mbarrier) -- the
+// staging north_star (4) names.  One 1 KB buffer and one mbarrier per warp: lane 0 arms the barrier with the byte count and
+// issues the copy of the NEXT tile as soon as every lane has moved the current one into registers (two 16-byte LDS per
+// lane; the lanes of the odd groups of four read their halves in the other order, which makes the 32-byte stride
+// conflict-free), so the copy runs under the current tile's walk and no registers hold data in flight.
+struct FsmCursorTma {
+    const uint8_t *src;            // next tile to fetch
+    unsigned long long bytes_left; // readable bytes (whole 16-byte vectors) from `src` on
+    uint32_t buf, bar;             // shared-memory addresses: this warp's tile buffer and its mbarrier
+    uint32_t phase;
+    bool pending;
+    int lane;
+    __device__ __forceinline__ void init(const uint8_t *d_bits, unsigned long long first_tile, unsigned long long nvec, int lane_,
+                                         uint32_t buf_, uint32_t bar_, uint32_t phase_) {
+        lane = lane_;
+        buf = buf_;
+        bar = bar_;
+        phase = phase_;
+        const unsigned long long vec0 = first_tile * kF_TileVecs;
+        src = d_bits + vec0 * 16;
+        bytes_left = nvec > vec0 ? (nvec - vec0) * 16 : 0;
+        pending = false;
+        fetch();
+    }
+    __device__ __forceinline__ void fetch() {
+        const uint32_t bytes = (uint32_t)min(bytes_left, (unsigned long long)(kF_TileVecs * 16));
+        pending = bytes != 0;
+        if (pending && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' reads of the buffer precede the engine's writes
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(buf), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+        src += kF_TileVecs * 16;
+        bytes_left -= bytes;
+    }
+    __device__ __forceinline__ void take(uint32_t (&w)[8], bool more) {
+        if (pending) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            phase ^= 1u;
+        }
+        const uint32_t swap = (lane >> 2) & 1u, a0 = buf + 32u * lane + 16u * swap;
+        uint4 r0, r1;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a0 ^ 16u) : "memory");
+        const uint4 lo = swap ? r1 : r0, hi = swap ? r0 : r1;
+        w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
+        w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+        __syncwarp();
+        if (more) fetch();
+    }
+};
+
 // ------------------------------------------------------------------------------------------ F1 (FSM)
 
 // replace byte k of `word` by byte `src_byte` of `from`
@@ -286,6 +343,7 @@ struct FsmSyncArgs {
     uint32_t start_token;          // first segment (lead == 0): kFsmToken | state, or a bit offset (< 256) of the first code
     int lead;
     const DecodeChain *chain;
+    uint32_t tma_table_bytes;      // TMA staging only: the table's share of shared memory, rounded up to 128 bytes
 };
 
 // slow tile: every lane walks its part digit by digit.  start: kFsmToken | state for a lane that begins at bit 0 of its
@@ -302,6 +360,7 @@ __device__ __forceinline__ void fsm_slow_sync_lane(const FsmHeader *h, const uin
     exit_state = fsm_state_id(h, d, v);
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTables t, FastWorkspace ws) {
     extern __shared__ __align__(16) uint8_t fsm_smem[];
     FsmHeader *s_h = (FsmHeader *)fsm_smem;
@@ -326,12 +385,26 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
     const unsigned long long tile_bits = 32ull * kF_SubBits;
+    // TMA: [header | table (a.tma_table_bytes, a multiple of 128) | one 1 KB tile buffer per warp | one mbarrier per warp]
+    uint32_t tma_buf = 0, tma_bar = 0, tma_phase = 0;
+    if (TMA) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(fsm_smem + kFsmHeaderBytes + a.tma_table_bytes);
+        tma_buf = base + 1024u * warp;
+        tma_bar = base + 1024u * warps + 8u * warp;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tma_bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (unsigned long long seg = (unsigned long long)blockIdx.x * warps + warp; seg < a.nseg; seg += (unsigned long long)gridDim.x * warps) {
         const bool exact = seg == 0 && a.lead == 0;
         const int warm = exact ? 0 : 1;
         const unsigned long long tile0 = (unsigned long long)a.lead + seg * kF_SegTiles - warm;
-        FsmCursor cur;
-        cur.init(a.d_bits, tile0, nvec, lane);
+        typename std::conditional<TMA, FsmCursorTma, FsmCursor>::type cur;
+        if constexpr (TMA) cur.init(a.d_bits, tile0, nvec, lane, tma_buf, tma_bar, tma_phase);
+        else cur.init(a.d_bits, tile0, nvec, lane);
         const uint32_t ntile = (uint32_t)min((unsigned long long)(kF_SegTiles + warm), a.ntiles - tile0);
         uint16_t *info = ws.sub_info + tile0 * 32 + lane;
         const unsigned long long sub_left = a.nsub - tile0 * 32;
@@ -397,6 +470,7 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
             ws.seg_assumed[seg] = assumed;
             ws.seg_exit[seg] = carry;
         }
+        if constexpr (TMA) tma_phase = cur.phase;   // every copy that was issued has been waited for (take(.., more) fetches only what is walked)
     }
 }
 
