@@ -4,6 +4,7 @@
 // the reference's verbatim names onto them): they stage the caller's host buffers into a grow-only device
 // arena, run the same device path as the dc_* entry points, copy the results back and synchronise.
 // There is no CPU implementation behind any of them: without a usable device they return DC_ERR_CUDA.
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -92,6 +93,145 @@ cudaError_t ensure_dynamic_smem(const void *func, size_t bytes) {
     e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) limit = bytes;
     return e;
+}
+
+// ---- host-visible table facts and flags: rings of mapped pinned words + events, one ring per device
+constexpr int kMetaSlots = 256, kFlagSlots = 64, kMaxDevices = 64;
+struct MetaSlot { cudaEvent_t ev; const dc_huff_table *tab; unsigned long long serial; };
+struct HostRing {
+    bool ready = false;
+    int32_t *pinned = nullptr;          // kMetaSlots x 16 words, then kFlagSlots x 16 words
+    MetaSlot meta[kMetaSlots];
+    cudaEvent_t flag_ev[kFlagSlots];
+    bool flag_busy[kFlagSlots];
+    unsigned next_meta = 0, next_flag = 0;
+};
+struct MetaRef { int dev, slot; unsigned long long serial; };
+static std::mutex g_meta_mu;
+static HostRing g_ring[kMaxDevices];
+static std::map<const dc_huff_table *, MetaRef> g_meta_of;
+static unsigned long long g_meta_serial = 0;
+
+static HostRing *host_ring(int *dev_out) {   // caller holds g_meta_mu
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return nullptr; }
+    HostRing &r = g_ring[dev];
+    if (!r.ready) {
+        if (cudaHostAlloc((void **)&r.pinned, (size_t)(kMetaSlots + kFlagSlots) * 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        memset(r.pinned, 0, (size_t)(kMetaSlots + kFlagSlots) * 64);
+        for (int i = 0; i < kMetaSlots; i++) {
+            r.meta[i].tab = nullptr;
+            r.meta[i].serial = 0;
+            if (cudaEventCreateWithFlags(&r.meta[i].ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        for (int i = 0; i < kFlagSlots; i++) {
+            r.flag_busy[i] = false;
+            if (cudaEventCreateWithFlags(&r.flag_ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        r.ready = true;
+    }
+    *dev_out = dev;
+    return &r;
+}
+
+void table_meta_begin(const dc_huff_table *d_table, TableMetaTicket *t) {
+    t->dev = nullptr;
+    std::lock_guard<std::mutex> lk(g_meta_mu);
+    g_meta_of.erase(d_table);   // whatever was known about this address is about to be overwritten
+    int dev = 0;
+    HostRing *r = host_ring(&dev);
+    if (!r) return;
+    const int slot = (int)(r->next_meta++ % kMetaSlots);
+    MetaSlot &m = r->meta[slot];
+    if (m.tab) {   // recycle: the table that held this slot falls back to a device read
+        auto it = g_meta_of.find(m.tab);
+        if (it != g_meta_of.end() && it->second.dev == dev && it->second.slot == slot) g_meta_of.erase(it);
+    }
+    m.tab = d_table;
+    m.serial = ++g_meta_serial;
+    int32_t *host = r->pinned + (size_t)slot * 16, *devp = nullptr;
+    if (cudaHostGetDevicePointer((void **)&devp, host, 0) != cudaSuccess) { cudaGetLastError(); m.tab = nullptr; return; }
+    t->dev = devp;
+    t->dev_index = dev;
+    t->slot = slot;
+    t->serial = m.serial;
+}
+
+void table_meta_end(const dc_huff_table *d_table, const TableMetaTicket &t, cudaStream_t st) {
+    if (!t.dev) return;
+    std::lock_guard<std::mutex> lk(g_meta_mu);
+    MetaSlot &m = g_ring[t.dev_index].meta[t.slot];
+    if (m.serial != t.serial) return;   // recycled in between (256 builds raced this one)
+    if (cudaEventRecord(m.ev, st) != cudaSuccess) { cudaGetLastError(); m.tab = nullptr; return; }
+    g_meta_of[d_table] = MetaRef{t.dev_index, t.slot, t.serial};
+}
+
+static int table_meta_read_device(const dc_huff_table *d_table, cudaStream_t st, int32_t out[kTableMetaWords]) {
+    DC_CUDA_TRY(cudaMemcpyAsync(out, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(out + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    return DC_OK;
+}
+
+int table_meta_fetch(const dc_huff_table *d_table, cudaStream_t st, int32_t out[kTableMetaWords], bool wait) {
+    MetaRef ref;
+    cudaEvent_t ev = nullptr;
+    bool known = false;
+    {
+        std::lock_guard<std::mutex> lk(g_meta_mu);
+        auto it = g_meta_of.find(d_table);
+        if (it != g_meta_of.end()) {
+            ref = it->second;
+            ev = g_ring[ref.dev].meta[ref.slot].ev;
+            known = g_ring[ref.dev].meta[ref.slot].serial == ref.serial;
+        }
+    }
+    if (known) {
+        cudaError_t e = wait ? cudaEventSynchronize(ev) : cudaEventQuery(ev);
+        if (e == cudaErrorNotReady) { cudaGetLastError(); return 1; }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_meta_mu);
+            const HostRing &r = g_ring[ref.dev];
+            if (r.meta[ref.slot].serial == ref.serial) {
+                const volatile int32_t *src = r.pinned + (size_t)ref.slot * 16;
+                for (int i = 0; i < kTableMetaWords; i++) out[i] = src[i];
+                return DC_OK;
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!wait) return 1;
+    return table_meta_read_device(d_table, st, out);
+}
+
+int host_flag_acquire(HostFlag *f) {
+    std::lock_guard<std::mutex> lk(g_meta_mu);
+    int dev = 0;
+    HostRing *r = host_ring(&dev);
+    if (!r) return DC_ERR_CUDA;
+    for (int k = 0; k < kFlagSlots; k++) {
+        const int slot = (int)(r->next_flag++ % kFlagSlots);
+        if (r->flag_busy[slot]) continue;
+        int32_t *host = r->pinned + (size_t)(kMetaSlots + slot) * 16, *devp = nullptr;
+        if (cudaHostGetDevicePointer((void **)&devp, host, 0) != cudaSuccess) { cudaGetLastError(); return DC_ERR_CUDA; }
+        r->flag_busy[slot] = true;
+        f->host = host;
+        f->dev = devp;
+        f->ev = r->flag_ev[slot];
+        f->dev_index = dev;
+        f->slot = slot;
+        return DC_OK;
+    }
+    return DC_ERR_CUDA;   // 64 calls in flight on one device
+}
+
+void host_flag_release(const HostFlag &f) {
+    std::lock_guard<std::mutex> lk(g_meta_mu);
+    g_ring[f.dev_index].flag_busy[f.slot] = false;
 }
 
 // grow-only device scratch for the host-pointer entry points (single-threaded use, like the reference)

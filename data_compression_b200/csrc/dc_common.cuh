@@ -73,6 +73,24 @@ int mtf_positions(const uint8_t *d_src, size_t n, uint8_t *d_pos, void *d_ws, cu
 // d_buf[1..*d_len): bytes with bit 7 are 0x80 | position and are replaced by the letter they mean (only if *d_mode == 0)
 int mtf_resolve(uint8_t *d_buf, const unsigned long long *d_len, const int32_t *d_mode, cudaStream_t st);
 
+// ---------------------------------------------------------------- what the host knows about a device table (capi.cu)
+// K2 leaves the table's first ten words, lut2_used and fsm_states in mapped host memory and the build records an event, so
+// the entry points that pick a kernel by the table's shape need neither a device-to-host copy nor a stream synchronise.
+constexpr int kTableMetaWords = 12;
+struct TableMetaTicket { int32_t *dev; int dev_index, slot; unsigned long long serial; };
+// before the K2 launch: a mapped slot for `d_table` (t.dev == nullptr if none could be had: K2 then publishes nothing)
+void table_meta_begin(const dc_huff_table *d_table, TableMetaTicket *t);
+// after the K2 launch on `st`
+void table_meta_end(const dc_huff_table *d_table, const TableMetaTicket &t, cudaStream_t st);
+// wait = true: DC_OK, blocks until the build of `d_table` has finished (a table this library did not build, or one whose slot
+// has been recycled, is read from the device after synchronising `st`).  wait = false: DC_OK only if the facts are known
+// already, 1 otherwise (never blocks).
+int table_meta_fetch(const dc_huff_table *d_table, cudaStream_t st, int32_t out[kTableMetaWords], bool wait);
+// a mapped int32 + an event: a kernel stores one word, the host waits for the event (not for the stream) and reads it
+struct HostFlag { volatile int32_t *host; int32_t *dev; cudaEvent_t ev; int dev_index, slot; };
+int host_flag_acquire(HostFlag *f);
+void host_flag_release(const HostFlag &f);
+
 // ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
 constexpr int kFsmMaxStates = 255;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
 // Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.

@@ -46,7 +46,8 @@ __device__ __forceinline__ bool t2_to_trits(unsigned int window, int window_bits
 
 __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long long *__restrict__ d_hist,
                                                             const int32_t *__restrict__ d_lengths_in, int nsym,
-                                                            int n_ary, dc_huff_table *__restrict__ tab, TableRaw raw) {
+                                                            int n_ary, dc_huff_table *__restrict__ tab, TableRaw raw,
+                                                            int32_t *__restrict__ host_meta) {
     __shared__ unsigned long long s_cnt[kTabCap];     // compacted leaf counts (index order)
     __shared__ unsigned long long s_scnt[kTabCap];    // leaf counts sorted by (count, index)
     __shared__ unsigned long long s_icount[kTabCap];  // internal node counts, creation order
@@ -399,6 +400,13 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         uint32_t cnt[32], ilo[32], ihi[32], base[32];
         for (int d = 0; d < 32; d++) cnt[d] = (d >= min_len && d <= max_len) ? s_lencount[d] : 0u;
         tab->fsm_states = (status == DC_OK && !t2 && max_len < 16) ? fsm_geometry(s_first, cnt, min_len, max_len, bpd, ilo, ihi, base) : 0;
+        if (host_meta) {   // mapped host memory (dc_common.cuh, table_meta_*): what the entry points pick their kernels by
+            const int32_t *words = (const int32_t *)tab;
+            for (int i = 0; i < 10; i++) host_meta[i] = words[i];
+            host_meta[10] = tab->lut2_used;
+            host_meta[11] = tab->fsm_states;
+            __threadfence_system();
+        }
     }
 }
 
@@ -420,8 +428,14 @@ int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int
                  TableRaw raw, cudaStream_t st) {
     if (n_ary < 2 || n_ary > 512 || nsym < 1 || nsym > DC_MAX_LEAVES) return DC_ERR_ARG;
     if (tab && nsym != DC_NSLOTS) return DC_ERR_ARG;
-    LaunchScope ls(DC_K_TABLE, st);
-    table_kernel<<<1, kTabThreads, 0, st>>>(d_hist, d_lengths, nsym, n_ary, tab, raw);
+    TableMetaTicket ticket;
+    ticket.dev = nullptr;
+    if (tab) table_meta_begin(tab, &ticket);
+    {
+        LaunchScope ls(DC_K_TABLE, st);
+        table_kernel<<<1, kTabThreads, 0, st>>>(d_hist, d_lengths, nsym, n_ary, tab, raw, ticket.dev);
+    }
+    if (tab) table_meta_end(tab, ticket, st);
     return cuda_status(cudaGetLastError());
 }
 

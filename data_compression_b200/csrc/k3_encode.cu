@@ -708,7 +708,7 @@ __device__ __forceinline__ void fw_group_barrier(int group) {
 }
 
 template <int MAXBITS>
-__global__ void __launch_bounds__(1024, 1) encode_fast_kernel(const uint8_t *__restrict__ in, size_t n,
+__device__ __forceinline__ void encode_fast_body(const uint8_t *__restrict__ in, size_t n,
                                                                     const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
                                                                     size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
                                                                     int32_t *__restrict__ d_status, uint32_t smem_bytes) {
@@ -887,6 +887,23 @@ __global__ void __launch_bounds__(1024, 1) encode_fast_kernel(const uint8_t *__r
     if (((bad >> 10) & 1u) != 0u) set_status(d_status, DC_ERR_SYMBOL);
 }
 
+// WHICH = 12 / 16: the host knows the table's longest code (table_meta_fetch) and launches the one instantiation that takes it.
+// WHICH = 0: it does not yet (the build is still queued): one launch that picks by the table it finds.
+template <int WHICH>
+__global__ void __launch_bounds__(1024, 1) encode_fast_kernel(const uint8_t *__restrict__ in, size_t n,
+                                                              const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
+                                                              size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
+                                                              int32_t *__restrict__ d_status, uint32_t smem_bytes) {
+    if (WHICH == kPlannedMaxBits) {
+        encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+    } else if (WHICH == kNarrowBits) {
+        encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+    } else {
+        if (tab->max_bits <= kPlannedMaxBits) encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+        else encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ plan (run offsets from run histograms)
 // bits of run r = sum over symbols of run_hist[r][s] * bits(s): one warp per run (a lane takes 8 of the 256 u16 counts with one
 // 16-byte load); the CTA that finishes last scans the run totals into exclusive offsets (E2's arithmetic) -- one launch.
@@ -1063,21 +1080,24 @@ static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table
     fw.bleft = ws.bleft;
     fw.bright = ws.bright;
     fw.d_phase = ws.d_phase;
-    DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel<kPlannedMaxBits>, kFwSmemBytes));
-    DC_CUDA_TRY(ensure_dynamic_smem((const void *)encode_fast_kernel<kNarrowBits>, kFwSmemBytes));
-    {   // codes up to 12 bits: two symbols per emit step
-        LaunchScope ls(DC_K_ENCODE_FAST, st);
-        encode_fast_kernel<kPlannedMaxBits><<<min((nruns + 1) / 2, sms), 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw,
-                                                                                                  nruns, d_status, (uint32_t)kFwSmemBytes);
+    // the table's longest code, if the host knows it already (the build's event has passed); else the kernels decide
+    int32_t tmeta[kTableMetaWords];
+    const bool known = table_meta_fetch(d_table, st, tmeta, false) == DC_OK;
+    const int mb = known ? tmeta[7] : -1;
+    if (!known || mb <= kNarrowBits) {
+        // codes up to 12 bits: two symbols per emit step; 13 .. 16 bits: one symbol per emit step
+        const bool pair = known && mb <= kPlannedMaxBits;
+        const void *fn = !known ? (const void *)encode_fast_kernel<0> : pair ? (const void *)encode_fast_kernel<kPlannedMaxBits> : (const void *)encode_fast_kernel<kNarrowBits>;
+        DC_CUDA_TRY(ensure_dynamic_smem(fn, kFwSmemBytes));
+        const unsigned int grid = pair ? min((nruns + 1) / 2, sms) : min(nruns, sms);
+        LaunchScope ls(known && !pair ? DC_K_ENCODE_MID : DC_K_ENCODE_FAST, st);
+        if (!known) encode_fast_kernel<0><<<grid, 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw, nruns, d_status, (uint32_t)kFwSmemBytes);
+        else if (pair) encode_fast_kernel<kPlannedMaxBits><<<grid, 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw, nruns, d_status, (uint32_t)kFwSmemBytes);
+        else encode_fast_kernel<kNarrowBits><<<grid, 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw, nruns, d_status, (uint32_t)kFwSmemBytes);
     }
-    {   // 13 .. 16 bits: one symbol per emit step
-        LaunchScope ls(DC_K_ENCODE_MID, st);
-        encode_fast_kernel<kNarrowBits><<<min(nruns, sms), 1024, kFwSmemBytes, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase, fw, nruns,
-                                                                                    d_status, (uint32_t)kFwSmemBytes);
-    }
-    {   // longer codes: 64-bit entries
+    if (!known || mb > kNarrowBits) {   // longer codes: 64-bit entries (returns at once for any other table)
         LaunchScope ls(DC_K_ENCODE_WIDE, st);
-        encode_run_kernel<true><<<min(nruns, sms * 4u), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
+        encode_run_kernel<true><<<min(nruns, known ? sms * 4u : sms), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
                                                                              ws, nruns, d_status);
     }
     return cuda_status(cudaGetLastError());

@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(kF_Threads, mode_t2(MODE) ? 3 : 4) decode_fast
 __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws, unsigned long long nseg, unsigned long long n_out,
                                                                 int32_t *__restrict__ d_status, DecodeChain *__restrict__ chain,
                                                                 int last_chunk, int check_input,
-                                                                DecodeChain *__restrict__ host_chain, ChainSlots slots) {
+                                                                DecodeChain *__restrict__ host_chain, ChainSlots slots,
+                                                                int32_t *__restrict__ host_flag) {
     // CTA b takes the contiguous segments [lo, hi); totals travel from CTA to CTA (chain_scan.cuh).  A CTA's value carries its
     // "some segment started on a wrong guess" flag above bit 56 (a symbol total stays far below).
     const int tid = threadIdx.x;
@@ -792,6 +793,10 @@ __global__ void __launch_bounds__(1024) decode_fast_scan_kernel(FastWorkspace ws
         int s_bad = ((before >> 56) != 0 || any_bad) ? 1 : 0;
         if (check_input && *ws.bad_input()) s_bad = 1;
         *ws.mismatch = s_bad;
+        if (host_flag) {   // mapped host memory (dc_huff_decode waits for this kernel's event, not for the stream)
+            *host_flag = s_bad;
+            __threadfence_system();
+        }
         if (chain) {
             chain->base = carry;
             chain->next_start = ws.seg_exit[nseg - 1];
@@ -1179,7 +1184,7 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
 static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
                             unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw,
                             size_t n_out, int32_t *d_status, int mode, DecodeChain *chain, int last_chunk, int lead, cudaStream_t st,
-                            DecodeChain *host_chain = nullptr) {
+                            DecodeChain *host_chain = nullptr, int32_t *host_flag = nullptr) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     if (mode & kModeFsm) {
@@ -1203,7 +1208,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
         DC_CUDA_TRY(cudaMemsetAsync(slots.flags, 0, 256 * sizeof(unsigned int), st));
         const unsigned int g2 = (unsigned int)min((unsigned long long)min(sm_count(), 256), (nseg + 255) / 256);
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots);
+        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots, host_flag);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1224,15 +1229,6 @@ static int launch_fast_write(const uint8_t *d_bits, unsigned long long end, unsi
     if (mode == 0) DC_F3(0); else if (mode == 1) DC_F3(1); else if (mode == 2) DC_F3(2); else DC_F3(3);
 #undef DC_F3
     return cuda_status(cudaGetLastError());
-}
-
-static int launch_fast(const uint8_t *d_bits, unsigned long long bit_start, unsigned long long end, unsigned long long nsubf,
-                       unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, uint8_t *d_out,
-                       size_t n_out, int32_t *d_status, int mode, uint32_t stage_bytes, DecodeChain *chain, int last_chunk,
-                       cudaStream_t st) {
-    const int rc = launch_fast_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, chain, last_chunk, 0, st);
-    if (rc != DC_OK) return rc;
-    return launch_fast_write(d_bits, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, 0, st);
 }
 
 // test hook: 1 = always take the robust path, 2 = pretend the fast path's guess failed after running it
@@ -1294,9 +1290,10 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
 
     // the table must be usable before any bit is interpreted
     int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    {   // known from the build's mapped words once its event has passed; only a foreign table costs a stream synchronise
+        const int rc = table_meta_fetch(d_table, st, tmeta, true);
+        if (rc != DC_OK) return rc;
+    }
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
 
@@ -1305,14 +1302,29 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
     const uint32_t stage_bytes = fast_stage_bytes(tmeta);
-    {
-        const int rc = launch_fast(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, nullptr, 1, st);
-        if (rc != DC_OK) return rc;
-    }
-    // did every segment start on a code boundary?  (blocking read of one flag)
+    // did every segment start on a code boundary?  F2 knows and stores the answer in mapped host memory as well; the host waits
+    // for F2's event only, so F3 (which returns at once on a mismatch) is already queued and the caller's next launches
+    // follow it without a gap.
     int32_t mismatch = 0;
-    DC_CUDA_TRY(cudaMemcpyAsync(&mismatch, fw.mismatch, sizeof mismatch, cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    {
+        HostFlag hf;
+        const int have_flag = host_flag_acquire(&hf) == DC_OK;
+        if (have_flag) *hf.host = -1;
+        int rc = launch_fast_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, n_out, d_status, mode, nullptr, 1, 0, st, nullptr,
+                                  have_flag ? hf.dev : nullptr);
+        if (rc == DC_OK && have_flag && cudaEventRecord(hf.ev, st) != cudaSuccess) rc = DC_ERR_CUDA;
+        if (rc == DC_OK) rc = launch_fast_write(d_bits, end, nsubf, nwt, nseg, d_table, fw, d_out, n_out, d_status, mode, stage_bytes, 0, st);
+        if (rc == DC_OK && have_flag) {
+            if (cudaEventSynchronize(hf.ev) != cudaSuccess) rc = DC_ERR_CUDA;
+            else mismatch = *hf.host;
+        }
+        if (have_flag) host_flag_release(hf);
+        if (rc != DC_OK) return rc;
+        if (!have_flag || mismatch < 0) {   // no mapped flag to be had: the blocking read
+            DC_CUDA_TRY(cudaMemcpyAsync(&mismatch, fw.mismatch, sizeof mismatch, cudaMemcpyDeviceToHost, st));
+            DC_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
     if (mismatch || force == 2) {
         if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
         return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
@@ -1362,9 +1374,10 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
 
     g->chain = (DecodeChain *)(w + 32);
     int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    {   // known from the build's mapped words once its event has passed; only a foreign table costs a stream synchronise
+        const int rc = table_meta_fetch(d_table, st, tmeta, true);
+        if (rc != DC_OK) return rc;
+    }
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     g->mode = fast_mode(tmeta);
@@ -1486,9 +1499,10 @@ static int host_decompress_pipelined_body(const uint8_t *h_payload, uint64_t tot
 
     // the table (built on the legacy stream by the caller) must be usable before any bit is interpreted
     int32_t tmeta[12];   // the table's first ten words, then lut2_used and fsm_states
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta, d_table, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    DC_CUDA_TRY(cudaMemcpyAsync(tmeta + 10, (const char *)d_table + offsetof(dc_huff_table, lut2_used), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    DC_CUDA_TRY(cudaStreamSynchronize(0));
+    {
+        const int rc = table_meta_fetch(d_table, 0, tmeta, true);
+        if (rc != DC_OK) return rc;
+    }
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     const int mode = fast_mode(tmeta);

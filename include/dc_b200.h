@@ -64,6 +64,11 @@ enum dc_status {
  *   lengths[]  == canonical_lengths of huffman()                       n_ary_huffman.c:1161-1208
  *   values[]   == encode_value_table of convert_lengths_to_encode_table n_ary_huffman.c:1382-1612
  * Lengths are in DIGITS of radix n_ary (the reference's unit); a digit is bits_per_digit bits.
+ * The two builders are the only writers: they also leave the table's header in host-visible (mapped) memory,
+ * keyed by the table's device address, so that the encoder and the decoder can choose their kernels without
+ * reading the table back.  A table that reaches a device buffer any other way (cudaMemcpy of a downloaded
+ * copy into a FRESH buffer) works too, through a blocking read; do not overwrite a built table behind the
+ * library's back -- build into the buffer again instead.
  */
 typedef struct dc_huff_table {
     int32_t n_ary;            /* compressed_symbols */
