@@ -258,7 +258,7 @@ def run_ours(args) -> None:
 
         def encode_path():
             # ONE C call per rank: local histogram -> all-gather of the histograms (NCCL) -> global table and every rank's
-            # bit total -> encode at this rank's bit phase -> shared edge bytes merged
+            # bit total -> encode at this rank's bit phase -> shared edge bytes completed from the neighbours' edge symbols
             S.encode(data, n_ary, ebuf)
             return None
 
@@ -400,7 +400,7 @@ def run_ours(args) -> None:
             "frac_of_aggregate_hbm": (2 * n + (bits16 + 7) // 8) / (t_enc16 * 1e-3) / 1e9 / peak,
             "gather_into_one_buffer_ms": t_gather, "stream_bytes": (total16 + 7) // 8,
             "equals_single_gpu_stream": check,
-            "collectives_per_encode": "ncclAllGather(259 x u64 per rank) + ncclAllGather(2 bytes per rank)"}
+            "collectives_per_encode": "one ncclAllGather (262 x u64 per rank: histogram, symbol count, first and last 8 symbols); shared edge bytes completed locally"}
         del b16, stream16
         torch.cuda.empty_cache()
         # config 5: n = 2 decode of ONE stream cut blindly into equal byte ranges, boundary sync between neighbours
@@ -503,7 +503,7 @@ def run_ours(args) -> None:
                                    f"(BASELINE configs[{CONFIG_INDEX}])",
                        "n_ary": n_ary, "bytes_per_gpu": n, "compressed_bytes_per_gpu": int(c_bytes),
                        "parallelism": (f"dp{world}: contiguous shards of one logical stream through dc_shard_huff_encode (C-ABI, NCCL inside the "
-                                       f"library): one all-gather of the local histograms, bit offsets from the gathered histograms, edge bytes merged"
+                                       f"library): one all-gather (local histograms + edge symbols), bit offsets from the gathered histograms, shared edge bytes completed locally"
                                        if world > 1 else "1 GPU"),
                        "l2": "inputs larger than L2 (1 GiB vs 126 MB); no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

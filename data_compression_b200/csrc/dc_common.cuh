@@ -47,8 +47,9 @@ struct TableRaw {
     int32_t *assigned;  // [nsym] 1 if convert_lengths_to_encode_table() assigns the slot
     int32_t *status;    // [1]
 };
+// nhist > 1: the counts are the sum of nhist histograms, hist_stride u64 apart (the gathered histograms of the shard layer)
 int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
-                 TableRaw raw, cudaStream_t st);
+                 TableRaw raw, cudaStream_t st, int nhist = 1, int hist_stride = 0);
 
 // pipelined form of dc_host_huff_decompress (k4_decode.cu): DC_OK / negative dc_status / +1 = use the one-shot path.
 // d_packed != nullptr: radix 3, h_payload is the 5-trits-per-byte payload (total_bits = 2 * trits) and every chunk is
@@ -60,7 +61,11 @@ int host_decompress_pipelined(const uint8_t *h_payload, uint64_t total_bits, con
 int trit_unpack_launch(const uint8_t *d_payload, unsigned long long ntrits, uint8_t *d_t2, int32_t *d_status, cudaStream_t st);
 
 // K1 with one 256 x u16 histogram per 32 KB run (k1_histogram.cu), for the planned encoder
-int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st);
+int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st,
+                          unsigned long long *d_edge = nullptr);
+// dc_histogram_u8_runs that also leaves {n, first eight symbols, last eight symbols} in d_edge[3] (k3_encode.cu knows the workspace layout)
+int histogram_runs_edges(const uint8_t *d_in, size_t n, unsigned long long *d_hist, void *d_encode_workspace, size_t workspace_bytes,
+                         unsigned long long *d_edge, cudaStream_t st);
 
 int encode_planned_device_phase(const uint8_t *d_in, size_t n, const dc_huff_table *d_table, uint8_t *d_out, size_t out_capacity,
                                 const uint32_t *d_phase, uint64_t *d_total_bits, int32_t *d_status, void *d_workspace,

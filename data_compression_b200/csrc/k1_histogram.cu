@@ -85,8 +85,22 @@ constexpr int kHistRunThreads = 512;
 template <bool RUNS>
 __global__ void __launch_bounds__(kHistRunThreads, 4) hist_runs_kernel(const uint8_t *__restrict__ in, size_t n,
                                                                         unsigned long long *__restrict__ hist,
-                                                                        uint16_t *__restrict__ run_hist, unsigned int nruns) {
+                                                                        uint16_t *__restrict__ run_hist, unsigned int nruns,
+                                                                        unsigned long long *__restrict__ edge) {
     __shared__ uint32_t s_cnt[256 * 32];
+    if (edge && blockIdx.x == 0 && threadIdx.x == 0) {
+        // what a neighbouring shard needs to complete the byte it shares with this one (shard_nccl.cu): the symbol count,
+        // the first and the last eight symbols (byte j of a word = symbol j of the eight)
+        const size_t m = n < 8 ? n : 8;
+        unsigned long long head = 0, tail = 0;
+        for (size_t j = 0; j < m; j++) {
+            head |= (unsigned long long)in[j] << (8 * j);
+            tail |= (unsigned long long)in[n - m + j] << (8 * j);
+        }
+        edge[0] = n;
+        edge[1] = head;
+        edge[2] = tail;
+    }
     for (int i = threadIdx.x; i < 256 * 32; i += kHistRunThreads) s_cnt[i] = 0;
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,7 +180,7 @@ int launch_histogram(const uint8_t *d_in, size_t n, unsigned long long *d_hist, 
         const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
         // (a CTA's u32 counters hold its share of the input: at most 2^32 bytes per column needs n / grid < 2^32)
         const unsigned int grid = (unsigned int)min(nruns, (size_t)sms * 4);
-        hist_runs_kernel<false><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, nullptr, (unsigned int)nruns);
+        hist_runs_kernel<false><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, nullptr, (unsigned int)nruns, nullptr);
     } else {
         const size_t nvec = n / 16 + 1;
         const int grid = (int)min((size_t)sms * 8, (nvec + 255) / 256);
@@ -183,14 +197,18 @@ extern "C" int dc_histogram_u8(const uint8_t *d_in, size_t n, uint64_t *d_hist, 
 }
 
 namespace dc {
-int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st) {
+int launch_histogram_runs(const uint8_t *d_in, size_t n, unsigned long long *d_hist, uint16_t *d_run_hist, cudaStream_t st,
+                          unsigned long long *d_edge) {
     DC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, DC_NSLOTS * sizeof(unsigned long long), st));
-    if (n == 0) return DC_OK;
+    if (n == 0) {
+        if (d_edge) DC_CUDA_TRY(cudaMemsetAsync(d_edge, 0, 3 * sizeof(unsigned long long), st));
+        return DC_OK;
+    }
     const size_t nruns = (n + kHistRunBytes - 1) / kHistRunBytes;
     if (nruns > 0x0FFFFFF0ull) return DC_ERR_ARG;
     LaunchScope ls(DC_K_HISTOGRAM, st);
     const unsigned int grid = (unsigned int)min(nruns, (size_t)sm_count() * 4);
-    hist_runs_kernel<true><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns);
+    hist_runs_kernel<true><<<grid, kHistRunThreads, 0, st>>>(d_in, n, d_hist, d_run_hist, (unsigned int)nruns, d_edge);
     return cuda_status(cudaGetLastError());
 }
 }  // namespace dc

@@ -47,7 +47,7 @@ __device__ __forceinline__ bool t2_to_trits(unsigned int window, int window_bits
 __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long long *__restrict__ d_hist,
                                                             const int32_t *__restrict__ d_lengths_in, int nsym,
                                                             int n_ary, dc_huff_table *__restrict__ tab, TableRaw raw,
-                                                            int32_t *__restrict__ host_meta) {
+                                                            int32_t *__restrict__ host_meta, int nhist, int hist_stride) {
     __shared__ unsigned long long s_cnt[kTabCap];     // compacted leaf counts (index order)
     __shared__ unsigned long long s_scnt[kTabCap];    // leaf counts sorted by (count, index)
     __shared__ unsigned long long s_icount[kTabCap];  // internal node counts, creation order
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     int nz = 0, dummies = 0;
     if (d_hist) {
         // ---- 1. compact the non-zero leaves in index order, append the dummy leaves
-        my_count = tid < nsym ? d_hist[tid] : 0ull;
+        if (tid < nsym)
+            for (int h = 0; h < nhist; h++) my_count += d_hist[(size_t)h * hist_stride + tid];
         const bool used = my_count != 0;
         const unsigned ball = __ballot_sync(0xFFFFFFFFu, used);
         if (lane == 0) s_warp[warp] = __popc(ball);
@@ -425,7 +426,7 @@ __global__ void bits_for_hist_kernel(const unsigned long long *__restrict__ d_hi
 }
 
 int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int nsym, int n_ary, dc_huff_table *tab,
-                 TableRaw raw, cudaStream_t st) {
+                 TableRaw raw, cudaStream_t st, int nhist, int hist_stride) {
     if (n_ary < 2 || n_ary > 512 || nsym < 1 || nsym > DC_MAX_LEAVES) return DC_ERR_ARG;
     if (tab && nsym != DC_NSLOTS) return DC_ERR_ARG;
     TableMetaTicket ticket;
@@ -433,7 +434,7 @@ int launch_table(const unsigned long long *d_hist, const int32_t *d_lengths, int
     if (tab) table_meta_begin(tab, &ticket);
     {
         LaunchScope ls(DC_K_TABLE, st);
-        table_kernel<<<1, kTabThreads, 0, st>>>(d_hist, d_lengths, nsym, n_ary, tab, raw, ticket.dev);
+        table_kernel<<<1, kTabThreads, 0, st>>>(d_hist, d_lengths, nsym, n_ary, tab, raw, ticket.dev, nhist < 1 ? 1 : nhist, hist_stride);
     }
     if (tab) table_meta_end(tab, ticket, st);
     return cuda_status(cudaGetLastError());

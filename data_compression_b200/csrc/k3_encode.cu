@@ -1059,6 +1059,17 @@ int encode_planned_device_phase(const uint8_t *d_in, size_t n, const dc_huff_tab
 }
 }  // namespace dc
 
+namespace dc {
+int histogram_runs_edges(const uint8_t *d_in, size_t n, unsigned long long *d_hist, void *d_encode_workspace, size_t workspace_bytes,
+                         unsigned long long *d_edge, cudaStream_t st) {
+    if (!d_hist || (n && (!d_in || !d_encode_workspace))) return DC_ERR_ARG;
+    if ((((uintptr_t)d_in | (uintptr_t)d_encode_workspace) & 15) != 0) return DC_ERR_ARG;
+    size_t off[10];
+    if (workspace_bytes < enc_ws_layout(n, off)) return DC_ERR_CAPACITY;
+    return launch_histogram_runs(d_in, n, d_hist, (uint16_t *)((char *)d_encode_workspace + off[8]), st, d_edge);
+}
+}  // namespace dc
+
 extern "C" int dc_histogram_u8_runs(const uint8_t *d_in, size_t n, uint64_t *d_hist, void *d_encode_workspace, size_t workspace_bytes,
                                     void *stream) {
     if (!d_hist || (n && (!d_in || !d_encode_workspace))) return DC_ERR_ARG;

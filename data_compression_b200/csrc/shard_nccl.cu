@@ -5,9 +5,11 @@
 //   encode   all-gather of the LOCAL histograms (259 x u64 per rank).  Every rank sums them (one global code table,
 //            built redundantly: K2 is deterministic) and computes EVERY rank's bit total = sum hist_r[s] * length[s],
 //            so the exclusive scan of bit totals needs no second collective.  Rank r encodes at bit phase O_r mod 8
-//            (read from device memory: nothing blocks) and the bytes two shards share are OR-merged after an all-gather
-//            of each shard's first and last byte.  The concatenation of the shard buffers at byte offsets O_r / 8 is
-//            the single-stream payload bit for bit; dc_shard_huff_gather() places them in one buffer.
+//            (read from device memory: nothing blocks).  The all-gather also carries every rank's symbol count and its
+//            first and last eight symbols: with the global table a rank re-creates the few bits its neighbours put into
+//            the byte it shares with them, so the shared bytes are completed without a second collective.  The
+//            concatenation of the shard buffers at byte offsets O_r / 8 is the single-stream payload bit for bit;
+//            dc_shard_huff_gather() places them in one buffer.
 //   decode   of ONE stream cut blindly into byte ranges (BASELINE config 5): neighbours exchange 1 KB halos
 //            (ncclSend/ncclRecv), every rank finds its first code by synchronising over its left neighbour's tail, the
 //            24-byte summaries are all-gathered, assumed starts are checked against real exits, symbol counts become
@@ -81,17 +83,11 @@ struct dc_shard_comm {
 namespace dc {
 
 // ---- device side of the encode plan.  all_hist: [world][259] u64 (what the all-gather left).
+constexpr int kShardSlots = DC_NSLOTS + 3;   // what a rank contributes to the all-gather: histogram, symbol count, first 8 and last 8 symbols
 struct ShardPlan {                        // one per call, in the workspace; read back by dc_shard_huff_encode_info
     unsigned long long bit_offset, bits, total_bits, reserved;
     uint32_t phase, pad[3];
 };
-__global__ void shard_sum_hist_kernel(const unsigned long long *__restrict__ all_hist, int world, unsigned long long *__restrict__ ghist) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= DC_NSLOTS) return;
-    unsigned long long t = 0;
-    for (int r = 0; r < world; r++) t += all_hist[(size_t)r * DC_NSLOTS + s];
-    ghist[s] = t;
-}
 // bits of every rank under the global table, their exclusive scan, this rank's phase
 __global__ void __launch_bounds__(256) shard_plan_kernel(const unsigned long long *__restrict__ all_hist, int world, int rank,
                                                         const dc_huff_table *__restrict__ tab, unsigned long long *__restrict__ rank_bits,
@@ -101,7 +97,7 @@ __global__ void __launch_bounds__(256) shard_plan_kernel(const unsigned long lon
     const unsigned long long len = tid < 256 ? (unsigned long long)(tab->lengths[tid] * tab->bits_per_digit) : 0ull;
     unsigned long long run = 0;
     for (int r = 0; r < world; r++) {
-        s_sum[tid] = all_hist[(size_t)r * DC_NSLOTS + tid] * len;
+        s_sum[tid] = all_hist[(size_t)r * kShardSlots + tid] * len;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
             if (tid < o) s_sum[tid] += s_sum[tid + o];
@@ -122,30 +118,50 @@ __global__ void __launch_bounds__(256) shard_plan_kernel(const unsigned long lon
         plan->phase = (uint32_t)(rank_off[rank] & 7ull);
     }
 }
-// edge[2 r] / edge[2 r + 1] = first / last byte of rank r's shard buffer.  The bytes of the stream that several shards
-// touch are the OR of what each of them wrote there (every shard writes zeros outside its own bits).
-__global__ void shard_pick_edges_kernel(const uint8_t *__restrict__ out, const ShardPlan *__restrict__ plan, uint8_t *__restrict__ mine) {
-    const unsigned long long nbytes = plan->bits ? ((plan->bit_offset & 7ull) + plan->bits + 7) / 8 : 0ull;
-    mine[0] = nbytes ? out[0] : 0;
-    mine[1] = nbytes ? out[nbytes - 1] : 0;
-}
-__global__ void shard_merge_edges_kernel(uint8_t *__restrict__ out, const uint8_t *__restrict__ edge, const unsigned long long *__restrict__ rank_bits,
-                                         const unsigned long long *__restrict__ rank_off, int world, int rank) {
+// The bytes of the stream that several shards touch are the OR of what each of them wrote there (every shard writes zeros
+// outside its own bits).  A rank completes its first and its last byte itself: the bits in front of its first bit are the
+// tail of the codes of the symbols before its shard, the bits behind its last bit the head of the codes of the symbols
+// after it -- at most 7 bits each way, i.e. at most 7 symbols, and the all-gather brought 8 from every rank.
+__global__ void shard_fix_edges_kernel(uint8_t *__restrict__ out, const unsigned long long *__restrict__ all, int world, int rank,
+                                       const dc_huff_table *__restrict__ tab, const unsigned long long *__restrict__ rank_bits,
+                                       const unsigned long long *__restrict__ rank_off) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (rank_bits[rank] == 0) return;
-    const unsigned long long lo = rank_off[rank] >> 3, hi = (rank_off[rank] + rank_bits[rank] + 7) >> 3;   // my bytes [lo, hi)
-    uint8_t first = 0, last = 0;
-    for (int r = 0; r < world; r++) {
-        if (rank_bits[r] == 0) continue;
-        const unsigned long long l = rank_off[r] >> 3, h = (rank_off[r] + rank_bits[r] + 7) >> 3;
-        // rank r's first byte is stream byte l, its last byte stream byte h - 1
-        if (l == lo) first |= edge[2 * r];
-        if (h - 1 == lo) first |= edge[2 * r + 1];
-        if (l == hi - 1) last |= edge[2 * r];
-        if (h - 1 == hi - 1) last |= edge[2 * r + 1];
+    const unsigned long long bits = rank_bits[rank];
+    if (bits == 0 || tab->status != DC_OK) return;
+    const unsigned long long off = rank_off[rank], e = off + bits, lo = off >> 3, hi1 = (e - 1) >> 3;
+    const uint32_t k = (uint32_t)(off & 7ull), m = (uint32_t)((8ull - (e & 7ull)) & 7ull);
+    uint32_t first = 0, last = 0;
+    if (k) {   // stream bits [off - k, off): walk the symbols in front of this shard backwards
+        unsigned long long acc = 0;
+        uint32_t have = 0;
+        for (int q = rank - 1; q >= 0 && have < k; q--) {
+            const unsigned long long nq = all[(size_t)q * kShardSlots + DC_NSLOTS], tail = all[(size_t)q * kShardSlots + DC_NSLOTS + 2];
+            const int cnt = nq < 8 ? (int)nq : 8;
+            for (int j = cnt - 1; j >= 0 && have < k; j--) {
+                const unsigned long long ent = tab->enc64[(tail >> (8 * j)) & 0xFFull];
+                acc |= (ent & 0xFFFFFFFFull) << have;   // bit 0 of acc = the bit just in front of `off`
+                have += (uint32_t)(ent >> 32);
+            }
+        }
+        first = (uint32_t)(acc & ((1ull << k) - 1ull)) << (8u - k);
     }
-    out[0] = first;
-    out[hi - 1 - lo] = last;
+    if (m) {   // stream bits [e, e + m): the symbols behind this shard, forwards; behind the end of the stream: zero padding
+        unsigned long long acc = 0;
+        uint32_t have = 0;
+        for (int q = rank + 1; q < world && have < m; q++) {
+            const unsigned long long nq = all[(size_t)q * kShardSlots + DC_NSLOTS], head = all[(size_t)q * kShardSlots + DC_NSLOTS + 1];
+            const int cnt = nq < 8 ? (int)nq : 8;
+            for (int j = 0; j < cnt && have < m; j++) {
+                const unsigned long long ent = tab->enc64[(head >> (8 * j)) & 0xFFull];
+                const uint32_t len = (uint32_t)(ent >> 32);
+                acc = (acc << len) | (ent & 0xFFFFFFFFull);
+                have += len;
+            }
+        }
+        last = (uint32_t)(have >= m ? acc >> (have - m) : acc << (m - have)) & ((1u << m) - 1u);
+    }
+    if (first) out[0] |= (uint8_t)first;
+    if (last) out[hi1 - lo] |= (uint8_t)last;
 }
 
 struct ShardEncLayout {
@@ -155,8 +171,8 @@ static ShardEncLayout shard_enc_layout(size_t n_local, int world) {
     ShardEncLayout L;
     size_t p = 0;
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 255) & ~(size_t)255; return o; };
-    L.local_hist = take(DC_NSLOTS * 8);
-    L.all_hist = take((size_t)world * DC_NSLOTS * 8);
+    L.local_hist = take(kShardSlots * 8);
+    L.all_hist = take((size_t)world * kShardSlots * 8);
     L.ghist = take(DC_NSLOTS * 8);
     L.rank_bits = take((size_t)world * 8);
     L.rank_off = take((size_t)(world + 1) * 8);
@@ -231,39 +247,36 @@ extern "C" int dc_shard_huff_encode(dc_shard_comm *c, const uint8_t *d_in, size_
     cudaStream_t st = (cudaStream_t)stream;
     char *w = (char *)d_workspace;
     unsigned long long *local_hist = (unsigned long long *)(w + L.local_hist), *all_hist = (unsigned long long *)(w + L.all_hist);
-    unsigned long long *ghist = (unsigned long long *)(w + L.ghist), *rank_bits = (unsigned long long *)(w + L.rank_bits);
+    unsigned long long *rank_bits = (unsigned long long *)(w + L.rank_bits);
     unsigned long long *rank_off = (unsigned long long *)(w + L.rank_off);
     ShardPlan *plan = (ShardPlan *)(w + L.plan);
-    uint8_t *edges = (uint8_t *)(w + L.edges), *my_edge = (uint8_t *)(w + L.my_edge);
     void *enc_ws = w + L.enc_ws;
     const size_t enc_ws_bytes = L.total - L.enc_ws;
 
-    // 1. local histogram (+ one small histogram per 32 KB run for the planned encoder)
-    int rc = n_local ? dc_histogram_u8_runs(d_in, n_local, (uint64_t *)local_hist, enc_ws, enc_ws_bytes, stream)
-                     : cuda_status(cudaMemsetAsync(local_hist, 0, DC_NSLOTS * 8, st));
+    // 1. local histogram (+ one small histogram per 32 KB run for the planned encoder, + the shard's edge symbols)
+    int rc = histogram_runs_edges(d_in, n_local, local_hist, enc_ws, enc_ws_bytes, local_hist + DC_NSLOTS, st);
     if (rc != DC_OK) return rc;
-    // 2. every rank gets every rank's histogram: the one collective of the encode path
-    DC_NCCL_TRY(N->AllGather(local_hist, all_hist, DC_NSLOTS, kNcclUint64, c->comm, st));
-    // 3. global table (redundantly on every rank), every rank's bit total, the exclusive scan, my phase
-    shard_sum_hist_kernel<<<(DC_NSLOTS + 127) / 128, 128, 0, st>>>(all_hist, c->world, ghist);
-    rc = dc_huff_build((const uint64_t *)ghist, n_ary, d_table, stream);
-    if (rc != DC_OK) return rc;
+    // 2. every rank gets every rank's histogram and edge symbols: the one collective of the encode path
+    DC_NCCL_TRY(N->AllGather(local_hist, all_hist, kShardSlots, kNcclUint64, c->comm, st));
+    // 3. global table from the sum of the histograms (redundantly on every rank), every rank's bit total, the exclusive
+    //    scan, my phase
+    {
+        TableRaw raw = {nullptr, nullptr, nullptr, nullptr};
+        rc = launch_table(all_hist, nullptr, DC_NSLOTS, n_ary, d_table, raw, st, c->world, kShardSlots);
+        if (rc != DC_OK) return rc;
+    }
     shard_plan_kernel<<<1, 256, 0, st>>>(all_hist, c->world, c->rank, d_table, rank_bits, rank_off, plan);
     // 4. encode at my phase (in device memory: the host never waits for the plan)
-    DC_CUDA_TRY(cudaMemsetAsync(d_out, 0, 16, st));   // a shard without bits still shows a defined first byte
     if (n_local) {
         rc = encode_planned_device_phase(d_in, n_local, d_table, d_out, out_capacity, &plan->phase, d_total_bits, d_status, enc_ws, enc_ws_bytes, st);
         if (rc != DC_OK) return rc;
     } else {
+        DC_CUDA_TRY(cudaMemsetAsync(d_out, 0, 16, st));   // a shard without bits still shows a defined first byte
         if (d_total_bits) DC_CUDA_TRY(cudaMemsetAsync(d_total_bits, 0, 8, st));
         if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
     }
-    // 5. the bytes that neighbouring shards share
-    if (c->world > 1) {
-        shard_pick_edges_kernel<<<1, 1, 0, st>>>(d_out, plan, my_edge);
-        DC_NCCL_TRY(N->AllGather(my_edge, edges, 2, kNcclUint8, c->comm, st));
-        shard_merge_edges_kernel<<<1, 32, 0, st>>>(d_out, edges, rank_bits, rank_off, c->world, c->rank);
-    }
+    // 5. the bytes that neighbouring shards share, completed locally
+    if (c->world > 1 && n_local) shard_fix_edges_kernel<<<1, 32, 0, st>>>(d_out, all_hist, c->world, c->rank, d_table, rank_bits, rank_off);
     return cuda_status(cudaGetLastError());
 }
 

@@ -293,7 +293,7 @@ int dc_huff_decode_shard_write(const uint8_t *d_bits, int has_halo, uint64_t sha
  * One process per GPU; every call below is made by all ranks of a communicator with the current device set to the
  * rank's GPU (SURVEY 8b last cell, 8e; BASELINE configs 4 and 5).  NCCL is bound at run time (dlopen of libnccl.so.2,
  * or the library named by $DC_NCCL_LIB); without it these return DC_ERR_NCCL.  The data path has no bulk collective:
- * the ranks exchange histograms (2 KB), shard edge bytes, 1 KB halos and 24-byte summaries.
+ * the ranks exchange histograms with edge symbols (2 KB), 1 KB halos and 24-byte summaries.
  */
 typedef struct dc_shard_comm dc_shard_comm;
 /* rank 0 makes an id (128 bytes = ncclUniqueId), hands it to the other ranks by any means, everybody creates */
@@ -307,9 +307,10 @@ int dc_shard_comm_world(const dc_shard_comm *comm);
 
 /*
  * Encode one logical stream whose bytes are spread over the ranks in rank order (BASELINE config 4).  Stream-ordered,
- * never blocks: local histogram -> ONE all-gather of the local histograms -> global table (d_table, identical on every
- * rank) and every rank's bit total -> encode at bit phase O_r mod 8 (O_r = bits of the ranks in front) -> the bytes that
- * neighbouring shards share are OR-merged.  d_out then holds stream bytes [O_r / 8, ceil((O_r + bits_r) / 8)); the
+ * never blocks: local histogram -> ONE all-gather (the local histograms, symbol counts, first and last eight symbols) ->
+ * global table (d_table, identical on every rank) and every rank's bit total -> encode at bit phase O_r mod 8 (O_r = bits
+ * of the ranks in front) -> the bytes that neighbouring shards share are completed locally (a rank re-creates its
+ * neighbours' few bits from their edge symbols).  d_out then holds stream bytes [O_r / 8, ceil((O_r + bits_r) / 8)); the
  * concatenation over the ranks IS the single-stream payload of dc_huff_encode on the concatenated input.
  *   d_total_bits  this rank's code bits (1 x u64, may be NULL);  d_status as dc_huff_encode
  * dc_shard_huff_encode_info (blocking) reads O_r, bits_r and the stream's bit total back from the workspace;

@@ -105,3 +105,46 @@ def test_shard_c_abi_world2(n_ary):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _edge_worker(rank, world, port, sizes, n_ary, q):
+    """Sharded encode only, many small streams in one process pair: the shared bytes are completed from the neighbours' edge
+    symbols (no second collective), including shards of fewer than eight symbols and empty shards."""
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from data_compression_b200 import shard
+    dev = torch.device("cuda", rank)
+    S = shard.NcclShards(dev)
+    bad = []
+    for n_total, cut in sizes:
+        host = _stream(n_total, seed=9 + n_total % 7)
+        lo, hi = (0, cut) if rank == 0 else (cut, n_total)
+        local = torch.from_numpy(host[lo:hi].copy()).to(dev)
+        buf = S.encode(local, n_ary)
+        off, bits, total = S.encode_info(buf, local.numel())
+        o_payload, o_bits, _ = _oracle_payload(host, n_ary)
+        nb = ((off % 8) + bits + 7) // 8 if bits else 0
+        if total != o_bits or not np.array_equal(buf["out"][:nb].cpu().numpy(), o_payload[off // 8: off // 8 + nb]):
+            bad.append((n_total, cut))
+    S.close()
+    dist.destroy_process_group()
+    q.put((rank, bad))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU)")
+@pytest.mark.parametrize("n_ary", [2, 16])
+def test_shard_edges_completed_locally_world2(n_ary):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    # (symbols in the stream, symbols on rank 0): cuts inside bytes, shards shorter than the eight edge symbols, empty shards
+    sizes = [(5, 5), (5, 0), (19, 16), (19, 3), (40, 32), (2, 1), (9, 1), (9, 8), (4097, 4096), (4097, 1), (100003, 50001), (100003, 99999)]
+    procs = [ctx.Process(target=_edge_worker, args=(r, 2, 29650 + n_ary, sizes, n_ary, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, []), (1, [])]
