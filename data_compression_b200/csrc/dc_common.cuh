@@ -98,21 +98,26 @@ void host_flag_release(const HostFlag &f);
 
 // ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
 constexpr int kFsmMaxStates = 255;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
-// Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.
-__host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_t *count, int min_len, int max_len, int bpd,
+// Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.  `radix` is the arity of the
+// code tree (values are base-`radix` numerals), `bpd` the bits a digit takes in the stream (radix 3: 2-bit fields).
+__host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_t *count, int min_len, int max_len, int bpd, int radix,
                                             uint32_t *ilo, uint32_t *ihi, uint32_t *base) {
-    if (!(bpd == 1 || bpd == 2 || bpd == 4)) return 0;
+    if (!(bpd == 1 || bpd == 2 || bpd == 4) || radix < 2 || radix > (1 << bpd)) return 0;
     if (min_len < 1 || max_len < min_len || max_len >= 16) return 0;
     if (min_len * bpd < 2) return 0;   // a 1-bit code: up to 8 symbols per byte
     if (count[max_len] == 0) return 0;
     const unsigned long long last = (unsigned long long)first[max_len] + count[max_len] - 1;
-    if (last >> (bpd * max_len)) return 0;   // over-subscribed lengths: values do not fit their digits
+    unsigned long long span = 1;       // radix ^ max_len
+    for (int d = 0; d < max_len; d++) span *= (unsigned long long)radix;
+    if (last >= span) return 0;        // over-subscribed lengths: values do not fit their digits
     unsigned total = 0;
+    unsigned long long div = span;     // radix ^ (max_len - d)
     for (int d = 0; d < max_len; d++) {
         const unsigned long long lo = d < min_len ? 0ull : (unsigned long long)first[d] + count[d];
-        const unsigned long long hi = last >> (bpd * (max_len - d));
+        const unsigned long long hi = last / div;
+        div /= (unsigned long long)radix;
         if (hi < lo) return 0;
-        if (d >= min_len && d + 1 <= max_len && (unsigned long long)first[d + 1] != (lo << bpd)) return 0;   // not the canonical chain
+        if (d >= min_len && d + 1 <= max_len && (unsigned long long)first[d + 1] != lo * (unsigned long long)radix) return 0;   // not the canonical chain
         ilo[d] = (uint32_t)lo;
         ihi[d] = (uint32_t)hi;
         base[d] = total;

@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         // the byte-stepped decoder (k4_fsm.cuh) applies if the code tree has at most 256 internal nodes, no 1-bit code
         uint32_t cnt[32], ilo[32], ihi[32], base[32];
         for (int d = 0; d < 32; d++) cnt[d] = (d >= min_len && d <= max_len) ? s_lencount[d] : 0u;
-        tab->fsm_states = (status == DC_OK && !t2 && max_len < 16) ? fsm_geometry(s_first, cnt, min_len, max_len, bpd, ilo, ihi, base) : 0;
+        tab->fsm_states = (status == DC_OK && bpd != 0 && max_len < 16) ? fsm_geometry(s_first, cnt, min_len, max_len, bpd, n_ary, ilo, ihi, base) : 0;
         if (host_meta) {   // mapped host memory (dc_common.cuh, table_meta_*): what the entry points pick their kernels by
             const int32_t *words = (const int32_t *)tab;
             for (int i = 0; i < 10; i++) host_meta[i] = words[i];

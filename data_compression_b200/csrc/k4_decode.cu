@@ -1051,13 +1051,14 @@ static bool fsm_rows_fit(const int32_t *tmeta) {
     const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
     const size_t per_lane = (size_t)(kF_SubBits / (min_bits < 8 ? min_bits : 8)) + 2, half = 16 * per_lane + 48, whole = 32 * per_lane + 48;
     const size_t want = half > 2176 ? half : 2176, stage = ((want < whole ? want : whole) + 15) & ~(size_t)15;
-    return kFsmHeaderBytes + (size_t)(tmeta[11] + 1) * (kFsmWriteRowBytes + kFsmWriteXRowBytes) + 24 * stage + 256 <= 227 * 1024 - 1024;
+    return kFsmHeaderBytes + (size_t)(tmeta[11] + 1) * kFsmWriteRowBytes + kFsmWriteXTableBytes + 24 * stage + 256 <= 227 * 1024 - 1024;
 }
 // which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table, lut2_used, fsm_states)
 static int fast_mode(const int32_t *tmeta) {
-    if (tmeta[9] == 3) return tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
     int mode;
-    if (tmeta[7] <= DC_LUT_BITS) {
+    if (tmeta[9] == 3) {
+        mode = tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
+    } else if (tmeta[7] <= DC_LUT_BITS) {
         mode = 0;                          // max_bits against the 12-bit index
     } else {
         const int sub = tmeta[10] < 0 ? 0 : (tmeta[10] > DC_LUT2_SUBTABLES ? DC_LUT2_SUBTABLES : tmeta[10]);
@@ -1115,7 +1116,7 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     const FsmTables t = fsm_tables_at(fw.fsm);
     {
         LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
-        fsm_build_kernel<<<nstates + 1, 256, 0, st>>>(d_table, t);
+        fsm_build_kernel<<<nstates + 1 + kFsmSuffixRows, 256, 0, st>>>(d_table, t);
     }
     size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
     int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
@@ -1149,15 +1150,10 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
     const int rows = fsm_states(mode) + 1;   // + DEAD
     const FsmTables t = fsm_tables_at(fw.fsm);
     const uint32_t stage = fsm_stage_bytes(mode);
-    const size_t budget = 227 * 1024 - 1024, row = kFsmWriteRowBytes + kFsmWriteXRowBytes;
-    int warps = 24;
-    size_t hot = rows;
-    if (kFsmHeaderBytes + hot * row + (size_t)warps * stage + 256 > budget)
-        hot = (budget - kFsmHeaderBytes - (size_t)warps * stage - 256) / row;
-    const bool split = hot < (size_t)rows;
-    const size_t smem = kFsmHeaderBytes + hot * row + (size_t)warps * stage + 256;
+    const int warps = 24;
+    const size_t smem = kFsmHeaderBytes + (size_t)rows * kFsmWriteRowBytes + kFsmWriteXTableBytes + (size_t)warps * stage + 256;   // (fsm_rows_fit: within the limit)
     const int per_sm = smem <= 56 * 1024 ? 2 : 1;   // (2 x 768 threads: the register file allows no more)
-    DC_CUDA_TRY(ensure_dynamic_smem(split ? (const void *)fsm_write_kernel<true> : (const void *)fsm_write_kernel<false>, smem));
+    DC_CUDA_TRY(ensure_dynamic_smem((const void *)fsm_write_kernel, smem));
     const unsigned long long want = (nseg + warps - 1) / warps, cap = (unsigned long long)sm_count() * per_sm;
     FsmWriteArgs a;
     a.d_bits = d_bits;
@@ -1169,12 +1165,11 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
     a.n_out = n_out;
     a.lead = lead;
     a.stage_bytes = stage;
-    a.hot_rows = (uint32_t)hot;
+    a.rows = (uint32_t)rows;
     a.d_status = d_status;
     LaunchScope ls(DC_K_DECODE_FSM_WRITE, st);
     const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-    if (split) fsm_write_kernel<true><<<grid, warps * 32, smem, st>>>(a, t, fw);
-    else fsm_write_kernel<false><<<grid, warps * 32, smem, st>>>(a, t, fw);
+    fsm_write_kernel<<<grid, warps * 32, smem, st>>>(a, t, fw);
     return cuda_status(cudaGetLastError());
 }
 

@@ -8,17 +8,20 @@
 // boundary is fully described by WHERE INSIDE A CODE the boundary falls -- one of the internal nodes of the code tree,
 // at most 256 of them for byte alphabets.  So the tables here are indexed by (state, next byte):
 //   F1  u16  number of codes that END in this byte | next state << 8
-//   F3  u32  symbol 0 | symbol 1 << 8 | next state << 16 | count << 24   (+ u16: symbols 2 and 3, read only by the
-//            few lanes whose byte completes more than two codes: a random 8-byte gather costs 5.9 shared-memory
-//            wavefronts, a 4-byte one 3.1, and the walks are bound by exactly those bank-conflict replays)
+//   F3  u32  symbol 0 | symbol 1 << 8 | next state << 16 | k << 24 | count << 27   (a random 8-byte gather costs 5.9
+//            shared-memory wavefronts, a 4-byte one 3.1, and the walks are bound by exactly those bank-conflict replays, so
+//            the third and fourth symbol of a byte -- rare -- are not in the entry: k is the digit at which the third code
+//            starts, and what a byte decodes to FROM THE ROOT from digit k on is a table of 8 x 256 u16 for the whole code,
+//            read only by the few lanes whose byte completes more than two codes)
 // and a walk is 32 fixed, fully unrolled steps per 256-bit subsequence: no positions, no windows, no look-ahead word,
 // no loop condition, no divergence, codes of any length at the same speed.  F1: PRMT (index = state, byte) + IMAD +
 // LDS + IADD per byte.  F3: the symbols of a step are appended to a 4-byte sliding window with one PRMT whose selector
 // comes from the table, completed 32-bit words go to the staging tile with a predicated STS (so the shared-memory
 // stores are words, not bytes), and the fill state advances with one IMAD: 4 ALU + 3 FMA + 2 LSU slots per byte.
 //
-// States.  Canonical n-ary code (n = 2, 4, 16; a digit is bpd bits): at depth d (digits) the values
-// [first[d], first[d] + count[d]) are leaves, [ilo[d], ihi[d]] = [first[d] + count[d], last >> bpd (max_len - d)] are
+// States.  Canonical n-ary code (n = 2, 3, 4, 16; a digit is bpd bits -- radix 3 runs on the stream with one 2-bit field per
+// trit, where a field of 3 is simply an unused slot): at depth d (digits) the values
+// [first[d], first[d] + count[d]) are leaves, [ilo[d], ihi[d]] = [first[d] + count[d], last / n ^ (max_len - d)] are
 // internal nodes, everything above is an unused slot (the reference's dummy leaves).  State id = base[d] + (v -
 // ilo[d]): breadth first, the root is 0.  Streams whose codes start on digit boundaries relative to the BYTE grid only
 // ever stop on such nodes at byte boundaries (bit_start % bpd == 0; anything else takes the window kernels).
@@ -26,8 +29,8 @@
 // walks true paths, into an absorbing DEAD state that is reported as DC_ERR_CORRUPT.
 //
 // Eligibility (fsm_geometry): bpd in {1, 2, 4}, shortest code >= 2 bits (at most 4 symbols per byte, 128 per
-// subsequence), <= 256 internal nodes, lengths < 16 digits.  Everything else (radix 3, 1-bit codes) keeps the window
-// kernels.  The first tile of a stream that does not start on a byte boundary and the ragged last tile are walked digit
+// subsequence), <= 255 internal nodes, lengths < 16 digits.  Everything else (1-bit codes, binary codes of full byte
+// alphabets) keeps the window kernels.  The first tile of a stream that does not start on a byte boundary and the ragged last tile are walked digit
 // by digit by a generic routine (two tiles per call).
 #pragma once
 
@@ -45,10 +48,11 @@ struct FsmHeader {
 constexpr size_t kFsmHeaderBytes = (sizeof(FsmHeader) + 255) & ~(size_t)255;
 constexpr size_t kFsmSyncRowBytes = 256 * sizeof(uint16_t);            // F1: one state
 constexpr size_t kFsmWriteRowBytes = 256 * sizeof(uint32_t);           // F3: one state, symbols 0 and 1
-constexpr size_t kFsmWriteXRowBytes = 256 * sizeof(uint16_t);          // F3: one state, symbols 2 and 3
+constexpr int kFsmSuffixRows = 16;                                     // F3: (count - 3) * 8 + k, k = first digit of the third code
+constexpr size_t kFsmWriteXRowBytes = 256 * sizeof(uint16_t);          // F3: one suffix row, symbols 2 and 3
 constexpr size_t kFsmSyncTableBytes = kFsmMaxStates * kFsmSyncRowBytes;
 constexpr size_t kFsmWriteTableBytes = (kFsmMaxStates + 1) * kFsmWriteRowBytes;
-constexpr size_t kFsmWriteXTableBytes = (kFsmMaxStates + 1) * kFsmWriteXRowBytes;
+constexpr size_t kFsmWriteXTableBytes = kFsmSuffixRows * kFsmWriteXRowBytes;
 constexpr size_t kFsmWorkspaceBytes = kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes + kFsmWriteXTableBytes;
 
 struct FsmTables {   // where the three pieces live in the decode workspace
@@ -69,8 +73,13 @@ static inline FsmTables fsm_tables_at(void *p) {
 
 // one digit x from node (d, v): a symbol (>= 0), nothing (-1, inside a code) or an unused slot (-2); (d, v) = next node
 __device__ __forceinline__ int fsm_digit(const FsmHeader *h, int &d, uint32_t &v, uint32_t x) {
+    if (x >= (uint32_t)h->n_ary) {   // not a digit of this radix (a 2-bit field of 3 in a radix-3 stream)
+        d = 0;
+        v = 0;
+        return -2;
+    }
     d++;
-    v = (v << h->bpd) | x;
+    v = v * (uint32_t)h->n_ary + x;
     if (d >= h->min_len) {
         const uint32_t c = h->count[d], f = h->first[d];
         if (c && v >= f && v - f < c) {
@@ -94,7 +103,8 @@ __device__ __forceinline__ void fsm_state_node(const FsmHeader *h, uint32_t id, 
 }
 
 // ------------------------------------------------------------------------------------------ table build
-// grid = nstates + 1 CTAs of 256 threads: CTA s fills row s of both tables (thread = byte value); row nstates is DEAD.
+// grid = nstates + 1 + kFsmSuffixRows CTAs of 256 threads: CTA s fills row s of both tables (thread = byte value); row nstates
+// is DEAD; the CTAs behind it fill the suffix rows.
 __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t) {
     __shared__ FsmHeader h;
     const int tid = threadIdx.x;
@@ -114,8 +124,8 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         // lengths outside [min_len, max_len] have no codes (K2 scans skip the last slot, as the reference does)
         for (int d = 0; d < kFsmMaxDepth; d++)
             if (d < h.min_len || d > h.max_len) h.count[d] = 0;
-        h.nstates = (tab->status == DC_OK && tab->packed_radix == 0)
-                        ? fsm_geometry(h.first, h.count, h.min_len, h.max_len, h.bpd, h.ilo, h.ihi, h.base) : 0;
+        h.nstates = (tab->status == DC_OK && h.bpd != 0)
+                        ? fsm_geometry(h.first, h.count, h.min_len, h.max_len, h.bpd, h.n_ary, h.ilo, h.ihi, h.base) : 0;
         h.reserved[0] = h.reserved[1] = h.reserved[2] = 0;
     }
     __syncthreads();
@@ -126,17 +136,28 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         for (int i = tid; i < (int)(sizeof(FsmHeader) / 4); i += 256) dst[i] = src[i];
     }
     const int s = blockIdx.x;
-    if (ns == 0 || s > ns) return;
+    if (ns == 0 || s > ns + kFsmSuffixRows) return;
+    const int bpd = h.bpd, steps = 8 / bpd;
+    const uint32_t mask = (1u << bpd) - 1u;
     if (s == ns) {  // DEAD: absorbs everything, emits nothing
         t.write[(size_t)s * 256 + tid] = (uint32_t)ns << 16;
-        t.writex[(size_t)s * 256 + tid] = 0;
+        return;
+    }
+    if (s > ns) {   // suffix row: what byte `tid` decodes to from the root, from digit k on (the third and fourth code of a byte)
+        const int row = s - ns - 1, k0 = row & 7;
+        int d = 0;
+        uint32_t v = 0, cnt = 0, syms = 0;
+        for (int k = k0; k < steps; k++) {
+            const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
+            if (r == -2) break;
+            if (r >= 0 && cnt < 2) { syms |= (uint32_t)r << (8 * cnt); cnt++; }
+        }
+        t.writex[(size_t)row * 256 + tid] = (uint16_t)syms;
         return;
     }
     int d0;
     uint32_t v0;
     fsm_state_node(&h, (uint32_t)s, d0, v0);
-    const int bpd = h.bpd, steps = 8 / bpd;
-    const uint32_t mask = (1u << bpd) - 1u;
     {   // F1: an unused slot sends the walk back to the root
         int d = d0;
         uint32_t v = v0, cnt = 0;
@@ -148,16 +169,19 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
     }
     {   // F3: an unused slot is the end of the true path
         int d = d0;
-        uint32_t v = v0, cnt = 0, syms = 0, next = 0;
+        uint32_t v = v0, cnt = 0, syms = 0, next = 0, third = 0;
         bool dead = false;
         for (int k = 0; k < steps && !dead; k++) {
             const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
-            if (r >= 0) { syms |= (uint32_t)r << (8 * cnt); cnt++; }
+            if (r >= 0) {
+                if (cnt < 2) syms |= (uint32_t)r << (8 * cnt);
+                cnt++;
+                if (cnt == 2) third = (uint32_t)(k + 1);   // the third code, if any, starts at the next digit
+            }
             dead = r == -2;
         }
         next = dead ? (uint32_t)ns : fsm_state_id(&h, d, v);
-        t.write[(size_t)s * 256 + tid] = (syms & 0xFFFFu) | (next << 16) | (cnt << 24);
-        t.writex[(size_t)s * 256 + tid] = (uint16_t)(syms >> 16);
+        t.write[(size_t)s * 256 + tid] = (syms & 0xFFFFu) | (next << 16) | ((cnt >= 3 ? third & 7u : 0u) << 24) | (cnt << 27);
     }
 }
 
@@ -483,7 +507,7 @@ struct FsmWriteArgs {
     unsigned long long n_out;
     int lead;
     uint32_t stage_bytes;      // per warp
-    uint32_t hot_rows;         // rows of the F3 table resident in shared memory (all of them unless SPLIT)
+    uint32_t rows;             // rows of the F3 table (states + DEAD), all resident in shared memory
     int32_t *d_status;
 };
 
@@ -492,26 +516,21 @@ __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool p) {
 }
 
 struct FsmWriteTabs {
-    uint32_t tab, xtab;            // shared-memory addresses of the resident rows
-    const uint32_t *gtab;          // the whole tables in global memory (SPLIT: rows behind hot_limit are read from here)
-    const uint16_t *gxtab;
-    uint32_t hot_limit;            // hot rows * 256
+    uint32_t tab, xtab;            // shared-memory addresses: the rows, and the suffix rows moved back by 24 rows (count 3, k 0 = row 24)
 };
 
 // One byte step of the write walk.  acc = the lane's last four symbols (newest in the top byte), G = 8 x pending bytes in its
 // low 5 bits (bit 5 toggles when a word completes), wptr = shared address of the word being filled, e = the previous entry.
-template <bool SPLIT, int J>
+template <int J>
 __device__ __forceinline__ void fsm_write_step(const FsmWriteTabs &T, uint32_t w, uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
     const uint32_t idx = prmt(w, e, 0xFF60u | (uint32_t)J);   // byte J | state << 8; bytes 2, 3 = sign of the count byte = 0
-    const bool hot = !SPLIT || idx < T.hot_limit;
-    if (hot) e = lds_u32_at(T.tab, idx);
-    else e = __ldg(T.gtab + idx);
-    const uint32_t c = e >> 24;
+    e = lds_u32_at(T.tab, idx);
+    const uint32_t c = e >> 27;
     uint32_t syms = e;   // symbols 0 and 1 (the state and the count above them are never taken: a window slides by c bytes)
-    if (c >= 3u) {
+    if (c >= 3u) {       // symbols 2 and 3: what the byte decodes to from digit k on, row = count * 8 + k
+        const uint32_t xi = prmt(w, e, 0xFF70u | (uint32_t)J);
         uint32_t x;
-        if (hot) asm volatile("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(x) : "r"(idx), "r"(T.xtab));
-        else x = __ldg(T.gxtab + idx);
+        asm volatile("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(x) : "r"(xi), "r"(T.xtab));
         syms = prmt(e, x, 0x5410u);
     }
     const uint32_t sw = __funnelshift_l(acc, syms, G);   // the pending bytes, then this step's symbols
@@ -533,23 +552,21 @@ __device__ __forceinline__ void fsm_write_step(const FsmWriteTabs &T, uint32_t w
         : "memory");
 }
 
-template <bool SPLIT>
 __device__ __forceinline__ void fsm_write_walk(const FsmWriteTabs &T, const uint32_t (&w)[8], uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        fsm_write_step<SPLIT, 0>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<SPLIT, 1>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<SPLIT, 2>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<SPLIT, 3>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<0>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<1>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<2>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<3>(T, w[k], e, acc, G, wptr);
     }
 }
 
-template <bool SPLIT>
 __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTables t, FastWorkspace ws) {
     extern __shared__ __align__(16) uint8_t fsm_smem[];
     FsmHeader *s_h = (FsmHeader *)fsm_smem;
     uint32_t *s_tab = (uint32_t *)(fsm_smem + kFsmHeaderBytes);
-    uint16_t *s_xtab = (uint16_t *)(fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * kFsmWriteRowBytes);
+    uint16_t *s_xtab = (uint16_t *)(fsm_smem + kFsmHeaderBytes + (size_t)a.rows * kFsmWriteRowBytes);
     if (*ws.mismatch) return;  // the robust path redoes the stream
     {
         const uint32_t *src = (const uint32_t *)t.hdr;
@@ -557,19 +574,16 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
         for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
         const uint4 *s4 = (const uint4 *)t.write, *x4 = (const uint4 *)t.writex;
         uint4 *d4 = (uint4 *)s_tab, *dx4 = (uint4 *)s_xtab;
-        for (int i = threadIdx.x; i < (int)a.hot_rows * 64; i += blockDim.x) d4[i] = s4[i];    // 1 KB per row
-        for (int i = threadIdx.x; i < (int)a.hot_rows * 32; i += blockDim.x) dx4[i] = x4[i];   // 512 bytes per row
+        for (int i = threadIdx.x; i < (int)a.rows * 64; i += blockDim.x) d4[i] = s4[i];            // 1 KB per row
+        for (int i = threadIdx.x; i < kFsmSuffixRows * 32; i += blockDim.x) dx4[i] = x4[i];        // 512 bytes per suffix row
         __syncthreads();
     }
     FsmWriteTabs T;
     T.tab = (uint32_t)__cvta_generic_to_shared(s_tab);
-    T.xtab = (uint32_t)__cvta_generic_to_shared(s_xtab);
+    T.xtab = (uint32_t)__cvta_generic_to_shared(s_xtab) - 24u * (uint32_t)kFsmWriteXRowBytes;
     asm volatile("" : "+r"(T.tab), "+r"(T.xtab));
-    T.gtab = t.write;
-    T.gxtab = t.writex;
-    T.hot_limit = a.hot_rows * 256u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    uint8_t *stage = fsm_smem + kFsmHeaderBytes + (size_t)a.hot_rows * (kFsmWriteRowBytes + kFsmWriteXRowBytes) + (size_t)warp * a.stage_bytes;
+    uint8_t *stage = fsm_smem + kFsmHeaderBytes + (size_t)a.rows * kFsmWriteRowBytes + kFsmWriteXTableBytes + (size_t)warp * a.stage_bytes;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
     const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
     const unsigned long long tile_bits = 32ull * kF_SubBits;
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
                 __syncwarp();
                 uint32_t wptr0 = stage_addr + (pos0 & ~3u), wptr = wptr0, G = 8u * (pos0 & 3u), acc = 0u;
                 uint32_t meta = (my_info & 0xFFu) << 16;
-                if (mine && my_cnt) fsm_write_walk<SPLIT>(T, w, meta, acc, G, wptr);
+                if (mine && my_cnt) fsm_write_walk(T, w, meta, acc, G, wptr);
                 __syncwarp();
                 if (mine && my_cnt) {
                     const uint32_t pend = (G >> 3) & 3u;
