@@ -97,7 +97,8 @@ int host_flag_acquire(HostFlag *f);
 void host_flag_release(const HostFlag &f);
 
 // ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
-constexpr int kFsmMaxStates = 255;   // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
+constexpr int kFsmMaxStates = 255;       // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
+constexpr int kFsmMaxSyncStates = 256;   // F1 alone has no sink: a binary code of all 256 byte values + the dummy leaf has exactly 256
 // Internal nodes per depth from the canonical arrays; returns their number, 0 = not eligible.  `radix` is the arity of the
 // code tree (values are base-`radix` numerals), `bpd` the bits a digit takes in the stream (radix 3: 2-bit fields).
 __host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_t *count, int min_len, int max_len, int bpd, int radix,
@@ -122,7 +123,7 @@ __host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_
         ihi[d] = (uint32_t)hi;
         base[d] = total;
         total += (unsigned)(hi - lo + 1);
-        if (total > (unsigned)kFsmMaxStates) return 0;
+        if (total > (unsigned)kFsmMaxSyncStates) return 0;
     }
     if (min_len <= max_len && first[min_len] != 0) return 0;
     return (int)total;

@@ -1044,6 +1044,7 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 
 
 constexpr int kSyncW14 = 0x10;
+constexpr int kModeFsmSync = 0x40;   // F1 through the state machine, F3 through the window kernel (k4_fsm.cuh, COMPAT): binary codes with 256 states
 constexpr int kModeFsm = 0x20;   // the byte-stepped kernels of k4_fsm.cuh; bits 20..28: states, bits 29..31: min(shortest code's bits, 8) - 1
 static int decode_force_mode();
 static bool decode_tma();
@@ -1069,6 +1070,10 @@ static int fast_mode(const int32_t *tmeta) {
     if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxStates && fsm_rows_fit(tmeta) && decode_force_mode() != 3) {
         const int min_bits = tmeta[5] * tmeta[1];
         mode |= kModeFsm | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
+    } else if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxSyncStates && tmeta[1] == 1 && tmeta[9] == 0 && decode_force_mode() != 3) {
+        // binary code, too many states for F3's rows: the state machine for F1 only (its table is at most 128 KB)
+        const int min_bits = tmeta[5] * tmeta[1];
+        mode |= kModeFsmSync | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
     }
     return mode;
 }
@@ -1079,7 +1084,7 @@ static int fsm_states(int mode) { return (mode >> 20) & 0x1FF; }
 static int fsm_min_bits(int mode) { return (int)(((unsigned)mode >> 29) & 7u) + 1; }
 // a stream whose first code does not start on a digit boundary of the byte grid keeps the window kernels
 static int mode_for_start(int mode, int bpd, unsigned long long start) {
-    if ((mode & kModeFsm) && !(start & kFsmToken) && bpd > 0 && start % (unsigned)bpd != 0) mode &= ~kModeFsm;
+    if ((mode & (kModeFsm | kModeFsmSync)) && !(start & kFsmToken) && bpd > 0 && start % (unsigned)bpd != 0) mode &= ~(kModeFsm | kModeFsmSync);
     return mode;
 }
 
@@ -1113,10 +1118,11 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
                            unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, int mode,
                            DecodeChain *chain, int lead, cudaStream_t st) {
     const int nstates = fsm_states(mode);
+    const bool compat = (mode & kModeFsmSync) != 0;
     const FsmTables t = fsm_tables_at(fw.fsm);
     {
         LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
-        fsm_build_kernel<<<nstates + 1 + kFsmSuffixRows, 256, 0, st>>>(d_table, t);
+        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0);
     }
     size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
     int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
@@ -1127,7 +1133,9 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     const bool tma = decode_tma();
     const uint32_t table_bytes = (uint32_t)(((size_t)nstates * kFsmSyncRowBytes + 127) & ~(size_t)127);
     if (tma) smem = kFsmHeaderBytes + table_bytes + (size_t)(threads / 32) * (1024 + 8);
-    DC_CUDA_TRY(ensure_dynamic_smem(tma ? (const void *)fsm_sync_kernel<true> : (const void *)fsm_sync_kernel<false>, smem));
+    const void *fn = compat ? (tma ? (const void *)fsm_sync_kernel<true, true> : (const void *)fsm_sync_kernel<false, true>)
+                            : (tma ? (const void *)fsm_sync_kernel<true, false> : (const void *)fsm_sync_kernel<false, false>);
+    DC_CUDA_TRY(ensure_dynamic_smem(fn, smem));
     const unsigned long long want = (nseg + (threads / 32) - 1) / (threads / 32), cap = (unsigned long long)sm_count() * per_sm;
     FsmSyncArgs a;
     a.d_bits = d_bits;
@@ -1140,8 +1148,14 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     a.chain = chain;
     LaunchScope ls(DC_K_DECODE_FSM_SYNC, st);
     a.tma_table_bytes = table_bytes;
-    if (tma) fsm_sync_kernel<true><<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
-    else fsm_sync_kernel<false><<<(unsigned int)(want < cap ? want : cap), threads, smem, st>>>(a, t, fw);
+    const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+    if (compat) {
+        if (tma) fsm_sync_kernel<true, true><<<grid, threads, smem, st>>>(a, t, fw);
+        else fsm_sync_kernel<false, true><<<grid, threads, smem, st>>>(a, t, fw);
+    } else {
+        if (tma) fsm_sync_kernel<true, false><<<grid, threads, smem, st>>>(a, t, fw);
+        else fsm_sync_kernel<false, false><<<grid, threads, smem, st>>>(a, t, fw);
+    }
     return cuda_status(cudaGetLastError());
 }
 static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
@@ -1182,7 +1196,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
                             DecodeChain *host_chain = nullptr, int32_t *host_flag = nullptr) {
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
-    if (mode & kModeFsm) {
+    if (mode & (kModeFsm | kModeFsmSync)) {
         const int rc = launch_fsm_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, mode, chain, lead, st);
         if (rc != DC_OK) return rc;
     } else {
@@ -1203,7 +1217,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
         DC_CUDA_TRY(cudaMemsetAsync(slots.flags, 0, 256 * sizeof(unsigned int), st));
         const unsigned int g2 = (unsigned int)min((unsigned long long)min(sm_count(), 256), (nseg + 255) / 256);
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & kModeFsm) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots, host_flag);
+        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & (kModeFsm | kModeFsmSync)) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots, host_flag);
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1390,7 +1404,7 @@ extern "C" int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, un
     int rc = shard_geometry(d_bits, has_halo, shard_bits, stream_bits_left, d_table, d_workspace, workspace_bytes, st, &g);
     if (rc != DC_OK) return rc;
     if (!has_halo) {
-        if ((first_code_bit & kFsmToken) && !(g.mode & kModeFsm)) return DC_ERR_ARG;   // a state token, but the table has no state machine
+        if ((first_code_bit & kFsmToken) && !(g.mode & (kModeFsm | kModeFsmSync))) return DC_ERR_ARG;   // a state token, but the table has no state machine
         g.mode = mode_for_start(g.mode, g.bpd, first_code_bit);
     }
     DC_CUDA_TRY(cudaMemcpyAsync(g.fw.mismatch + 1, &g.mode, sizeof(int), cudaMemcpyHostToDevice, st));   // the write phase takes the same kernels

@@ -32,6 +32,13 @@
 // subsequence), <= 255 internal nodes, lengths < 16 digits.  Everything else (1-bit codes, binary codes of full byte
 // alphabets) keeps the window kernels.  The first tile of a stream that does not start on a byte boundary and the ragged last tile are walked digit
 // by digit by a generic routine (two tiles per call).
+//
+// Binary codes of full byte alphabets (257 leaves with the reference's dummy: 256 internal nodes) have an F1 table of 128 KB,
+// which fits, and F3 rows of 256 KB, which do not.  They take F1 here and the window kernel for F3 (COMPAT): F1 then stores
+// what the window kernel expects -- the bit offset of the first code that STARTS in the subsequence and the number of codes
+// that start in it -- which it gets from its own results: a lane that begins inside a code finds the end of that code
+// with at most two more look-ups (codes are shorter than 16 bits; the entry also holds the bit at which the first code of
+// the byte ends), and codes that start = codes that end - (began inside a code) + (ends inside a code).
 #pragma once
 
 namespace dc {
@@ -50,7 +57,7 @@ constexpr size_t kFsmSyncRowBytes = 256 * sizeof(uint16_t);            // F1: on
 constexpr size_t kFsmWriteRowBytes = 256 * sizeof(uint32_t);           // F3: one state, symbols 0 and 1
 constexpr int kFsmSuffixRows = 16;                                     // F3: (count - 3) * 8 + k, k = first digit of the third code
 constexpr size_t kFsmWriteXRowBytes = 256 * sizeof(uint16_t);          // F3: one suffix row, symbols 2 and 3
-constexpr size_t kFsmSyncTableBytes = kFsmMaxStates * kFsmSyncRowBytes;
+constexpr size_t kFsmSyncTableBytes = kFsmMaxSyncStates * kFsmSyncRowBytes;
 constexpr size_t kFsmWriteTableBytes = (kFsmMaxStates + 1) * kFsmWriteRowBytes;
 constexpr size_t kFsmWriteXTableBytes = kFsmSuffixRows * kFsmWriteXRowBytes;
 constexpr size_t kFsmWorkspaceBytes = kFsmHeaderBytes + kFsmSyncTableBytes + kFsmWriteTableBytes + kFsmWriteXTableBytes;
@@ -105,7 +112,7 @@ __device__ __forceinline__ void fsm_state_node(const FsmHeader *h, uint32_t id, 
 // ------------------------------------------------------------------------------------------ table build
 // grid = nstates + 1 + kFsmSuffixRows CTAs of 256 threads: CTA s fills row s of both tables (thread = byte value); row nstates
 // is DEAD; the CTAs behind it fill the suffix rows.
-__global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t) {
+__global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t, int sync_only) {
     __shared__ FsmHeader h;
     const int tid = threadIdx.x;
     for (int i = tid; i < kFsmMaxDepth; i += 256) {
@@ -137,6 +144,7 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
     }
     const int s = blockIdx.x;
     if (ns == 0 || s > ns + kFsmSuffixRows) return;
+    if (sync_only && s >= ns) return;   // F1 rows only (the F3 rows of 256 states would not fit anyway)
     const int bpd = h.bpd, steps = 8 / bpd;
     const uint32_t mask = (1u << bpd) - 1u;
     if (s == ns) {  // DEAD: absorbs everything, emits nothing
@@ -160,13 +168,16 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
     fsm_state_node(&h, (uint32_t)s, d0, v0);
     {   // F1: an unused slot sends the walk back to the root
         int d = d0;
-        uint32_t v = v0, cnt = 0;
+        uint32_t v = v0, cnt = 0, first_end = 0;
         for (int k = 0; k < steps; k++) {
             const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
+            if (r >= 0 && cnt == 0) first_end = (uint32_t)((k + 1) * bpd - 1);   // last bit of the first code that ends in this byte
             cnt += r >= 0;
         }
-        t.sync[(size_t)s * 256 + tid] = (uint16_t)(cnt | (fsm_state_id(&h, d, v) << 8));
+        // (COMPAT reads bits 5..7; the plain walk adds whole entries up, so they are only set for it)
+        t.sync[(size_t)s * 256 + tid] = (uint16_t)(cnt | (sync_only ? first_end << 5 : 0u) | (fsm_state_id(&h, d, v) << 8));
     }
+    if (sync_only) return;
     {   // F3: an unused slot is the end of the true path
         int d = d0;
         uint32_t v = v0, cnt = 0, syms = 0, next = 0, third = 0;
@@ -372,19 +383,30 @@ struct FsmSyncArgs {
 
 // slow tile: every lane walks its part digit by digit.  start: kFsmToken | state for a lane that begins at bit 0 of its
 // subsequence, else the bit offset (lane 0 only) of the first code.
+// first_end: bits from the lane's first bit to the end of the first code that ends in its part (lim if none does)
 __device__ __forceinline__ void fsm_slow_sync_lane(const FsmHeader *h, const uint8_t *__restrict__ d_bits, unsigned long long sub_bit0,
-                                                   uint32_t lim, uint32_t start, uint32_t &cnt, uint32_t &exit_state) {
+                                                   uint32_t lim, uint32_t start, uint32_t &cnt, uint32_t &exit_state, uint32_t &first_end) {
     int d = 0;
     uint32_t v = 0;
     unsigned long long p = sub_bit0;
     if (start & kFsmToken) fsm_state_node(h, start & 0x1FFu, d, v);
     else p += start;
-    bool dead = false;
-    cnt = fsm_walk_digits(h, d_bits, p, sub_bit0 + lim, d, v, dead, [](uint32_t, uint32_t) {});
+    cnt = 0;
+    first_end = lim;
+    const int bpd = h->bpd;
+    const unsigned long long stop = sub_bit0 + lim;
+    while (p + bpd <= stop) {
+        const int r = fsm_digit(h, d, v, stream_digit(d_bits, p, bpd));
+        p += bpd;
+        if (r >= 0) {
+            if (cnt == 0) first_end = (uint32_t)(p - sub_bit0);
+            cnt++;
+        }
+    }
     exit_state = fsm_state_id(h, d, v);
 }
 
-template <bool TMA>
+template <bool TMA, bool COMPAT>
 __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTables t, FastWorkspace ws) {
     extern __shared__ __align__(16) uint8_t fsm_smem[];
     FsmHeader *s_h = (FsmHeader *)fsm_smem;
@@ -453,15 +475,27 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
                     fsm_sync_walk<false>(tab, w, start, !redo, chk, wc);
                 }
                 exit_state = chk[1] >> 24;
+                if (COMPAT) { wc[0] &= 0x1F1F1F1Fu; wc[1] &= 0x1F1F1F1Fu; }   // bits 5..7 of an entry's low byte: where the first code ends
                 cnt = __dp4a(wc[0], 0x01010101u, __dp4a(wc[1], 0x01010101u, 0u));
+                if (COMPAT) {
+                    // what the window kernel wants: where the first code that starts here starts, how many start here
+                    uint32_t off = 0;
+                    if (start != 0u) {
+                        const uint32_t e0 = lds_u16_at(tab, prmt(w[0], start << 8, 0x7750u));
+                        const uint32_t e1 = lds_u16_at(tab, prmt(w[0], e0, 0x7751u));
+                        off = (e0 & 7u) ? ((e0 >> 5) & 7u) + 1u : 8u + ((e1 >> 5) & 7u) + 1u;
+                    }
+                    cnt = cnt - (start != 0u ? 1u : 0u) + (exit_state != 0u ? 1u : 0u);
+                    start = off;
+                }
             } else {
                 const unsigned long long sub_bit0 = tbit0 + (unsigned long long)lane * kF_SubBits;
                 const bool active = sub_bit0 < a.end;
                 const uint32_t lim = active ? (uint32_t)min((unsigned long long)kF_SubBits, a.end - sub_bit0) : 0u;
-                uint32_t st = lane == 0 ? carry : kFsmToken;
+                uint32_t st = lane == 0 ? carry : kFsmToken, first_end = 0;
                 cnt = 0;
                 exit_state = st & 0x1FFu;
-                if (active) fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state);
+                if (active) fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state, first_end);
                 while (true) {
                     uint32_t ns = __shfl_up_sync(0xFFFFFFFFu, exit_state, 1) | kFsmToken;
                     if (lane == 0) ns = st;
@@ -469,21 +503,30 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
                     if (!__any_sync(0xFFFFFFFFu, redo)) break;
                     if (redo) {
                         st = ns;
-                        fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state);
+                        fsm_slow_sync_lane(s_h, a.d_bits, sub_bit0, lim, st, cnt, exit_state, first_end);
                     }
                 }
                 // lanes behind the end pass the last active lane's exit on
                 const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
                 const int last = act ? 31 - __clz(act) : 0;
                 const uint32_t ex = __shfl_sync(0xFFFFFFFFu, exit_state, last);
+                const uint32_t own_exit = exit_state;
                 if (!active) exit_state = ex;
                 start = st & kFsmToken ? (st & 0xFFu) : 0u;   // (a bit-offset start: F3 gets the offset from its own arguments)
+                if (COMPAT) {   // the first code that STARTS in the lane's part, the codes that start there
+                    const uint32_t more = own_exit != 0u ? 1u : 0u;   // a code begins here and ends further on
+                    if (!active) { start = 0u; }
+                    else if (!(st & kFsmToken)) { start = st; cnt += more; }                  // the stream's first code, at its given bit
+                    else if ((st & 0x1FFu) == 0u) { start = 0u; cnt += more; }
+                    else if (cnt == 0u) { start = 0u; }                                        // all of it inside one code: nothing starts here
+                    else { start = first_end; cnt = cnt - 1u + more; }
+                }
             }
             carry = __shfl_sync(0xFFFFFFFFu, exit_state, 31) | kFsmToken;
             if (tt < (uint32_t)warm) {
                 assumed = carry;
             } else {
-                if ((unsigned long long)tt * 32 + lane < sub_left) *info = (uint16_t)(start | (cnt << 8));
+                if ((unsigned long long)tt * 32 + lane < sub_left) *info = (uint16_t)(COMPAT ? (start | (cnt << 7)) : (start | (cnt << 8)));   // COMPAT: the window kernels' form
                 total += cnt;
             }
         }
