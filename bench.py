@@ -491,6 +491,7 @@ def run_ours(args) -> None:
                "e2e_copy_floor": {"value": n * world * args.e2e_steps / floor_s / 1e9, "unit": UNIT,
                                   "what": "the same bytes moved with bare pinned cudaMemcpyAsync by all ranks at once, no kernels"}}
 
+    peer_exchange = bool(L.dc_debug_shard_peer_active(S.comm)) if S is not None else False
     if S is not None:
         S.close()
     if rank == 0:
@@ -505,6 +506,8 @@ def run_ours(args) -> None:
                        "parallelism": (f"dp{world}: contiguous shards of one logical stream through dc_shard_huff_encode (C-ABI, NCCL inside the "
                                        f"library): one all-gather (local histograms + edge symbols), bit offsets from the gathered histograms, shared edge bytes completed locally"
                                        if world > 1 else "1 GPU"),
+                       "shard_exchange": (("peer memory (CUDA IPC: stores over NVLink + flags, one single-CTA kernel)"
+                                           if peer_exchange else "ncclAllGather") if world > 1 else None),
                        "l2": "inputs larger than L2 (1 GiB vs 126 MB); no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,

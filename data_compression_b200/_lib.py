@@ -124,6 +124,7 @@ SYMBOLS = [
 EXTRA_SYMBOLS = [
     ("dc_histogram_u8_variant", _i, [_vp, _sz, _vp, _i, _vp]),
     ("dc_debug_decode_mode", _i, [_i]),
+    ("dc_debug_shard_peer_active", _i, [_vp]),
 ]
 
 _lib = None

@@ -308,7 +308,7 @@ extern "C" int dc_profile_kernel(int id, double *total_ms, uint64_t *launches) {
 }
 extern "C" const char *dc_profile_kernel_name(int id) {
     static const char *names[DC_K_COUNT] = {"histogram", "table", "bits_for_hist", "encode_count", "encode_scan", "encode", "encode_mid", "encode_wide", "decode_sync", "decode_handoff",
-                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "b64_pack", "b64_unpack", "mtf_walk", "mtf_scan", "mtf_resolve", "text_batch", "synth", "decode_fsm_build", "decode_fsm_sync", "decode_fsm_write", "encode_plan", "encode_fast"};
+                                            "decode_scan", "decode_write", "decode_fast_sync", "decode_fast_scan", "decode_fast_write", "nybble_pack", "nybble_unpack", "nybble_tail", "text_summary", "text_scan", "text_emit", "trit_pack", "trit_unpack", "b64_pack", "b64_unpack", "mtf_walk", "mtf_scan", "mtf_resolve", "text_batch", "synth", "decode_fsm_build", "decode_fsm_sync", "decode_fsm_write", "encode_plan", "encode_fast", "shard_exchange", "shard_plan"};
     return id >= 0 && id < DC_K_COUNT ? names[id] : "?";
 }
 

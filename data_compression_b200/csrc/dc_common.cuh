@@ -108,15 +108,24 @@ __host__ __device__ inline int fsm_geometry(const uint32_t *first, const uint32_
     if (min_len * bpd < 2) return 0;   // a 1-bit code: up to 8 symbols per byte
     if (count[max_len] == 0) return 0;
     const unsigned long long last = (unsigned long long)first[max_len] + count[max_len] - 1;
+    // hi(d) = last / radix ^ (max_len - d): shifts for the power-of-two radices (no 64-bit division on the device: K2 runs this
+    // on one thread), 32-bit divisions otherwise (radix 3: 3 ^ 15 < 2 ^ 32)
+    const bool pow2 = (radix & (radix - 1)) == 0;
     unsigned long long span = 1;       // radix ^ max_len
     for (int d = 0; d < max_len; d++) span *= (unsigned long long)radix;
     if (last >= span) return 0;        // over-subscribed lengths: values do not fit their digits
+    if (!pow2 && span > 0xFFFFFFFFull) return 0;
     unsigned total = 0;
-    unsigned long long div = span;     // radix ^ (max_len - d)
+    uint32_t div32 = pow2 ? 0u : (uint32_t)span;     // radix ^ (max_len - d)
     for (int d = 0; d < max_len; d++) {
         const unsigned long long lo = d < min_len ? 0ull : (unsigned long long)first[d] + count[d];
-        const unsigned long long hi = last / div;
-        div /= (unsigned long long)radix;
+        unsigned long long hi;
+        if (pow2) {
+            hi = last >> (bpd * (max_len - d));
+        } else {
+            hi = (unsigned long long)((uint32_t)last / div32);
+            div32 /= (uint32_t)radix;
+        }
         if (hi < lo) return 0;
         if (d >= min_len && d + 1 <= max_len && (unsigned long long)first[d + 1] != lo * (unsigned long long)radix) return 0;   // not the canonical chain
         ilo[d] = (uint32_t)lo;

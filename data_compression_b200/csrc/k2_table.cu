@@ -104,28 +104,36 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         }
         __syncthreads();
 
-        // ---- 3. two-queue n-way merge (serial: every step depends on the previous sum)
+        // ---- 3. two-queue n-way merge (serial: every step depends on the previous sum).  This loop is most of the kernel's
+        // time, and most of its time was the shared-memory load of the next queue head sitting in the dependent chain
+        // (compare -> pop -> load -> compare): the next four leaf counts and the next three internal counts are kept in
+        // registers, so a pop is a few moves and the load it issues is not needed before three pops later.
         if (tid == 0) {
             int lh = 0, ih = 0, it = 0, remaining = nleaf;
-            unsigned long long lc = nleaf > 0 ? s_scnt[0] : 0ull, ic = 0ull;
+            auto leaf_at = [&](int i) { return i < nleaf ? s_scnt[i] : ~0ull; };
+            unsigned long long l0 = leaf_at(0), l1 = leaf_at(1), l2 = leaf_at(2), l3 = leaf_at(3);
+            unsigned long long i0 = 0ull, i1 = 0ull, i2 = 0ull;   // s_icount[ih], [ih + 1], [ih + 2] where those exist (< it)
             while (remaining > 1) {
                 unsigned long long sum = 0;
                 for (int c = 0; c < n_ary; c++) {
                     const bool leaf_ok = lh < nleaf, int_ok = ih < it;
-                    if (leaf_ok && (!int_ok || lc <= ic)) {  // leaf wins ties
-                        sum += lc;
+                    if (leaf_ok && (!int_ok || l0 <= i0)) {  // leaf wins ties
+                        sum += l0;
                         s_lparent[lh] = it;
                         lh++;
-                        if (lh < nleaf) lc = s_scnt[lh];
+                        l0 = l1; l1 = l2; l2 = l3;
+                        l3 = leaf_at(lh + 3);
                     } else {
-                        sum += ic;
+                        sum += i0;
                         s_iparent[ih] = it;
                         ih++;
-                        if (ih < it) ic = s_icount[ih];
+                        i0 = i1; i1 = i2;
+                        i2 = ih + 2 < it ? s_icount[ih + 2] : 0ull;
                     }
                 }
                 s_icount[it] = sum;
-                if (ih == it) ic = sum;  // the new node is now the head of the internal FIFO
+                const int d = it - ih;   // the new node joins the internal FIFO d places behind its head
+                if (d == 0) i0 = sum; else if (d == 1) i1 = sum; else if (d == 2) i2 = sum;
                 it++;
                 remaining -= k;
             }

@@ -19,6 +19,7 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2, or $DC_NCCL_LIB): libdc_b200.so has no link-time dependency on it,
 // and a process that already loaded NCCL (torch) shares that copy.
 #include <dlfcn.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -74,10 +75,29 @@ static const NcclApi *nccl() {
 
 }  // namespace dc
 
+namespace dc {
+// ---- peer-memory exchange: every rank owns one small buffer that all the others map (CUDA IPC); a rank STORES its 2 KB
+// contribution straight into its peers' buffers over NVLink and raises a flag there, and spins on the flags in its own.
+// One single-CTA kernel, a few microseconds, against 25-30 us for the same all-gather through NCCL (whose cost at this size
+// is all latency).  Two slots used alternately: a rank can be at most one call ahead of its slowest peer (to finish call e
+// it needs every peer's flag of call e), and it overwrites slot (e & 1) of its peers next in call e + 2.
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    unsigned long long *buf[kMaxPeers];   // buf[r] = rank r's exchange buffer as mapped in this process (buf[rank] = my own)
+};
+struct PeerXchg {
+    int state = 0;                        // 0 = not tried yet, 1 = in use, -1 = unavailable (NCCL does the exchange)
+    PeerPtrs ptrs;
+    unsigned long long epoch = 0;
+    size_t flags_off = 0;                 // in u64: [2][world][kShardSlots] data, then [2][world] flags
+};
+}  // namespace dc
+
 struct dc_shard_comm {
     dc::ncclComm_t comm;
     int rank, world;
     bool owned;
+    dc::PeerXchg peer;
 };
 
 namespace dc {
@@ -124,8 +144,10 @@ __global__ void __launch_bounds__(256) shard_plan_kernel(const unsigned long lon
 // after it -- at most 7 bits each way, i.e. at most 7 symbols, and the all-gather brought 8 from every rank.
 __global__ void shard_fix_edges_kernel(uint8_t *__restrict__ out, const unsigned long long *__restrict__ all, int world, int rank,
                                        const dc_huff_table *__restrict__ tab, const unsigned long long *__restrict__ rank_bits,
-                                       const unsigned long long *__restrict__ rank_off) {
+                                       const unsigned long long *__restrict__ rank_off, const ShardPlan *__restrict__ plan,
+                                       int32_t *__restrict__ d_status) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (plan && plan->reserved && d_status) atomicCAS(d_status, 0, DC_ERR_NCCL);   // the peer-memory exchange gave up waiting (plan == nullptr: NCCL did the exchange)
     const unsigned long long bits = rank_bits[rank];
     if (bits == 0 || tab->status != DC_OK) return;
     const unsigned long long off = rank_off[rank], e = off + bits, lo = off >> 3, hi1 = (e - 1) >> 3;
@@ -162,6 +184,44 @@ __global__ void shard_fix_edges_kernel(uint8_t *__restrict__ out, const unsigned
     }
     if (first) out[0] |= (uint8_t)first;
     if (last) out[hi1 - lo] |= (uint8_t)last;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one CTA: push my kShardSlots words into slot (epoch & 1), row `rank`, of every rank's buffer, flag them, wait for everybody's
+__global__ void __launch_bounds__(320) shard_exchange_kernel(PeerPtrs p, const unsigned long long *__restrict__ local, int rank, int world,
+                                                             unsigned long long epoch, size_t flags_off, unsigned long long *__restrict__ timed_out) {
+    const int t = threadIdx.x;
+    const size_t slot = (size_t)(epoch & 1ull);
+    if (t == 0) *timed_out = 0ull;
+    __syncthreads();
+    if (t < kShardSlots) {
+        const unsigned long long v = local[t];
+        for (int r = 0; r < world; r++) p.buf[r][(slot * world + rank) * kShardSlots + t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) st_release_sys_u64(p.buf[t] + flags_off + slot * world + rank, epoch);
+    if (t < world) {
+        const unsigned long long *flag = p.buf[rank] + flags_off + slot * world + t;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys_u64(flag) != epoch) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) {   // 20 s: a peer never made this call; report instead of hanging the device
+                *timed_out = 1ull;   // (shard_fix_edges_kernel turns it into DC_ERR_NCCL behind the encoder's own status)
+                break;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 struct ShardEncLayout {
@@ -207,19 +267,110 @@ extern "C" int dc_shard_comm_create(const void *id128, int rank, int world, dc_s
     memcpy(&id, id128, sizeof id);
     ncclComm_t c = nullptr;
     DC_NCCL_TRY(N->CommInitRank(&c, world, id, rank));
-    *out = new dc_shard_comm{c, rank, world, true};
+    *out = new dc_shard_comm{c, rank, world, true, PeerXchg()};
     return DC_OK;
 }
 
 extern "C" int dc_shard_comm_from_nccl(void *nccl_comm, int rank, int world, dc_shard_comm **out) {
     if (!nccl()) return DC_ERR_NCCL;
     if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world) return DC_ERR_ARG;
-    *out = new dc_shard_comm{(ncclComm_t)nccl_comm, rank, world, false};
+    *out = new dc_shard_comm{(ncclComm_t)nccl_comm, rank, world, false, PeerXchg()};
     return DC_OK;
 }
 
+// Maps every rank's exchange buffer into this process.  Collective (two small NCCL all-gathers, blocking); every rank
+// reaches the same verdict.  Returns true if the peer path is in use.
+static bool peer_setup(dc_shard_comm *c, cudaStream_t st) {
+    PeerXchg &x = c->peer;
+    if (x.state != 0) return x.state > 0;
+    x.state = -1;
+    const NcclApi *N = nccl();
+    const char *env = getenv("DC_SHARD_PEER");
+    // (the decision below must be the same on every rank: it only depends on the world size, the environment -- assumed
+    // equal across ranks, like NCCL's own -- and the all-gathered outcome)
+    if (!N || c->world < 2 || c->world > kMaxPeers || (env && atoi(env) == 0)) return false;
+    const size_t data_words = (size_t)2 * c->world * kShardSlots, words = data_words + (size_t)2 * c->world;
+    unsigned long long *mine = nullptr;
+    unsigned char *d_h = nullptr;
+    int okay = 1;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof h);
+    const bool dbg = getenv("DC_SHARD_DEBUG") != nullptr;
+    cudaError_t ce;
+    if ((ce = cudaMalloc((void **)&mine, words * 8)) != cudaSuccess) okay = 0;
+    if (okay && (ce = cudaMemsetAsync(mine, 0, words * 8, st)) != cudaSuccess) okay = 0;
+    if (okay && (ce = cudaIpcGetMemHandle(&h, mine)) != cudaSuccess) okay = 0;
+    if (dbg && !okay) fprintf(stderr, "[dc_shard] rank %d: exchange buffer / IPC handle: %s\n", c->rank, cudaGetErrorString(ce));
+    cudaGetLastError();
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;   // handle + "okay so far"
+    std::vector<unsigned char> mine_rec(rec, 0), all((size_t)c->world * rec, 0);
+    memcpy(mine_rec.data(), &h, sizeof h);
+    mine_rec[sizeof h] = (unsigned char)okay;
+    if (cudaMalloc((void **)&d_h, (size_t)(c->world + 1) * rec) != cudaSuccess) { cudaGetLastError(); if (mine) cudaFree(mine); return false; }
+    bool comm_ok = cudaMemcpyAsync(d_h, mine_rec.data(), rec, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                   N->AllGather(d_h, d_h + rec, rec, kNcclUint8, c->comm, st) == 0 &&
+                   cudaMemcpyAsync(all.data(), d_h + rec, (size_t)c->world * rec, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                   cudaStreamSynchronize(st) == cudaSuccess;
+    for (int r = 0; comm_ok && r < c->world; r++) okay &= all[(size_t)r * rec + sizeof h];
+    // second round: did every rank manage to map every buffer?
+    int mapped = comm_ok && okay;
+    for (int r = 0; r < kMaxPeers; r++) x.ptrs.buf[r] = nullptr;
+    if (mapped) {
+        x.ptrs.buf[c->rank] = mine;
+        for (int r = 0; r < c->world && mapped; r++) {
+            if (r == c->rank) continue;
+            cudaIpcMemHandle_t hr;
+            memcpy(&hr, all.data() + (size_t)r * rec, sizeof hr);
+            void *ptr = nullptr;
+            if ((ce = cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) {
+                if (dbg) fprintf(stderr, "[dc_shard] rank %d: cudaIpcOpenMemHandle(rank %d): %s\n", c->rank, r, cudaGetErrorString(ce));
+                cudaGetLastError();
+                mapped = 0;
+            }
+            else x.ptrs.buf[r] = (unsigned long long *)ptr;
+        }
+    }
+    if (comm_ok) {
+        mine_rec[0] = (unsigned char)mapped;
+        comm_ok = cudaMemcpyAsync(d_h, mine_rec.data(), 1, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                  N->AllGather(d_h, d_h + rec, 1, kNcclUint8, c->comm, st) == 0 &&
+                  cudaMemcpyAsync(all.data(), d_h + rec, (size_t)c->world, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                  cudaStreamSynchronize(st) == cudaSuccess;
+        for (int r = 0; comm_ok && r < c->world; r++) mapped &= all[r];
+    }
+    cudaFree(d_h);
+    if (dbg) fprintf(stderr, "[dc_shard] rank %d: peer-memory exchange %s (collectives ok %d, buffers ok %d, mapped everywhere %d)\n", c->rank,
+                     comm_ok && mapped ? "in use" : "unavailable, using ncclAllGather", (int)comm_ok, okay, mapped);
+    if (!comm_ok || !mapped) {
+        for (int r = 0; r < c->world; r++)
+            if (r != c->rank && x.ptrs.buf[r]) cudaIpcCloseMemHandle(x.ptrs.buf[r]);
+        if (mine) cudaFree(mine);
+        for (int r = 0; r < kMaxPeers; r++) x.ptrs.buf[r] = nullptr;
+        cudaGetLastError();
+        return false;
+    }
+    x.flags_off = data_words;
+    x.epoch = 0;
+    x.state = 1;
+    return true;
+}
+static void peer_teardown(dc_shard_comm *c) {
+    PeerXchg &x = c->peer;
+    if (x.state <= 0) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; r++)
+        if (r != c->rank && x.ptrs.buf[r]) cudaIpcCloseMemHandle(x.ptrs.buf[r]);
+    if (x.ptrs.buf[c->rank]) cudaFree(x.ptrs.buf[c->rank]);
+    x.state = -1;
+    cudaGetLastError();
+}
+
+// test / bench hook (not in the public header): 1 if this communicator exchanges through peer memory
+extern "C" int dc_debug_shard_peer_active(const dc_shard_comm *c) { return c && c->peer.state > 0 ? 1 : 0; }
+
 extern "C" int dc_shard_comm_destroy(dc_shard_comm *c) {
     if (!c) return DC_OK;
+    peer_teardown(c);
     int rc = DC_OK;
     if (c->owned && nccl() && nccl()->CommDestroy(c->comm) != 0) rc = DC_ERR_NCCL;
     delete c;
@@ -256,8 +407,20 @@ extern "C" int dc_shard_huff_encode(dc_shard_comm *c, const uint8_t *d_in, size_
     // 1. local histogram (+ one small histogram per 32 KB run for the planned encoder, + the shard's edge symbols)
     int rc = histogram_runs_edges(d_in, n_local, local_hist, enc_ws, enc_ws_bytes, local_hist + DC_NSLOTS, st);
     if (rc != DC_OK) return rc;
-    // 2. every rank gets every rank's histogram and edge symbols: the one collective of the encode path
-    DC_NCCL_TRY(N->AllGather(local_hist, all_hist, kShardSlots, kNcclUint64, c->comm, st));
+    // 2. every rank gets every rank's histogram and edge symbols: the one exchange of the encode path -- through peer memory
+    //    (stores over NVLink + flags, one single-CTA kernel) when the ranks could map each other's buffers, else ncclAllGather
+    const bool peer = peer_setup(c, st);
+    {
+        LaunchScope ls(DC_K_SHARD_EXCHANGE, st);
+        if (peer) {
+            PeerXchg &x = c->peer;
+            x.epoch++;
+            shard_exchange_kernel<<<1, 320, 0, st>>>(x.ptrs, local_hist, c->rank, c->world, x.epoch, x.flags_off, &plan->reserved);
+            all_hist = x.ptrs.buf[c->rank] + (size_t)(x.epoch & 1ull) * c->world * kShardSlots;
+        } else {
+            DC_NCCL_TRY(N->AllGather(local_hist, all_hist, kShardSlots, kNcclUint64, c->comm, st));
+        }
+    }
     // 3. global table from the sum of the histograms (redundantly on every rank), every rank's bit total, the exclusive
     //    scan, my phase
     {
@@ -265,7 +428,10 @@ extern "C" int dc_shard_huff_encode(dc_shard_comm *c, const uint8_t *d_in, size_
         rc = launch_table(all_hist, nullptr, DC_NSLOTS, n_ary, d_table, raw, st, c->world, kShardSlots);
         if (rc != DC_OK) return rc;
     }
-    shard_plan_kernel<<<1, 256, 0, st>>>(all_hist, c->world, c->rank, d_table, rank_bits, rank_off, plan);
+    {
+        LaunchScope ls(DC_K_SHARD_PLAN, st);
+        shard_plan_kernel<<<1, 256, 0, st>>>(all_hist, c->world, c->rank, d_table, rank_bits, rank_off, plan);
+    }
     // 4. encode at my phase (in device memory: the host never waits for the plan)
     if (n_local) {
         rc = encode_planned_device_phase(d_in, n_local, d_table, d_out, out_capacity, &plan->phase, d_total_bits, d_status, enc_ws, enc_ws_bytes, st);
@@ -276,7 +442,10 @@ extern "C" int dc_shard_huff_encode(dc_shard_comm *c, const uint8_t *d_in, size_
         if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, st));
     }
     // 5. the bytes that neighbouring shards share, completed locally
-    if (c->world > 1 && n_local) shard_fix_edges_kernel<<<1, 32, 0, st>>>(d_out, all_hist, c->world, c->rank, d_table, rank_bits, rank_off);
+    if (c->world > 1 && n_local) {
+        LaunchScope ls(DC_K_SHARD_PLAN, st);
+        shard_fix_edges_kernel<<<1, 32, 0, st>>>(d_out, all_hist, c->world, c->rank, d_table, rank_bits, rank_off, c->peer.state > 0 ? plan : nullptr, d_status);
+    }
     return cuda_status(cudaGetLastError());
 }
 

@@ -164,6 +164,8 @@ enum dc_kernel_id {
     DC_K_DECODE_FSM_WRITE,
     DC_K_ENCODE_PLAN,
     DC_K_ENCODE_FAST,
+    DC_K_SHARD_EXCHANGE,   /* the shard layer's exchange: peer-memory kernel or ncclAllGather (incl. the wait for the slowest rank) */
+    DC_K_SHARD_PLAN,       /* every rank's bit total + exclusive scan; the edge-byte completion */
     DC_K_COUNT
 };
 /* on != 0: bracket every kernel launch with CUDA events on its launching stream */
