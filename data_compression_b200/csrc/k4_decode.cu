@@ -1052,7 +1052,7 @@ static bool fsm_rows_fit(const int32_t *tmeta) {
     const int min_bits = tmeta[5] * tmeta[1] > 0 ? tmeta[5] * tmeta[1] : 1;
     const size_t per_lane = (size_t)(kF_SubBits / (min_bits < 8 ? min_bits : 8)) + 2, half = 16 * per_lane + 48, whole = 32 * per_lane + 48;
     const size_t want = half > 2176 ? half : 2176, stage = ((want < whole ? want : whole) + 15) & ~(size_t)15;
-    return kFsmHeaderBytes + (size_t)(tmeta[11] + 1) * kFsmWriteRowBytes + kFsmWriteXTableBytes + 24 * stage + 256 <= 227 * 1024 - 1024;
+    return kFsmHeaderBytes + (size_t)(tmeta[11] + 1 + kFsmEntryRows) * kFsmWriteRowBytes + kFsmWriteXTableBytes + 24 * stage + 256 <= 227 * 1024 - 1024;
 }
 // which instantiation of the fast kernels a table takes (tmeta = the first ten words of dc_huff_table, lut2_used, fsm_states)
 static int fast_mode(const int32_t *tmeta) {
@@ -1122,17 +1122,21 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     const FsmTables t = fsm_tables_at(fw.fsm);
     {
         LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
-        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0);
+        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmEntryRows + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0);
     }
-    size_t smem = kFsmHeaderBytes + (size_t)nstates * kFsmSyncRowBytes;
-    int threads = smem <= 48 * 1024 ? 256 : smem <= 100 * 1024 ? 512 : 1024;
-    int per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
-
     // north_star (4): the tile staged by the bulk-copy engine instead of a 32-byte load per lane (DC_DECODE_TMA=1; measured
     // in DESIGN.md -- the default is whichever is faster)
     const bool tma = decode_tma();
-    const uint32_t table_bytes = (uint32_t)(((size_t)nstates * kFsmSyncRowBytes + 127) & ~(size_t)127);
-    if (tma) smem = kFsmHeaderBytes + table_bytes + (size_t)(threads / 32) * (1024 + 8);
+    const size_t table = (size_t)(nstates + (!compat && fsm_has_entry_rows(nstates) ? 1 + kFsmEntryRows : 0)) * kFsmSyncRowBytes;
+    const uint32_t table_bytes = (uint32_t)((table + 127) & ~(size_t)127);
+    // as many CTAs per SM as the table allows (each keeps its own copy), 32 warps per SM in every case
+    int threads = 1024, per_sm = 1;
+    size_t smem = 0;
+    for (int ctas = 4; ctas >= 1; ctas >>= 1) {
+        const int warps = 32 / ctas;
+        smem = kFsmHeaderBytes + table_bytes + (tma ? (size_t)warps * (1024 + 8) : 0);
+        if ((size_t)ctas * (smem + 1024) <= 227 * 1024) { threads = warps * 32; per_sm = ctas; break; }
+    }
     const void *fn = compat ? (tma ? (const void *)fsm_sync_kernel<true, true> : (const void *)fsm_sync_kernel<false, true>)
                             : (tma ? (const void *)fsm_sync_kernel<true, false> : (const void *)fsm_sync_kernel<false, false>);
     DC_CUDA_TRY(ensure_dynamic_smem(fn, smem));
@@ -1161,7 +1165,7 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
 static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsigned long long nsubf, unsigned long long nwt,
                             unsigned long long nseg, FastWorkspace fw, uint8_t *d_out, size_t n_out, int32_t *d_status, int mode,
                             int lead, cudaStream_t st) {
-    const int rows = fsm_states(mode) + 1;   // + DEAD
+    const int rows = fsm_states(mode) + 1 + (fsm_has_entry_rows(fsm_states(mode)) ? kFsmEntryRows : 0);   // + DEAD + the entry rows
     const FsmTables t = fsm_tables_at(fw.fsm);
     const uint32_t stage = fsm_stage_bytes(mode);
     const int warps = 24;

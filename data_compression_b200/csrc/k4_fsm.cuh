@@ -55,6 +55,7 @@ struct FsmHeader {
 constexpr size_t kFsmHeaderBytes = (sizeof(FsmHeader) + 255) & ~(size_t)255;
 constexpr size_t kFsmSyncRowBytes = 256 * sizeof(uint16_t);            // F1: one state
 constexpr size_t kFsmWriteRowBytes = 256 * sizeof(uint32_t);           // F3: one state, symbols 0 and 1
+constexpr int kFsmEntryRows = 7;                                       // rows nstates + k: a stream that starts at digit k of its first byte
 constexpr int kFsmSuffixRows = 16;                                     // F3: (count - 3) * 8 + k, k = first digit of the third code
 constexpr size_t kFsmWriteXRowBytes = 256 * sizeof(uint16_t);          // F3: one suffix row, symbols 2 and 3
 constexpr size_t kFsmSyncTableBytes = kFsmMaxSyncStates * kFsmSyncRowBytes;
@@ -110,8 +111,11 @@ __device__ __forceinline__ void fsm_state_node(const FsmHeader *h, uint32_t id, 
 }
 
 // ------------------------------------------------------------------------------------------ table build
-// grid = nstates + 1 + kFsmSuffixRows CTAs of 256 threads: CTA s fills row s of both tables (thread = byte value); row nstates
-// is DEAD; the CTAs behind it fill the suffix rows.
+// grid = nstates + 1 + kFsmEntryRows + kFsmSuffixRows CTAs of 256 threads: CTA s fills row s of both tables (thread = byte
+// value); row nstates is DEAD; rows nstates + k (k = 1 .. 7, tables with at most 248 states) are ENTRY rows -- the root, but
+// the first k digits of the byte belong to somebody else (a shard that starts at bit phase k * bpd of its first byte begins
+// in that state and needs no digit-by-digit walk of its first tile); the CTAs behind them fill the suffix rows.
+__host__ __device__ inline bool fsm_has_entry_rows(int nstates) { return nstates > 0 && nstates + kFsmEntryRows <= 255; }
 __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t, int sync_only) {
     __shared__ FsmHeader h;
     const int tid = threadIdx.x;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         for (int i = tid; i < (int)(sizeof(FsmHeader) / 4); i += 256) dst[i] = src[i];
     }
     const int s = blockIdx.x;
-    if (ns == 0 || s > ns + kFsmSuffixRows) return;
+    if (ns == 0 || s > ns + kFsmEntryRows + kFsmSuffixRows) return;
     if (sync_only && s >= ns) return;   // F1 rows only (the F3 rows of 256 states would not fit anyway)
     const int bpd = h.bpd, steps = 8 / bpd;
     const uint32_t mask = (1u << bpd) - 1u;
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         t.write[(size_t)s * 256 + tid] = (uint32_t)ns << 16;
         return;
     }
-    if (s > ns) {   // suffix row: what byte `tid` decodes to from the root, from digit k on (the third and fourth code of a byte)
-        const int row = s - ns - 1, k0 = row & 7;
+    if (s > ns + kFsmEntryRows) {   // suffix row: what byte `tid` decodes to from the root, from digit k on (the third and fourth code of a byte)
+        const int row = s - ns - kFsmEntryRows - 1, k0 = row & 7;
         int d = 0;
         uint32_t v = 0, cnt = 0, syms = 0;
         for (int k = k0; k < steps; k++) {
@@ -163,13 +167,18 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         t.writex[(size_t)row * 256 + tid] = (uint16_t)syms;
         return;
     }
-    int d0;
-    uint32_t v0;
-    fsm_state_node(&h, (uint32_t)s, d0, v0);
+    int d0 = 0, kstart = 0;
+    uint32_t v0 = 0;
+    if (s > ns) {   // entry row: from the root, from digit s - ns on
+        kstart = s - ns;
+        if (!fsm_has_entry_rows(ns) || kstart >= steps) return;
+    } else {
+        fsm_state_node(&h, (uint32_t)s, d0, v0);
+    }
     {   // F1: an unused slot sends the walk back to the root
         int d = d0;
         uint32_t v = v0, cnt = 0, first_end = 0;
-        for (int k = 0; k < steps; k++) {
+        for (int k = kstart; k < steps; k++) {
             const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
             if (r >= 0 && cnt == 0) first_end = (uint32_t)((k + 1) * bpd - 1);   // last bit of the first code that ends in this byte
             cnt += r >= 0;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
         int d = d0;
         uint32_t v = v0, cnt = 0, syms = 0, next = 0, third = 0;
         bool dead = false;
-        for (int k = 0; k < steps && !dead; k++) {
+        for (int k = kstart; k < steps && !dead; k++) {
             const int r = fsm_digit(&h, d, v, ((uint32_t)tid >> (8 - bpd * (k + 1))) & mask);
             if (r >= 0) {
                 if (cnt < 2) syms |= (uint32_t)r << (8 * cnt);
@@ -389,8 +398,9 @@ __device__ __forceinline__ void fsm_slow_sync_lane(const FsmHeader *h, const uin
     int d = 0;
     uint32_t v = 0;
     unsigned long long p = sub_bit0;
-    if (start & kFsmToken) fsm_state_node(h, start & 0x1FFu, d, v);
-    else p += start;
+    if (!(start & kFsmToken)) p += start;
+    else if ((start & 0x1FFu) > (uint32_t)h->nstates) p += ((start & 0x1FFu) - (uint32_t)h->nstates) * (uint32_t)h->bpd;   // an entry row: the root, that many digits in
+    else fsm_state_node(h, start & 0x1FFu, d, v);
     cnt = 0;
     first_end = lim;
     const int bpd = h->bpd;
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
         uint32_t *dst = (uint32_t *)s_h;
         for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
-        const int words = s_h->nstates * 128;
+        const int words = (s_h->nstates + (!COMPAT && fsm_has_entry_rows(s_h->nstates) ? 1 + kFsmEntryRows : 0)) * 128;
         const uint4 *s4 = (const uint4 *)t.sync;
         uint4 *d4 = (uint4 *)s_tab;
         for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d4[i] = s4[i];
@@ -427,6 +437,8 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
     uint32_t start_token = a.start_token;
     if (a.chain) start_token = a.chain->next_start;
     if (start_token == 0) start_token = kFsmToken;   // bit 0 of the first byte = the root at a byte boundary
+    else if (!COMPAT && start_token < 8u && start_token % (uint32_t)s_h->bpd == 0u && fsm_has_entry_rows(s_h->nstates))
+        start_token = kFsmToken | ((uint32_t)s_h->nstates + start_token / (uint32_t)s_h->bpd);   // inside the first byte: an entry row
     if (blockIdx.x == 0 && threadIdx.x == 0) *ws.start_slot() = start_token;   // F3 walks the first lane the same way
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const unsigned long long nvec = ((a.end + 7) / 8 + 15) / 16;
@@ -669,6 +681,7 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
                     uint32_t v = 0;
                     unsigned long long p = sub_bit0;
                     if (first_lane_offset && lane == 0) p += start_token;
+                    else if ((my_info & 0xFFu) > dead_state) p += ((my_info & 0xFFu) - dead_state) * (uint32_t)s_h->bpd;   // an entry row
                     else fsm_state_node(s_h, my_info & 0xFFu, d, v);
                     bool dead = false;
                     uint8_t *dst = a.out + ob + excl;
