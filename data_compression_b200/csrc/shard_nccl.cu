@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(320) shard_exchange_kernel(PeerPtrs p, const u
         while (ld_acquire_sys_u64(flag) != epoch) {
             __nanosleep(200);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) {   // 20 s: a peer never made this call; report instead of hanging the device
+            if (t1 - t0 > 60000000000ull) {   // 60 s: a peer never made this call; report instead of hanging the device
                 *timed_out = 1ull;   // (shard_fix_edges_kernel turns it into DC_ERR_NCCL behind the encoder's own status)
                 break;
             }

@@ -12,3 +12,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'fsm_sync|fsm_write|encode_fast|hist_runs|encode_plan|table_kernel' -s 6 -c 6 \
     -o gpurun_out/prof_r2_final python tools/profile_target.py --size-mib 1024 > gpurun_out/r2_ncu_full.log 2>&1
 tail -3 gpurun_out/r2_ncu_full.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
