@@ -1,0 +1,101 @@
+"""GPU: what round 2 added around the kernels -- the host-visible table header (and a table the library did not build), the
+byte-stepped decoder's corner tables (binary codes of all 256 byte values: 256 states, F1 state machine + window F3; streams
+that start inside a byte: entry rows), the TMA-staged variant of F1, and the encoder's dispatch with and without a known header."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _bytes_all_256(n, seed=11):
+    rng = np.random.default_rng(seed)
+    w = 1.0 / np.arange(1, 257) ** 1.05
+    return rng.choice(np.arange(256, dtype=np.uint8), size=n, p=w / w.sum()).astype(np.uint8)
+
+
+@pytest.mark.parametrize("n_ary", [2, 4, 16])
+def test_full_byte_alphabet_roundtrip_matches_oracle(dc, oracle, n_ary):
+    """All 256 byte values (0x00 included): 257 leaves with the dummy, i.e. exactly 256 internal nodes at n = 2."""
+    host = _bytes_all_256((1 << 20) + 77)
+    host[:256] = np.arange(256, dtype=np.uint8)
+    data = torch.from_numpy(host).cuda()
+    hist = dc.histogram(data)
+    table = dc.huff_build(hist, n_ary)
+    t = table.download()
+    ln, el, ev, st = oracle.build_tables(hist.cpu().numpy().astype(np.uint64), n_ary)
+    if n_ary == 2:
+        assert t.fsm_states == 256   # one more than the write pass can name: F1 alone takes the state machine
+    for phase in (0, 1, 6):
+        res = dc.huff_encode(data, table, bit_phase=phase)
+        nbits = res.bits()
+        want, wbits = oracle.pack(host, el, ev, oracle.bits_per_digit(n_ary), phase)
+        assert nbits == wbits
+        assert np.array_equal(res.payload[: (nbits + phase + 7) // 8].cpu().numpy(), want)
+        out, status = dc.huff_decode(res.payload, nbits, table, host.size, bit_start=phase)
+        assert int(status.item()) == 0 and torch.equal(out, data), (n_ary, phase)
+
+
+def test_decode_with_a_table_the_library_did_not_build(dc, oracle):
+    """A table copied into a fresh device buffer has no host-visible header: the decoder reads it back (blocking) instead."""
+    from data_compression_b200.api import HuffTable
+    host = _bytes_all_256(300007, seed=5)
+    data = torch.from_numpy(host).cuda()
+    table = dc.huff_build(dc.histogram(data), 4)
+    res = dc.huff_encode(data, table)
+    nbits = res.bits()
+    foreign = HuffTable(data.device)
+    foreign.buf.copy_(table.buf)          # a plain device copy: the library has never seen this address
+    foreign.n_ary = 4
+    out, status = dc.huff_decode(res.payload, nbits, foreign, host.size)
+    assert int(status.item()) == 0 and torch.equal(out, data)
+    res2 = dc.huff_encode(data, foreign)   # and the encoder, which then lets its kernels pick by the table they find
+    assert res2.bits() == nbits and torch.equal(res2.payload[: (nbits + 7) // 8], res.payload[: (nbits + 7) // 8])
+
+
+def test_encoder_dispatch_known_and_unknown_header(dc, oracle):
+    """The same payload whether the host already knows the table's longest code (build finished) or not (still queued)."""
+    host = _bytes_all_256(1 << 20, seed=9)
+    data = torch.from_numpy(host).cuda()
+    hist = dc.histogram(data)
+    for n_ary in (2, 3, 4):
+        table = dc.huff_build(hist, n_ary)
+        torch.cuda.synchronize()                    # the build's event has passed: one matching launch
+        a = dc.huff_encode(data, table, out=torch.empty(host.size * 2 + 64, dtype=torch.uint8, device="cuda"))
+        na = a.bits()
+        filler = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+        filler.random_(0, 255)                      # something long in front of the build ...
+        table2 = dc.huff_build(hist, n_ary)         # ... so its header is not there yet when the encoder asks
+        b = dc.huff_encode(data, table2, out=torch.empty(host.size * 2 + 64, dtype=torch.uint8, device="cuda"))
+        nb = b.bits()
+        assert na == nb and torch.equal(a.payload[: (na + 7) // 8], b.payload[: (nb + 7) // 8]), n_ary
+
+
+def test_tma_staged_sync_pass_is_bit_exact():
+    """north_star (4): DC_DECODE_TMA=1 stages the bitstream tiles with cp.async.bulk + mbarrier; same results."""
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import data_compression_b200 as dc
+from data_compression_b200 import synth
+thr, base = synth.zipf_bytes_spec()
+for n in (1, 4097, (1 << 22) + 13):
+    data = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc.synth_fill(data, synth.SEED_BASE + n, synth.device_thresholds(thr, "cuda"), base)
+    hist = dc.histogram(data)
+    for n_ary in (3, 4, 16):
+        table = dc.huff_build(hist, n_ary)
+        for phase in (0, 2):
+            res = dc.huff_encode(data, table, bit_phase=phase, out=torch.empty(n * 2 + 64, dtype=torch.uint8, device="cuda"))
+            out, st = dc.huff_decode(res.payload, res.bits(), table, n, bit_start=phase)
+            assert int(st.item()) == 0 and torch.equal(out, data), (n, n_ary, phase)
+print("tma ok")
+''' % ROOT
+    env = dict(os.environ, DC_DECODE_TMA="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "tma ok" in r.stdout, r.stdout + r.stderr

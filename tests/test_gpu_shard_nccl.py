@@ -148,3 +148,20 @@ def test_shard_edges_completed_locally_world2(n_ary):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, []), (1, [])]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU)")
+def test_shard_exchange_nccl_fallback_world2(monkeypatch):
+    """DC_SHARD_PEER=0: the histogram exchange through ncclAllGather instead of peer memory -- same streams."""
+    import torch.multiprocessing as mp
+    monkeypatch.setenv("DC_SHARD_PEER", "0")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    sizes = [(19, 16), (4097, 4096), (100003, 50001)]
+    procs = [ctx.Process(target=_edge_worker, args=(r, 2, 29671, sizes, 4, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, []), (1, [])]
