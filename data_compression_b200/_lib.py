@@ -68,6 +68,7 @@ SYMBOLS = [
     ("dc_huff_build", _i, [_vp, _i, _vp, _vp]),
     ("dc_huff_table_from_lengths", _i, [_vp, _i, _vp, _vp]),
     ("dc_huff_table_download", _i, [_vp, _vp, _vp]),
+    ("dc_huff_table_forget", _i, [_vp]),
     ("dc_huff_bits_for_hist", _i, [_vp, _vp, _vp, _vp]),
     ("dc_huff_encode_workspace_bytes", _sz, [_sz]),
     ("dc_huff_encode", _i, [_vp, _sz, _vp, _vp, _sz, _u, _vp, _vp, _vp, _sz, _vp]),

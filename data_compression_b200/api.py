@@ -40,6 +40,13 @@ class HuffTable:
     def ptr(self) -> int:
         return self.buf.data_ptr()
 
+    def __del__(self):
+        # the library keeps the header of every table it built, keyed by address: drop it before the allocator reuses the memory
+        try:
+            lib().dc_huff_table_forget(self.buf.data_ptr())
+        except Exception:
+            pass
+
     def download(self) -> HuffTableStruct:
         """Blocking copy to the host."""
         h = HuffTableStruct()

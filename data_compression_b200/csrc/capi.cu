@@ -208,6 +208,11 @@ int table_meta_fetch(const dc_huff_table *d_table, cudaStream_t st, int32_t out[
     return table_meta_read_device(d_table, st, out);
 }
 
+void table_meta_forget(const dc_huff_table *d_table) {
+    std::lock_guard<std::mutex> lk(g_meta_mu);
+    g_meta_of.erase(d_table);
+}
+
 int host_flag_acquire(HostFlag *f) {
     std::lock_guard<std::mutex> lk(g_meta_mu);
     int dev = 0;

@@ -91,6 +91,7 @@ void table_meta_end(const dc_huff_table *d_table, const TableMetaTicket &t, cuda
 // has been recycled, is read from the device after synchronising `st`).  wait = false: DC_OK only if the facts are known
 // already, 1 otherwise (never blocks).
 int table_meta_fetch(const dc_huff_table *d_table, cudaStream_t st, int32_t out[kTableMetaWords], bool wait);
+void table_meta_forget(const dc_huff_table *d_table);
 // a mapped int32 + an event: a kernel stores one word, the host waits for the event (not for the stream) and reads it
 struct HostFlag { volatile int32_t *host; int32_t *dev; cudaEvent_t ev; int dev_index, slot; };
 int host_flag_acquire(HostFlag *f);

@@ -464,6 +464,12 @@ extern "C" int dc_huff_table_from_lengths(const int32_t *d_lengths, int n_ary, d
     return launch_table(nullptr, d_lengths, DC_NSLOTS, n_ary, d_table, raw, (cudaStream_t)stream);
 }
 
+extern "C" int dc_huff_table_forget(const dc_huff_table *d_table) {
+    if (!d_table) return DC_ERR_ARG;
+    table_meta_forget(d_table);
+    return DC_OK;
+}
+
 extern "C" int dc_huff_table_download(const dc_huff_table *d_table, dc_huff_table *h_table, void *stream) {
     if (!d_table || !h_table) return DC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;

@@ -269,7 +269,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(const uint8_t *__restrict__ in, size_t n,
                                                                  const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
                                                                  size_t out_cap, unsigned phase, EncWorkspace ws,
-                                                                 unsigned int nruns, int32_t *__restrict__ d_status) {
+                                                                 unsigned int nruns, int32_t *__restrict__ d_status, int exact) {
     typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type entry_t;
     constexpr int kStageWords = EncCfg<WIDE>::kStageWords;
     constexpr int kItems = WIDE ? kEncPerThread : kEncPerThread / 2;  // codes (WIDE) or code pairs per lane
@@ -278,7 +278,11 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
 
     if (tab->status != DC_OK || tab->bits_per_digit == 0) return;  // reported by the count kernel
     if (ws.d_phase) phase = *ws.d_phase & 7u;
-    if (WIDE && tab->max_bits <= kNarrowBits) return;             // the single-pass kernels handle this table
+    if (WIDE && tab->max_bits <= kNarrowBits) {                   // the single-pass kernels handle this table
+        // (exact: launched alone because the host's copy of the table header said so -- that header was not this table's)
+        if (exact && blockIdx.x == 0 && threadIdx.x == 0) set_status(d_status, DC_ERR_ARG);
+        return;
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // bytes [0, stream_bytes) of `out` are written, nothing else; refuse the whole stream if they do not fit
@@ -711,7 +715,7 @@ template <int MAXBITS>
 __device__ __forceinline__ void encode_fast_body(const uint8_t *__restrict__ in, size_t n,
                                                                     const dc_huff_table *__restrict__ tab, uint8_t *__restrict__ out,
                                                                     size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
-                                                                    int32_t *__restrict__ d_status, uint32_t smem_bytes) {
+                                                                    int32_t *__restrict__ d_status, uint32_t smem_bytes, bool exact) {
     typedef FwCfg<MAXBITS> Cfg;
     constexpr int kFwWarps = Cfg::kWarps, kFwGroups = Cfg::kGroups, kFwThreads = Cfg::kThreads, kFwChunkBytes = Cfg::kChunkBytes;
     constexpr int kFwChunkSubs = Cfg::kChunkSubs, kFwStageWords = Cfg::kStageWords;
@@ -720,7 +724,11 @@ __device__ __forceinline__ void encode_fast_body(const uint8_t *__restrict__ in,
     if (!table_usable(tab, d_status)) return;
     {   // this instantiation's tables: [1, 12] (pairs) or (12, 16] (single symbols); longer codes take the 64-bit-entry kernel
         const int mb = tab->max_bits;
-        if (mb > MAXBITS || (!Cfg::kPair && mb <= kPlannedMaxBits)) return;
+        if (mb > MAXBITS || (!Cfg::kPair && mb <= kPlannedMaxBits)) {
+            // launched alone because the host's copy of the table header said so: that header was not this table's
+            if (exact && blockIdx.x == 0 && threadIdx.x == 0) set_status(d_status, DC_ERR_ARG);
+            return;
+        }
     }
     if (ws.d_phase) phase = *ws.d_phase & 7u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = warp / kFwWarps, gw = warp % kFwWarps;
@@ -895,12 +903,12 @@ __global__ void __launch_bounds__(1024, 1) encode_fast_kernel(const uint8_t *__r
                                                               size_t out_cap, unsigned phase, FwWorkspace ws, unsigned int nruns,
                                                               int32_t *__restrict__ d_status, uint32_t smem_bytes) {
     if (WHICH == kPlannedMaxBits) {
-        encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+        encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes, true);
     } else if (WHICH == kNarrowBits) {
-        encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+        encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes, true);
     } else {
-        if (tab->max_bits <= kPlannedMaxBits) encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
-        else encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes);
+        if (tab->max_bits <= kPlannedMaxBits) encode_fast_body<kPlannedMaxBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes, false);
+        else encode_fast_body<kNarrowBits>(in, n, tab, out, out_cap, phase, ws, nruns, d_status, smem_bytes, false);
     }
 }
 
@@ -1109,7 +1117,7 @@ static int launch_encode_body(const uint8_t *d_in, size_t n, const dc_huff_table
     if (!known || mb > kNarrowBits) {   // longer codes: 64-bit entries (returns at once for any other table)
         LaunchScope ls(DC_K_ENCODE_WIDE, st);
         encode_run_kernel<true><<<min(nruns, known ? sms * 4u : sms), kEncThreads, 0, st>>>(d_in, n, d_table, d_out, out_capacity, bit_phase,
-                                                                             ws, nruns, d_status);
+                                                                             ws, nruns, d_status, known ? 1 : 0);
     }
     return cuda_status(cudaGetLastError());
 }

@@ -1122,7 +1122,7 @@ static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsi
     const FsmTables t = fsm_tables_at(fw.fsm);
     {
         LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
-        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmEntryRows + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0);
+        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmEntryRows + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0, nstates);
     }
     // north_star (4): the tile staged by the bulk-copy engine instead of a 32-byte load per lane (DC_DECODE_TMA=1; measured
     // in DESIGN.md -- the default is whichever is faster)
@@ -1201,6 +1201,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
     const unsigned long long sms = (unsigned long long)sm_count();
     const unsigned long long want = (nseg + kF_Warps - 1) / kF_Warps;
     if (mode & (kModeFsm | kModeFsmSync)) {
+        DC_CUDA_TRY(cudaMemsetAsync(fw.bad_input(), 0, sizeof(int32_t), st));   // set by F1 if the table is not the one the host thinks it is
         const int rc = launch_fsm_sync(d_bits, bit_start, end, nsubf, nwt, nseg, d_table, fw, mode, chain, lead, st);
         if (rc != DC_OK) return rc;
     } else {
@@ -1221,7 +1222,7 @@ static int launch_fast_sync(const uint8_t *d_bits, unsigned long long bit_start,
         DC_CUDA_TRY(cudaMemsetAsync(slots.flags, 0, 256 * sizeof(unsigned int), st));
         const unsigned int g2 = (unsigned int)min((unsigned long long)min(sm_count(), 256), (nseg + 255) / 256);
         LaunchScope ls(DC_K_DECODE_FAST_SCAN, st);
-        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, (!(mode & (kModeFsm | kModeFsmSync)) && mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots, host_flag);
+        decode_fast_scan_kernel<<<g2 ? g2 : 1, 1024, 0, st>>>(fw, nseg, n_out, d_status, chain, last_chunk, ((mode & (kModeFsm | kModeFsmSync)) || mode_t2(write_mode(mode))) ? 1 : 0, host_chain, slots, host_flag);
     }
     return cuda_status(cudaGetLastError());
 }

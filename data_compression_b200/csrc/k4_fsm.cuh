@@ -116,7 +116,7 @@ __device__ __forceinline__ void fsm_state_node(const FsmHeader *h, uint32_t id, 
 // the first k digits of the byte belong to somebody else (a shard that starts at bit phase k * bpd of its first byte begins
 // in that state and needs no digit-by-digit walk of its first tile); the CTAs behind them fill the suffix rows.
 __host__ __device__ inline bool fsm_has_entry_rows(int nstates) { return nstates > 0 && nstates + kFsmEntryRows <= 255; }
-__global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t, int sync_only) {
+__global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__restrict__ tab, FsmTables t, int sync_only, int expected_states) {
     __shared__ FsmHeader h;
     const int tid = threadIdx.x;
     for (int i = tid; i < kFsmMaxDepth; i += 256) {
@@ -137,6 +137,10 @@ __global__ void __launch_bounds__(256) fsm_build_kernel(const dc_huff_table *__r
             if (d < h.min_len || d > h.max_len) h.count[d] = 0;
         h.nstates = (tab->status == DC_OK && h.bpd != 0)
                         ? fsm_geometry(h.first, h.count, h.min_len, h.max_len, h.bpd, h.n_ary, h.ilo, h.ihi, h.base) : 0;
+        // the host sized this launch and the walks' shared memory from the table header it knows; a header that is not this
+        // table's (dc_huff_table_forget was owed) must not be walked with: no states = the walks return, F2 flags the stream,
+        // the window kernels -- which only trust the table itself -- redo it
+        if (h.nstates != expected_states) h.nstates = 0;
         h.reserved[0] = h.reserved[1] = h.reserved[2] = 0;
     }
     __syncthreads();
@@ -426,6 +430,10 @@ __global__ void __launch_bounds__(1024, 1) fsm_sync_kernel(FsmSyncArgs a, FsmTab
         uint32_t *dst = (uint32_t *)s_h;
         for (int i = threadIdx.x; i < (int)(sizeof(FsmHeader) / 4); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
+        if (s_h->nstates == 0) {   // fsm_build_kernel refused the table (stale header): F2 sends the stream to the robust path
+            if (blockIdx.x == 0 && threadIdx.x == 0) *ws.bad_input() = 1;
+            return;
+        }
         const int words = (s_h->nstates + (!COMPAT && fsm_has_entry_rows(s_h->nstates) ? 1 + kFsmEntryRows : 0)) * 128;
         const uint4 *s4 = (const uint4 *)t.sync;
         uint4 *d4 = (uint4 *)s_tab;

@@ -197,6 +197,12 @@ int dc_huff_build(const uint64_t *d_hist, int n_ary, dc_huff_table *d_table, voi
 /* Decode side: rebuild values/LUT from 259 lengths (digits), as read from a table header (:1727-1744). */
 int dc_huff_table_from_lengths(const int32_t *d_lengths, int n_ary, dc_huff_table *d_table, void *stream);
 
+/* The library keeps the header of every table it built, keyed by the table's device address (see dc_huff_table above).
+ * Call this before the memory behind `d_table` is freed or reused for anything but another build -- an allocator may hand
+ * the same address out again.  (A stale header is caught where it can be: the kernels it selects refuse a table that is
+ * not theirs -- the decoder then takes its slow path, the encoder reports DC_ERR_ARG -- but forgetting is the contract.) */
+int dc_huff_table_forget(const dc_huff_table *d_table);
+
 /* Blocking copy of the table to host memory. */
 int dc_huff_table_download(const dc_huff_table *d_table, dc_huff_table *h_table, void *stream);
 

@@ -99,3 +99,41 @@ print("tma ok")
     env = dict(os.environ, DC_DECODE_TMA="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "tma ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_stale_table_header_is_caught_and_forget_clears_it(dc, oracle):
+    """A built table overwritten behind the library's back (the contract asks for dc_huff_table_forget): the header the host
+    kept is another table's.  The decoder's state-machine kernels refuse it and the window kernels -- which only trust the
+    table itself -- redo the stream; the encoder, launched for the wrong code lengths, reports DC_ERR_ARG.  After forget()
+    everything takes its normal path."""
+    from data_compression_b200.api import HuffTable
+    host = _bytes_all_256(200003, seed=21)
+    data = torch.from_numpy(host).cuda()
+    hist = dc.histogram(data)
+    a = dc.huff_build(hist, 4)                       # the library now knows a header for a.buf's address
+    assert a.download().max_bits > 12                # (256 symbols at n = 4: codes of 7 digits)
+    # another code: binary, codes of at most 12 bits (a table from lengths) -- it wants the other encoder instantiation
+    ln = np.zeros(259, dtype=np.int32)
+    s = 1
+    for depth in range(1, 12):
+        ln[s] = depth
+        s += 1
+    ln[s] = 12; ln[s + 1] = 12
+    nsym = s + 2
+    b = dc.huff_table_from_lengths(torch.from_numpy(ln).cuda(), 2)
+    small = torch.from_numpy(np.random.default_rng(3).integers(1, nsym, 100001).astype(np.uint8)).cuda()
+    good = dc.huff_encode(small, b, out=torch.empty(small.numel() * 2 + 64, dtype=torch.uint8, device="cuda"))
+    nbits = good.bits()
+    torch.cuda.synchronize()
+    a.buf.copy_(b.buf)                               # behind the library's back
+    a.n_ary = 2
+    torch.cuda.synchronize()
+    out, status = dc.huff_decode(good.payload, nbits, a, small.numel())
+    assert int(status.item()) == 0 and torch.equal(out, small)      # slow path, right answer
+    bad = dc.huff_encode(small, a, out=torch.empty(small.numel() * 2 + 64, dtype=torch.uint8, device="cuda"))
+    assert int(bad.status.item()) == dc.DC_ERR_ARG
+    assert dc.lib().dc_huff_table_forget(a.ptr) == 0
+    again = dc.huff_encode(small, a, out=torch.empty(small.numel() * 2 + 64, dtype=torch.uint8, device="cuda"))
+    assert again.bits() == nbits and torch.equal(again.payload[: (nbits + 7) // 8], good.payload[: (nbits + 7) // 8])
+    out, status = dc.huff_decode(again.payload, nbits, a, small.numel())
+    assert int(status.item()) == 0 and torch.equal(out, small)
