@@ -445,11 +445,8 @@ __global__ void __launch_bounds__(kEncThreads, WIDE ? 2 : 5) encode_run_kernel(c
 constexpr int kSpZeroPrefix = 4;                                            // words of zeros in front of the data
 
 struct SpWorkspace {
-    unsigned int *ticket;          // [1]          next run to hand out
-    unsigned long long *desc;      // [nruns]      status << 62 | bits of the run
     uint32_t *bstate;              // [nchunks+1]  arrivals at the boundary word between chunk b-1 and chunk b
     uint4 *bleft, *bright;         // [nchunks+1]
-    const uint32_t *d_phase;
 };
 
 // The 16-byte word shared by the last chunk of one run and the first chunk of the next: both sides deposit
@@ -829,9 +826,6 @@ __device__ __forceinline__ void encode_fast_body(const uint8_t *__restrict__ in,
                 const uint32_t sbit0 = 32u * kSpZeroPrefix - r;            // staging bit of the first bit of 16-byte word v0
                 const uint32_t sbit1 = nvec * 128u + sbit0;                // ... of 16-byte word v1
                 SpWorkspace sp;
-                sp.ticket = nullptr;
-                sp.desc = nullptr;
-                sp.d_phase = nullptr;
                 sp.bstate = ws.bstate;
                 sp.bleft = ws.bleft;
                 sp.bright = ws.bright;
@@ -972,9 +966,8 @@ static size_t enc_ws_layout(size_t n, size_t off[10]) {
     o[0] = take(nruns * 4);              // run_bits
     o[1] = take(nruns * kEncWarps * 4);  // chunk_rel                 (64-bit-entry path)
     o[2] = take((nruns + 1) * 8);        // run_off
-    o[3] = take((nchunks + 1) * 4 + 64); // bstate, then the ticket and the plan's counter (zeroed together)
-    o[6] = o[3] + (nchunks + 1) * 4;     // ticket (4-byte aligned, inside the bstate block); the plan's counter follows it
-    o[7] = take(64);                     // (unused)
+    o[3] = take((nchunks + 1) * 4 + 64); // bstate: arrival counters of the 16-byte words that two runs (64-bit-entry path: chunks) share
+    o[6] = o[7] = 0;                     // (slots of the look-back encoder of round 1: gone)
     o[4] = take((nchunks + 1) * 16);     // bleft
     o[5] = take((nchunks + 1) * 16);     // bright
     o[8] = take(nruns * 512);            // run histograms (dc_histogram_u8_runs -> dc_huff_encode_planned)

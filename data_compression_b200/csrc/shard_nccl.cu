@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(320) shard_exchange_kernel(PeerPtrs p, const u
 }
 
 struct ShardEncLayout {
-    size_t local_hist, all_hist, ghist, rank_bits, rank_off, plan, edges, my_edge, enc_ws, total;
+    size_t local_hist, all_hist, rank_bits, rank_off, plan, enc_ws, total;
 };
 static ShardEncLayout shard_enc_layout(size_t n_local, int world) {
     ShardEncLayout L;
@@ -233,12 +233,9 @@ static ShardEncLayout shard_enc_layout(size_t n_local, int world) {
     auto take = [&](size_t bytes) { size_t o = p; p += (bytes + 255) & ~(size_t)255; return o; };
     L.local_hist = take(kShardSlots * 8);
     L.all_hist = take((size_t)world * kShardSlots * 8);
-    L.ghist = take(DC_NSLOTS * 8);
     L.rank_bits = take((size_t)world * 8);
     L.rank_off = take((size_t)(world + 1) * 8);
     L.plan = take(sizeof(ShardPlan));
-    L.edges = take((size_t)world * 2);
-    L.my_edge = take(16);
     L.enc_ws = take(dc_huff_encode_workspace_bytes(n_local));
     L.total = p;
     return L;
