@@ -344,6 +344,24 @@ def run_ours(args) -> None:
         barrier()
         return all_max(a.elapsed_time(b) / reps)[0]
 
+    # ---- opt-in: a stream kept with its index (what the decoder's first pass finds): the write pass alone
+    if not args.no_extras:
+        nb, ph = state["nbits"], state["phase"]
+        built = dc.huff_index_build(payload, nb, table, n, bit_start=ph, workspace=state["dec_ws"])
+        assert built is not None, "the bench stream self-synchronises"
+        index, info = built
+        t_build = timed(lambda: dc.huff_index_build(payload, nb, table, n, bit_start=ph, workspace=state["dec_ws"]), reps=3, warm=1)
+        t_idx = timed(lambda: dc.huff_decode_indexed(payload, index, info, table, out=decoded, workspace=state["dec_ws"], status=dec_status))
+        dc._lib.check(int(dec_status.item()), "decode_indexed")
+        assert torch.equal(decoded, data), "indexed decode failed"
+        breakdown["decode_with_index"] = {
+            "what": "opt-in: the producer keeps sub_info + segment offsets (dc_huff_index_build), the consumer runs the write pass only "
+                    "(dc_huff_decode_indexed); not part of `value`",
+            "index_bytes": int(index.numel()), "index_frac_of_payload": index.numel() / float(c_bytes),
+            "index_build_ms": t_build, "decode_ms": t_idx, "decode_gbs": n * world / (t_idx * 1e-3) / 1e9,
+            "decode_frac_of_hbm": (c_bytes + index.numel() + n) / (t_idx * 1e-3) / 1e9 / peak}
+        del index
+
     # ---- BASELINE configs[1]: nybble pack / unpack of 2^30 four-bit symbols per GPU (shards start on even symbols: no exchange)
     if not args.no_extras:
         thr4, base4 = synth.zipf_nybble_spec()

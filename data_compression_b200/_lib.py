@@ -47,6 +47,12 @@ class HuffTableStruct(C.Structure):
 TABLE_BYTES = C.sizeof(HuffTableStruct)
 
 
+class HuffIndexInfo(C.Structure):
+    """dc_huff_index_info: what the host keeps with a stream's index (include/dc_b200.h)."""
+    _fields_ = [("magic", C.c_uint64), ("bit_start", C.c_uint64), ("nbits", C.c_uint64), ("n_symbols", C.c_uint64),
+                ("mode", C.c_uint32), ("start_token", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+
+
 class ShardSummaryStruct(C.Structure):
     """Mirror of ``struct dc_shard_summary`` (include/dc_b200.h)."""
     _fields_ = [("symbols", C.c_uint64), ("exit", C.c_uint32), ("resync", C.c_int32), ("assumed_start", C.c_uint32),
@@ -69,6 +75,9 @@ SYMBOLS = [
     ("dc_huff_table_from_lengths", _i, [_vp, _i, _vp, _vp]),
     ("dc_huff_table_download", _i, [_vp, _vp, _vp]),
     ("dc_huff_table_forget", _i, [_vp]),
+    ("dc_huff_index_bytes", _sz, [_u64, _u64]),
+    ("dc_huff_index_build", _i, [_vp, _u64, _u64, _vp, _u64, _vp, _sz, _vp, _vp, _sz, _vp]),
+    ("dc_huff_decode_indexed", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     ("dc_huff_bits_for_hist", _i, [_vp, _vp, _vp, _vp]),
     ("dc_huff_encode_workspace_bytes", _sz, [_sz]),
     ("dc_huff_encode", _i, [_vp, _sz, _vp, _vp, _sz, _u, _vp, _vp, _vp, _sz, _vp]),

@@ -171,6 +171,43 @@ def huff_decode(bits: torch.Tensor, nbits: int, table: HuffTable, n_out: int, bi
     return out[:n_out], status
 
 
+def huff_index_build(bits: torch.Tensor, nbits: int, table: HuffTable, n_symbols: int, bit_start: int = 0,
+                     workspace: torch.Tensor | None = None):
+    """Opt-in: the index of a finished stream (what the decoder's first pass would find), to be kept beside the payload.
+    Blocking.  Returns (index tensor, HuffIndexInfo), or None if the stream does not self-synchronise (decode it blindly)."""
+    from ._lib import HuffIndexInfo
+    _need_cuda(bits, "bits")
+    need = lib().dc_huff_decode_workspace_bytes(bit_start, nbits)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=bits.device)
+    index = torch.empty(max(lib().dc_huff_index_bytes(bit_start, nbits), 16), dtype=torch.uint8, device=bits.device)
+    info = HuffIndexInfo()
+    rc = lib().dc_huff_index_build(bits.data_ptr(), bit_start, nbits, table.ptr, n_symbols, index.data_ptr(), index.numel(),
+                                   C.addressof(info), workspace.data_ptr(), workspace.numel(), _stream())
+    if rc == 1:
+        return None
+    check(rc, "dc_huff_index_build")
+    return index, info
+
+
+def huff_decode_indexed(bits: torch.Tensor, index: torch.Tensor, info, table: HuffTable, out: torch.Tensor | None = None,
+                        workspace: torch.Tensor | None = None, status: torch.Tensor | None = None):
+    """The decoder's write pass alone, from a stream's index (huff_index_build).  Returns (out, status); nothing blocks."""
+    _need_cuda(bits, "bits")
+    n_out = int(info.n_symbols)
+    if out is None:
+        out = torch.empty(max(n_out, 1), dtype=torch.uint8, device=bits.device)
+    need = lib().dc_huff_decode_workspace_bytes(int(info.bit_start), int(info.nbits))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=bits.device)
+    if status is None:
+        status = torch.empty(1, dtype=torch.int32, device=bits.device)
+    check(lib().dc_huff_decode_indexed(bits.data_ptr(), C.addressof(info), table.ptr, index.data_ptr(), index.numel(), out.data_ptr(),
+                                       n_out, status.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()),
+          "dc_huff_decode_indexed")
+    return out[:n_out], status
+
+
 SHARD_ALIGN = 1024  # a longer stream is cut into shards at multiples of this many bytes
 
 

@@ -1114,16 +1114,19 @@ static uint32_t fsm_stage_bytes(int mode) {
     const uint32_t want = half > 2176u ? half : 2176u;
     return ((want < whole ? want : whole) + 15u) & ~15u;
 }
+static void launch_fsm_build(const dc_huff_table *d_table, FastWorkspace fw, int mode, cudaStream_t st) {
+    const int nstates = fsm_states(mode);
+    const bool compat = (mode & kModeFsmSync) != 0;
+    LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
+    fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmEntryRows + kFsmSuffixRows, 256, 0, st>>>(d_table, fsm_tables_at(fw.fsm), compat ? 1 : 0, nstates);
+}
 static int launch_fsm_sync(const uint8_t *d_bits, unsigned long long start, unsigned long long end, unsigned long long nsubf,
                            unsigned long long nwt, unsigned long long nseg, const dc_huff_table *d_table, FastWorkspace fw, int mode,
                            DecodeChain *chain, int lead, cudaStream_t st) {
     const int nstates = fsm_states(mode);
     const bool compat = (mode & kModeFsmSync) != 0;
     const FsmTables t = fsm_tables_at(fw.fsm);
-    {
-        LaunchScope ls(DC_K_DECODE_FSM_BUILD, st);
-        fsm_build_kernel<<<compat ? nstates : nstates + 1 + kFsmEntryRows + kFsmSuffixRows, 256, 0, st>>>(d_table, t, compat ? 1 : 0, nstates);
-    }
+    launch_fsm_build(d_table, fw, mode, st);
     // north_star (4): the tile staged by the bulk-copy engine instead of a 32-byte load per lane (DC_DECODE_TMA=1; measured
     // in DESIGN.md -- the default is whichever is faster)
     const bool tma = decode_tma();
@@ -1344,6 +1347,112 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
         return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
     }
     return DC_OK;
+}
+
+// ================================================================================================ a stream with its index (opt-in)
+// The index is what F1 + F2 leave behind -- sub_info (2 bytes per 256-bit subsequence) and seg_off (8 bytes per 16 KB segment) --
+// kept by the producer, so that the consumer runs F3 only.  Both calls point the workspace's two arrays INTO the index buffer:
+// nothing is copied.
+namespace {
+constexpr uint64_t kIndexMagic = 0x3149444358464344ull;   // "DCFXIDI1"
+struct IndexGeom {
+    unsigned long long end, nsubf, nwt, nseg;
+    size_t sub_info_off, seg_off_off, total;
+};
+IndexGeom index_geom(uint64_t bit_start, uint64_t nbits) {
+    IndexGeom g;
+    g.end = bit_start + nbits;
+    g.nsubf = (g.end + kF_SubBits - 1) / kF_SubBits;
+    g.nwt = (g.nsubf + 31) / 32;
+    g.nseg = (g.nwt + kF_SegTiles - 1) / kF_SegTiles;
+    g.sub_info_off = 0;
+    g.seg_off_off = ((size_t)g.nwt * 32 * 2 + 63) & ~(size_t)63;
+    g.total = g.seg_off_off + (size_t)g.nseg * 8;
+    return g;
+}
+}  // namespace
+
+extern "C" size_t dc_huff_index_bytes(uint64_t bit_start, uint64_t nbits) { return nbits ? index_geom(bit_start, nbits).total : 0; }
+
+static int index_workspace(uint64_t bit_start, uint64_t nbits, void *d_workspace, size_t workspace_bytes, void *d_index, FastWorkspace *fw) {
+    size_t off[12];
+    unsigned long long nsub, ntiles;
+    if (workspace_bytes < dec_ws_layout(bit_start, nbits, off, &nsub, &ntiles)) return DC_ERR_CAPACITY;
+    const IndexGeom g = index_geom(bit_start, nbits);
+    char *w = (char *)d_workspace, *x = (char *)d_index;
+    fw->mismatch = (int32_t *)(w + 16);
+    fw->sub_info = (uint16_t *)(x + g.sub_info_off);
+    fw->seg_cnt = (uint32_t *)(w + off[7]);
+    fw->seg_assumed = (uint32_t *)(w + off[8]);
+    fw->seg_exit = (uint32_t *)(w + off[9]);
+    fw->seg_off = (unsigned long long *)(x + g.seg_off_off);
+    fw->fsm = w + off[11];
+    fw->chain_slots = w + off[11] + kFsmWorkspaceBytes;
+    return DC_OK;
+}
+
+extern "C" int dc_huff_index_build(const uint8_t *d_bits, uint64_t bit_start, uint64_t nbits, const dc_huff_table *d_table, uint64_t n_symbols,
+                                   void *d_index, size_t index_bytes, dc_huff_index_info *info, void *d_workspace, size_t workspace_bytes,
+                                   void *stream) {
+    if (!d_bits || !d_table || !d_index || !info || !d_workspace || nbits == 0 || bit_start >= (uint64_t)kSubBits) return DC_ERR_ARG;
+    if ((((uintptr_t)d_bits | (uintptr_t)d_workspace | (uintptr_t)d_index) & 15) != 0) return DC_ERR_ARG;
+    const IndexGeom g = index_geom(bit_start, nbits);
+    if (index_bytes < g.total) return DC_ERR_CAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    FastWorkspace fw;
+    int rc = index_workspace(bit_start, nbits, d_workspace, workspace_bytes, d_index, &fw);
+    if (rc != DC_OK) return rc;
+    int32_t tmeta[12];
+    rc = table_meta_fetch(d_table, st, tmeta, true);
+    if (rc != DC_OK) return rc;
+    if (tmeta[8] != DC_OK) return tmeta[8];
+    if (tmeta[1] == 0) return DC_ERR_RADIX;
+    const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], bit_start);
+    int32_t *d_st = (int32_t *)d_workspace;   // (the robust path's scratch word: not used here)
+    DC_CUDA_TRY(cudaMemsetAsync(d_st, 0, sizeof(int32_t), st));
+    rc = launch_fast_sync(d_bits, bit_start, g.end, g.nsubf, g.nwt, g.nseg, d_table, fw, (size_t)n_symbols, d_st, mode, nullptr, 1, 0, st);
+    if (rc != DC_OK) return rc;
+    int32_t words[4] = {0, 0, 0, 0};   // mismatch, (mode), bad_input, start token
+    int32_t status = 0;
+    DC_CUDA_TRY(cudaMemcpyAsync(words, fw.mismatch, sizeof words, cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaMemcpyAsync(&status, d_st, sizeof status, cudaMemcpyDeviceToHost, st));
+    DC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (words[0]) return 1;              // some segment started on a wrong guess: this stream has no index
+    if (status != DC_OK) return status;  // the symbol total does not match n_symbols
+    info->magic = kIndexMagic;
+    info->bit_start = bit_start;
+    info->nbits = nbits;
+    info->n_symbols = n_symbols;
+    info->mode = (uint32_t)mode;
+    info->start_token = (uint32_t)words[3];
+    info->reserved[0] = info->reserved[1] = 0;
+    return DC_OK;
+}
+
+extern "C" int dc_huff_decode_indexed(const uint8_t *d_bits, const dc_huff_index_info *info, const dc_huff_table *d_table, const void *d_index,
+                                      size_t index_bytes, uint8_t *d_out, size_t n_out, int32_t *d_status, void *d_workspace,
+                                      size_t workspace_bytes, void *stream) {
+    if (!d_bits || !info || !d_table || !d_index || !d_workspace || (n_out && !d_out)) return DC_ERR_ARG;
+    if (info->magic != kIndexMagic || info->nbits == 0 || info->bit_start >= (uint64_t)kSubBits || info->n_symbols != (uint64_t)n_out) return DC_ERR_ARG;
+    if ((((uintptr_t)d_bits | (uintptr_t)d_workspace | (uintptr_t)d_index) & 15) != 0) return DC_ERR_ARG;
+    const IndexGeom g = index_geom(info->bit_start, info->nbits);
+    if (index_bytes < g.total) return DC_ERR_CAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    FastWorkspace fw;
+    int rc = index_workspace(info->bit_start, info->nbits, d_workspace, workspace_bytes, (void *)d_index, &fw);
+    if (rc != DC_OK) return rc;
+    int32_t tmeta[12];
+    rc = table_meta_fetch(d_table, st, tmeta, true);
+    if (rc != DC_OK) return rc;
+    if (tmeta[8] != DC_OK) return tmeta[8];
+    if (tmeta[1] == 0) return DC_ERR_RADIX;
+    const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], info->bit_start);
+    if ((uint32_t)mode != info->mode) return DC_ERR_ARG;   // another table (or another build of the library) made this index
+    const int32_t words[4] = {0, mode, 0, (int32_t)info->start_token};
+    DC_CUDA_TRY(cudaMemcpyAsync(fw.mismatch, words, sizeof words, cudaMemcpyHostToDevice, st));
+    if (mode & kModeFsm) launch_fsm_build(d_table, fw, mode, st);
+    return launch_fast_write(d_bits, g.end, g.nsubf, g.nwt, g.nseg, d_table, fw, d_out, n_out, d_status, mode, fast_stage_bytes(tmeta), 0, st);
 }
 
 // ================================================================================================ shards of a longer stream

@@ -716,6 +716,10 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
                 const unsigned long long pob = ob + pass_excl0;
                 const uint32_t al = (uint32_t)(((uintptr_t)a.out + pob) & 15);
                 const uint32_t pos0 = al + (excl - pass_excl0);
+                if (al + pass_total + 8u > a.stage_bytes) {   // counts that no walk of F1 can have produced (a damaged index): do not stage them
+                    corrupt = true;
+                    continue;
+                }
                 __syncwarp();  // the previous copy-out has read the staging tile
                 if (lane == 0) *(uint32_t *)(stage + ((al + pass_total) & ~3u)) = 0u;   // the one boundary word nobody's first store initialises
                 __syncwarp();

@@ -137,3 +137,25 @@ def test_stale_table_header_is_caught_and_forget_clears_it(dc, oracle):
     assert again.bits() == nbits and torch.equal(again.payload[: (nbits + 7) // 8], good.payload[: (nbits + 7) // 8])
     out, status = dc.huff_decode(again.payload, nbits, a, small.numel())
     assert int(status.item()) == 0 and torch.equal(out, small)
+
+
+@pytest.mark.parametrize("n_ary", [2, 3, 4, 16])
+def test_indexed_decode_matches_blind_decode(dc, oracle, n_ary):
+    """Opt-in index (what F1 + F2 find, kept by the producer): the write pass alone reproduces the input."""
+    for n, seed in ((1, 1), (4097, 2), ((1 << 21) + 5, 3)):
+        host = _bytes_all_256(n, seed=seed)
+        data = torch.from_numpy(host).cuda()
+        table = dc.huff_build(dc.histogram(data), n_ary)
+        for phase in (0, 4):
+            res = dc.huff_encode(data, table, bit_phase=phase, out=torch.empty(n * 2 + 64, dtype=torch.uint8, device="cuda"))
+            nbits = res.bits()
+            built = dc.huff_index_build(res.payload, nbits, table, n, bit_start=phase)
+            assert built is not None
+            index, info = built
+            assert index.numel() >= dc.lib().dc_huff_index_bytes(phase, nbits) and index.numel() <= (nbits // 8) // 14 + 4096
+            out, status = dc.huff_decode_indexed(res.payload, index, info, table)
+            assert int(status.item()) == 0 and torch.equal(out, data), (n_ary, n, phase)
+    # an index that belongs to another table is refused where the host can tell
+    other = dc.huff_build(dc.histogram(data), 16 if n_ary != 16 else 4)
+    with pytest.raises(dc.DcError):
+        dc.huff_decode_indexed(res.payload, index, info, other)
