@@ -346,6 +346,10 @@ int dc_shard_comm_world(const dc_shard_comm *comm);
  * neighbours' few bits from their edge symbols).  d_out then holds stream bytes [O_r / 8, ceil((O_r + bits_r) / 8)); the
  * concatenation over the ranks IS the single-stream payload of dc_huff_encode on the concatenated input.
  *   d_total_bits  this rank's code bits (1 x u64, may be NULL);  d_status as dc_huff_encode
+ * The exchange goes through peer memory (every rank stores its 2 KB into buffers its peers have mapped with CUDA IPC, over
+ * NVLink, and raises a flag; one single-CTA kernel) when the ranks can map each other's buffers, else through ncclAllGather
+ * (also under DC_SHARD_PEER=0).  The FIRST call on a communicator sets this up and blocks once (two small all-gathers);
+ * calls on one communicator must be issued in the same order on every rank and on one stream.
  * dc_shard_huff_encode_info (blocking) reads O_r, bits_r and the stream's bit total back from the workspace;
  * dc_shard_huff_gather (blocking) places all shards in one buffer on `root`.
  */
