@@ -140,7 +140,9 @@ def huff_encode(data: torch.Tensor, table: HuffTable, out: torch.Tensor | None =
     if out is None:
         # a Huffman code of byte data never exceeds 8 bits per symbol by more than the skew allows: n + n / 4 covers every
         # power-of-two radix; radix 3 runs on 2 bits per trit (uniform bytes: 5.08 trits = 10.2 bits per symbol)
-        cap = n + n // 2 + 64 if table.n_ary == 3 else n + n // 4 + 64
+        # nibble-per-digit radices (5 .. 15): up to log_n(256) + 1 digits of 4 bits per symbol (n = 5: 17.8 bits)
+        nib = table.n_ary is not None and 5 <= table.n_ary < 16
+        cap = 2 * n + n // 2 + 64 if nib else n + n // 2 + 64 if table.n_ary == 3 else n + n // 4 + 64
         out = torch.empty(cap, dtype=torch.uint8, device=data.device)
     need = lib().dc_huff_encode_workspace_bytes(n)
     if workspace is None or workspace.numel() < need:

@@ -277,7 +277,7 @@ extern "C" const char *dc_status_string(int s) {
         case DC_ERR_CAPACITY: return "output capacity too small";
         case DC_ERR_CORRUPT: return "corrupt bitstream";
         case DC_ERR_SYMBOL: return "symbol without a code / nibble symbol >= 16";
-        case DC_ERR_RADIX: return "payload packing needs n in {2,4,16}";
+        case DC_ERR_RADIX: return "payload packing needs a radix n <= 16";
         case DC_ERR_NCCL: return "NCCL unavailable (libnccl.so.2 / $DC_NCCL_LIB) or a collective failed";
         default: return "unknown status";
     }

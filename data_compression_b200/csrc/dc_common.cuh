@@ -97,6 +97,9 @@ struct HostFlag { volatile int32_t *host; int32_t *dev; cudaEvent_t ev; int dev_
 int host_flag_acquire(HostFlag *f);
 void host_flag_release(const HostFlag &f);
 
+// radices whose payload is one nibble per digit (k2_table.cu): no window LUTs, decoded by the byte-stepped state machine only
+__host__ __device__ inline bool nibble_radix(int n) { return n >= 5 && n < 16; }
+
 // ---------------------------------------------------------------- byte-stepped decoder geometry (k4_fsm.cuh; K2 records the state count)
 constexpr int kFsmMaxStates = 255;       // internal nodes of the code tree; F3 adds the DEAD sink with id nstates: 8 bits in all
 constexpr int kFsmMaxSyncStates = 256;   // F1 alone has no sink: a binary code of all 256 byte values + the dummy leaf has exactly 256

@@ -24,8 +24,18 @@ constexpr int kTabCap = 1040;  // >= DC_MAX_LEAVES + max dummy leaves (n_ary <= 
 
 // bits a digit occupies in the stream the encode / decode kernels work on.  n = 3 (the reference's default radix) is
 // handled as 2 bits per trit -- an intermediate "T2" stream that dc_trit_pack() turns into the 5-trits-per-byte payload
-// (tab->packed_radix = 3 marks such a table); every other radix without a power-of-two digit has tables only.
-__device__ __forceinline__ int bits_per_digit_of(int n) { return n == 2 ? 1 : n == 4 ? 2 : n == 16 ? 4 : n == 3 ? 2 : 0; }
+// (tab->packed_radix = 3 marks such a table).  The other radices up to 16 (5, 6, 7, 9, 10, ... -- SURVEY N4 names 9 and 10) take
+// one NIBBLE per digit, most significant digit first, high nibble first: binary-coded digits, the layout n = 16 has anyway, and
+// the stream is the payload.  Their tables carry no window LUTs (those index by the numeric value of a bit window, which a
+// nibble-per-digit code is not): the decoder walks them with the byte-stepped state machine only (k4_fsm.cuh), which is
+// radix-generic.  Radices above 16 have tables only.
+__device__ __forceinline__ int bits_per_digit_of(int n) { return n == 2 ? 1 : n == 4 ? 2 : n == 3 ? 2 : (n >= 5 && n <= 16) ? 4 : 0; }
+// a base-n numeral of `len` digits rewritten with one nibble per digit (most significant first)
+__device__ __forceinline__ unsigned int digits_to_nibbles(unsigned int v, int len, unsigned int n) {
+    unsigned int r = 0;
+    for (int k = 0; k < len; k++) { r |= (v % n) << (4 * k); v /= n; }
+    return r;
+}
 // a base-3 numeral of `len` digits rewritten with one 2-bit field per digit (most significant first)
 __device__ __forceinline__ unsigned int trits_to_t2(unsigned int v, int len) {
     unsigned int r = 0;
@@ -203,7 +213,9 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     const int nbits = my_len * bpd;
     const bool t2 = n_ary == 3;
     // what the kernels emit / match for this symbol: the canonical value itself, or its trits as 2-bit fields
-    const unsigned int my_stream_value = (t2 && assigned && my_len <= 16) ? trits_to_t2(my_value, my_len) : my_value;
+    const bool nib = nibble_radix(n_ary);
+    const unsigned int my_stream_value = (t2 && assigned && my_len <= 16) ? trits_to_t2(my_value, my_len)
+                                         : (nib && assigned && my_len <= 8) ? digits_to_nibbles(my_value, my_len, (unsigned int)n_ary) : my_value;
     if (tid <= DC_NSLOTS) {
         tab->lengths[tid] = tid < nsym ? my_len : 0;
         tab->values[tid] = tid < nsym ? my_value : 0u;
@@ -229,7 +241,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
     __syncthreads();
     for (int e = tid; e < (1 << DC_LUT_BITS); e += kTabThreads) {
         unsigned int entry = 0;
-        if (bpd) {
+        if (bpd && !nib) {
             for (int l = min_len; l <= max_len && l < 32; l++) {
                 const int lb = l * bpd;
                 if (lb > DC_LUT_BITS) break;
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
                                  : (total_lut ? ((dead << 16) | (dead << 24) | (1u << 29)) : (DC_LUT_PAIR_MARK | DC_LUT_NO_SUBTABLE));
     }
     // ---- 7. second level for codes of 13..16 bits (tables whose longest code exceeds the 12 index bits)
-    const bool need2 = bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead (block-uniform)
+    const bool need2 = bpd != 0 && !t2 && !nib && max_len * bpd > DC_LUT_BITS;   // radix 3 has its own, wider index instead (block-uniform)
     if (!need2) {
         if (tid == 0) tab->lut2_used = 0;
     } else {
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(kTabThreads) table_kernel(const unsigned long 
         }
     }
     // ---- 8. 14-bit count table for the decoder's synchronisation pass (tables whose longest code has 13 or 14 bits)
-    if (bpd != 0 && !t2 && max_len * bpd > DC_LUT_BITS && max_len * bpd <= DC_LUT14_BITS) {
+    if (bpd != 0 && !t2 && !nib && max_len * bpd > DC_LUT_BITS && max_len * bpd <= DC_LUT14_BITS) {
         // the code a left-aligned 14-bit window starts with, among those of at most `avail` bits: bits << 8 | 1, or 0
         auto code_bits = [&](unsigned int w14, int avail) -> unsigned int {
             for (int l = min_len; l <= max_len; l++) {

@@ -1059,6 +1059,8 @@ static int fast_mode(const int32_t *tmeta) {
     int mode;
     if (tmeta[9] == 3) {
         mode = tmeta[6] > DC_TRIT_WINDOW ? 3 : 2;   // radix 3: max_len in trits against the 8-trit index
+    } else if (nibble_radix(tmeta[0])) {
+        mode = 0;                          // (no window LUTs: only the state-machine bits below count -- see decode_mode_usable)
     } else if (tmeta[7] <= DC_LUT_BITS) {
         mode = 0;                          // max_bits against the 12-bit index
     } else {
@@ -1077,6 +1079,8 @@ static int fast_mode(const int32_t *tmeta) {
     }
     return mode;
 }
+// nibble-per-digit radices (5 .. 15) have no window LUTs: only the byte-stepped kernels can decode them
+static bool decode_mode_usable(const int32_t *tmeta, int mode) { return !nibble_radix(tmeta[0]) || (mode & kModeFsm) != 0; }
 static int write_mode(int mode) { return mode & 3; }
 static int lut2_tables(int mode) { return (mode >> 8) & 0x1FF; }   // second-level tables in use (F3 keeps only those in shared memory)
 static int sync_mode(int mode) { return (mode & kSyncW14) ? 4 : (mode & 3); }
@@ -1315,8 +1319,16 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     if (tmeta[1] == 0) return DC_ERR_RADIX;
 
     const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], bit_start);
+    if (!decode_mode_usable(tmeta, mode)) return (bit_start % 4) ? DC_ERR_ARG : DC_ERR_RADIX;   // (a nibble code off the nibble grid / too many states)
     const int force = decode_force_mode();
-    if (force == 1) return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
+    const bool nib = nibble_radix(tmeta[0]);
+    auto serial = [&]() -> int {   // the nibble radices' last resort (their tables have no window LUTs for the robust path)
+        launch_fsm_build(d_table, fw, mode, st);
+        LaunchScope ls(DC_K_DECODE_SYNC, st);
+        fsm_serial_kernel<<<1, 32, 0, st>>>(d_bits, bit_start, end, fsm_tables_at(fw.fsm), d_out, n_out, d_status);
+        return cuda_status(cudaGetLastError());
+    };
+    if (force == 1) return nib ? serial() : decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
 
     const uint32_t stage_bytes = fast_stage_bytes(tmeta);
     // did every segment start on a code boundary?  F2 knows and stores the answer in mapped host memory as well; the host waits
@@ -1344,6 +1356,7 @@ extern "C" int dc_huff_decode(const uint8_t *d_bits, uint64_t bit_start, uint64_
     }
     if (mismatch || force == 2) {
         if (d_status) DC_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+        if (nib) return serial();
         return decode_robust(d_bits, bit_start, end, d_table, d_out, n_out, d_status, ws, nsub, ntiles, st);
     }
     return DC_OK;
@@ -1408,6 +1421,7 @@ extern "C" int dc_huff_index_build(const uint8_t *d_bits, uint64_t bit_start, ui
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], bit_start);
+    if (!decode_mode_usable(tmeta, mode)) return DC_ERR_RADIX;
     int32_t *d_st = (int32_t *)d_workspace;   // (the robust path's scratch word: not used here)
     DC_CUDA_TRY(cudaMemsetAsync(d_st, 0, sizeof(int32_t), st));
     rc = launch_fast_sync(d_bits, bit_start, g.end, g.nsubf, g.nwt, g.nseg, d_table, fw, (size_t)n_symbols, d_st, mode, nullptr, 1, 0, st);
@@ -1448,7 +1462,7 @@ extern "C" int dc_huff_decode_indexed(const uint8_t *d_bits, const dc_huff_index
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     const int mode = mode_for_start(fast_mode(tmeta), tmeta[1], info->bit_start);
-    if ((uint32_t)mode != info->mode) return DC_ERR_ARG;   // another table (or another build of the library) made this index
+    if ((uint32_t)mode != info->mode || !decode_mode_usable(tmeta, mode)) return DC_ERR_ARG;   // another table (or another build of the library) made this index
     const int32_t words[4] = {0, mode, 0, (int32_t)info->start_token};
     DC_CUDA_TRY(cudaMemcpyAsync(fw.mismatch, words, sizeof words, cudaMemcpyHostToDevice, st));
     if (mode & kModeFsm) launch_fsm_build(d_table, fw, mode, st);
@@ -1465,6 +1479,7 @@ struct ShardGeom {
     FastWorkspace fw;
     DecodeChain *chain;
     int mode, bpd;
+    bool nib;                         // nibble-per-digit radix: the state machine or nothing
     uint32_t stage_bytes;
 };
 }  // namespace
@@ -1504,7 +1519,9 @@ static int shard_geometry(const uint8_t *d_bits, int has_halo, uint64_t shard_bi
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     g->mode = fast_mode(tmeta);
+    if (!decode_mode_usable(tmeta, g->mode)) return DC_ERR_RADIX;
     g->bpd = tmeta[1];
+    g->nib = nibble_radix(tmeta[0]);
     g->stage_bytes = fast_stage_bytes(tmeta);
     return DC_OK;
 }
@@ -1520,6 +1537,7 @@ extern "C" int dc_huff_decode_shard_sync(const uint8_t *d_bits, int has_halo, un
     if (!has_halo) {
         if ((first_code_bit & kFsmToken) && !(g.mode & (kModeFsm | kModeFsmSync))) return DC_ERR_ARG;   // a state token, but the table has no state machine
         g.mode = mode_for_start(g.mode, g.bpd, first_code_bit);
+        if (g.nib && !(g.mode & kModeFsm)) return DC_ERR_ARG;   // a nibble code cannot start off the nibble grid
     }
     DC_CUDA_TRY(cudaMemcpyAsync(g.fw.mismatch + 1, &g.mode, sizeof(int), cudaMemcpyHostToDevice, st));   // the write phase takes the same kernels
     DecodeChain init = {0ull, has_halo ? 0u : first_code_bit, 0, 0u, 0u};
@@ -1629,6 +1647,7 @@ static int host_decompress_pipelined_body(const uint8_t *h_payload, uint64_t tot
     if (tmeta[8] != DC_OK) return tmeta[8];
     if (tmeta[1] == 0) return DC_ERR_RADIX;
     const int mode = fast_mode(tmeta);
+    if (!decode_mode_usable(tmeta, mode)) return 1;   // (not taken: the one-shot path reports it)
     const uint32_t stage_bytes = fast_stage_bytes(tmeta);
 
     cudaStream_t up = g_pipe.up, cp = g_pipe.cp, dn = g_pipe.dn;

@@ -755,4 +755,32 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
     if (corrupt) set_status(a.d_status, DC_ERR_CORRUPT);
 }
 
+// ------------------------------------------------------------------------------------------ last resort: one thread, whole stream
+// For the nibble-per-digit radices (5 .. 15), whose tables have no window LUTs: a stream that does not self-synchronise
+// (codes that all have the same odd number of digits, say) cannot go to the window kernels' robust path.  One thread walks it
+// digit by digit from its first bit.  Slow (tens of MB/s) and exact; such streams are degenerate.
+__global__ void fsm_serial_kernel(const uint8_t *__restrict__ d_bits, unsigned long long bit_start, unsigned long long end, FsmTables t,
+                                  uint8_t *__restrict__ out, unsigned long long n_out, int32_t *__restrict__ d_status) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const FsmHeader *h = t.hdr;
+    if (h->nstates == 0) { set_status(d_status, DC_ERR_ARG); return; }
+    const int bpd = h->bpd;
+    int d = 0;
+    uint32_t v = 0;
+    unsigned long long p = bit_start, o = 0;
+    bool bad = false;
+    while (p + bpd <= end) {
+        const int r = fsm_digit(h, d, v, stream_digit(d_bits, p, bpd));
+        p += bpd;
+        if (r >= 0) {
+            if (o < n_out) out[o] = (uint8_t)r;
+            o++;
+        } else if (r == -2) {
+            bad = true;
+            break;
+        }
+    }
+    if (bad || d != 0 || p != end || o != n_out) set_status(d_status, o > n_out && !bad ? DC_ERR_CAPACITY : DC_ERR_CORRUPT);
+}
+
 }  // namespace dc

@@ -8,9 +8,10 @@
  *
  * Differences, all additive:
  *   --n N        radix (compressed_symbols).  The reference hard-codes 3 (:2529); so does the default here.
- *                For N in {2,3,4,16} the block is really Huffman-coded -- radix 3 as 5 trits per byte, the storage
- *                its author sketches at :745-748 -- while the reference's emit loop and decoder are assert(0)
- *                stubs, so it can only ever produce the pass-through block.  Other radices: tables + raw block.
+ *                For N <= 16 the block is really Huffman-coded -- radix 3 as 5 trits per byte, the storage its author
+ *                sketches at :745-748, radices 5 .. 15 as one nibble per digit -- while the reference's emit loop and
+ *                decoder are assert(0) stubs, so it can only ever produce the pass-through block.  Larger radices:
+ *                tables + raw block.
  *   --quiet      only the `Successful test.` lines
  *   the block is the whole of stdin (up to 1 GiB), not the first 65 000 bytes (:2513)
  *

@@ -89,7 +89,7 @@ def huff_compress(data, compressed_symbols: int, out: np.ndarray | None = None):
     """Returns (payload ndarray view, total_bits, lengths[259])."""
     d = _u8(data)
     if out is None:
-        out = np.empty(d.size + d.size // 4 + 64, dtype=np.uint8)
+        out = np.empty((2 * d.size + d.size // 2 if 5 <= compressed_symbols < 16 else d.size + d.size // 4) + 64, dtype=np.uint8)
     lengths = np.zeros(DC_NSLOTS, dtype=np.int32)
     bits = C.c_uint64(0)
     rc = lib().dc_host_huff_compress(d.ctypes.data, d.size, compressed_symbols, out.ctypes.data, out.size,

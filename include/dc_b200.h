@@ -53,7 +53,7 @@ enum dc_status {
     DC_ERR_CAPACITY = -4,      /* output buffer too small */
     DC_ERR_CORRUPT = -5,       /* bitstream hits an unused code slot / ends inside a code */
     DC_ERR_SYMBOL = -6,        /* input symbol has no code (length 0), or nibble symbol >= 16 (:1093) */
-    DC_ERR_RADIX = -7,         /* payload packing is defined for n in {2,4,16} only */
+    DC_ERR_RADIX = -7,         /* payload packing is defined for radices n <= 16 only */
     DC_ERR_NCCL = -8           /* NCCL could not be loaded (libnccl.so.2 / $DC_NCCL_LIB) or a collective failed */
 };
 
@@ -72,7 +72,9 @@ enum dc_status {
  */
 typedef struct dc_huff_table {
     int32_t n_ary;            /* compressed_symbols */
-    int32_t bits_per_digit;   /* 1, 2, 4 for n = 2, 4, 16; 2 for n = 3 (see packed_radix); 0 = table only (no payload packing) */
+    int32_t bits_per_digit;   /* 1, 2, 4 for n = 2, 4, 16; 2 for n = 3 (see packed_radix); 4 for n = 5 .. 15 (one nibble per digit,
+                               * most significant digit first -- the stream is the payload; such tables carry no window LUTs and
+                               * are decoded by the byte-stepped state machine only); 0 = table only (n > 16: no payload packing) */
     int32_t max_symbol_value; /* 258 */
     int32_t nonzero_symbols;  /* :880-886 */
     int32_t dummy_nodes;      /* :900-903, as written */

@@ -132,6 +132,41 @@ def bits_per_digit(n: int) -> int:
     return lib().orc_bits_per_digit(n)
 
 
+def nibble_values(elen, evalue, n: int) -> np.ndarray:
+    """Radices 5 .. 15 (one nibble per digit, most significant digit first): the canonical code values -- base-n numerals, as
+    convert_lengths_to_encode_table() n_ary_huffman.c:1382-1612 assigns them -- rewritten as nibble strings for pack(.., bpd = 4)."""
+    el = np.asarray(elen, dtype=np.int64)
+    ev = np.asarray(evalue, dtype=np.uint64)
+    out = np.zeros(el.size, dtype=np.uint32)
+    for s in range(el.size):
+        v, r = int(ev[s]), 0
+        for k in range(int(el[s])):
+            r |= (v % n) << (4 * k)
+            v //= n
+        out[s] = r
+    return out
+
+
+def unpack_nibble_digits(payload, bit_start: int, nbits: int, elen, evalue, n: int) -> np.ndarray:
+    """Pure-Python reader of a nibble-per-digit payload (small cases): digits accumulate into a base-n numeral until (length,
+    value) names a symbol.  Independent of every table the library builds."""
+    el = np.asarray(elen, dtype=np.int64)
+    ev = np.asarray(evalue, dtype=np.uint64)
+    code = {(int(el[s]), int(ev[s])): s for s in range(min(el.size, 256)) if el[s] > 0}
+    p = np.asarray(payload, dtype=np.uint8)
+    out, length, value = [], 0, 0
+    assert bit_start % 4 == 0 and nbits % 4 == 0
+    for i in range(bit_start // 4, (bit_start + nbits) // 4):
+        d = (int(p[i >> 1]) >> (4 if i % 2 == 0 else 0)) & 15
+        assert d < n, "not a digit of this radix"
+        length, value = length + 1, value * n + d
+        if (length, value) in code:
+            out.append(code[(length, value)])
+            length, value = 0, 0
+    assert length == 0, "the stream ends inside a code"
+    return np.array(out, dtype=np.uint8)
+
+
 def pack(data, elen, evalue, bpd: int, bit_phase: int = 0):
     """Returns (payload bytes, total_bits).  Raises on status != 0."""
     d = _u8(data)

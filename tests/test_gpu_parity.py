@@ -73,7 +73,8 @@ def test_tables_match_reference_golden(dc, oracle, table_cases):
                 assert t.status == 0
                 assert np.array_equal(np.array(t.values[:259], dtype=np.uint32), dense(rec["values"], dtype=np.uint32)), \
                     (case["name"], n)
-                bpd = 2 if n == 3 else oracle.bits_per_digit(n)   # radix 3: one 2-bit field per trit in the kernels' stream
+                # radix 3: one 2-bit field per trit in the kernels' stream; 5 .. 15: one nibble per digit
+                bpd = 2 if n == 3 else 4 if 5 <= n < 16 else oracle.bits_per_digit(n)
                 assert t.packed_radix == (3 if n == 3 else 0)
                 assert t.bits_per_digit == bpd and t.max_bits == int(want_len.max()) * bpd
                 assert t.total_bits == int((dense(case["hist"]) * want_len * bpd).sum())
@@ -403,7 +404,7 @@ def test_decode_reports_corruption(dc, oracle):
 
 def test_radix_without_packing_is_table_only(dc):
     data = _zipf(dc, 4096)
-    table = dc.huff_build(dc.histogram(data), 5)
+    table = dc.huff_build(dc.histogram(data), 17)     # (radices up to 16 have a payload: a nibble per digit)
     assert table.download().bits_per_digit == 0
     res = dc.huff_encode(data, table)
     assert int(res.status.item()) == dc.DC_ERR_RADIX

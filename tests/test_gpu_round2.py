@@ -159,3 +159,65 @@ def test_indexed_decode_matches_blind_decode(dc, oracle, n_ary):
     other = dc.huff_build(dc.histogram(data), 16 if n_ary != 16 else 4)
     with pytest.raises(dc.DcError):
         dc.huff_decode_indexed(res.payload, index, info, other)
+
+
+@pytest.mark.parametrize("n_ary", [5, 9, 10, 12, 15])
+def test_nibble_per_digit_radices(dc, oracle, n_ary):
+    """SURVEY N4 (n = 9, 10 by name): radices 5 .. 15 pack one nibble per digit, most significant digit first.  The payload
+    equals the oracle's (its packer fed with the canonical base-n values rewritten as nibbles by an independent routine), a
+    pure-Python digit reader gets the input back from it, and the GPU decoder -- state machine only -- round-trips it."""
+    for n, seed in ((1, 1), (257, 2), (4099, 3), ((1 << 20) + 9, 4)):
+        host = _bytes_all_256(n, seed=seed)
+        data = torch.from_numpy(host).cuda()
+        hist = dc.histogram(data)
+        table = dc.huff_build(hist, n_ary)
+        t = table.download()
+        assert t.bits_per_digit == 4 and t.packed_radix == 0 and t.fsm_states > 0
+        ln, el, ev, st = oracle.build_tables(hist.cpu().numpy().astype(np.uint64), n_ary)
+        assert st == 0 and np.array_equal(np.array(t.lengths[:259]), ln)
+        nv = oracle.nibble_values(el, ev, n_ary)
+        for phase in (0, 4):
+            res = dc.huff_encode(data, table, bit_phase=phase)
+            nbits = res.bits()
+            want, wbits = oracle.pack(host, el, nv, 4, phase)
+            assert nbits == wbits and nbits % 4 == 0
+            got = res.payload[: (nbits + phase + 7) // 8].cpu().numpy()
+            assert np.array_equal(got, want), (n_ary, n, phase)
+            if n <= 4099:
+                assert np.array_equal(oracle.unpack_nibble_digits(got, phase, nbits, el, ev, n_ary), host)
+            out, status = dc.huff_decode(res.payload, nbits, table, n, bit_start=phase)
+            assert int(status.item()) == 0 and torch.equal(out, data), (n_ary, n, phase)
+    # a nibble that is not a digit of the radix
+    bad = res.payload.clone()
+    bad[1000] = 0xFF
+    out, status = dc.huff_decode(bad, nbits, table, n, bit_start=4)
+    assert int(status.item()) == dc.DC_ERR_CORRUPT
+    # off the nibble grid: refused
+    with pytest.raises(dc.DcError):
+        dc.huff_decode(res.payload, nbits, table, n, bit_start=2)
+
+
+def test_nibble_radix_stream_that_does_not_self_synchronise(dc, oracle):
+    """124 equally likely symbols at n = 5 (the as-written dummy rule adds the 125th leaf): every code has 3 digits, so a decoder
+    that starts in the wrong place never finds its way back.  The window kernels' robust path has no tables for such a radix:
+    one thread walks the stream instead."""
+    rng = np.random.default_rng(8)
+    host = rng.integers(1, 125, size=300001).astype(np.uint8)
+    host[:124] = np.arange(1, 125, dtype=np.uint8)
+    data = torch.from_numpy(host).cuda()
+    hist = dc.histogram(data)
+    hist[1:125] = 1000                                # exactly uniform: a complete 5-ary tree of depth 3 (one leaf is the dummy)
+    table = dc.huff_build(hist, 5)
+    t = table.download()
+    assert t.min_len == 3 and t.max_len == 3
+    res = dc.huff_encode(data, table)
+    nbits = res.bits()
+    assert nbits == host.size * 12
+    out, status = dc.huff_decode(res.payload, nbits, table, host.size)
+    assert int(status.item()) == 0 and torch.equal(out, data)
+    assert dc.huff_index_build(res.payload, nbits, table, host.size) is None     # no index for such a stream
+    # the host entry points, the reference's call shape: huffman(.., 10, ..) -> compress -> decompress
+    from data_compression_b200 import hostapi
+    payload, bits, lengths = hostapi.huff_compress(host, 10)
+    back = hostapi.huff_decompress(payload, bits, lengths, 10, host.size)
+    assert np.array_equal(back, host)

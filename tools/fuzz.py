@@ -14,7 +14,7 @@ t_end = time.time() + budget
 it = fails = 0
 while time.time() < t_end:
     it += 1
-    n_ary = int(rng.choice([2, 3, 4, 16]))
+    n_ary = int(rng.choice([2, 3, 4, 16, 5, 7, 9, 10, 13]))   # 5 .. 15: one nibble per digit
     nsym = int(rng.integers(1, 256))
     alphabet = rng.choice(np.arange(1, 256), size=nsym, replace=False).astype(np.uint8)
     skew = float(rng.choice([0.0, 0.5, 1.0, 1.5, 2.5, 4.0]))
@@ -50,7 +50,9 @@ while time.time() < t_end:
         ok = int(pst.item()) == 0 and np.array_equal(pay.cpu().numpy(), want)
         stream, ust = dc.trit_unpack(pay, wtr)
     else:
-        want, wbits = O.pack(data, el, ev, O.bits_per_digit(n_ary))
+        nib = 5 <= n_ary < 16
+        sv, bpd = (O.nibble_values(el, ev, n_ary), 4) if nib else (ev, O.bits_per_digit(n_ary))
+        want, wbits = O.pack(data, el, sv, bpd)
         ok = nbits == wbits and np.array_equal(res.payload[: (nbits + 7) // 8].cpu().numpy(), want)
         stream = res.payload
     out, status = dc.huff_decode(stream, nbits, table, size)
@@ -60,9 +62,9 @@ while time.time() < t_end:
         print("MISMATCH", it, n_ary, nsym, skew, size, t.max_bits, flush=True)
     # a shard's view: the same input at a non-zero bit phase (leading bits belong to the previous shard)
     if n_ary != 3:
-        phase = int(rng.integers(1, 8))
+        phase = 4 if nib else int(rng.integers(1, 8))   # (a nibble code cannot be decoded off the nibble grid)
         res_p = dc.huff_encode(d, table, out=torch.empty(size * 4 + 64, dtype=torch.uint8, device="cuda"), bit_phase=phase)
-        want_p, wb = O.pack(data, el, ev, O.bits_per_digit(n_ary), phase)
+        want_p, wb = O.pack(data, el, sv, bpd, phase)
         okp = res_p.bits() == wb and np.array_equal(res_p.payload[: (wb + phase + 7) // 8].cpu().numpy(), want_p)
         out_p, st_p = dc.huff_decode(res_p.payload, wb, table, size, bit_start=phase)
         okp = okp and int(st_p.item()) == 0 and np.array_equal(out_p.cpu().numpy(), data)
