@@ -25,7 +25,10 @@ def _oracle_payload(host, n_ary):
     hist = O.histogram_u8(host)
     lengths, el, ev, st = O.build_tables(hist, n_ary)
     assert st == 0
-    payload, bits = O.pack(host, el, ev, O.bits_per_digit(n_ary))
+    if 5 <= n_ary < 16:   # one nibble per digit
+        payload, bits = O.pack(host, el, O.nibble_values(el, ev, n_ary), 4)
+    else:
+        payload, bits = O.pack(host, el, ev, O.bits_per_digit(n_ary))
     return payload, bits, lengths
 
 
@@ -83,7 +86,7 @@ def _worker(rank, world, port, n_total, n_ary, q):
     q.put((rank, bool(ok)))
 
 
-@pytest.mark.parametrize("n_ary", [2, 4, 16])
+@pytest.mark.parametrize("n_ary", [2, 4, 16, 10])
 def test_shard_c_abi_world1(n_ary):
     import queue
     q = queue.Queue()
@@ -92,7 +95,7 @@ def test_shard_c_abi_world1(n_ary):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU)")
-@pytest.mark.parametrize("n_ary", [4, 16])
+@pytest.mark.parametrize("n_ary", [4, 16, 10])
 def test_shard_c_abi_world2(n_ary):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
