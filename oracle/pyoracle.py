@@ -132,19 +132,24 @@ def bits_per_digit(n: int) -> int:
     return lib().orc_bits_per_digit(n)
 
 
-def nibble_values(elen, evalue, n: int) -> np.ndarray:
-    """Radices 5 .. 15 (one nibble per digit, most significant digit first): the canonical code values -- base-n numerals, as
-    convert_lengths_to_encode_table() n_ary_huffman.c:1382-1612 assigns them -- rewritten as nibble strings for pack(.., bpd = 4)."""
+def field_values(elen, evalue, n: int, bits: int) -> np.ndarray:
+    """The canonical code values -- base-n numerals, as convert_lengths_to_encode_table() n_ary_huffman.c:1382-1612 assigns them --
+    rewritten with one `bits`-wide field per digit, most significant digit first, for pack(.., bpd = bits)."""
     el = np.asarray(elen, dtype=np.int64)
     ev = np.asarray(evalue, dtype=np.uint64)
     out = np.zeros(el.size, dtype=np.uint32)
     for s in range(el.size):
         v, r = int(ev[s]), 0
         for k in range(int(el[s])):
-            r |= (v % n) << (4 * k)
+            r |= (v % n) << (bits * k)
             v //= n
         out[s] = r
     return out
+
+
+def nibble_values(elen, evalue, n: int) -> np.ndarray:
+    """Radices 5 .. 15: one nibble per digit."""
+    return field_values(elen, evalue, n, 4)
 
 
 def unpack_nibble_digits(payload, bit_start: int, nbits: int, elen, evalue, n: int) -> np.ndarray:

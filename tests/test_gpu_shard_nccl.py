@@ -25,7 +25,9 @@ def _oracle_payload(host, n_ary):
     hist = O.histogram_u8(host)
     lengths, el, ev, st = O.build_tables(hist, n_ary)
     assert st == 0
-    if 5 <= n_ary < 16:   # one nibble per digit
+    if n_ary == 3:        # the kernels' stream for radix 3: one 2-bit field per trit (the octet payload is packed from it)
+        payload, bits = O.pack(host, el, O.field_values(el, ev, 3, 2), 2)
+    elif 5 <= n_ary < 16:   # one nibble per digit
         payload, bits = O.pack(host, el, O.nibble_values(el, ev, n_ary), 4)
     else:
         payload, bits = O.pack(host, el, ev, O.bits_per_digit(n_ary))
@@ -86,7 +88,7 @@ def _worker(rank, world, port, n_total, n_ary, q):
     q.put((rank, bool(ok)))
 
 
-@pytest.mark.parametrize("n_ary", [2, 4, 16, 10])
+@pytest.mark.parametrize("n_ary", [2, 4, 16, 10, 3])
 def test_shard_c_abi_world1(n_ary):
     import queue
     q = queue.Queue()
@@ -95,7 +97,7 @@ def test_shard_c_abi_world1(n_ary):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU)")
-@pytest.mark.parametrize("n_ary", [4, 16, 10])
+@pytest.mark.parametrize("n_ary", [4, 16, 10, 3])
 def test_shard_c_abi_world2(n_ary):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
