@@ -209,3 +209,29 @@ def test_base64url_text_form(oracle):
     assert oracle.base64url_unpack(b"t0", 11).tobytes() == bytes([0b10110111, 0b01000000])
     with pytest.raises(ValueError):
         oracle.base64url_unpack(b"t!", 11)
+
+
+def test_nibble_per_digit_layout_statement_roundtrips_on_cpu():
+    """Radices 5 .. 15 (9 and 10 by name): the oracle's statement of the payload -- canonical base-n values rewritten
+    with one nibble per digit, packed MSB first -- read back by an independent pure-Python digit reader."""
+    import numpy as np
+    from oracle import pyoracle as O
+    O.build()
+    rng = np.random.default_rng(4)
+    for n in (5, 9, 10, 15):
+        w = 1.0 / np.arange(1, 201) ** 1.1
+        data = rng.choice(np.arange(1, 201, dtype=np.uint8), size=5000, p=w / w.sum()).astype(np.uint8)
+        ln, el, ev, st = O.build_tables(O.histogram_u8(data), n)
+        assert st == 0
+        nv = O.nibble_values(el, ev, n)
+        for s in range(1, 201):   # every nibble is a digit of the radix, and the numeral is the canonical value
+            digits = [(int(nv[s]) >> (4 * k)) & 15 for k in range(int(el[s]))][::-1]
+            assert all(d < n for d in digits)
+            v = 0
+            for d in digits:
+                v = v * n + d
+            assert el[s] == 0 or v == int(ev[s])
+        for phase in (0, 4):
+            payload, bits = O.pack(data, el, nv, 4, phase)
+            assert bits == int(sum(int(el[b]) for b in data)) * 4
+            assert np.array_equal(O.unpack_nibble_digits(payload, phase, bits, el, ev, n), data)
