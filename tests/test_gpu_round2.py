@@ -88,7 +88,7 @@ for n in (1, 4097, (1 << 22) + 13):
     data = torch.empty(n, dtype=torch.uint8, device="cuda")
     dc.synth_fill(data, synth.SEED_BASE + n, synth.device_thresholds(thr, "cuda"), base)
     hist = dc.histogram(data)
-    for n_ary in (3, 4, 16):
+    for n_ary in (2, 3, 4, 16):   # n = 2: the state machine for F1 only (COMPAT), window kernel behind it
         table = dc.huff_build(hist, n_ary)
         for phase in (0, 2):
             res = dc.huff_encode(data, table, bit_phase=phase, out=torch.empty(n * 2 + 64, dtype=torch.uint8, device="cuda"))
