@@ -112,28 +112,34 @@ struct ShardPlan {                        // one per call, in the workspace; rea
 __global__ void __launch_bounds__(256) shard_plan_kernel(const unsigned long long *__restrict__ all_hist, int world, int rank,
                                                         const dc_huff_table *__restrict__ tab, unsigned long long *__restrict__ rank_bits,
                                                         unsigned long long *__restrict__ rank_off, ShardPlan *__restrict__ plan) {
-    __shared__ unsigned long long s_sum[256];
-    const int tid = threadIdx.x;
-    const unsigned long long len = tid < 256 ? (unsigned long long)(tab->lengths[tid] * tab->bits_per_digit) : 0ull;
-    unsigned long long run = 0;
-    for (int r = 0; r < world; r++) {
-        s_sum[tid] = all_hist[(size_t)r * kShardSlots + tid] * len;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (tid < o) s_sum[tid] += s_sum[tid + o];
-            __syncthreads();
+    // one warp per rank (8 at a time): a lane takes 8 of the 256 symbols, the warp adds up; then one thread scans the totals
+    __shared__ unsigned long long s_bits[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long len[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) len[k] = (unsigned long long)(tab->lengths[lane + 32 * k] * tab->bits_per_digit);
+    for (int r = warp; r < world; r += 8) {
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += all_hist[(size_t)r * kShardSlots + lane + 32 * k] * len[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if (lane == 0) {
+            if (r < 64) s_bits[r] = sum;
+            rank_bits[r] = sum;
         }
-        if (tid == 0) {
-            rank_bits[r] = s_sum[0];
-            rank_off[r] = run;
-        }
-        run += s_sum[0];
-        __syncthreads();
     }
+    __syncthreads();
     if (tid == 0) {
+        unsigned long long run = 0;
+        for (int r = 0; r < world; r++) {
+            const unsigned long long bits_r = r < 64 ? s_bits[r] : rank_bits[r];
+            rank_off[r] = run;
+            run += bits_r;
+        }
         rank_off[world] = run;
         plan->bit_offset = rank_off[rank];
-        plan->bits = rank_bits[rank];
+        plan->bits = world <= 64 ? s_bits[rank] : rank_bits[rank];
         plan->total_bits = run;
         plan->phase = (uint32_t)(rank_off[rank] & 7ull);
     }
