@@ -1045,6 +1045,7 @@ static int decode_robust(const uint8_t *d_bits, unsigned long long bit_start, un
 
 constexpr int kSyncW14 = 0x10;
 constexpr int kModeFsmSync = 0x40;   // F1 through the state machine, F3 through the window kernel (k4_fsm.cuh, COMPAT): binary codes with 256 states
+constexpr int kModeFsmWide = 0x80;   // with kModeFsm: 4-bit digits, at most two codes end in a byte (the write kernel without its suffix look-up)
 constexpr int kModeFsm = 0x20;   // the byte-stepped kernels of k4_fsm.cuh; bits 20..28: states, bits 29..31: min(shortest code's bits, 8) - 1
 static int decode_force_mode();
 static bool decode_tma();
@@ -1071,7 +1072,7 @@ static int fast_mode(const int32_t *tmeta) {
     // sits in the walk's dependent chain, and with 32 lanes some lane needs one in most steps -- measured 2.5x slower)
     if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxStates && fsm_rows_fit(tmeta) && decode_force_mode() != 3) {
         const int min_bits = tmeta[5] * tmeta[1];
-        mode |= kModeFsm | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
+        mode |= kModeFsm | (tmeta[1] == 4 ? kModeFsmWide : 0) | (tmeta[11] << 20) | ((min_bits < 8 ? min_bits : 8) - 1) << 29;
     } else if (tmeta[11] > 0 && tmeta[11] <= kFsmMaxSyncStates && tmeta[1] == 1 && tmeta[9] == 0 && decode_force_mode() != 3) {
         // binary code, too many states for F3's rows: the state machine for F1 only (its table is at most 128 KB)
         const int min_bits = tmeta[5] * tmeta[1];
@@ -1178,7 +1179,8 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
     const int warps = 24;
     const size_t smem = kFsmHeaderBytes + (size_t)rows * kFsmWriteRowBytes + kFsmWriteXTableBytes + (size_t)warps * stage + 256;   // (fsm_rows_fit: within the limit)
     const int per_sm = smem <= 56 * 1024 ? 2 : 1;   // (2 x 768 threads: the register file allows no more)
-    DC_CUDA_TRY(ensure_dynamic_smem((const void *)fsm_write_kernel, smem));
+    const bool xtab = !(mode & kModeFsmWide);
+    DC_CUDA_TRY(ensure_dynamic_smem(xtab ? (const void *)fsm_write_kernel<true> : (const void *)fsm_write_kernel<false>, smem));
     const unsigned long long want = (nseg + warps - 1) / warps, cap = (unsigned long long)sm_count() * per_sm;
     FsmWriteArgs a;
     a.d_bits = d_bits;
@@ -1194,7 +1196,8 @@ static int launch_fsm_write(const uint8_t *d_bits, unsigned long long end, unsig
     a.d_status = d_status;
     LaunchScope ls(DC_K_DECODE_FSM_WRITE, st);
     const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-    fsm_write_kernel<<<grid, warps * 32, smem, st>>>(a, t, fw);
+    if (xtab) fsm_write_kernel<true><<<grid, warps * 32, smem, st>>>(a, t, fw);
+    else fsm_write_kernel<false><<<grid, warps * 32, smem, st>>>(a, t, fw);
     return cuda_status(cudaGetLastError());
 }
 

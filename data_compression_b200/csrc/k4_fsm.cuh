@@ -584,13 +584,15 @@ struct FsmWriteTabs {
 
 // One byte step of the write walk.  acc = the lane's last four symbols (newest in the top byte), G = 8 x pending bytes in its
 // low 5 bits (bit 5 toggles when a word completes), wptr = shared address of the word being filled, e = the previous entry.
-template <int J>
+// XTAB = false: a byte holds at most two digits (4-bit digits: n = 16 and the nibble-per-digit radices), so no byte completes a third
+// code and the suffix look-up is not compiled in (its predicated-off instructions alone cost 7 % of the kernel at n = 16).
+template <int J, bool XTAB>
 __device__ __forceinline__ void fsm_write_step(const FsmWriteTabs &T, uint32_t w, uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
     const uint32_t idx = prmt(w, e, 0xFF60u | (uint32_t)J);   // byte J | state << 8; bytes 2, 3 = sign of the count byte = 0
     e = lds_u32_at(T.tab, idx);
     const uint32_t c = e >> 27;
     uint32_t syms = e;   // symbols 0 and 1 (the state and the count above them are never taken: a window slides by c bytes)
-    if (c >= 3u) {       // symbols 2 and 3: what the byte decodes to from digit k on, row = count * 8 + k
+    if (XTAB && c >= 3u) {       // symbols 2 and 3: what the byte decodes to from digit k on, row = count * 8 + k
         const uint32_t xi = prmt(w, e, 0xFF70u | (uint32_t)J);
         uint32_t x;
         asm volatile("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %1, 2, %2;\n\tld.shared.u16 %0, [a];\n\t}" : "=r"(x) : "r"(xi), "r"(T.xtab));
@@ -615,16 +617,18 @@ __device__ __forceinline__ void fsm_write_step(const FsmWriteTabs &T, uint32_t w
         : "memory");
 }
 
+template <bool XTAB>
 __device__ __forceinline__ void fsm_write_walk(const FsmWriteTabs &T, const uint32_t (&w)[8], uint32_t &e, uint32_t &acc, uint32_t &G, uint32_t &wptr) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        fsm_write_step<0>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<1>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<2>(T, w[k], e, acc, G, wptr);
-        fsm_write_step<3>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<0, XTAB>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<1, XTAB>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<2, XTAB>(T, w[k], e, acc, G, wptr);
+        fsm_write_step<3, XTAB>(T, w[k], e, acc, G, wptr);
     }
 }
 
+template <bool XTAB>
 __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTables t, FastWorkspace ws) {
     extern __shared__ __align__(16) uint8_t fsm_smem[];
     FsmHeader *s_h = (FsmHeader *)fsm_smem;
@@ -725,7 +729,7 @@ __global__ void __launch_bounds__(768, 1) fsm_write_kernel(FsmWriteArgs a, FsmTa
                 __syncwarp();
                 uint32_t wptr0 = stage_addr + (pos0 & ~3u), wptr = wptr0, G = 8u * (pos0 & 3u), acc = 0u;
                 uint32_t meta = (my_info & 0xFFu) << 16;
-                if (mine && my_cnt) fsm_write_walk(T, w, meta, acc, G, wptr);
+                if (mine && my_cnt) fsm_write_walk<XTAB>(T, w, meta, acc, G, wptr);
                 __syncwarp();
                 if (mine && my_cnt) {
                     const uint32_t pend = (G >> 3) & 3u;
